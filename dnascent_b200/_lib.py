@@ -1,0 +1,117 @@
+"""ctypes loader for the in-tree CUDA library.  There is no fallback: if the shared object is missing the import
+of anything that computes fails loudly (the oracle under oracle/ is test infrastructure and is never used here)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libdnascent_b200.so")
+
+_lib = None
+
+
+class DnbError(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{where}: error {code}" + (f" ({detail})" if detail else ""))
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int),
+        ("window_length1", C.c_uint32), ("window_length2", C.c_uint32),
+        ("threshold1", C.c_float), ("threshold2", C.c_float), ("peak_height", C.c_float),
+        ("min_average_log_emission", C.c_double), ("max_gap_threshold", C.c_int), ("bandwidth", C.c_int),
+        ("use_fit_pore_model", C.c_int), ("event_capacity_per_sample", C.c_float), ("keep_debug", C.c_int),
+        ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class ReadDesc(C.Structure):
+    _fields_ = [
+        ("raw_pA", C.c_void_p), ("raw_dac", C.c_void_p), ("dac_offset", C.c_float), ("dac_scale", C.c_float),
+        ("n_samples", C.c_uint64),
+        ("query", C.c_char_p), ("query_len", C.c_uint32),
+        ("ref", C.c_char_p), ("ref_len", C.c_uint32),
+        ("query_to_ref", C.c_void_p),
+    ]
+
+
+class ReadResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int), ("et_n", C.c_uint32), ("n_events", C.c_uint32),
+        ("event_start", C.POINTER(C.c_uint32)), ("event_mean", C.POINTER(C.c_float)),
+        ("n_align", C.c_uint32), ("align_pairs", C.POINTER(C.c_uint32)),
+        ("shift", C.c_double), ("scale", C.c_double), ("events_per_base", C.c_double),
+        ("rough_shift", C.c_double), ("rough_scale", C.c_double),
+        ("avg_log_emission", C.c_double), ("spanned", C.c_int), ("max_gap", C.c_int),
+        ("n_cleaned", C.c_uint32), ("cleaned_signal", C.POINTER(C.c_double)), ("cleaned_rank", C.POINTER(C.c_uint32)),
+    ]
+
+
+class EventT(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("length", C.c_float), ("mean", C.c_float), ("stdv", C.c_float),
+                ("pos", C.c_int), ("state", C.c_int)]
+
+
+# every symbol include/dnascent_b200.h declares
+EXPORTS = [
+    "dnb_default_config", "dnb_create", "dnb_destroy", "dnb_strerror", "dnb_last_error", "dnb_load_model",
+    "dnb_submit", "dnb_wait", "dnb_result", "dnb_release",
+    "dnb_batch_upload", "dnb_batch_run", "dnb_batch_fetch", "dnb_batch_timings",
+    "dnb_detect_events",
+    "dnb_eexp", "dnb_eln", "dnb_lnSum", "dnb_lnProd", "dnb_lnGreaterThan", "dnb_uniformPDF", "dnb_normalPDF",
+    "dnb_cauchyPDF", "dnb_sequence_probability_batch",
+]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C dnascent_b200/csrc).  dnascent_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, d = C.c_void_p, C.c_size_t, C.c_double
+    L.dnb_default_config.argtypes = [C.POINTER(Config)]
+    L.dnb_default_config.restype = None
+    L.dnb_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    L.dnb_destroy.argtypes = [vp]
+    L.dnb_destroy.restype = None
+    L.dnb_strerror.restype = C.c_char_p
+    L.dnb_strerror.argtypes = [C.c_int]
+    L.dnb_last_error.restype = C.c_char_p
+    L.dnb_load_model.argtypes = [vp, C.c_int, vp, vp, sz]
+    L.dnb_submit.argtypes = [vp, C.POINTER(ReadDesc), sz, C.POINTER(vp)]
+    L.dnb_batch_upload.argtypes = [vp, C.POINTER(ReadDesc), sz, C.POINTER(vp)]
+    L.dnb_wait.argtypes = [vp]
+    L.dnb_batch_run.argtypes = [vp]
+    L.dnb_batch_fetch.argtypes = [vp]
+    L.dnb_result.argtypes = [vp, sz, C.POINTER(ReadResult)]
+    L.dnb_release.argtypes = [vp]
+    L.dnb_release.restype = None
+    L.dnb_batch_timings.argtypes = [vp, C.POINTER(d * 6), C.POINTER(C.c_uint64 * 6)]
+    L.dnb_detect_events.argtypes = [vp, vp, sz, C.POINTER(EventT), sz, C.POINTER(sz)]
+    L.dnb_eexp.restype = d
+    L.dnb_eexp.argtypes = [d]
+    L.dnb_eln.argtypes = [d, C.POINTER(d)]
+    for f in ("dnb_lnSum", "dnb_lnProd"):
+        getattr(L, f).restype = d
+        getattr(L, f).argtypes = [d, d]
+    L.dnb_lnGreaterThan.argtypes = [d, d]
+    for f in ("dnb_uniformPDF", "dnb_normalPDF", "dnb_cauchyPDF"):
+        getattr(L, f).restype = d
+        getattr(L, f).argtypes = [d, d, d]
+    L.dnb_sequence_probability_batch.argtypes = [vp, vp, vp, C.c_char_p, vp, vp, vp, sz, C.c_uint32, vp, vp]
+    _lib = L
+    return L
+
+
+def check(code: int, where: str):
+    if code != 0:
+        L = lib()
+        detail = L.dnb_strerror(code).decode()
+        last = L.dnb_last_error().decode()
+        raise DnbError(code, where, detail + (": " + last if last else ""))

@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference interface for the detect signal hot path, over the C ABI.
+
+The reference's interface for this path is one C++ call per read, ``normaliseEvents(DNAscent::read&, bool)``
+(/root/reference/src/event_handling.h:13), plus ``detect_events`` (src/scrappie/event_detection.h:35), the
+log-space helpers of src/probability.h:26-33 and ``sequenceProbability`` (src/detect.h:119).  The names, argument
+meaning and failure convention (empty ``eventAlignment`` == failed read, src/detect.cpp:879) are kept; the call is
+batched because a GPU wants many reads per launch.  PyTorch is not involved: the library owns its device memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import numpy as np
+
+from . import _lib
+from ._lib import Config, ReadDesc, ReadResult, EventT, DnbError
+
+MODEL_PORE, MODEL_UNLABELLED, MODEL_ANALOGUE = 0, 1, 2
+READ_OK, READ_QC_FAIL, READ_SCALE_FAIL, READ_UNDEFINED, READ_OVERFLOW = 0, 1, 2, 3, 4
+ERR_NEGATIVE_LOG = 6
+
+
+class NegativeLog(ValueError):
+    """src/probability.h:11-17"""
+
+    def __str__(self):
+        return "Negative value passed to natural log function."
+
+
+@dataclasses.dataclass
+class Read:
+    """The fields of DNAscent::read that normaliseEvents consumes (src/reads.h:178-208)."""
+    raw: np.ndarray | None          # float32 pA (float32-exact, src/pod5.cpp:60) ...
+    basecall: bytes
+    referenceSeqMappedTo: bytes
+    queryToRef: np.ndarray          # dense int32, -1 = no entry
+    dac: np.ndarray | None = None   # ... or int16 DAC with calibration
+    dac_offset: float = 0.0
+    dac_scale: float = 1.0
+
+    @classmethod
+    def from_synth(cls, sr, use_dac: bool = False):
+        from .synth import DAC_OFFSET, DAC_SCALE
+        if use_dac:
+            return cls(None, sr.basecall, sr.refseq, sr.query_to_ref, dac=sr.dac, dac_offset=float(DAC_OFFSET),
+                       dac_scale=float(DAC_SCALE))
+        return cls(sr.raw, sr.basecall, sr.refseq, sr.query_to_ref)
+
+
+@dataclasses.dataclass
+class Normalised:
+    """What normaliseEvents leaves in DNAscent::read: events, eventAlignment, scalings, alignmentQCs."""
+    status: int
+    et_n: int
+    event_start: np.ndarray     # uint32 [n_events+1]; events[j].raw == raw[event_start[j]:event_start[j+1]]
+    event_mean: np.ndarray      # float32 [n_events]  events[j].mean
+    eventAlignment: np.ndarray  # uint32 [n_align, 2] (event_idx, kmer_idx); empty == failed read
+    shift: float
+    scale: float
+    eventsPerBase: float
+    rough_shift: float
+    rough_scale: float
+    avg_log_emission: float
+    spanned: bool
+    maxGap: int
+    cleaned_signal: np.ndarray | None = None
+    cleaned_rank: np.ndarray | None = None
+
+
+def _as(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class Batch:
+    def __init__(self, ctx: "Context", handle, n_reads: int, keepalive):
+        self.ctx, self.h, self.n, self._keep = ctx, handle, n_reads, keepalive
+
+    def wait(self):
+        _lib.check(self.ctx.L.dnb_wait(self.h), "dnb_wait")
+
+    def run(self):
+        _lib.check(self.ctx.L.dnb_batch_run(self.h), "dnb_batch_run")
+
+    def fetch(self):
+        _lib.check(self.ctx.L.dnb_batch_fetch(self.h), "dnb_batch_fetch")
+
+    def timings(self):
+        ms = (C.c_double * 6)()
+        cnt = (C.c_uint64 * 6)()
+        _lib.check(self.ctx.L.dnb_batch_timings(self.h, C.byref(ms), C.byref(cnt)), "dnb_batch_timings")
+        names = ("segmentation", "prep", "banded_dp", "backtrace", "theil_sen", "total")
+        cn = ("samples", "events", "kmers", "bands", "cells", "launches")
+        return dict(zip(names, ms)), dict(zip(cn, (int(x) for x in cnt)))
+
+    def result(self, i: int) -> Normalised:
+        r = ReadResult()
+        _lib.check(self.ctx.L.dnb_result(self.h, i, C.byref(r)), "dnb_result")
+        ne = r.n_events
+        pairs = _as(r.align_pairs, 2 * r.n_align, np.uint32).reshape(-1, 2)
+        return Normalised(
+            status=r.status, et_n=r.et_n, event_start=_as(r.event_start, ne + 1 if ne else 0, np.uint32),
+            event_mean=_as(r.event_mean, ne, np.float32), eventAlignment=pairs, shift=r.shift, scale=r.scale,
+            eventsPerBase=r.events_per_base, rough_shift=r.rough_shift, rough_scale=r.rough_scale,
+            avg_log_emission=r.avg_log_emission, spanned=bool(r.spanned), maxGap=r.max_gap,
+            cleaned_signal=_as(r.cleaned_signal, r.n_cleaned, np.float64) if r.n_cleaned else None,
+            cleaned_rank=_as(r.cleaned_rank, r.n_cleaned, np.uint32) if r.n_cleaned else None)
+
+    def results(self):
+        return [self.result(i) for i in range(self.n)]
+
+    def release(self):
+        if self.h:
+            self.ctx.L.dnb_release(self.h)
+            self.h = None
+            self._keep = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Context:
+    """One per process and GPU (``dnb_ctx``).  Fails loudly without a CUDA device: there is no CPU path."""
+
+    def __init__(self, device: int = 0, keep_debug: bool = False, event_capacity_per_sample: float | None = None):
+        self.L = _lib.lib()
+        cfg = Config()
+        self.L.dnb_default_config(C.byref(cfg))
+        cfg.device = device
+        cfg.keep_debug = int(keep_debug)
+        if event_capacity_per_sample is not None:
+            cfg.event_capacity_per_sample = event_capacity_per_sample
+        self.cfg = cfg
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_create(C.byref(h), C.byref(cfg)), "dnb_create")
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.dnb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_model(self, which: int, mean: np.ndarray, stdv: np.ndarray | None = None):
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        sd = None if stdv is None else np.ascontiguousarray(stdv, dtype=np.float64)
+        _lib.check(self.L.dnb_load_model(self.h, which, mean.ctypes.data, None if sd is None else sd.ctypes.data,
+                                         mean.size), "dnb_load_model")
+
+    # -- batches ------------------------------------------------------------------------------------
+    @staticmethod
+    def _descs(reads):
+        n = len(reads)
+        arr = (ReadDesc * n)()
+        keep = []
+        for i, r in enumerate(reads):
+            d = arr[i]
+            if r.dac is not None:
+                dac = np.ascontiguousarray(r.dac, dtype=np.int16)
+                keep.append(dac)
+                d.raw_dac, d.raw_pA, d.n_samples = dac.ctypes.data, None, dac.size
+                d.dac_offset, d.dac_scale = r.dac_offset, r.dac_scale
+            else:
+                raw = np.ascontiguousarray(r.raw, dtype=np.float32)
+                keep.append(raw)
+                d.raw_pA, d.raw_dac, d.n_samples = raw.ctypes.data, None, raw.size
+            q2r = np.ascontiguousarray(r.queryToRef, dtype=np.int32)
+            keep.append(q2r)
+            d.query, d.query_len = r.basecall, len(r.basecall)
+            d.ref, d.ref_len = r.referenceSeqMappedTo, len(r.referenceSeqMappedTo)
+            d.query_to_ref = q2r.ctypes.data
+            keep.append((r.basecall, r.referenceSeqMappedTo))
+        return arr, keep
+
+    def submit(self, reads) -> Batch:
+        arr, keep = self._descs(reads)
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_submit(self.h, arr, len(reads), C.byref(h)), "dnb_submit")
+        return Batch(self, h, len(reads), (arr, keep))
+
+    def upload(self, reads) -> Batch:
+        arr, keep = self._descs(reads)
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_batch_upload(self.h, arr, len(reads), C.byref(h)), "dnb_batch_upload")
+        return Batch(self, h, len(reads), None)   # inputs are resident in HBM; host copies may be dropped
+
+    def normaliseEvents(self, reads) -> list[Normalised]:
+        """Batched normaliseEvents(r, false): src/event_handling.cpp:544."""
+        b = self.submit(reads)
+        try:
+            b.wait()
+            return b.results()
+        finally:
+            b.release()
+
+    # -- detect_events ------------------------------------------------------------------------------
+    def detect_events(self, raw: np.ndarray):
+        """event_table detect_events(raw, n, event_detection_defaults): src/scrappie/event_detection.c:268."""
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        cap = raw.size + 2
+        ev = (EventT * cap)()
+        n = C.c_size_t(0)
+        _lib.check(self.L.dnb_detect_events(self.h, raw.ctypes.data, raw.size, ev, cap, C.byref(n)), "dnb_detect_events")
+        a = np.ctypeslib.as_array(ev)[: n.value]
+        return (a["start"].astype(np.uint64), a["length"].astype(np.float32), a["mean"].astype(np.float32),
+                a["stdv"].astype(np.float32))
+
+    # -- analogue likelihood ------------------------------------------------------------------------
+    def sequence_probability_batch(self, obs_list, snippets, shift, scale, events_per_base, window: int = 12):
+        """Both passes of sequenceProbability for every site (src/detect.cpp:235-378, 546-547)."""
+        n = len(obs_list)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(o) for o in obs_list])
+        obs = np.ascontiguousarray(np.concatenate([np.asarray(o, dtype=np.float64) for o in obs_list])
+                                   if n else np.zeros(0), dtype=np.float64)
+        seq = b"".join(snippets)
+        assert len(seq) == n * (2 * window + 9)
+        shift = np.ascontiguousarray(np.broadcast_to(shift, (n,)), dtype=np.float64)
+        scale = np.ascontiguousarray(np.broadcast_to(scale, (n,)), dtype=np.float64)
+        epb = np.ascontiguousarray(np.broadcast_to(events_per_base, (n,)), dtype=np.float64)
+        oa = np.zeros(n)
+        ot = np.zeros(n)
+        _lib.check(self.L.dnb_sequence_probability_batch(self.h, obs.ctypes.data, off.ctypes.data, seq, shift.ctypes.data,
+                                                         scale.ctypes.data, epb.ctypes.data, n, window, oa.ctypes.data,
+                                                         ot.ctypes.data), "dnb_sequence_probability_batch")
+        return oa, ot
+
+
+# ---- probability.h drop-ins (scalar, host) ------------------------------------------------------------
+def eexp(x: float) -> float:
+    return _lib.lib().dnb_eexp(x)
+
+
+def eln(x: float) -> float:
+    o = C.c_double(0.0)
+    rc = _lib.lib().dnb_eln(x, C.byref(o))
+    if rc == ERR_NEGATIVE_LOG:
+        raise NegativeLog()
+    _lib.check(rc, "dnb_eln")
+    return o.value
+
+
+def lnSum(a: float, b: float) -> float:
+    return _lib.lib().dnb_lnSum(a, b)
+
+
+def lnProd(a: float, b: float) -> float:
+    return _lib.lib().dnb_lnProd(a, b)
+
+
+def lnGreaterThan(a: float, b: float) -> bool:
+    return bool(_lib.lib().dnb_lnGreaterThan(a, b))
+
+
+def uniformPDF(lb: float, ub: float, x: float) -> float:
+    return _lib.lib().dnb_uniformPDF(lb, ub, x)
+
+
+def normalPDF(mu: float, sigma: float, x: float) -> float:
+    return _lib.lib().dnb_normalPDF(mu, sigma, x)
+
+
+def cauchyPDF(loc: float, scale: float, x: float) -> float:
+    return _lib.lib().dnb_cauchyPDF(loc, scale, x)

@@ -1,0 +1,729 @@
+// capi.cu -- the C ABI of libdnascent_b200.so (include/dnascent_b200.h): contexts, model tables, batch staging
+// (pinned host <-> HBM), the two-phase device pipeline and result hand-out.
+//
+// Host-side counterpart of the reference's per-read call
+//     normaliseEvents(r, false)                      /root/reference/src/detect.cpp:876
+// turned into a batch: the OpenMP read loop (detect.cpp:852) hands a buffer of reads to dnb_submit.
+//
+// Pipeline of one batch (all on the batch's own stream):
+//   phase A   segmentation -> k-mer ranks -> quantile scaling -> event scaling
+//   host      n_events comes back (one small D2H); the per-read transition constants need glibc's log/exp to be
+//             bit-identical with the reference (event_handling.cpp:174-183), and the trace/alignment workspaces
+//             are sized from n_events, so both are done here and sent down
+//   phase B   banded DP -> backtrace/QC -> Theil-Sen
+//   fetch     alignment compaction -> D2H of events, alignment pairs and per-read scalars
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+#include "dnb_internal.cuh"
+#include "../../include/dnascent_b200.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t _e = (call);                                                                              \
+        if (_e != cudaSuccess) {                                                                              \
+            g_last_error = std::string(#call) + ": " + cudaGetErrorString(_e);                                \
+            return DNB_ERR_CUDA;                                                                              \
+        }                                                                                                     \
+    } while (0)
+
+struct ModelHost {
+    bool loaded = false;
+    double *d_mean = nullptr, *d_stdv = nullptr, *d_sorted = nullptr;
+    uint32_t *d_order = nullptr;
+    DnbModelDev dev() const { return DnbModelDev{d_mean, d_stdv, d_order, d_sorted}; }
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+};
+
+}  // namespace
+
+struct dnb_ctx {
+    dnb_config cfg;
+    ModelHost model[3];
+    double emit_const = 0.0;
+    std::mutex mu;
+};
+
+struct dnb_batch {
+    dnb_ctx *ctx = nullptr;
+    size_t R = 0;
+    cudaStream_t stream = nullptr;
+    bool want_table = false;     // dnb_detect_events: keep the full scrappie table, segmentation only
+    bool uploaded = false, ran = false, fetched = false;
+    // ---- host-side shapes ----
+    std::vector<uint64_t> raw_off, q_off, r_off, ev_off, band_off, al_off, cl_off, out_off;
+    std::vector<uint32_t> n_samples, order;
+    std::vector<uint32_t> qlen, rlen;
+    bool i16 = false;
+    uint64_t tot_raw = 0, tot_q = 0, tot_r = 0, tot_ev = 0, tot_bands = 0, tot_al = 0, tot_cl = 0, tot_out = 0;
+    // ---- device: inputs ----
+    void *d_raw = nullptr;
+    float *d_dac_off = nullptr, *d_dac_scl = nullptr;
+    char *d_query = nullptr, *d_ref = nullptr;
+    int32_t *d_q2r = nullptr;
+    uint64_t *d_raw_off = nullptr, *d_q_off = nullptr, *d_r_off = nullptr, *d_ev_off = nullptr;
+    uint32_t *d_n_samples = nullptr, *d_order = nullptr;
+    // ---- device: phase A outputs ----
+    uint32_t *d_et_n = nullptr, *d_n_events = nullptr, *d_ev_start = nullptr;
+    float *d_ev_mean = nullptr;
+    int *d_status = nullptr;
+    uint64_t *d_et_start = nullptr;
+    float *d_et_length = nullptr, *d_et_mean = nullptr, *d_et_stdv = nullptr;
+    double *d_mu_q = nullptr, *d_x_e = nullptr, *d_rough_shift = nullptr, *d_rough_scale = nullptr;
+    uint32_t *d_rank_ref = nullptr;
+    // ---- device: phase B ----
+    double *d_lp = nullptr;
+    uint64_t *d_band_off = nullptr, *d_al_off = nullptr, *d_cl_off = nullptr, *d_out_off = nullptr;
+    uint8_t *d_trace = nullptr;
+    int32_t *d_end_event = nullptr, *d_end_ll = nullptr;
+    float *d_end_score = nullptr;
+    unsigned long long *d_cells = nullptr;
+    uint32_t *d_al_rev = nullptr, *d_n_align = nullptr, *d_cl_rank = nullptr, *d_n_cleaned = nullptr, *d_out_pairs = nullptr;
+    double *d_cl_signal = nullptr, *d_avg = nullptr, *d_shift = nullptr, *d_scale = nullptr;
+    int *d_spanned = nullptr, *d_max_gap = nullptr;
+    // ---- host results (pinned where they are DMA targets) ----
+    uint32_t *h_et_n = nullptr, *h_n_events = nullptr, *h_n_align = nullptr, *h_n_cleaned = nullptr;
+    int *h_status = nullptr, *h_spanned = nullptr, *h_max_gap = nullptr;
+    double *h_rough_shift = nullptr, *h_rough_scale = nullptr, *h_shift = nullptr, *h_scale = nullptr, *h_avg = nullptr;
+    uint32_t *h_ev_start = nullptr, *h_out_pairs = nullptr, *h_cl_rank = nullptr;
+    float *h_ev_mean = nullptr;
+    double *h_cl_signal = nullptr;
+    uint64_t *h_et_start = nullptr;
+    float *h_et_length = nullptr, *h_et_mean = nullptr, *h_et_stdv = nullptr;
+    std::vector<double> lp;
+    // ---- timings ----
+    cudaEvent_t ev[8] = {};
+    double ms[6] = {};
+    uint64_t counts[6] = {};
+    unsigned long long h_cells = 0;
+    std::vector<void *> dev_allocs, host_allocs;
+};
+
+namespace {
+
+template <class T>
+int dalloc(dnb_batch *b, T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    void *q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, n * sizeof(T), b->stream);
+    if (e != cudaSuccess) {
+        g_last_error = std::string("cudaMallocAsync(") + std::to_string(n * sizeof(T)) + " B): " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? DNB_ERR_NOMEM : DNB_ERR_CUDA;
+    }
+    b->dev_allocs.push_back(q);
+    *p = (T *)q;
+    return DNB_OK;
+}
+
+template <class T>
+int halloc(dnb_batch *b, T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    void *q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, n * sizeof(T));
+    if (e != cudaSuccess) {
+        g_last_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return DNB_ERR_NOMEM;
+    }
+    b->host_allocs.push_back(q);
+    *p = (T *)q;
+    return DNB_OK;
+}
+
+#define TRY(x)                    \
+    do {                          \
+        int _rc = (x);            \
+        if (_rc != DNB_OK) return _rc; \
+    } while (0)
+
+template <class T>
+int h2d(dnb_batch *b, T *dst, const T *src, size_t n) {
+    if (n == 0) return DNB_OK;
+    CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, b->stream));
+    return DNB_OK;
+}
+template <class T>
+int d2h(dnb_batch *b, T *dst, const T *src, size_t n) {
+    if (n == 0) return DNB_OK;
+    CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, b->stream));
+    return DNB_OK;
+}
+
+DnbBatchView make_view(const dnb_batch *b) {
+    DnbBatchView v;
+    memset(&v, 0, sizeof(v));
+    v.n_reads = (uint32_t)b->R;
+    v.order = b->d_order;
+    v.raw_f32 = b->i16 ? nullptr : (const float *)b->d_raw;
+    v.raw_i16 = b->i16 ? (const int16_t *)b->d_raw : nullptr;
+    v.dac_offset = b->d_dac_off;
+    v.dac_scale = b->d_dac_scl;
+    v.raw_off = b->d_raw_off;
+    v.n_samples = b->d_n_samples;
+    v.query = b->d_query;
+    v.ref = b->d_ref;
+    v.q_off = b->d_q_off;
+    v.r_off = b->d_r_off;
+    v.q2r = b->d_q2r;
+    v.et_n = b->d_et_n;
+    v.n_events = b->d_n_events;
+    v.ev_off = b->d_ev_off;
+    v.ev_start = b->d_ev_start;
+    v.ev_mean = b->d_ev_mean;
+    v.status = b->d_status;
+    v.et_start = b->d_et_start;
+    v.et_length = b->d_et_length;
+    v.et_mean = b->d_et_mean;
+    v.et_stdv = b->d_et_stdv;
+    return v;
+}
+
+void free_batch(dnb_batch *b) {
+    if (!b) return;
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void *p : b->dev_allocs) cudaFreeAsync(p, b->stream);
+    for (void *p : b->host_allocs) cudaFreeHost(p);
+    for (auto &e : b->ev)
+        if (e) cudaEventDestroy(e);
+    if (b->stream) {
+        cudaStreamSynchronize(b->stream);
+        cudaStreamDestroy(b->stream);
+    }
+    delete b;
+}
+
+int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, dnb_batch **out) {
+    if (!ctx || (!reads && R) || !out) return DNB_ERR_ARG;
+    if (!ctx->model[DNB_MODEL_PORE].loaded && !want_table) return DNB_ERR_MODEL;
+    if (ctx->cfg.use_fit_pore_model) {
+        g_last_error = "use_fit_pore_model=1 is not implemented on the device path (all reference callers pass false)";
+        return DNB_ERR_ARG;
+    }
+    CK(cudaSetDevice(ctx->cfg.device));
+    dnb_batch *b = new dnb_batch();
+    b->ctx = ctx;
+    b->R = R;
+    b->want_table = want_table;
+    cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); delete b; return DNB_ERR_CUDA; }
+    for (auto &ev : b->ev) cudaEventCreate(&ev);
+
+    // ---- shapes ----
+    b->raw_off.resize(R + 1); b->q_off.resize(R + 1); b->r_off.resize(R + 1); b->ev_off.resize(R + 1);
+    b->n_samples.resize(R); b->qlen.resize(R); b->rlen.resize(R); b->order.resize(R);
+    bool any_i16 = false, any_f32 = false;
+    uint64_t ro = 0, qo = 0, fo = 0, eo = 0;
+    const double cap_per_sample = ctx->cfg.event_capacity_per_sample > 0 ? ctx->cfg.event_capacity_per_sample : 0.4;
+    for (size_t i = 0; i < R; i++) {
+        const dnb_read_desc &d = reads[i];
+        if ((!d.raw_pA && !d.raw_dac) || d.n_samples == 0 || d.n_samples >= (1ull << 31) || !d.query || !d.ref ||
+            (!want_table && !d.query_to_ref)) {
+            free_batch(b);
+            g_last_error = "read descriptor " + std::to_string(i) + " is incomplete";
+            return DNB_ERR_ARG;
+        }
+        (d.raw_pA ? any_f32 : any_i16) = true;
+        b->raw_off[i] = ro; b->q_off[i] = qo; b->r_off[i] = fo; b->ev_off[i] = eo;
+        b->n_samples[i] = (uint32_t)d.n_samples; b->qlen[i] = d.query_len; b->rlen[i] = d.ref_len;
+        ro += (d.n_samples + 31) & ~31ull;                 // 128-byte aligned read starts (float4 loads)
+        qo += d.query_len; fo += d.ref_len;
+        eo += (uint64_t)(cap_per_sample * (double)d.n_samples) + 16;
+    }
+    if (any_i16 && any_f32) { free_batch(b); g_last_error = "mixing raw_pA and raw_dac reads in one batch"; return DNB_ERR_ARG; }
+    b->i16 = any_i16;
+    b->raw_off[R] = ro; b->q_off[R] = qo; b->r_off[R] = fo; b->ev_off[R] = eo;
+    b->tot_raw = ro; b->tot_q = qo; b->tot_r = fo; b->tot_ev = eo;
+    std::iota(b->order.begin(), b->order.end(), 0u);
+    std::stable_sort(b->order.begin(), b->order.end(),
+                     [&](uint32_t x, uint32_t y) { return b->n_samples[x] > b->n_samples[y]; });   // longest first
+
+    // ---- pinned staging + device inputs ----
+    const size_t esz = b->i16 ? 2 : 4;
+    uint8_t *h_raw = nullptr; char *h_q = nullptr, *h_r = nullptr; int32_t *h_q2r = nullptr;
+    float *h_doff = nullptr, *h_dscl = nullptr;
+    int rc = DNB_OK;
+#define TRYF(x) do { rc = (x); if (rc != DNB_OK) { free_batch(b); return rc; } } while (0)
+    TRYF(halloc(b, &h_raw, ro * esz));
+    TRYF(halloc(b, &h_q, qo)); TRYF(halloc(b, &h_r, fo)); TRYF(halloc(b, &h_q2r, qo));
+    TRYF(halloc(b, &h_doff, R)); TRYF(halloc(b, &h_dscl, R));
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t i = 0; i < R; i++) {
+        const dnb_read_desc &d = reads[i];
+        uint8_t *dst = h_raw + b->raw_off[i] * esz;
+        const size_t padded = (size_t)(b->raw_off[i + 1] - b->raw_off[i]);
+        if (b->i16) memcpy(dst, d.raw_dac, d.n_samples * 2); else memcpy(dst, d.raw_pA, d.n_samples * 4);
+        memset(dst + d.n_samples * esz, 0, (padded - d.n_samples) * esz);
+        memcpy(h_q + b->q_off[i], d.query, d.query_len);
+        memcpy(h_r + b->r_off[i], d.ref, d.ref_len);
+        if (d.query_to_ref) memcpy(h_q2r + b->q_off[i], d.query_to_ref, (size_t)d.query_len * 4);
+        h_doff[i] = d.dac_offset; h_dscl[i] = d.dac_scale;
+    }
+    TRYF(dalloc(b, (uint8_t **)&b->d_raw, ro * esz));
+    TRYF(dalloc(b, &b->d_query, qo)); TRYF(dalloc(b, &b->d_ref, fo)); TRYF(dalloc(b, &b->d_q2r, qo));
+    TRYF(dalloc(b, &b->d_dac_off, R)); TRYF(dalloc(b, &b->d_dac_scl, R));
+    TRYF(dalloc(b, &b->d_raw_off, R + 1)); TRYF(dalloc(b, &b->d_q_off, R + 1)); TRYF(dalloc(b, &b->d_r_off, R + 1));
+    TRYF(dalloc(b, &b->d_ev_off, R + 1)); TRYF(dalloc(b, &b->d_n_samples, R)); TRYF(dalloc(b, &b->d_order, R));
+    TRYF(h2d(b, (uint8_t *)b->d_raw, h_raw, ro * esz));
+    TRYF(h2d(b, b->d_query, h_q, qo)); TRYF(h2d(b, b->d_ref, h_r, fo)); TRYF(h2d(b, b->d_q2r, h_q2r, qo));
+    TRYF(h2d(b, b->d_dac_off, h_doff, R)); TRYF(h2d(b, b->d_dac_scl, h_dscl, R));
+    TRYF(h2d(b, b->d_raw_off, b->raw_off.data(), R + 1)); TRYF(h2d(b, b->d_q_off, b->q_off.data(), R + 1));
+    TRYF(h2d(b, b->d_r_off, b->r_off.data(), R + 1)); TRYF(h2d(b, b->d_ev_off, b->ev_off.data(), R + 1));
+    TRYF(h2d(b, b->d_n_samples, b->n_samples.data(), R)); TRYF(h2d(b, b->d_order, b->order.data(), R));
+
+    // ---- phase A outputs + small per-read arrays ----
+    TRYF(dalloc(b, &b->d_et_n, R)); TRYF(dalloc(b, &b->d_n_events, R)); TRYF(dalloc(b, &b->d_status, R));
+    TRYF(dalloc(b, &b->d_ev_start, eo + R)); TRYF(dalloc(b, &b->d_ev_mean, eo));
+    TRYF(halloc(b, &b->h_et_n, R)); TRYF(halloc(b, &b->h_n_events, R)); TRYF(halloc(b, &b->h_status, R));
+    if (want_table) {
+        TRYF(dalloc(b, &b->d_et_start, eo + R)); TRYF(dalloc(b, &b->d_et_length, eo + R));
+        TRYF(dalloc(b, &b->d_et_mean, eo + R)); TRYF(dalloc(b, &b->d_et_stdv, eo + R));
+        TRYF(halloc(b, &b->h_et_start, eo + R)); TRYF(halloc(b, &b->h_et_length, eo + R));
+        TRYF(halloc(b, &b->h_et_mean, eo + R)); TRYF(halloc(b, &b->h_et_stdv, eo + R));
+    } else {
+        TRYF(dalloc(b, &b->d_mu_q, qo)); TRYF(dalloc(b, &b->d_rank_ref, fo)); TRYF(dalloc(b, &b->d_x_e, eo));
+        TRYF(dalloc(b, &b->d_rough_shift, R)); TRYF(dalloc(b, &b->d_rough_scale, R));
+        TRYF(dalloc(b, &b->d_lp, 4 * R));
+        TRYF(dalloc(b, &b->d_band_off, R + 1)); TRYF(dalloc(b, &b->d_al_off, R + 1)); TRYF(dalloc(b, &b->d_cl_off, R + 1));
+        TRYF(dalloc(b, &b->d_out_off, R + 1));
+        TRYF(dalloc(b, &b->d_end_event, R)); TRYF(dalloc(b, &b->d_end_ll, R)); TRYF(dalloc(b, &b->d_end_score, R));
+        TRYF(dalloc(b, &b->d_cells, 1));
+        TRYF(dalloc(b, &b->d_n_align, R)); TRYF(dalloc(b, &b->d_n_cleaned, R)); TRYF(dalloc(b, &b->d_avg, R));
+        TRYF(dalloc(b, &b->d_shift, R)); TRYF(dalloc(b, &b->d_scale, R));
+        TRYF(dalloc(b, &b->d_spanned, R)); TRYF(dalloc(b, &b->d_max_gap, R));
+        TRYF(halloc(b, &b->h_n_align, R)); TRYF(halloc(b, &b->h_n_cleaned, R)); TRYF(halloc(b, &b->h_spanned, R));
+        TRYF(halloc(b, &b->h_max_gap, R)); TRYF(halloc(b, &b->h_rough_shift, R)); TRYF(halloc(b, &b->h_rough_scale, R));
+        TRYF(halloc(b, &b->h_shift, R)); TRYF(halloc(b, &b->h_scale, R)); TRYF(halloc(b, &b->h_avg, R));
+    }
+    TRYF(halloc(b, &b->h_ev_start, eo + R)); TRYF(halloc(b, &b->h_ev_mean, eo));
+    e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); free_batch(b); return DNB_ERR_CUDA; }
+    // staging buffers for the inputs are no longer needed
+    for (void *p : {(void *)h_raw, (void *)h_q, (void *)h_r, (void *)h_q2r, (void *)h_doff, (void *)h_dscl}) {
+        cudaFreeHost(p);
+        b->host_allocs.erase(std::find(b->host_allocs.begin(), b->host_allocs.end(), p));
+    }
+    b->uploaded = true;
+    *out = b;
+    return DNB_OK;
+#undef TRYF
+}
+
+int run(dnb_batch *b) {
+    if (!b || !b->uploaded) return DNB_ERR_STATE;
+    dnb_ctx *ctx = b->ctx;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const size_t R = b->R;
+    cudaStream_t s = b->stream;
+    DnbBatchView v = make_view(b);
+    DnbDetector det = {ctx->cfg.window_length1, ctx->cfg.window_length2, ctx->cfg.threshold1, ctx->cfg.threshold2,
+                       ctx->cfg.peak_height};
+    uint64_t launches = 0;
+    // phase-B buffers of a previous run are released first
+    CK(cudaEventRecord(b->ev[0], s));
+    dnb_launch_segmentation(v, det, s); launches++;
+    CK(cudaEventRecord(b->ev[1], s));
+    CK(cudaMemcpyAsync(b->h_n_events, b->d_n_events, R * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(b->h_et_n, b->d_et_n, R * 4, cudaMemcpyDeviceToHost, s));
+    if (b->want_table) {
+        CK(cudaMemcpyAsync(b->h_status, b->d_status, R * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        b->ran = true;
+        return DNB_OK;
+    }
+    const DnbModelDev pore = ctx->model[DNB_MODEL_PORE].dev();
+    dnb_launch_ranks(v, pore, b->d_mu_q, b->d_rank_ref, s); launches++;
+    dnb_launch_quantile_scaling(v, pore, b->d_rank_ref, b->d_rough_shift, b->d_rough_scale, s); launches++;
+    dnb_launch_scale_events(v, b->d_rough_shift, b->d_rough_scale, b->d_x_e, s); launches++;
+    CK(cudaEventRecord(b->ev[2], s));
+    CK(cudaStreamSynchronize(s));   // n_events is on the host (copy was enqueued before the prep kernels)
+    CK(cudaGetLastError());
+
+    // ---- host step: transition constants with glibc (event_handling.cpp:174-183) + workspace shapes ----
+    b->lp.resize(4 * R);
+    b->band_off.assign(R + 1, 0); b->al_off.assign(R + 1, 0); b->cl_off.assign(R + 1, 0);
+    uint64_t bo = 0, ao = 0, co = 0, n_ev = 0, n_km = 0;
+    for (size_t i = 0; i < R; i++) {
+        const uint32_t E = b->h_n_events[i];
+        const int64_t K = (int64_t)b->qlen[i] - DNB_K + 1;
+        b->band_off[i] = bo; b->al_off[i] = ao; b->cl_off[i] = co;
+        if (K >= 1 && E >= 1) {
+            const double epk = (double)E / (double)K;
+            const double p_stay = 1 - (1 / (epk + 1));
+            const double lp_skip = log(1e-30), lp_stay = log(p_stay);
+            const double lp_step = log(1.0 - exp(lp_skip) - exp(lp_stay)), lp_trim = log(0.01);
+            b->lp[4 * i + 0] = lp_skip; b->lp[4 * i + 1] = lp_stay; b->lp[4 * i + 2] = lp_step; b->lp[4 * i + 3] = lp_trim;
+            const uint64_t nb = (uint64_t)E + (uint64_t)K + 2;
+            bo += nb; ao += nb; co += (uint64_t)K;
+            n_ev += E; n_km += (uint64_t)K;
+        }
+    }
+    b->band_off[R] = bo; b->al_off[R] = ao; b->cl_off[R] = co;
+    b->tot_bands = bo; b->tot_al = ao; b->tot_cl = co;
+    if (!b->d_trace) {
+        TRY(dalloc(b, &b->d_trace, bo * DNB_TRACE_ROW + 64));
+        TRY(dalloc(b, &b->d_al_rev, 2 * ao)); TRY(dalloc(b, &b->d_cl_signal, co)); TRY(dalloc(b, &b->d_cl_rank, co));
+    }
+    TRY(h2d(b, b->d_lp, b->lp.data(), 4 * R));
+    TRY(h2d(b, b->d_band_off, b->band_off.data(), R + 1));
+    TRY(h2d(b, b->d_al_off, b->al_off.data(), R + 1));
+    TRY(h2d(b, b->d_cl_off, b->cl_off.data(), R + 1));
+    CK(cudaMemsetAsync(b->d_cells, 0, sizeof(unsigned long long), s));
+
+    DnbDpArgs dp;
+    dp.x_e = b->d_x_e; dp.mu_q = b->d_mu_q; dp.lp = b->d_lp; dp.emit_const = ctx->emit_const; dp.inv_sigma = 1.0 / 0.14;
+    dp.band_off = b->d_band_off; dp.trace = b->d_trace; dp.end_event = b->d_end_event; dp.end_ll_event = b->d_end_ll;
+    dp.end_score = b->d_end_score; dp.cells = b->d_cells;
+    CK(cudaEventRecord(b->ev[3], s));
+    dnb_launch_banded_dp(v, dp, s); launches++;
+    CK(cudaEventRecord(b->ev[4], s));
+    DnbBtArgs bt;
+    bt.dp = dp; bt.rank_ref = b->d_rank_ref; bt.al_off = b->d_al_off; bt.al_pairs_rev = b->d_al_rev; bt.n_align = b->d_n_align;
+    bt.cl_off = b->d_cl_off; bt.cl_signal = b->d_cl_signal; bt.cl_rank = b->d_cl_rank; bt.n_cleaned = b->d_n_cleaned;
+    bt.avg_log_emission = b->d_avg; bt.spanned = b->d_spanned; bt.max_gap = b->d_max_gap;
+    bt.min_avg_log_emission = ctx->cfg.min_average_log_emission; bt.max_gap_threshold = ctx->cfg.max_gap_threshold;
+    dnb_launch_backtrace(v, bt, s); launches++;
+    CK(cudaEventRecord(b->ev[5], s));
+    DnbTsArgs ts;
+    ts.cl_off = b->d_cl_off; ts.cl_signal = b->d_cl_signal; ts.cl_rank = b->d_cl_rank; ts.n_cleaned = b->d_n_cleaned;
+    ts.rough_shift = b->d_rough_shift; ts.rough_scale = b->d_rough_scale; ts.shift = b->d_shift; ts.scale = b->d_scale;
+    dnb_launch_theil_sen(v, pore, ts, s); launches++;
+    CK(cudaEventRecord(b->ev[6], s));
+    CK(cudaMemcpyAsync(&b->h_cells, b->d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    float t;
+    cudaEventElapsedTime(&t, b->ev[0], b->ev[1]); b->ms[0] = t;
+    cudaEventElapsedTime(&t, b->ev[1], b->ev[2]); b->ms[1] = t;
+    cudaEventElapsedTime(&t, b->ev[3], b->ev[4]); b->ms[2] = t;
+    cudaEventElapsedTime(&t, b->ev[4], b->ev[5]); b->ms[3] = t;
+    cudaEventElapsedTime(&t, b->ev[5], b->ev[6]); b->ms[4] = t;
+    cudaEventElapsedTime(&t, b->ev[0], b->ev[6]); b->ms[5] = t;
+    uint64_t n_samp = 0;
+    for (size_t i = 0; i < R; i++) n_samp += b->n_samples[i];
+    b->counts[0] = n_samp; b->counts[1] = n_ev; b->counts[2] = n_km; b->counts[3] = bo; b->counts[4] = b->h_cells;
+    b->counts[5] = launches;
+    b->ran = true;
+    b->fetched = false;
+    return DNB_OK;
+}
+
+int fetch(dnb_batch *b) {
+    if (!b || !b->ran) return DNB_ERR_STATE;
+    if (b->fetched) return DNB_OK;
+    dnb_ctx *ctx = b->ctx;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const size_t R = b->R;
+    cudaStream_t s = b->stream;
+    TRY(d2h(b, b->h_ev_start, b->d_ev_start, b->tot_ev + R));
+    TRY(d2h(b, b->h_ev_mean, b->d_ev_mean, b->tot_ev));
+    if (b->want_table) {
+        TRY(d2h(b, b->h_et_start, b->d_et_start, b->tot_ev + R)); TRY(d2h(b, b->h_et_length, b->d_et_length, b->tot_ev + R));
+        TRY(d2h(b, b->h_et_mean, b->d_et_mean, b->tot_ev + R)); TRY(d2h(b, b->h_et_stdv, b->d_et_stdv, b->tot_ev + R));
+        CK(cudaStreamSynchronize(s));
+        b->fetched = true;
+        return DNB_OK;
+    }
+    TRY(d2h(b, b->h_status, b->d_status, R)); TRY(d2h(b, b->h_n_align, b->d_n_align, R));
+    TRY(d2h(b, b->h_n_cleaned, b->d_n_cleaned, R)); TRY(d2h(b, b->h_spanned, b->d_spanned, R));
+    TRY(d2h(b, b->h_max_gap, b->d_max_gap, R)); TRY(d2h(b, b->h_rough_shift, b->d_rough_shift, R));
+    TRY(d2h(b, b->h_rough_scale, b->d_rough_scale, R)); TRY(d2h(b, b->h_shift, b->d_shift, R));
+    TRY(d2h(b, b->h_scale, b->d_scale, R)); TRY(d2h(b, b->h_avg, b->d_avg, R));
+    CK(cudaStreamSynchronize(s));
+    // alignment compaction: reversed, capacity-strided device layout -> dense forward pairs
+    b->out_off.assign(R + 1, 0);
+    uint64_t oo = 0;
+    for (size_t i = 0; i < R; i++) { b->out_off[i] = oo; oo += b->h_n_align[i]; }
+    b->out_off[R] = oo;
+    if (!b->d_out_pairs || oo > b->tot_out) {
+        TRY(dalloc(b, &b->d_out_pairs, 2 * oo));
+        TRY(halloc(b, &b->h_out_pairs, 2 * oo));
+        b->tot_out = oo;
+    }
+    TRY(h2d(b, b->d_out_off, b->out_off.data(), R + 1));
+    dnb_launch_compact_alignment(make_view(b), b->d_al_off, b->d_al_rev, b->d_n_align, b->d_out_off, b->d_out_pairs, s);
+    TRY(d2h(b, b->h_out_pairs, b->d_out_pairs, 2 * oo));
+    if (ctx->cfg.keep_debug) {
+        if (!b->h_cl_signal) { TRY(halloc(b, &b->h_cl_signal, b->tot_cl)); TRY(halloc(b, &b->h_cl_rank, b->tot_cl)); }
+        TRY(d2h(b, b->h_cl_signal, b->d_cl_signal, b->tot_cl));
+        TRY(d2h(b, b->h_cl_rank, b->d_cl_rank, b->tot_cl));
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    b->fetched = true;
+    return DNB_OK;
+}
+
+}  // namespace
+
+// ================================================== exported C ABI ==================================================
+extern "C" {
+
+void dnb_default_config(dnb_config *c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->device = 0;
+    c->window_length1 = 3; c->window_length2 = 6;                   // event_detection.h:19-25
+    c->threshold1 = 1.4f; c->threshold2 = 9.0f; c->peak_height = 0.2f;
+    c->min_average_log_emission = -2.0; c->max_gap_threshold = 5; c->bandwidth = DNB_BW;   // config.h:41
+    c->use_fit_pore_model = 0;
+    c->event_capacity_per_sample = 0.40f;
+    c->keep_debug = 0;
+    c->workspace_bytes = 0;
+}
+
+const char *dnb_strerror(int code) {
+    switch (code) {
+        case DNB_OK: return "ok";
+        case DNB_ERR_ARG: return "invalid argument";
+        case DNB_ERR_CUDA: return "CUDA error (see dnb_last_error)";
+        case DNB_ERR_NOMEM: return "out of memory";
+        case DNB_ERR_MODEL: return "pore model table not loaded";
+        case DNB_ERR_STATE: return "call order violated";
+        case DNB_ERR_NEGATIVE_LOG: return "Negative value passed to natural log function.";
+        default: return "unknown error";
+    }
+}
+
+const char *dnb_last_error(void) { return g_last_error.c_str(); }
+
+int dnb_create(dnb_ctx **out, const dnb_config *cfg) {
+    if (!out) return DNB_ERR_ARG;
+    dnb_config c;
+    if (cfg) c = *cfg; else dnb_default_config(&c);
+    if (c.bandwidth != DNB_BW || c.window_length2 > 7 || c.window_length1 > c.window_length2 || c.window_length1 < 1) {
+        g_last_error = "unsupported configuration (bandwidth must be 100, window lengths <= 7)";
+        return DNB_ERR_ARG;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libdnascent_b200 has no CPU fallback)";
+        cudaGetLastError();
+        return DNB_ERR_CUDA;
+    }
+    if (c.device < 0 || c.device >= n) return DNB_ERR_ARG;
+    CK(cudaSetDevice(c.device));
+    // keep freed stream-ordered allocations cached in the pool: batches reuse them
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    dnb_ctx *ctx = new dnb_ctx();
+    ctx->cfg = c;
+    // log_inv_sqrt_2pi is a float in the reference (event_handling.cpp:134); sigma is 0.14 for every k-mer
+    const float log_inv_sqrt_2pi = (float)log(0.3989422804014327);
+    ctx->emit_const = (double)log_inv_sqrt_2pi - log(0.14);
+    *out = ctx;
+    return DNB_OK;
+}
+
+void dnb_destroy(dnb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    for (auto &m : ctx->model) {
+        cudaFree(m.d_mean); cudaFree(m.d_stdv); cudaFree(m.d_sorted); cudaFree(m.d_order);
+    }
+    delete ctx;
+}
+
+int dnb_load_model(dnb_ctx *ctx, int which, const double *mean, const double *stdv, size_t n) {
+    if (!ctx || which < 0 || which > 2 || !mean || n != DNB_N_KMERS) return DNB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->cfg.device));
+    ModelHost &m = ctx->model[which];
+    if (!m.d_mean) {
+        CK(cudaMalloc(&m.d_mean, n * 8)); CK(cudaMalloc(&m.d_stdv, n * 8));
+        CK(cudaMalloc(&m.d_sorted, n * 8)); CK(cudaMalloc(&m.d_order, n * 4));
+    }
+    std::vector<uint32_t> idx(n), order(n);
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return mean[a] < mean[b]; });
+    std::vector<double> sorted(n), sd(n, 0.14);
+    for (size_t i = 0; i < n; i++) { sorted[i] = mean[idx[i]]; order[idx[i]] = (uint32_t)i; }
+    if (stdv) sd.assign(stdv, stdv + n);
+    CK(cudaMemcpy(m.d_mean, mean, n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.d_stdv, sd.data(), n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.d_sorted, sorted.data(), n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.d_order, order.data(), n * 4, cudaMemcpyHostToDevice));
+    m.loaded = true;
+    return DNB_OK;
+}
+
+int dnb_batch_upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch) {
+    return upload(ctx, reads, n_reads, false, batch);
+}
+int dnb_batch_run(dnb_batch *batch) { return run(batch); }
+int dnb_batch_fetch(dnb_batch *batch) { return fetch(batch); }
+
+int dnb_submit(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch) {
+    dnb_batch *b = nullptr;
+    TRY(upload(ctx, reads, n_reads, false, &b));
+    int rc = run(b);
+    if (rc == DNB_OK) rc = fetch(b);
+    if (rc != DNB_OK) { free_batch(b); return rc; }
+    *batch = b;
+    return DNB_OK;
+}
+
+int dnb_wait(dnb_batch *b) {
+    if (!b) return DNB_ERR_ARG;
+    CK(cudaSetDevice(b->ctx->cfg.device));
+    CK(cudaStreamSynchronize(b->stream));
+    return DNB_OK;
+}
+
+int dnb_result(dnb_batch *b, size_t i, dnb_read_result *o) {
+    if (!b || !o || i >= b->R) return DNB_ERR_ARG;
+    if (!b->fetched || b->want_table) return DNB_ERR_STATE;
+    memset(o, 0, sizeof(*o));
+    o->status = b->h_status[i];
+    o->et_n = b->h_et_n[i];
+    o->n_events = b->h_n_events[i];
+    if (o->status == DNB_READ_OVERFLOW) o->n_events = 0;
+    o->event_start = b->h_ev_start + b->ev_off[i] + i;
+    o->event_mean = b->h_ev_mean + b->ev_off[i];
+    o->n_align = o->status == DNB_READ_OK ? b->h_n_align[i] : 0;
+    o->align_pairs = b->h_out_pairs + 2 * b->out_off[i];
+    o->rough_shift = b->h_rough_shift[i]; o->rough_scale = b->h_rough_scale[i];
+    o->shift = b->h_shift[i]; o->scale = b->h_scale[i];
+    const int64_t denom = (int64_t)b->qlen[i] - DNB_K;
+    o->events_per_base = (double)o->et_n / (double)denom;                      // event_handling.cpp:606 (quirk Q4)
+    o->avg_log_emission = b->h_avg[i]; o->spanned = b->h_spanned[i]; o->max_gap = b->h_max_gap[i];
+    if (b->ctx->cfg.keep_debug && b->h_cl_signal) {
+        o->n_cleaned = b->h_n_cleaned[i];
+        o->cleaned_signal = b->h_cl_signal + b->cl_off[i];
+        o->cleaned_rank = b->h_cl_rank + b->cl_off[i];
+    }
+    return DNB_OK;
+}
+
+void dnb_release(dnb_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->cfg.device);
+    free_batch(b);
+}
+
+int dnb_batch_timings(dnb_batch *b, double ms[6], uint64_t counts[6]) {
+    if (!b || !b->ran) return DNB_ERR_STATE;
+    for (int i = 0; i < 6; i++) { if (ms) ms[i] = b->ms[i]; if (counts) counts[i] = b->counts[i]; }
+    return DNB_OK;
+}
+
+int dnb_detect_events(dnb_ctx *ctx, const float *raw_pA, size_t n, dnb_event_t *events, size_t cap, size_t *n_events) {
+    if (!ctx || !raw_pA || n == 0 || !n_events) return DNB_ERR_ARG;
+    dnb_read_desc d;
+    memset(&d, 0, sizeof(d));
+    d.raw_pA = raw_pA; d.n_samples = n; d.query = ""; d.ref = "";
+    dnb_batch *b = nullptr;
+    TRY(upload(ctx, &d, 1, true, &b));
+    int rc = run(b);
+    if (rc == DNB_OK) rc = fetch(b);
+    if (rc == DNB_OK) {
+        const size_t ne = b->h_et_n[0];
+        *n_events = ne;
+        if (b->h_status[0] == DNB_READ_OVERFLOW) rc = DNB_ERR_NOMEM;
+        for (size_t i = 0; rc == DNB_OK && i < ne && i < cap; i++) {
+            events[i].start = b->h_et_start[i]; events[i].length = b->h_et_length[i];
+            events[i].mean = b->h_et_mean[i]; events[i].stdv = b->h_et_stdv[i];
+            events[i].pos = -1; events[i].state = -1;                         // event_detection.c:219-220
+        }
+    }
+    free_batch(b);
+    return rc;
+}
+
+// ---- probability.cpp drop-ins: scalar host functions, semantics of src/probability.cpp:23-154 ----
+double dnb_eexp(double x) { return std::isnan(x) ? 0.0 : exp(x); }
+int dnb_eln(double x, double *out) {
+    if (!out) return DNB_ERR_ARG;
+    if (x == 0.0) { *out = NAN; return DNB_OK; }
+    if (x > 0.0) { *out = log(x); return DNB_OK; }
+    return DNB_ERR_NEGATIVE_LOG;
+}
+static double eln_nothrow(double x) { double o = NAN; dnb_eln(x, &o); return o; }
+double dnb_lnSum(double a, double b) {
+    if (std::isnan(a) || std::isnan(b)) {
+        if (std::isnan(a) && std::isnan(b)) return NAN;
+        return std::isnan(a) ? b : a;
+    }
+    if (a > b) return a + eln_nothrow(1.0 + dnb_eexp(b - a));
+    return b + eln_nothrow(1.0 + dnb_eexp(a - b));
+}
+double dnb_lnProd(double a, double b) { return (std::isnan(a) || std::isnan(b)) ? NAN : a + b; }
+int dnb_lnGreaterThan(double a, double b) {
+    if (std::isnan(a) || std::isnan(b)) {
+        if (std::isnan(a) || !std::isnan(b)) return 0;
+        return 1;
+    }
+    return a > b ? 1 : 0;
+}
+double dnb_uniformPDF(double lb, double ub, double x) { return (x >= lb && x <= ub) ? 1.0 / (ub - lb) : 0.0; }
+double dnb_normalPDF(double mu, double sigma, double x) {
+    return (1.0 / sqrt(2.0 * pow(sigma, 2.0) * M_PI)) * exp(-pow(x - mu, 2.0) / (2.0 * pow(sigma, 2.0)));
+}
+double dnb_cauchyPDF(double loc, double scale, double x) { return 1. / ((scale * M_PI) * (1. + pow((x - loc) / scale, 2.))); }
+
+int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64_t *obs_off, const char *seq,
+                                   const double *shift, const double *scale, const double *epb, size_t n_sites,
+                                   uint32_t window, double *out_analogue, double *out_thymidine) {
+    if (!ctx || !obs_off || !seq || !shift || !scale || !epb || !out_analogue || !out_thymidine) return DNB_ERR_ARG;
+    if (window < 5 || window > 16) return DNB_ERR_ARG;
+    if (!ctx->model[DNB_MODEL_UNLABELLED].loaded || !ctx->model[DNB_MODEL_ANALOGUE].loaded) return DNB_ERR_MODEL;
+    if (n_sites == 0) return DNB_OK;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const size_t n_obs = obs_off[n_sites], snip = 2 * (size_t)window + DNB_K;
+    double *d_obs = nullptr, *d_shift = nullptr, *d_scale = nullptr, *d_epb = nullptr, *d_oa = nullptr, *d_ot = nullptr;
+    uint64_t *d_off = nullptr;
+    char *d_seq = nullptr;
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = DNB_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DNB_OK) { g_last_error = cudaGetErrorString(e); rc = DNB_ERR_CUDA; } };
+    fail(cudaMallocAsync(&d_obs, (n_obs ? n_obs : 1) * 8, s)); fail(cudaMallocAsync(&d_off, (n_sites + 1) * 8, s));
+    fail(cudaMallocAsync(&d_seq, n_sites * snip, s)); fail(cudaMallocAsync(&d_shift, n_sites * 8, s));
+    fail(cudaMallocAsync(&d_scale, n_sites * 8, s)); fail(cudaMallocAsync(&d_epb, n_sites * 8, s));
+    fail(cudaMallocAsync(&d_oa, n_sites * 8, s)); fail(cudaMallocAsync(&d_ot, n_sites * 8, s));
+    if (rc == DNB_OK) {
+        if (n_obs) fail(cudaMemcpyAsync(d_obs, obs, n_obs * 8, cudaMemcpyHostToDevice, s));
+        fail(cudaMemcpyAsync(d_off, obs_off, (n_sites + 1) * 8, cudaMemcpyHostToDevice, s));
+        fail(cudaMemcpyAsync(d_seq, seq, n_sites * snip, cudaMemcpyHostToDevice, s));
+        fail(cudaMemcpyAsync(d_shift, shift, n_sites * 8, cudaMemcpyHostToDevice, s));
+        fail(cudaMemcpyAsync(d_scale, scale, n_sites * 8, cudaMemcpyHostToDevice, s));
+        fail(cudaMemcpyAsync(d_epb, epb, n_sites * 8, cudaMemcpyHostToDevice, s));
+        dnb_launch_hmm_forward(d_obs, d_off, d_seq, d_shift, d_scale, d_epb, n_sites, window,
+                               ctx->model[DNB_MODEL_UNLABELLED].dev(), ctx->model[DNB_MODEL_ANALOGUE].dev(), d_oa, d_ot, s);
+        fail(cudaMemcpyAsync(out_analogue, d_oa, n_sites * 8, cudaMemcpyDeviceToHost, s));
+        fail(cudaMemcpyAsync(out_thymidine, d_ot, n_sites * 8, cudaMemcpyDeviceToHost, s));
+        fail(cudaStreamSynchronize(s));
+        fail(cudaGetLastError());
+    }
+    for (void *p : {(void *)d_obs, (void *)d_off, (void *)d_seq, (void *)d_shift, (void *)d_scale, (void *)d_epb, (void *)d_oa, (void *)d_ot})
+        if (p) cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// dnb_internal.cuh -- shared device/host declarations of libdnascent_b200 (sm_100a only).
+//
+// Arithmetic discipline: the reference is x86-64 baseline code (no FMA, float ops in
+// SSE single, double ops in SSE double), so every operation whose rounding is observable is written with an
+// explicit IEEE round-to-nearest intrinsic (__dadd_rn, __fmul_rn, ...) -- these are never contracted into
+// FMAs by nvcc -- and the library is additionally built with -fmad=false -prec-div=true -prec-sqrt=true
+// -ftz=false.  Where an FMA is used on purpose its product is exact and the comment says why.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cuda_runtime.h>
+
+#define DNB_BW 100          // AdaptiveBanded_Params.bandwidth, src/config.h:41
+#define DNB_K 9
+#define DNB_TRACE_ROW 32    // bytes per band in HBM: 25 B of 2-bit trace codes, byte 25 = move bit, rest 0
+#define DNB_CELLS_PER_LANE 4
+
+enum { DNB_FROM_D = 0, DNB_FROM_U = 1, DNB_FROM_L = 2 };   // event_handling.cpp:160-162
+
+// ---- typed arithmetic helpers: one rounding each, exactly as written -------------------------------------------
+__device__ __forceinline__ double dAdd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dSub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dMul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dDiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float fAdd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fSub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fMul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fDiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float d2f(double a) { return __double2float_rn(a); }
+
+// base code of the reference alphabet A=0 T=1 G=2 C=3, anything else 0 (src/data_IO.cpp:131-137, quirk Q11)
+__host__ __device__ __forceinline__ uint32_t dnb_base_code(char c) {
+    return c == 'T' ? 1u : c == 'G' ? 2u : c == 'C' ? 3u : 0u;
+}
+
+// ---- per-batch device view handed to the kernels ---------------------------------------------------------------
+struct DnbDetector {
+    uint32_t w1, w2;
+    float thr1, thr2, peak_height;
+};
+
+struct DnbBatchView {
+    uint32_t n_reads;
+    const uint32_t *order;        // processing order (longest first); kernels map slot -> read = order[slot]
+    // inputs (SoA, concatenated; offsets in elements)
+    const float *raw_f32;         // or nullptr
+    const int16_t *raw_i16;       // or nullptr
+    const float *dac_offset, *dac_scale;   // per read (i16 input only)
+    const uint64_t *raw_off;      // [R+1], each read starts 32-element aligned
+    const uint32_t *n_samples;    // [R]
+    const char *query;            // concatenated
+    const char *ref;
+    const uint64_t *q_off;        // [R+1]
+    const uint64_t *r_off;        // [R+1]
+    const int32_t *q2r;           // indexed like query
+    // segmentation outputs
+    uint32_t *et_n;               // [R] scrappie event count (0 = undefined)
+    uint32_t *n_events;           // [R] r.events.size()
+    const uint64_t *ev_off;       // [R+1] event slot offsets (capacity per read)
+    uint32_t *ev_start;           // [ev_off[R] + R]  (n_events+1 entries per read, slot base ev_off[r] + r)
+    float *ev_mean;               // [ev_off[R]]
+    int *status;                  // [R] DNB_READ_*
+    // optional full scrappie table (dnb_detect_events)
+    uint64_t *et_start;
+    float *et_length, *et_mean, *et_stdv;
+};
+
+// ---- kernel launchers (host side, defined next to each kernel) -----------------------------------------------------
+struct DnbModelDev {
+    const double *mean;           // [4^9]
+    const double *stdv;           // [4^9] or nullptr (static 0.14)
+    const uint32_t *mean_order;   // [4^9] position of mean[rank] in the ascending sort of all means
+    const double *sorted_mean;    // [4^9]
+};
+
+void dnb_launch_segmentation(const DnbBatchView &v, DnbDetector det, cudaStream_t s);
+void dnb_launch_ranks(const DnbBatchView &v, const DnbModelDev &m, double *mu_q, uint32_t *rank_ref, cudaStream_t s);
+void dnb_launch_quantile_scaling(const DnbBatchView &v, const DnbModelDev &m, const uint32_t *rank_ref,
+                                 double *rough_shift, double *rough_scale, cudaStream_t s);
+void dnb_launch_scale_events(const DnbBatchView &v, const double *rough_shift, const double *rough_scale, double *x_e,
+                             cudaStream_t s);
+
+struct DnbDpArgs {
+    const double *x_e;            // indexed like ev_mean
+    const double *mu_q;           // indexed like query (K entries used per read)
+    const double *lp;             // [R][4] lp_skip, lp_stay, lp_step, lp_trim (host glibc, event_handling.cpp:174-183)
+    double emit_const;            // (double)(float)log(1/sqrt(2pi)) - log(0.14)
+    double inv_sigma;             // unused by the exact path (kept for the guarded fast path)
+    const uint64_t *band_off;     // [R+1] band-row offsets
+    uint8_t *trace;               // [band_off[R]] rows of DNB_TRACE_ROW bytes
+    int32_t *end_event;           // [R] event index of the best end cell, -1 if none
+    int32_t *end_ll_event;        // [R] band_lower_left.event_idx of that band
+    float *end_score;             // [R]
+    unsigned long long *cells;    // [1] total DP cells filled (the reference's `fills`)
+};
+void dnb_launch_banded_dp(const DnbBatchView &v, const DnbDpArgs &a, cudaStream_t s);
+
+struct DnbBtArgs {
+    DnbDpArgs dp;
+    const uint32_t *rank_ref;     // indexed like ref
+    const uint64_t *al_off;       // [R+1] alignment slot offsets (capacity n_bands per read)
+    uint32_t *al_pairs_rev;       // [2*al_off[R]] (event,kmer) in backtrace order
+    uint32_t *n_align;            // [R]
+    const uint64_t *cl_off;       // [R+1] cleaned slot offsets (capacity K per read)
+    double *cl_signal;
+    uint32_t *cl_rank;
+    uint32_t *n_cleaned;          // [R]
+    double *avg_log_emission;     // [R]
+    int *spanned, *max_gap;       // [R]
+    double min_avg_log_emission;
+    int max_gap_threshold;
+};
+void dnb_launch_backtrace(const DnbBatchView &v, const DnbBtArgs &a, cudaStream_t s);
+
+struct DnbTsArgs {
+    const uint64_t *cl_off;
+    const double *cl_signal;
+    const uint32_t *cl_rank;
+    const uint32_t *n_cleaned;
+    const double *rough_shift, *rough_scale;
+    double *shift, *scale;        // [R] refined
+};
+void dnb_launch_theil_sen(const DnbBatchView &v, const DnbModelDev &m, const DnbTsArgs &a, cudaStream_t s);
+
+void dnb_launch_compact_alignment(const DnbBatchView &v, const uint64_t *al_off, const uint32_t *al_pairs_rev,
+                                  const uint32_t *n_align, const uint64_t *out_off, uint32_t *out_pairs,
+                                  cudaStream_t s);
+
+void dnb_launch_hmm_forward(const double *obs, const uint64_t *obs_off, const char *seq, const double *shift,
+                            const double *scale, const double *epb, size_t n_sites, uint32_t window,
+                            const DnbModelDev &unl, const DnbModelDev &ana, double *out_analogue, double *out_thymidine,
+                            cudaStream_t s);

@@ -1,0 +1,176 @@
+/* dnascent_b200.h -- C ABI of libdnascent_b200.so
+ *
+ * B200-native (sm_100a CUDA) implementation of the per-read signal hot path of `DNAscent detect`
+ * (MBoemo/DNAscent v4.1.1).  The reference has no plugin/FFI layer: the seam is the direct C++ call
+ *     void normaliseEvents(DNAscent::read&, bool)            src/event_handling.h:13
+ * made from the OpenMP read loops at src/detect.cpp:876, src/alignment.cpp:856, src/trainCNN.cpp:319,
+ * plus   event_table detect_events(double*, size_t, detector_param)   src/scrappie/event_detection.h:35
+ *        eexp/eln/lnSum/lnProd/lnGreaterThan/uniformPDF/normalPDF/cauchyPDF   src/probability.h:26-33
+ *        sequenceProbability / llAcrossRead                  src/detect.h:119,121
+ * This header is the batched, plain-C boundary those C++ symbols are re-implemented on (see
+ * dnascent_b200/csrc/shim/ and INTEGRATION.md).  Plain pointers and sizes only, int error codes, no
+ * exceptions cross the ABI.  There is NO CPU fallback: every entry point that computes needs a CUDA
+ * device and fails with DNB_ERR_CUDA otherwise.
+ */
+#ifndef DNASCENT_B200_H
+#define DNASCENT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNB_API __attribute__((visibility("default")))
+
+/* ---- error codes (returned by every int function; 0 = success) ------------------------------ */
+enum {
+    DNB_OK = 0,
+    DNB_ERR_ARG = 1,      /* NULL / out-of-range argument */
+    DNB_ERR_CUDA = 2,     /* CUDA runtime error or no device (dnb_last_error() has the text) */
+    DNB_ERR_NOMEM = 3,    /* host or device allocation failed */
+    DNB_ERR_MODEL = 4,    /* required pore-model table not loaded */
+    DNB_ERR_STATE = 5,    /* call order violated (e.g. result before wait) */
+    DNB_ERR_NEGATIVE_LOG = 6 /* dnb_eln(x<0): the reference throws NegativeLog (src/probability.cpp:45) */
+};
+
+/* ---- per-read status (dnb_read_result.status) ------------------------------------------------
+ * The reference signals failure by leaving r.eventAlignment empty (src/detect.cpp:879); the status says why. */
+enum {
+    DNB_READ_OK = 0,
+    DNB_READ_QC_FAIL = 1,      /* avg emission / spanned / max_gap / <1000 cleaned points  (event_handling.cpp:433-441) */
+    DNB_READ_SCALE_FAIL = 2,   /* Theil-Sen slope == 0 -> scalings {-1,-1}               (event_handling.cpp:90-95,604) */
+    DNB_READ_UNDEFINED = 3,    /* inputs for which the reference itself is undefined (no peak found, no event,
+                                  query shorter than k+1, end cell outside the band: it would index out of range) */
+    DNB_READ_OVERFLOW = 4      /* more events than the per-read device capacity (resubmit with a larger
+                                  dnb_config.event_capacity_per_sample) */
+};
+
+/* which table dnb_load_model fills; src/config.h:39 (pore_model, unlabelled_model, analogue_model) */
+enum { DNB_MODEL_PORE = 0, DNB_MODEL_UNLABELLED = 1, DNB_MODEL_ANALOGUE = 2 };
+
+#define DNB_KMER_LEN 9
+#define DNB_N_KMERS 262144 /* 4^9 */
+
+typedef struct dnb_ctx dnb_ctx;
+typedef struct dnb_batch dnb_batch;
+
+/* Everything the reference keeps in compile-time constants / Global_Config (src/config.h:41-63,
+ * src/scrappie/event_detection.h:19-25). dnb_default_config() fills the R10.4.1 DNA values. */
+typedef struct {
+    int device;                       /* CUDA ordinal */
+    uint32_t window_length1;          /* 3     detector_param */
+    uint32_t window_length2;          /* 6 */
+    float threshold1;                 /* 1.4f */
+    float threshold2;                 /* 9.0f */
+    float peak_height;                /* 0.2f */
+    double min_average_log_emission;  /* -2.0  AdaptiveBanded_Params */
+    int max_gap_threshold;            /* 5 */
+    int bandwidth;                    /* 100 (only value supported) */
+    int use_fit_pore_model;           /* the `useFitPoreModel` argument of normaliseEvents; all reference callers pass false */
+    float event_capacity_per_sample;  /* device event slots per raw sample (default 0.40; observed ~0.2) */
+    int keep_debug;                   /* also return rough scalings' inputs: cleaned (signal,rank) vectors */
+    size_t workspace_bytes;           /* cap for per-bin device workspace; 0 = derive from free memory */
+} dnb_config;
+
+/* One read, exactly the fields normaliseEvents reads from DNAscent::read (src/reads.h:178-208):
+ * raw (float32-exact pA, src/pod5.cpp:60), basecall, referenceSeqMappedTo, queryToRef. */
+typedef struct {
+    const float *raw_pA;          /* n_samples values, or NULL when raw_dac is given */
+    const int16_t *raw_dac;       /* optional: int16 DAC; pA = ((float)dac + dac_offset) * dac_scale (pod5.cpp:60) */
+    float dac_offset, dac_scale;
+    uint64_t n_samples;
+    const char *query;            /* r.basecall, sequencing orientation */
+    uint32_t query_len;
+    const char *ref;              /* r.referenceSeqMappedTo, sequencing orientation */
+    uint32_t ref_len;
+    const int32_t *query_to_ref;  /* dense r.queryToRef: query_len entries, -1 = no entry */
+} dnb_read_desc;
+
+typedef struct {
+    int status;                   /* DNB_READ_* */
+    uint32_t et_n;                /* scrappie event count (event_table.n) */
+    uint32_t n_events;            /* r.events.size() */
+    const uint32_t *event_start;  /* [n_events+1]: r.events[j].raw == raw[event_start[j] .. event_start[j+1]) */
+    const float *event_mean;      /* [n_events]:   r.events[j].mean (float32-exact; [0] is 0.0, quirk Q1) */
+    uint32_t n_align;             /* r.eventAlignment.size(); 0 unless status == DNB_READ_OK */
+    const uint32_t *align_pairs;  /* [2*n_align] interleaved (event_idx, kmer_idx) == vector<pair<unsigned,unsigned>> layout */
+    double shift, scale, events_per_base;  /* r.scalings (Theil-Sen refined) */
+    double rough_shift, rough_scale;       /* quantile scaling used by the alignment (event_handling.cpp:595) */
+    double avg_log_emission;               /* r.alignmentQCs */
+    int spanned;
+    int max_gap;
+    uint32_t n_cleaned;           /* keep_debug only */
+    const double *cleaned_signal;
+    const uint32_t *cleaned_rank;
+} dnb_read_result;
+
+/* scrappie event table entry (src/scrappie/scrappie_structures.h:8-15) for the detect_events drop-in */
+typedef struct {
+    uint64_t start;
+    float length;
+    float mean;
+    float stdv;
+    int pos;
+    int state;
+} dnb_event_t;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+DNB_API void dnb_default_config(dnb_config *cfg);
+DNB_API int dnb_create(dnb_ctx **ctx, const dnb_config *cfg);
+DNB_API void dnb_destroy(dnb_ctx *ctx);
+DNB_API const char *dnb_strerror(int code);
+DNB_API const char *dnb_last_error(void); /* thread-local detail of the last DNB_ERR_CUDA */
+/* replaces import_poreModel_staticStdv / import_poreModel_fitStdv results (src/data_IO.cpp:144-242):
+ * mean/stdv indexed by kmer2index (A=0,T=1,G=2,C=3, first base most significant); n must be 4^9. */
+DNB_API int dnb_load_model(dnb_ctx *ctx, int which, const double *mean, const double *stdv, size_t n);
+
+/* ---- the hot path: batched normaliseEvents (src/event_handling.cpp:544-607) ---------------- */
+/* Asynchronous: stages the reads into pinned memory, copies to the device, runs segmentation ->
+ * quantile scaling -> banded alignment -> backtrace/QC -> Theil-Sen, copies results back.
+ * Thread-safe: may be called concurrently from the OpenMP read loop of detect.cpp:852. */
+DNB_API int dnb_submit(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch);
+DNB_API int dnb_wait(dnb_batch *batch);
+DNB_API int dnb_result(dnb_batch *batch, size_t i, dnb_read_result *out);
+DNB_API void dnb_release(dnb_batch *batch);
+
+/* Split form of dnb_submit for callers that keep inputs resident in HBM (bench `value` leg):
+ * upload once, run the device pipeline any number of times, fetch results when wanted. */
+DNB_API int dnb_batch_upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch);
+DNB_API int dnb_batch_run(dnb_batch *batch);     /* device pipeline only; blocks until done */
+DNB_API int dnb_batch_fetch(dnb_batch *batch);   /* device -> pinned host results */
+/* device-time breakdown of the last dnb_batch_run, milliseconds, measured with CUDA events on the
+ * pipeline stream: [0]=segmentation [1]=ranks+scaling+prep [2]=banded DP [3]=backtrace+QC [4]=Theil-Sen [5]=total;
+ * counts: [0]=samples [1]=events [2]=k-mers [3]=bands [4]=DP cells [5]=kernel launches */
+DNB_API int dnb_batch_timings(dnb_batch *batch, double ms[6], uint64_t counts[6]);
+
+/* ---- detect_events drop-in (src/scrappie/event_detection.h:35) ------------------------------ */
+/* raw_pA: n float32-exact samples.  events: caller array of capacity cap; *n_events receives event_table.n. */
+DNB_API int dnb_detect_events(dnb_ctx *ctx, const float *raw_pA, size_t n, dnb_event_t *events, size_t cap,
+                              size_t *n_events);
+
+/* ---- probability.cpp drop-ins (src/probability.h:26-33); NaN == log(0) convention ------------- */
+DNB_API double dnb_eexp(double x);
+DNB_API int dnb_eln(double x, double *out); /* DNB_ERR_NEGATIVE_LOG where the reference throws */
+DNB_API double dnb_lnSum(double ln_x, double ln_y);
+DNB_API double dnb_lnProd(double ln_x, double ln_y);
+DNB_API int dnb_lnGreaterThan(double ln_x, double ln_y);
+DNB_API double dnb_uniformPDF(double lb, double ub, double x);
+DNB_API double dnb_normalPDF(double mu, double sigma, double x);
+DNB_API double dnb_cauchyPDF(double loc, double scale, double x);
+
+/* ---- analogue likelihood: batched sequenceProbability (src/detect.cpp:235-378) ---------------- */
+/* One "site" = one call of sequenceProbability: observations obs[obs_off[s] .. obs_off[s+1]) (event means, pA),
+ * a (2*window + 9)-base snippet at seq + s*(2*window+9), per-site scalings.  Computes both the analogue pass
+ * (useBrdU=true, BrdUStart/End = window -/+ 4) and the thymidine pass, as llAcrossRead does (detect.cpp:546-548).
+ * out_analogue / out_thymidine: log forward probabilities (NaN == log 0); LLR = analogue - thymidine. */
+DNB_API int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64_t *obs_off, const char *seq,
+                                           const double *shift, const double *scale, const double *events_per_base,
+                                           size_t n_sites, uint32_t window, double *out_analogue,
+                                           double *out_thymidine);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNASCENT_B200_H */

@@ -88,10 +88,10 @@ class Batch:
 
     def timings(self):
         ms = (C.c_double * 6)()
-        cnt = (C.c_uint64 * 6)()
+        cnt = (C.c_uint64 * 8)()
         _lib.check(self.ctx.L.dnb_batch_timings(self.h, C.byref(ms), C.byref(cnt)), "dnb_batch_timings")
         names = ("segmentation", "prep", "banded_dp", "backtrace", "theil_sen", "total")
-        cn = ("samples", "events", "kmers", "bands", "cells", "launches")
+        cn = ("samples", "events", "kmers", "bands", "cells", "launches", "seg_serial_reads", "failed_reads")
         return dict(zip(names, ms)), dict(zip(cn, (int(x) for x in cnt)))
 
     def result(self, i: int) -> Normalised:

@@ -108,10 +108,17 @@ struct dnb_batch {
     uint64_t *h_et_start = nullptr;
     float *h_et_length = nullptr, *h_et_mean = nullptr, *h_et_stdv = nullptr;
     std::vector<double> lp;
+    // ---- tiled segmentation workspace ----
+    std::vector<uint32_t> tile_off, tile_read;
+    std::vector<uint64_t> ck_off;
+    DnbSegTiles seg = {};
+    uint32_t *d_tile_off = nullptr, *d_tile_read = nullptr;
+    uint64_t *d_ck_off = nullptr;
     // ---- timings ----
     cudaEvent_t ev[8] = {};
     double ms[6] = {};
-    uint64_t counts[6] = {};
+    uint64_t counts[8] = {};
+    std::vector<uint32_t> h_redo;
     unsigned long long h_cells = 0;
     std::vector<void *> dev_allocs, host_allocs;
 };
@@ -257,6 +264,22 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
     std::stable_sort(b->order.begin(), b->order.end(),
                      [&](uint32_t x, uint32_t y) { return b->n_samples[x] > b->n_samples[y]; });   // longest first
 
+    // ---- tile bookkeeping of the tiled segmentation ----
+    b->tile_off.resize(R + 1); b->ck_off.resize(R + 1);
+    {
+        uint64_t to = 0, co = 0;
+        for (size_t i = 0; i < R; i++) {
+            b->tile_off[i] = (uint32_t)to; b->ck_off[i] = co;
+            to += (b->n_samples[i] + DNB_SEG_TILE - 1) / DNB_SEG_TILE;
+            co += (b->n_samples[i] + DNB_SEG_CK - 1) / DNB_SEG_CK + 1;
+        }
+        if (to >= (1ull << 32)) { free_batch(b); g_last_error = "batch too large (tile index overflows 32 bits)"; return DNB_ERR_ARG; }
+        b->tile_off[R] = (uint32_t)to; b->ck_off[R] = co;
+        b->tile_read.resize(to);
+        for (size_t i = 0; i < R; i++)
+            for (uint32_t g = b->tile_off[i]; g < b->tile_off[i + 1]; g++) b->tile_read[g] = (uint32_t)i;
+    }
+
     // ---- pinned staging + device inputs ----
     const size_t esz = b->i16 ? 2 : 4;
     uint8_t *h_raw = nullptr; char *h_q = nullptr, *h_r = nullptr; int32_t *h_q2r = nullptr;
@@ -289,6 +312,16 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
     TRYF(h2d(b, b->d_raw_off, b->raw_off.data(), R + 1)); TRYF(h2d(b, b->d_q_off, b->q_off.data(), R + 1));
     TRYF(h2d(b, b->d_r_off, b->r_off.data(), R + 1)); TRYF(h2d(b, b->d_ev_off, b->ev_off.data(), R + 1));
     TRYF(h2d(b, b->d_n_samples, b->n_samples.data(), R)); TRYF(h2d(b, b->d_order, b->order.data(), R));
+    if (!want_table) {
+        double *d_tot = nullptr; uint32_t *d_redo = nullptr;
+        TRYF(dalloc(b, &b->d_tile_off, R + 1)); TRYF(dalloc(b, &b->d_tile_read, b->tile_read.size()));
+        TRYF(dalloc(b, &b->d_ck_off, R + 1)); TRYF(dalloc(b, &d_tot, R)); TRYF(dalloc(b, &d_redo, R));
+        TRYF(h2d(b, b->d_tile_off, b->tile_off.data(), R + 1));
+        TRYF(h2d(b, b->d_tile_read, b->tile_read.data(), b->tile_read.size()));
+        TRYF(h2d(b, b->d_ck_off, b->ck_off.data(), R + 1));
+        b->seg.n_tiles = b->tile_off[R]; b->seg.tile_off = b->d_tile_off; b->seg.tile_read = b->d_tile_read;
+        b->seg.ck_off = b->d_ck_off; b->seg.tot_sum = d_tot; b->seg.redo = d_redo;
+    }
 
     // ---- phase A outputs + small per-read arrays ----
     TRYF(dalloc(b, &b->d_et_n, R)); TRYF(dalloc(b, &b->d_n_events, R)); TRYF(dalloc(b, &b->d_status, R));
@@ -340,7 +373,24 @@ int run(dnb_batch *b) {
     uint64_t launches = 0;
     // phase-B buffers of a previous run are released first
     CK(cudaEventRecord(b->ev[0], s));
-    dnb_launch_segmentation(v, det, s); launches++;
+    if (b->want_table) {
+        dnb_launch_segmentation_serial(v, det, nullptr, s); launches++;
+    } else {
+        // per-run scratch of the tiled segmentation (returned to the pool before the DP workspace is taken)
+        const size_t nt = b->seg.n_tiles, nck = b->ck_off[R];
+        void *scratch[10] = {};
+        auto sal = [&](int i, size_t bytes) -> cudaError_t { return cudaMallocAsync(&scratch[i], bytes ? bytes : 1, s); };
+        CK(sal(0, nck * 8)); CK(sal(1, nck * 8)); CK(sal(2, nt * DNB_SEG_PEAK_CAP * 4)); CK(sal(3, nt * DNB_SEG_PEAK_CAP * 8));
+        CK(sal(4, nt * 4)); CK(sal(5, nt * DNB_SEG_BOUNDARY_BYTES)); CK(sal(6, nt * DNB_SEG_BOUNDARY_BYTES));
+        CK(sal(7, nt * 4)); CK(sal(8, nt * 4)); CK(sal(9, nt * 8));
+        DnbSegTiles t = b->seg;
+        t.ck_sum = (double *)scratch[0]; t.ck_sq = (double *)scratch[1]; t.pk_pos = (uint32_t *)scratch[2];
+        t.pk_sum = (double *)scratch[3]; t.pk_count = (uint32_t *)scratch[4]; t.b_start = (SegBoundary *)scratch[5];
+        t.b_end = (SegBoundary *)scratch[6]; t.tile_prefix = (uint32_t *)scratch[7]; t.tile_prev_pos = (uint32_t *)scratch[8];
+        t.tile_prev_sum = (double *)scratch[9];
+        dnb_launch_segmentation_tiled(v, det, t, s); launches += 6;
+        for (void *p : scratch) CK(cudaFreeAsync(p, s));
+    }
     CK(cudaEventRecord(b->ev[1], s));
     CK(cudaMemcpyAsync(b->h_n_events, b->d_n_events, R * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(b->h_et_n, b->d_et_n, R * 4, cudaMemcpyDeviceToHost, s));
@@ -355,6 +405,8 @@ int run(dnb_batch *b) {
     dnb_launch_ranks(v, pore, b->d_mu_q, b->d_rank_ref, s); launches++;
     dnb_launch_quantile_scaling(v, pore, b->d_rank_ref, b->d_rough_shift, b->d_rough_scale, s); launches++;
     dnb_launch_scale_events(v, b->d_rough_shift, b->d_rough_scale, b->d_x_e, s); launches++;
+    b->h_redo.resize(R);
+    CK(cudaMemcpyAsync(b->h_redo.data(), b->seg.redo, R * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(b->ev[2], s));
     CK(cudaStreamSynchronize(s));   // n_events is on the host (copy was enqueued before the prep kernels)
     CK(cudaGetLastError());
@@ -423,6 +475,8 @@ int run(dnb_batch *b) {
     for (size_t i = 0; i < R; i++) n_samp += b->n_samples[i];
     b->counts[0] = n_samp; b->counts[1] = n_ev; b->counts[2] = n_km; b->counts[3] = bo; b->counts[4] = b->h_cells;
     b->counts[5] = launches;
+    b->counts[6] = 0;
+    for (size_t i = 0; i < R; i++) b->counts[6] += b->h_redo[i] ? 1 : 0;
     b->ran = true;
     b->fetched = false;
     return DNB_OK;
@@ -625,9 +679,10 @@ void dnb_release(dnb_batch *b) {
     free_batch(b);
 }
 
-int dnb_batch_timings(dnb_batch *b, double ms[6], uint64_t counts[6]) {
+int dnb_batch_timings(dnb_batch *b, double ms[6], uint64_t counts[8]) {
     if (!b || !b->ran) return DNB_ERR_STATE;
-    for (int i = 0; i < 6; i++) { if (ms) ms[i] = b->ms[i]; if (counts) counts[i] = b->counts[i]; }
+    for (int i = 0; i < 6; i++) if (ms) ms[i] = b->ms[i];
+    for (int i = 0; i < 8; i++) if (counts) counts[i] = b->counts[i];
     return DNB_OK;
 }
 

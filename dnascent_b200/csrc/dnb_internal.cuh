@@ -73,7 +73,39 @@ struct DnbModelDev {
     const double *sorted_mean;    // [4^9]
 };
 
-void dnb_launch_segmentation(const DnbBatchView &v, DnbDetector det, cudaStream_t s);
+// ---- tiled segmentation workspace (seg.cu) ----------------------------------------------------------------------
+#define DNB_SEG_TILE 512u       // samples per lane in the tile kernel
+#define DNB_SEG_HALO 64         // samples the detectors run before their tile, from a fresh state
+#define DNB_SEG_CK 64u          // checkpoint spacing of the serial (sum, sumsq) chains
+#define DNB_SEG_PEAK_CAP 224u   // peak slots per tile (observed ~0.2 peaks/sample -> ~100 per tile)
+
+// detector state at a tile boundary, normalised so that equal records <=> identical future behaviour
+struct __align__(8) SegBoundary {
+    int s_pos, l_pos;
+    float s_val, l_val;
+    uint32_t masked;   // long detector's masked_to if it still masks a position >= the boundary, else 0
+    uint32_t valid;    // bit0 short.valid, bit1 long.valid
+};
+struct DnbSegTiles {
+    uint32_t n_tiles;
+    const uint32_t *tile_off;     // [R+1] first global tile of each read
+    const uint32_t *tile_read;    // [n_tiles]
+    const uint64_t *ck_off;       // [R+1] checkpoint slot offsets
+    double *ck_sum, *ck_sq;       // [ck_off[R]]
+    double *tot_sum;              // [R] sums[N]
+    uint32_t *pk_pos;             // [n_tiles * DNB_SEG_PEAK_CAP]
+    double *pk_sum;               // [n_tiles * DNB_SEG_PEAK_CAP] sums[peak]
+    uint32_t *pk_count;           // [n_tiles]
+    SegBoundary *b_start, *b_end; // [n_tiles] detector state assumed at the tile start / reached at its end
+    uint32_t *tile_prefix;        // [n_tiles] peaks of the read before this tile
+    uint32_t *tile_prev_pos;      // [n_tiles] last peak before this tile (0 if none) ...
+    double *tile_prev_sum;        // ... and sums[] there
+    uint32_t *redo;               // [R] 1 = redo this read with the serial kernel
+};
+#define DNB_SEG_BOUNDARY_BYTES sizeof(SegBoundary)
+
+void dnb_launch_segmentation_serial(const DnbBatchView &v, DnbDetector det, const uint32_t *only_flagged, cudaStream_t s);
+void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s);
 void dnb_launch_ranks(const DnbBatchView &v, const DnbModelDev &m, double *mu_q, uint32_t *rank_ref, cudaStream_t s);
 void dnb_launch_quantile_scaling(const DnbBatchView &v, const DnbModelDev &m, const uint32_t *rank_ref,
                                  double *rough_shift, double *rough_scale, cudaStream_t s);

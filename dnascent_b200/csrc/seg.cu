@@ -1,4 +1,4 @@
-// seg.cu -- scrappie t-statistic event segmentation + the r.events filter, fused, one lane per read.
+// seg.cu -- scrappie t-statistic event segmentation + the r.events filter.
 //
 // Replaces (reference, paths relative to /root/reference):
 //   compute_sum_sumsq            src/scrappie/event_detection.c:35-48
@@ -7,13 +7,27 @@
 //   create_event(s)              src/scrappie/event_detection.c:213-266
 //   event table -> r.events      src/event_handling.cpp:549-575   (quirks Q1-Q3)
 //
-// Why one lane per read: the double prefix sum of squares rounds at EVERY step (x*x needs up to 48 bits, the
-// running sum passes 2^19 within ~100 samples), so its value depends on the serial order -- the survey
-// measured 10 % of reads changing boundaries under a different summation.  Each lane therefore carries the
-// reference's own serial chain; everything downstream of the sums (both t-statistics, both peak detectors,
-// event construction and the r.events filter) is streamed in the same pass from a 16-deep ring of
-// (sum, sumsq) kept in shared memory, so the signal is read from HBM exactly once and only the event table
-// (u32 start + f32 mean per event) is written: 4 B/sample + 8 B/event algorithmic traffic.
+// Exactness constraints.  (1) The double prefix sum of squares rounds at EVERY step (x*x needs up to 48 bits, the
+// running sum passes 2^19 within ~100 samples), so its value depends on the serial order; the survey measured 10 %
+// of reads changing boundaries under a different summation.  (2) The two peak detectors are a sequential state
+// machine over the samples.  Both are made parallel here without giving up a single bit:
+//
+//   K1 checkpoint   one lane per read runs ONLY the two serial double chains (3 flops per sample) and stores
+//                   (sum, sumsq) every 64 samples.
+//   K2 tiles        one lane per 512-sample tile restarts the chains from the exact checkpoint, streams both
+//                   t-statistics from a 16-deep shared-memory ring and runs the detector pair SPECULATIVELY from a
+//                   fresh state 64 samples before its tile; peaks emitted inside the tile go to a per-tile list.
+//                   The detector state it assumed at the tile start and the state it ends with are recorded.
+//   K3 stitch       per read: a tile's assumed start state must equal its predecessor's end state (tile 0 starts
+//                   from the true initial state), which by induction makes every emitted peak the serial one;
+//                   otherwise the read is flagged.  Also prefix-counts the peaks.
+//   K4 events       one thread per peak builds the scrappie event ending there and the r.events arrays.
+//   K5 serial       flagged reads (state mismatch, list overflow, a non-positive event mean -- all rare) are redone by
+//                   the one-lane-per-read serial kernel, which is a literal transcription and also serves
+//                   dnb_detect_events (full event table with stdv).
+//
+// The signal is read twice (K1, K2 + halo) and only the event table is written: algorithmic traffic is
+// 4 B/sample + 8 B/event (2 B/sample for int16 DAC input).
 #include <cfloat>
 #include "dnb_internal.cuh"
 #include "../../include/dnascent_b200.h"
@@ -30,50 +44,67 @@ struct Detector {
     double psum, psq; // sums[peak_pos], sumsqs[peak_pos] (carried so that create_event needs no array)
 };
 
+// ---- sinks: what happens to an emitted peak -------------------------------------------------------------------
+// serial kernel: events are built on the fly (event_detection.c:213-266 + event_handling.cpp:549-575)
 struct EventSink {
-    // scrappie event under construction starts at prev_peak
     uint32_t prev_peak;
     double prev_sum, prev_sq;
     uint32_t et_count;
-    // event_handling.cpp:549-575 filter state
     uint32_t E;
     float pend_mean;
     uint32_t pend_start;
-    // destinations
     uint32_t cap;
     uint32_t *ev_start;
     float *ev_mean;
     uint64_t *et_start;
     float *et_length, *et_mean, *et_stdv;
+
+    __device__ __forceinline__ void finish_event(uint32_t end, double esum, double esq) {
+        unsigned long long span = (unsigned long long)((long long)end - (long long)prev_peak);  // size_t arithmetic
+        float length = (float)span;
+        float mean = fDiv(d2f(dSub(esum, prev_sum)), length);
+        uint32_t idx = et_count++;
+        if (et_start && idx <= cap) {
+            float dsq = d2f(dSub(esq, prev_sq));
+            float var = fSub(fDiv(dsq, length), fMul(mean, mean));
+            et_start[idx] = prev_peak;
+            et_length[idx] = length;
+            et_mean[idx] = mean;
+            et_stdv[idx] = __fsqrt_rn(fmaxf(var, 0.0f));
+        }
+        if ((double)mean > 0.0 && idx > 0) {
+            if (E < cap) {
+                ev_mean[E] = pend_mean;
+                ev_start[E] = pend_start;
+            }
+            E++;
+            pend_mean = mean;
+            pend_start = prev_peak;
+        }
+        prev_peak = end;
+        prev_sum = esum;
+        prev_sq = esq;
+    }
+    __device__ __forceinline__ void on_peak(int /*i_emit*/, int pos, double psum, double psq) {
+        finish_event((uint32_t)pos, psum, psq);
+    }
 };
 
-// event_detection.c:213-232 + event_handling.cpp:553-573 for one finished scrappie event [prev_peak, end)
-__device__ __forceinline__ void finish_event(EventSink &k, uint32_t end, double esum, double esq) {
-    unsigned long long span = (unsigned long long)((long long)end - (long long)k.prev_peak);  // size_t arithmetic
-    float length = (float)span;
-    float mean = fDiv(d2f(dSub(esum, k.prev_sum)), length);
-    uint32_t idx = k.et_count++;
-    if (k.et_start && idx <= k.cap) {
-        float dsq = d2f(dSub(esq, k.prev_sq));
-        float var = fSub(fDiv(dsq, length), fMul(mean, mean));
-        k.et_start[idx] = k.prev_peak;
-        k.et_length[idx] = length;
-        k.et_mean[idx] = mean;
-        k.et_stdv[idx] = __fsqrt_rn(fmaxf(var, 0.0f));
-    }
-    if ((double)mean > 0.0 && idx > 0) {
-        if (k.E < k.cap) {
-            k.ev_mean[k.E] = k.pend_mean;
-            k.ev_start[k.E] = k.pend_start;
+// tile kernel: peaks emitted at a time inside the tile are listed
+struct PeakSink {
+    int t0;
+    uint32_t count, cap;
+    uint32_t *pos_out;
+    double *sum_out;
+    __device__ __forceinline__ void on_peak(int i_emit, int pos, double psum, double /*psq*/) {
+        if (i_emit < t0) return;   // emitted while still warming up in the halo: belongs to the previous tile
+        if (count < cap) {
+            pos_out[count] = (uint32_t)pos;
+            sum_out[count] = psum;
         }
-        k.E++;
-        k.pend_mean = mean;
-        k.pend_start = k.prev_peak;
+        count++;
     }
-    k.prev_peak = end;
-    k.prev_sum = esum;
-    k.prev_sq = esq;
-}
+};
 
 // event_detection.c:89-112 for one position; sm/qm = sums at i-w, s0/q0 at i, sp/qp at i+w
 __device__ __forceinline__ float tstat_at(double sm, double qm, double s0, double q0, double sp, double qp, float wf) {
@@ -93,23 +124,177 @@ __device__ __forceinline__ float tstat_at(double sm, double qm, double s0, doubl
     return d2f(dDiv(fabs((double)dm), __dsqrt_rn((double)fDiv(cv, wf))));
 }
 
+__device__ __forceinline__ bool same_boundary(const SegBoundary &a, const SegBoundary &b) {
+    return a.s_pos == b.s_pos && a.l_pos == b.l_pos && __float_as_uint(a.s_val) == __float_as_uint(b.s_val) &&
+           __float_as_uint(a.l_val) == __float_as_uint(b.l_val) && a.masked == b.masked && a.valid == b.valid;
+}
+
+// ---- the streaming engine: serial chains + t-statistics + detector pair over positions [first_pos, end_pos) ------
+template <class Sink>
+struct SegEngine {
+    uint32_t N;
+    DnbDetector det;
+    int w1, w2;
+    float w1f, w2f;
+    bool t1_on, t2_on;
+    double *rs, *rq;            // this thread's column of the shared-memory rings (stride SEG_THREADS)
+    Detector ds, dl;
+    uint32_t l_masked_to;
+    double sum, sumsq;
+    int next_pos, end_pos;      // positions still to run through the detectors: [next_pos, end_pos)
+    int capture_at;             // position before which the detector state is snapshotted (-1: never)
+    SegBoundary snap;
+    Sink sink;
+
+    __device__ __forceinline__ double &RS(int i) { return rs[(i & (SEG_RING - 1)) * SEG_THREADS]; }
+    __device__ __forceinline__ double &RQ(int i) { return rq[(i & (SEG_RING - 1)) * SEG_THREADS]; }
+
+    __device__ void init(uint32_t n, const DnbDetector &d, double *ring_s, double *ring_q, int chain_start, double s0, double q0) {
+        N = n; det = d; w1 = (int)d.w1; w2 = (int)d.w2; w1f = (float)d.w1; w2f = (float)d.w2;
+        t1_on = (n >= 2u * d.w1) && d.w1 >= 2; t2_on = (n >= 2u * d.w2) && d.w2 >= 2;
+        rs = ring_s; rq = ring_q;
+        ds = {-1, FLT_MAX, false, 0.0, 0.0}; dl = {-1, FLT_MAX, false, 0.0, 0.0};
+        l_masked_to = 0;
+        sum = s0; sumsq = q0;
+        RS(chain_start) = s0; RQ(chain_start) = q0;
+        capture_at = -1;
+    }
+
+    __device__ __forceinline__ SegBoundary boundary(int p) const {
+        SegBoundary b;
+        b.s_pos = ds.pos; b.l_pos = dl.pos; b.s_val = ds.val; b.l_val = dl.val;
+        b.masked = (l_masked_to >= (uint32_t)p) ? l_masked_to : 0u;
+        b.valid = (ds.valid ? 1u : 0u) | (dl.valid ? 2u : 0u);
+        return b;
+    }
+
+    // one position of both detectors (event_detection.c:136-194); t1/t2 are the t-statistics at i
+    __device__ __forceinline__ void fsm(int i, float t1, float t2) {
+        if (i > 0) {   // short detector: masked_to stays 0, so only i == 0 is skipped (:140)
+            const float cur = t1;
+            if (ds.pos == -1) {
+                if (cur < ds.val) {
+                    ds.val = cur;
+                } else if (fSub(cur, ds.val) > det.peak_height) {
+                    ds.val = cur; ds.pos = i; ds.psum = RS(i); ds.psq = RQ(i);
+                }
+            } else {
+                if (cur > ds.val) { ds.val = cur; ds.pos = i; ds.psum = RS(i); ds.psq = RQ(i); }
+                if (ds.val > det.thr1) {   // :165-176 the short detector dominates the long one
+                    l_masked_to = (uint32_t)ds.pos + det.w1;
+                    dl.pos = -1; dl.val = FLT_MAX; dl.valid = false;
+                }
+                if (fSub(ds.val, cur) > det.peak_height && ds.val > det.thr1) ds.valid = true;
+                if (ds.valid && (uint32_t)(i - ds.pos) > det.w1 / 2) {
+                    sink.on_peak(i, ds.pos, ds.psum, ds.psq);
+                    ds.pos = -1; ds.val = cur; ds.valid = false;
+                }
+            }
+        }
+        if (!(l_masked_to >= (uint32_t)i)) {
+            const float cur = t2;
+            if (dl.pos == -1) {
+                if (cur < dl.val) {
+                    dl.val = cur;
+                } else if (fSub(cur, dl.val) > det.peak_height) {
+                    dl.val = cur; dl.pos = i; dl.psum = RS(i); dl.psq = RQ(i);
+                }
+            } else {
+                if (cur > dl.val) { dl.val = cur; dl.pos = i; dl.psum = RS(i); dl.psq = RQ(i); }
+                if (fSub(dl.val, cur) > det.peak_height && dl.val > det.thr2) dl.valid = true;
+                if (dl.valid && (uint32_t)(i - dl.pos) > det.w2 / 2) {
+                    sink.on_peak(i, dl.pos, dl.psum, dl.psq);
+                    dl.pos = -1; dl.val = cur; dl.valid = false;
+                }
+            }
+        }
+    }
+
+    __device__ __forceinline__ void position(int i) {
+        if (i == capture_at) snap = boundary(i);
+        float t1 = 0.0f, t2 = 0.0f;
+        const double s0 = RS(i), q0 = RQ(i);
+        if (t1_on && i >= w1 && (uint32_t)i <= N - det.w1)
+            t1 = tstat_at(RS(i - w1), RQ(i - w1), s0, q0, RS(i + w1), RQ(i + w1), w1f);
+        if (t2_on && i >= w2 && (uint32_t)i <= N - det.w2)
+            t2 = tstat_at(RS(i - w2), RQ(i - w2), s0, q0, RS(i + w2), RQ(i + w2), w2f);
+        fsm(i, t1, t2);
+    }
+
+    __device__ __forceinline__ void consume(int j, float xf) {
+        const double x = (double)xf;
+        sum = dAdd(sum, x);                 // event_detection.c:45
+        sumsq = dAdd(sumsq, dMul(x, x));    // :46 (x*x is exact for a float-valued x)
+        RS(j + 1) = sum;
+        RQ(j + 1) = sumsq;
+        const int i = j + 1 - w2;           // newest position whose look-ahead is complete
+        if (i >= next_pos && next_pos < end_pos) { position(next_pos); next_pos++; }
+    }
+
+    // positions whose look-ahead runs past the end of the read (their t2 is 0 by definition)
+    __device__ __forceinline__ void drain() {
+        while (next_pos < end_pos) { position(next_pos); next_pos++; }
+    }
+};
+
 template <bool kI16>
-__global__ void __launch_bounds__(SEG_THREADS) seg_kernel(DnbBatchView v, DnbDetector det) {
+struct SampleReader {
+    const float *f32;
+    const int16_t *i16;
+    float dac_off, dac_scl;
+    __device__ __forceinline__ float one(uint64_t idx) const {
+        if (kI16) return fMul(fAdd((float)i16[idx], dac_off), dac_scl);   // src/pod5.cpp:60
+        return f32[idx];
+    }
+    // four consecutive samples starting at a multiple of 4
+    __device__ __forceinline__ void four(uint64_t idx, float o[4]) const {
+        if (kI16) {
+            const short4 s = __ldg(reinterpret_cast<const short4 *>(i16 + idx));
+            o[0] = fMul(fAdd((float)s.x, dac_off), dac_scl); o[1] = fMul(fAdd((float)s.y, dac_off), dac_scl);
+            o[2] = fMul(fAdd((float)s.z, dac_off), dac_scl); o[3] = fMul(fAdd((float)s.w, dac_off), dac_scl);
+        } else {
+            const float4 s = __ldg(reinterpret_cast<const float4 *>(f32 + idx));
+            o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w;
+        }
+    }
+};
+
+template <bool kI16, class Engine>
+__device__ __forceinline__ void stream(Engine &en, const SampleReader<kI16> &rd, uint64_t base, int j0, int j1) {
+    // j0 is a multiple of 4 and base + j0 is 16-byte aligned (read starts are 32-element aligned)
+    const int j4 = j0 + ((j1 - j0) & ~3);
+    float cur[4], nxt[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j0 < j4) rd.four(base + j0, cur);
+    for (int j = j0; j < j4; j += 4) {
+        if (j + 4 < j4) rd.four(base + j + 4, nxt);
+        en.consume(j + 0, cur[0]);
+        en.consume(j + 1, cur[1]);
+        en.consume(j + 2, cur[2]);
+        en.consume(j + 3, cur[3]);
+        cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2]; cur[3] = nxt[3];
+    }
+    for (int j = j4; j < j1; j++) en.consume(j, rd.one(base + j));
+}
+
+// ---- K5 / dnb_detect_events: literal serial transcription, one lane per read ----------------------------------------
+template <bool kI16>
+__global__ void __launch_bounds__(SEG_THREADS) seg_serial_kernel(DnbBatchView v, DnbDetector det, const uint32_t *only_flagged) {
     __shared__ double ring_s[SEG_RING][SEG_THREADS];
     __shared__ double ring_q[SEG_RING][SEG_THREADS];
     const int tid = threadIdx.x;
     const uint32_t slot = blockIdx.x * SEG_THREADS + tid;
     if (slot >= v.n_reads) return;
     const uint32_t r = v.order[slot];
+    if (only_flagged && !only_flagged[r]) return;
     const uint32_t N = v.n_samples[r];
     const uint64_t base = v.raw_off[r];
-    const int w1 = (int)det.w1, w2 = (int)det.w2;
-    const float w1f = (float)det.w1, w2f = (float)det.w2;
-    const bool t1_on = (N >= 2u * det.w1) && det.w1 >= 2, t2_on = (N >= 2u * det.w2) && det.w2 >= 2;
-    float dac_off = 0.f, dac_scl = 1.f;
-    if (kI16) { dac_off = v.dac_offset[r]; dac_scl = v.dac_scale[r]; }
+    SampleReader<kI16> rd{v.raw_f32, v.raw_i16, 0.f, 1.f};
+    if (kI16) { rd.dac_off = v.dac_offset[r]; rd.dac_scl = v.dac_scale[r]; }
 
-    EventSink sink;
+    SegEngine<EventSink> en;
+    en.init(N, det, &ring_s[0][tid], &ring_q[0][tid], 0, 0.0, 0.0);
+    en.next_pos = 0; en.end_pos = (int)N;
+    EventSink &sink = en.sink;
     sink.prev_peak = 0; sink.prev_sum = 0.0; sink.prev_sq = 0.0; sink.et_count = 0;
     sink.E = 0; sink.pend_mean = 0.0f; sink.pend_start = 0;
     sink.cap = (uint32_t)(v.ev_off[r + 1] - v.ev_off[r]);
@@ -120,117 +305,8 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_kernel(DnbBatchView v, DnbDet
     sink.et_mean = v.et_start ? v.et_mean + v.ev_off[r] + r : nullptr;
     sink.et_stdv = v.et_start ? v.et_stdv + v.ev_off[r] + r : nullptr;
 
-    Detector ds = {-1, FLT_MAX, false, 0.0, 0.0}, dl = {-1, FLT_MAX, false, 0.0, 0.0};
-    uint32_t l_masked_to = 0;
-    double sum = 0.0, sumsq = 0.0;
-    ring_s[0][tid] = 0.0;
-    ring_q[0][tid] = 0.0;
-
-    // one position of both detectors (event_detection.c:136-194); t1/t2 are the t-statistics at i
-    auto fsm = [&](int i, float t1, float t2) {
-        if (i > 0) {   // short detector: masked_to stays 0, so only i == 0 is skipped (:140)
-            float cur = t1;
-            if (ds.pos == -1) {
-                if (cur < ds.val) {
-                    ds.val = cur;
-                } else if (fSub(cur, ds.val) > det.peak_height) {
-                    ds.val = cur; ds.pos = i;
-                    ds.psum = ring_s[i & (SEG_RING - 1)][tid]; ds.psq = ring_q[i & (SEG_RING - 1)][tid];
-                }
-            } else {
-                if (cur > ds.val) {
-                    ds.val = cur; ds.pos = i;
-                    ds.psum = ring_s[i & (SEG_RING - 1)][tid]; ds.psq = ring_q[i & (SEG_RING - 1)][tid];
-                }
-                if (ds.val > det.thr1) {   // :165-176 the short detector dominates the long one
-                    l_masked_to = (uint32_t)ds.pos + det.w1;
-                    dl.pos = -1; dl.val = FLT_MAX; dl.valid = false;
-                }
-                if (fSub(ds.val, cur) > det.peak_height && ds.val > det.thr1) ds.valid = true;
-                if (ds.valid && (uint32_t)(i - ds.pos) > det.w1 / 2) {
-                    finish_event(sink, (uint32_t)ds.pos, ds.psum, ds.psq);
-                    ds.pos = -1; ds.val = cur; ds.valid = false;
-                }
-            }
-        }
-        if (!(l_masked_to >= (uint32_t)i)) {
-            float cur = t2;
-            if (dl.pos == -1) {
-                if (cur < dl.val) {
-                    dl.val = cur;
-                } else if (fSub(cur, dl.val) > det.peak_height) {
-                    dl.val = cur; dl.pos = i;
-                    dl.psum = ring_s[i & (SEG_RING - 1)][tid]; dl.psq = ring_q[i & (SEG_RING - 1)][tid];
-                }
-            } else {
-                if (cur > dl.val) {
-                    dl.val = cur; dl.pos = i;
-                    dl.psum = ring_s[i & (SEG_RING - 1)][tid]; dl.psq = ring_q[i & (SEG_RING - 1)][tid];
-                }
-                if (fSub(dl.val, cur) > det.peak_height && dl.val > det.thr2) dl.valid = true;
-                if (dl.valid && (uint32_t)(i - dl.pos) > det.w2 / 2) {
-                    finish_event(sink, (uint32_t)dl.pos, dl.psum, dl.psq);
-                    dl.pos = -1; dl.val = cur; dl.valid = false;
-                }
-            }
-        }
-    };
-
-    auto position = [&](int i) {
-        float t1 = 0.0f, t2 = 0.0f;
-        const double s0 = ring_s[i & (SEG_RING - 1)][tid], q0 = ring_q[i & (SEG_RING - 1)][tid];
-        if (t1_on && i >= w1 && (uint32_t)i <= N - det.w1)
-            t1 = tstat_at(ring_s[(i - w1) & (SEG_RING - 1)][tid], ring_q[(i - w1) & (SEG_RING - 1)][tid], s0, q0,
-                          ring_s[(i + w1) & (SEG_RING - 1)][tid], ring_q[(i + w1) & (SEG_RING - 1)][tid], w1f);
-        if (t2_on && i >= w2 && (uint32_t)i <= N - det.w2)
-            t2 = tstat_at(ring_s[(i - w2) & (SEG_RING - 1)][tid], ring_q[(i - w2) & (SEG_RING - 1)][tid], s0, q0,
-                          ring_s[(i + w2) & (SEG_RING - 1)][tid], ring_q[(i + w2) & (SEG_RING - 1)][tid], w2f);
-        fsm(i, t1, t2);
-    };
-
-    auto consume = [&](int j, float xf) {
-        double x = (double)xf;
-        sum = dAdd(sum, x);                 // event_detection.c:45
-        sumsq = dAdd(sumsq, dMul(x, x));    // :46 (x*x is exact for a float-valued x)
-        ring_s[(j + 1) & (SEG_RING - 1)][tid] = sum;
-        ring_q[(j + 1) & (SEG_RING - 1)][tid] = sumsq;
-        int i = j + 1 - w2;
-        if (i >= 0) position(i);
-    };
-
-    // stream the signal, 4 samples per load, next load in flight while the current four are consumed
-    const uint32_t n4 = N & ~3u;
-    if (kI16) {
-        const short4 *p = reinterpret_cast<const short4 *>(v.raw_i16 + base);
-        short4 cur = n4 ? __ldg(p) : make_short4(0, 0, 0, 0);
-        for (uint32_t j = 0; j < n4; j += 4) {
-            short4 nxt = (j + 4 < n4) ? __ldg(p + (j >> 2) + 1) : make_short4(0, 0, 0, 0);
-            consume((int)j + 0, fMul(fAdd((float)cur.x, dac_off), dac_scl));   // src/pod5.cpp:60
-            consume((int)j + 1, fMul(fAdd((float)cur.y, dac_off), dac_scl));
-            consume((int)j + 2, fMul(fAdd((float)cur.z, dac_off), dac_scl));
-            consume((int)j + 3, fMul(fAdd((float)cur.w, dac_off), dac_scl));
-            cur = nxt;
-        }
-        for (uint32_t j = n4; j < N; j++) consume((int)j, fMul(fAdd((float)v.raw_i16[base + j], dac_off), dac_scl));
-    } else {
-        const float4 *p = reinterpret_cast<const float4 *>(v.raw_f32 + base);
-        float4 cur = n4 ? __ldg(p) : make_float4(0, 0, 0, 0);
-        for (uint32_t j = 0; j < n4; j += 4) {
-            float4 nxt = (j + 4 < n4) ? __ldg(p + (j >> 2) + 1) : make_float4(0, 0, 0, 0);
-            consume((int)j + 0, cur.x);
-            consume((int)j + 1, cur.y);
-            consume((int)j + 2, cur.z);
-            consume((int)j + 3, cur.w);
-            cur = nxt;
-        }
-        for (uint32_t j = n4; j < N; j++) consume((int)j, v.raw_f32[base + j]);
-    }
-    // tail positions whose look-ahead runs past the end (t2 == 0 there)
-    {
-        int i0 = (int)N - w2 + 1;
-        if (i0 < 0) i0 = 0;
-        for (int i = i0; i < (int)N; i++) position(i);
-    }
+    stream<kI16>(en, rd, base, 0, (int)N);
+    en.drain();
 
     int status = DNB_READ_OK;
     if (sink.et_count == 0) {
@@ -239,7 +315,7 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_kernel(DnbBatchView v, DnbDet
         v.n_events[r] = 0;
         status = DNB_READ_UNDEFINED;
     } else {
-        finish_event(sink, N, sum, sumsq);      // last event ends at nsample (:263)
+        sink.finish_event(N, en.sum, en.sumsq);      // last event ends at nsample (:263)
         if (sink.E <= sink.cap) sink.ev_start[sink.E] = sink.pend_start;
         v.et_n[r] = sink.et_count;
         v.n_events[r] = sink.E;
@@ -254,13 +330,182 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_kernel(DnbBatchView v, DnbDet
     v.status[r] = status;
 }
 
+// ---- K1: exact (sum, sumsq) checkpoints every DNB_SEG_CK samples, one lane per read ------------------------------------
+template <bool kI16>
+__global__ void __launch_bounds__(128) seg_checkpoint_kernel(DnbBatchView v, DnbSegTiles t) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= v.n_reads) return;
+    const uint32_t r = v.order[slot];
+    const uint32_t N = v.n_samples[r];
+    const uint64_t base = v.raw_off[r];
+    SampleReader<kI16> rd{v.raw_f32, v.raw_i16, 0.f, 1.f};
+    if (kI16) { rd.dac_off = v.dac_offset[r]; rd.dac_scl = v.dac_scale[r]; }
+    double *cs = t.ck_sum + t.ck_off[r], *cq = t.ck_sq + t.ck_off[r];
+    double sum = 0.0, sumsq = 0.0;
+    const uint32_t n4 = N & ~3u;
+    float cur[4], nxt[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n4) rd.four(base, cur);
+    for (uint32_t j = 0; j < n4; j += 4) {
+        if (j + 4 < n4) rd.four(base + j + 4, nxt);
+        if ((j & (DNB_SEG_CK - 1)) == 0) { cs[j / DNB_SEG_CK] = sum; cq[j / DNB_SEG_CK] = sumsq; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const double x = (double)cur[u];
+            sum = dAdd(sum, x);
+            sumsq = dAdd(sumsq, dMul(x, x));
+        }
+        cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2]; cur[3] = nxt[3];
+    }
+    for (uint32_t j = n4; j < N; j++) {
+        if ((j & (DNB_SEG_CK - 1)) == 0) { cs[j / DNB_SEG_CK] = sum; cq[j / DNB_SEG_CK] = sumsq; }
+        const double x = (double)rd.one(base + j);
+        sum = dAdd(sum, x);
+        sumsq = dAdd(sumsq, dMul(x, x));
+    }
+    t.tot_sum[r] = sum;
+}
+
+// ---- K2: one lane per tile ------------------------------------------------------------------------------------------
+template <bool kI16>
+__global__ void __launch_bounds__(SEG_THREADS) seg_tile_kernel(DnbBatchView v, DnbDetector det, DnbSegTiles t) {
+    __shared__ double ring_s[SEG_RING][SEG_THREADS];
+    __shared__ double ring_q[SEG_RING][SEG_THREADS];
+    const int tid = threadIdx.x;
+    const uint32_t g = blockIdx.x * SEG_THREADS + tid;
+    if (g >= t.n_tiles) return;
+    const uint32_t r = t.tile_read[g];
+    const uint32_t tile = g - t.tile_off[r];
+    const uint32_t N = v.n_samples[r];
+    const uint64_t base = v.raw_off[r];
+    SampleReader<kI16> rd{v.raw_f32, v.raw_i16, 0.f, 1.f};
+    if (kI16) { rd.dac_off = v.dac_offset[r]; rd.dac_scl = v.dac_scale[r]; }
+    const int w2 = (int)det.w2;
+    const int t0 = (int)(tile * DNB_SEG_TILE);
+    const int t1 = (int)min((uint32_t)t0 + DNB_SEG_TILE, N);
+    const int s0 = tile == 0 ? 0 : t0 - DNB_SEG_HALO;                       // detectors start here, fresh
+    const int c0 = tile == 0 ? 0 : ((s0 - w2) / DNB_SEG_CK) * DNB_SEG_CK;   // chains restart at this checkpoint
+    const uint64_t ck = t.ck_off[r] + (uint32_t)c0 / DNB_SEG_CK;
+
+    SegEngine<PeakSink> en;
+    en.init(N, det, &ring_s[0][tid], &ring_q[0][tid], c0, t.ck_sum[ck], t.ck_sq[ck]);
+    en.next_pos = s0; en.end_pos = t1;
+    en.capture_at = tile == 0 ? -1 : t0;
+    en.sink.t0 = t0; en.sink.count = 0; en.sink.cap = DNB_SEG_PEAK_CAP;
+    en.sink.pos_out = t.pk_pos + (size_t)g * DNB_SEG_PEAK_CAP;
+    en.sink.sum_out = t.pk_sum + (size_t)g * DNB_SEG_PEAK_CAP;
+    en.snap = en.boundary(0);
+
+    const int j1 = (int)min((uint32_t)(t1 + w2 - 1), N);   // last sample needed so that position t1-1 has its look-ahead
+    stream<kI16>(en, rd, base, c0, j1);
+    if ((uint32_t)j1 == N) en.drain();                       // tile touches the end of the read
+
+    t.pk_count[g] = en.sink.count;
+    t.b_start[g] = en.snap;
+    t.b_end[g] = en.boundary(t1);
+}
+
+// ---- K3: stitch the tiles of a read -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) seg_stitch_kernel(DnbBatchView v, DnbSegTiles t) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= v.n_reads) return;
+    const uint32_t r = v.order[slot];
+    const uint32_t g0 = t.tile_off[r], g1 = t.tile_off[r + 1];
+    bool bad = false;
+    uint32_t prefix = 0, last_pos = 0;
+    double last_sum = 0.0;
+    for (uint32_t g = g0; g < g1; g++) {
+        if (g > g0 && !same_boundary(t.b_start[g], t.b_end[g - 1])) bad = true;
+        const uint32_t c = t.pk_count[g];
+        if (c > DNB_SEG_PEAK_CAP) bad = true;
+        if (bad) break;
+        t.tile_prefix[g] = prefix;
+        t.tile_prev_pos[g] = last_pos;
+        t.tile_prev_sum[g] = last_sum;
+        if (c > 0) {
+            last_pos = t.pk_pos[(size_t)g * DNB_SEG_PEAK_CAP + c - 1];
+            last_sum = t.pk_sum[(size_t)g * DNB_SEG_PEAK_CAP + c - 1];
+        }
+        prefix += c;
+    }
+    const uint32_t cap = (uint32_t)(v.ev_off[r + 1] - v.ev_off[r]);
+    int status = DNB_READ_OK;
+    t.redo[r] = bad ? 1u : 0u;
+    if (!bad) {
+        const uint32_t m = prefix;                 // peaks; scrappie events n = m + 1; r.events (all means > 0) = m
+        if (m == 0) { v.et_n[r] = 0; v.n_events[r] = 0; status = DNB_READ_UNDEFINED; }
+        else {
+            v.et_n[r] = m + 1; v.n_events[r] = m;
+            if (m > cap) status = DNB_READ_OVERFLOW;
+        }
+        const uint64_t ql = v.q_off[r + 1] - v.q_off[r], rl = v.r_off[r + 1] - v.r_off[r];
+        if (ql <= DNB_K || rl < DNB_K) status = DNB_READ_UNDEFINED;
+        v.status[r] = status;
+    }
+}
+
+// ---- K4: events from peaks, one warp per tile ---------------------------------------------------------------------
+// Peak k (global index within the read) ends scrappie event k and starts event k+1 (event_detection.c:257-263).
+// With every event mean > 0 the filter of event_handling.cpp:549-575 is the identity shifted by one:
+// r.events[0] = {0.0, raw from 0}, r.events[k] = {mean_k, raw from peak k-1}, the last scrappie event is dropped.
+__global__ void __launch_bounds__(128) seg_events_kernel(DnbBatchView v, DnbSegTiles t) {
+    const uint32_t g = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= t.n_tiles) return;
+    const uint32_t r = t.tile_read[g];
+    if (t.redo[r] || v.status[r] == DNB_READ_OVERFLOW) return;
+    const uint32_t c = t.pk_count[g];
+    if (c == 0) return;
+    const uint32_t prefix = t.tile_prefix[g];
+    const uint32_t m = v.n_events[r];
+    const uint32_t *pp = t.pk_pos + (size_t)g * DNB_SEG_PEAK_CAP;
+    const double *ps = t.pk_sum + (size_t)g * DNB_SEG_PEAK_CAP;
+    uint32_t *ev_start = v.ev_start + v.ev_off[r] + r;
+    float *ev_mean = v.ev_mean + v.ev_off[r];
+    for (uint32_t j = lane; j < c; j += 32) {
+        const uint32_t k = prefix + j;
+        const uint32_t pos = pp[j];
+        const double sm = ps[j];
+        const uint32_t ppos = j > 0 ? pp[j - 1] : t.tile_prev_pos[g];
+        const double psum = j > 0 ? ps[j - 1] : t.tile_prev_sum[g];
+        const unsigned long long span = (unsigned long long)((long long)pos - (long long)ppos);
+        const float mean = fDiv(d2f(dSub(sm, psum)), (float)span);     // event_detection.c:225-226
+        bool redo = false;
+        if (k >= 1 && !((double)mean > 0.0)) redo = true;              // the filter would drop it: serial path
+        ev_mean[k] = k >= 1 ? mean : 0.0f;                              // quirk Q1
+        if (k == 0) ev_start[0] = 0;
+        ev_start[k + 1] = pos;
+        if (k == m - 1) {                                               // last scrappie event [pos, N)
+            const uint32_t N = v.n_samples[r];
+            const float lmean = fDiv(d2f(dSub(t.tot_sum[r], sm)), (float)(unsigned long long)(N - pos));
+            if (!((double)lmean > 0.0)) redo = true;
+        }
+        if (redo) t.redo[r] = 1u;
+    }
+}
+
 }  // namespace
 
-void dnb_launch_segmentation(const DnbBatchView &v, DnbDetector det, cudaStream_t s) {
+void dnb_launch_segmentation_serial(const DnbBatchView &v, DnbDetector det, const uint32_t *only_flagged, cudaStream_t s) {
     if (v.n_reads == 0) return;
     dim3 grid((v.n_reads + SEG_THREADS - 1) / SEG_THREADS);
     if (v.raw_i16)
-        seg_kernel<true><<<grid, SEG_THREADS, 0, s>>>(v, det);
+        seg_serial_kernel<true><<<grid, SEG_THREADS, 0, s>>>(v, det, only_flagged);
     else
-        seg_kernel<false><<<grid, SEG_THREADS, 0, s>>>(v, det);
+        seg_serial_kernel<false><<<grid, SEG_THREADS, 0, s>>>(v, det, only_flagged);
+}
+
+void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s) {
+    if (v.n_reads == 0) return;
+    const unsigned gr = (v.n_reads + 127) / 128;
+    const unsigned gt = (t.n_tiles + SEG_THREADS - 1) / SEG_THREADS;
+    if (v.raw_i16) {
+        seg_checkpoint_kernel<true><<<gr, 128, 0, s>>>(v, t);
+        seg_tile_kernel<true><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
+    } else {
+        seg_checkpoint_kernel<false><<<gr, 128, 0, s>>>(v, t);
+        seg_tile_kernel<false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
+    }
+    seg_stitch_kernel<<<gr, 128, 0, s>>>(v, t);
+    seg_events_kernel<<<(t.n_tiles + 3) / 4, 128, 0, s>>>(v, t);
+    dnb_launch_segmentation_serial(v, det, t.redo, s);
 }

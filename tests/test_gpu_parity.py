@@ -44,3 +44,77 @@ def test_detect_events_drop_in(ctx, golden_reads):
         np.testing.assert_array_equal(ln, g.et_length)
         np.testing.assert_array_equal(mn, g.et_mean)
         np.testing.assert_array_equal(sd, g.et_stdv)
+
+
+def _compare_with_port(res, p, tag=""):
+    """CUDA result vs the CPU oracle port on the same input: everything bit-exact."""
+    assert res.et_n == p["et_n"], tag
+    np.testing.assert_array_equal(res.event_mean.astype(np.float64), p["event_mean"], err_msg=tag)
+    if p["event_mean"].size:
+        np.testing.assert_array_equal(res.event_start, p["event_start"], err_msg=tag)
+    if p["status"] == 3:   # undefined in the reference
+        assert res.status == api.READ_UNDEFINED, tag
+        return
+    assert res.status == p["status"], tag
+    assert res.rough_shift == p["rough_shift"] and res.rough_scale == p["rough_scale"], tag
+    assert res.shift == p["shift"] and res.scale == p["scale"], tag
+    assert res.avg_log_emission == p["avg_log_emission"], tag
+    assert res.spanned == p["spanned"] and res.maxGap == p["max_gap"], tag
+    if p["status"] == 0:
+        np.testing.assert_array_equal(res.eventAlignment[:, 0], p["align_event"], err_msg=tag)
+        np.testing.assert_array_equal(res.eventAlignment[:, 1], p["align_kmer"], err_msg=tag)
+    else:
+        assert res.eventAlignment.shape[0] == 0, tag
+    if res.cleaned_signal is not None:
+        np.testing.assert_array_equal(res.cleaned_signal, p["cleaned_signal"], err_msg=tag)
+        np.testing.assert_array_equal(res.cleaned_rank, p["cleaned_rank"], err_msg=tag)
+
+
+def test_random_reads_vs_oracle(ctx, port, pore_mean):
+    """Seeded reads, both strands, with and without substitutions, lengths straddling the 512-sample tiles."""
+    ref = synth.make_reference(400_000, 11)
+    rng = np.random.default_rng(12)
+    lengths = [int(x) for x in rng.integers(1100, 9000, size=20)] + [12000, 15000, 20000, 1024, 2048, 4096]
+    reads = []
+    for i, L in enumerate(lengths):
+        reads.append(synth.simulate_read(ref, int(rng.integers(0, len(ref) - L)), L, bool(i % 2), pore_mean, rng,
+                                         name=f"t{i}", sub_rate=0.03 if i % 3 == 0 else 0.0))
+    out = ctx.normaliseEvents([api.Read.from_synth(r) for r in reads])
+    n_ok = 0
+    for i, (r, o) in enumerate(zip(reads, out)):
+        p = port.normalise(r.raw, r.basecall, r.refseq, r.query_to_ref, pore_mean)
+        _compare_with_port(o, p, tag=f"read {i} L={lengths[i]}")
+        n_ok += o.status == api.READ_OK
+    assert n_ok >= len(reads) - 2
+
+
+def test_segmentation_edge_shapes(ctx, port, pore_mean):
+    """Signals the simulator never produces: tiny reads, exact tile multiples, noise, constants, a long stall,
+    zero / negative levels (exercise the r.events filter, quirk Q3, and the serial fallback)."""
+    rng = np.random.default_rng(5)
+    ref = synth.make_reference(20_000, 6)
+    base = synth.simulate_read(ref, 100, 3000, False, pore_mean, rng)
+    sig = base.raw
+    cases = []
+    for n in (1, 2, 5, 6, 11, 12, 13, 31, 64, 100, 511, 512, 513, 1023, 1024, 1025, 1536, 4096, 4101):
+        cases.append(("prefix%d" % n, sig[:n].copy()))
+    cases.append(("noise", (90 + 2.0 * rng.standard_normal(5000)).astype(np.float32)))
+    cases.append(("const", np.full(3000, 87.25, dtype=np.float32)))
+    stall = sig[:6000].copy(); stall[2000:4500] = np.float32(71.5)
+    cases.append(("stall", stall))
+    neg = sig[:4000].copy() - np.float32(95.0)
+    cases.append(("negative_levels", neg))
+    zero = sig[:4000].copy(); zero[1000:1400] = 0.0
+    cases.append(("zero_stretch", zero))
+    steps = np.repeat(rng.normal(90, 12, size=700), 7).astype(np.float32)
+    cases.append(("clean_steps", steps))
+    reads = [api.Read(raw, base.basecall, base.refseq, base.query_to_ref) for _, raw in cases]
+    out = ctx.normaliseEvents(reads)
+    for (name, raw), o in zip(cases, out):
+        p = port.normalise(raw, base.basecall, base.refseq, base.query_to_ref, pore_mean)
+        _compare_with_port(o, p, tag=name)
+        st, ln, mn, sd = ctx.detect_events(raw) if p["et_n"] else (None,) * 4
+        if p["et_n"]:
+            np.testing.assert_array_equal(st, p["et_start"], err_msg=name)
+            np.testing.assert_array_equal(mn, p["et_mean"], err_msg=name)
+            np.testing.assert_array_equal(sd, p["et_stdv"], err_msg=name)

@@ -38,6 +38,15 @@ class ReadDesc(C.Structure):
     ]
 
 
+# numpy mirror of dnb_read_desc (C layout, natural alignment) for building descriptor arrays without a Python loop
+import numpy as _np
+READ_DESC_DTYPE = _np.dtype([
+    ("raw_pA", _np.uint64), ("raw_dac", _np.uint64), ("dac_offset", _np.float32), ("dac_scale", _np.float32),
+    ("n_samples", _np.uint64), ("query", _np.uint64), ("query_len", _np.uint32), ("ref", _np.uint64),
+    ("ref_len", _np.uint32), ("query_to_ref", _np.uint64)], align=True)
+assert READ_DESC_DTYPE.itemsize == C.sizeof(ReadDesc), (READ_DESC_DTYPE.itemsize, C.sizeof(ReadDesc))
+
+
 class ReadResult(C.Structure):
     _fields_ = [
         ("status", C.c_int), ("et_n", C.c_uint32), ("n_events", C.c_uint32),
@@ -59,7 +68,7 @@ class EventT(C.Structure):
 EXPORTS = [
     "dnb_default_config", "dnb_create", "dnb_destroy", "dnb_strerror", "dnb_last_error", "dnb_load_model",
     "dnb_submit", "dnb_wait", "dnb_result", "dnb_release",
-    "dnb_batch_upload", "dnb_batch_run", "dnb_batch_fetch", "dnb_batch_timings",
+    "dnb_batch_upload", "dnb_batch_run", "dnb_batch_fetch", "dnb_batch_drop_workspace", "dnb_batch_timings",
     "dnb_detect_events",
     "dnb_eexp", "dnb_eln", "dnb_lnSum", "dnb_lnProd", "dnb_lnGreaterThan", "dnb_uniformPDF", "dnb_normalPDF",
     "dnb_cauchyPDF", "dnb_sequence_probability_batch",
@@ -84,11 +93,12 @@ def lib():
     L.dnb_strerror.argtypes = [C.c_int]
     L.dnb_last_error.restype = C.c_char_p
     L.dnb_load_model.argtypes = [vp, C.c_int, vp, vp, sz]
-    L.dnb_submit.argtypes = [vp, C.POINTER(ReadDesc), sz, C.POINTER(vp)]
-    L.dnb_batch_upload.argtypes = [vp, C.POINTER(ReadDesc), sz, C.POINTER(vp)]
+    L.dnb_submit.argtypes = [vp, vp, sz, C.POINTER(vp)]
+    L.dnb_batch_upload.argtypes = [vp, vp, sz, C.POINTER(vp)]
     L.dnb_wait.argtypes = [vp]
     L.dnb_batch_run.argtypes = [vp]
     L.dnb_batch_fetch.argtypes = [vp]
+    L.dnb_batch_drop_workspace.argtypes = [vp]
     L.dnb_result.argtypes = [vp, sz, C.POINTER(ReadResult)]
     L.dnb_release.argtypes = [vp]
     L.dnb_release.restype = None

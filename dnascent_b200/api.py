@@ -86,6 +86,9 @@ class Batch:
     def fetch(self):
         _lib.check(self.ctx.L.dnb_batch_fetch(self.h), "dnb_batch_fetch")
 
+    def drop_workspace(self):
+        _lib.check(self.ctx.L.dnb_batch_drop_workspace(self.h), "dnb_batch_drop_workspace")
+
     def timings(self):
         ms = (C.c_double * 6)()
         cnt = (C.c_uint64 * 8)()
@@ -184,14 +187,25 @@ class Context:
     def submit(self, reads) -> Batch:
         arr, keep = self._descs(reads)
         h = C.c_void_p()
-        _lib.check(self.L.dnb_submit(self.h, arr, len(reads), C.byref(h)), "dnb_submit")
+        _lib.check(self.L.dnb_submit(self.h, C.addressof(arr), len(reads), C.byref(h)), "dnb_submit")
         return Batch(self, h, len(reads), (arr, keep))
 
     def upload(self, reads) -> Batch:
         arr, keep = self._descs(reads)
         h = C.c_void_p()
-        _lib.check(self.L.dnb_batch_upload(self.h, arr, len(reads), C.byref(h)), "dnb_batch_upload")
+        _lib.check(self.L.dnb_batch_upload(self.h, C.addressof(arr), len(reads), C.byref(h)), "dnb_batch_upload")
         return Batch(self, h, len(reads), None)   # inputs are resident in HBM; host copies may be dropped
+
+    # descriptor arrays built with numpy (dtype _lib.READ_DESC_DTYPE): no per-read Python objects
+    def submit_descs(self, descs: np.ndarray) -> Batch:
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_submit(self.h, descs.ctypes.data, descs.size, C.byref(h)), "dnb_submit")
+        return Batch(self, h, descs.size, descs)
+
+    def upload_descs(self, descs: np.ndarray) -> Batch:
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_batch_upload(self.h, descs.ctypes.data, descs.size, C.byref(h)), "dnb_batch_upload")
+        return Batch(self, h, descs.size, None)
 
     def normaliseEvents(self, reads) -> list[Normalised]:
         """Batched normaliseEvents(r, false): src/event_handling.cpp:544."""

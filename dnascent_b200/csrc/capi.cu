@@ -12,6 +12,13 @@
 //             are sized from n_events, so both are done here and sent down
 //   phase B   banded DP -> backtrace/QC -> Theil-Sen
 //   fetch     alignment compaction -> D2H of events, alignment pairs and per-read scalars
+//
+// Memory classes of a batch:
+//   inputs     signal, sequences, offsets: allocated by upload, resident until release   (~2.6 B/sample as int16)
+//   workspace  everything the kernels write: allocated by run, freed by drop_workspace    (~27 B/sample)
+//   results    pinned host copies handed out by dnb_result: allocated by fetch, from the context's pinned pool
+// Device memory comes from the stream-ordered pool (release threshold = infinity), so a freed workspace is what
+// the next batch's run gets back without touching the driver.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -35,8 +42,15 @@ thread_local std::string g_last_error;
         cudaError_t _e = (call);                                                                              \
         if (_e != cudaSuccess) {                                                                              \
             g_last_error = std::string(#call) + ": " + cudaGetErrorString(_e);                                \
+            cudaGetLastError();                                                                               \
             return DNB_ERR_CUDA;                                                                              \
         }                                                                                                     \
+    } while (0)
+
+#define TRY(x)                         \
+    do {                               \
+        int _rc = (x);                 \
+        if (_rc != DNB_OK) return _rc; \
     } while (0)
 
 struct ModelHost {
@@ -46,10 +60,33 @@ struct ModelHost {
     DnbModelDev dev() const { return DnbModelDev{d_mean, d_stdv, d_order, d_sorted}; }
 };
 
-template <class T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
+// pinned host buffers are expensive to create (page locking): keep them for the life of the context
+struct PinnedPool {
+    struct Block { void *p; size_t n; bool used; };
+    std::vector<Block> blocks;
+    std::mutex mu;
+    void *acquire(size_t n) {
+        if (n == 0) n = 1;
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        for (size_t i = 0; i < blocks.size(); i++)
+            if (!blocks[i].used && blocks[i].n >= n && (best < 0 || blocks[i].n < blocks[best].n)) best = (int)i;
+        if (best >= 0 && blocks[best].n <= 4 * n + (1u << 20)) { blocks[best].used = true; return blocks[best].p; }
+        const size_t gran = 1u << 20;
+        const size_t sz = (n + gran - 1) / gran * gran;
+        void *p = nullptr;
+        if (cudaMallocHost(&p, sz) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        blocks.push_back({p, sz, true});
+        return p;
+    }
+    void release(void *p) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+    void destroy() {
+        for (auto &b : blocks) cudaFreeHost(b.p);
+        blocks.clear();
+    }
 };
 
 }  // namespace
@@ -59,74 +96,77 @@ struct dnb_ctx {
     ModelHost model[3];
     double emit_const = 0.0;
     std::mutex mu;
+    PinnedPool pinned;
 };
+
+namespace {
+
+// device workspace: everything the kernels write (re-created by every run, dropped on request)
+struct Work {
+    uint32_t *et_n, *n_events, *ev_start;
+    float *ev_mean;
+    int *status;
+    uint64_t *et_start;
+    float *et_length, *et_mean, *et_stdv;
+    double *mu_q, *x_e, *rough_shift, *rough_scale, *lp, *tot_sum;
+    uint32_t *rank_ref, *redo;
+    uint64_t *band_off, *al_off, *cl_off, *out_off;
+    uint8_t *trace;
+    int32_t *end_event, *end_ll;
+    float *end_score;
+    unsigned long long *cells;
+    uint32_t *al_rev, *n_align, *cl_rank, *n_cleaned, *out_pairs;
+    double *cl_signal, *avg, *shift, *scale;
+    int *spanned, *max_gap;
+};
+
+// pinned host results
+struct HostRes {
+    uint32_t *et_n, *n_events, *n_align, *n_cleaned, *redo;
+    int *status, *spanned, *max_gap;
+    double *rough_shift, *rough_scale, *shift, *scale, *avg;
+    uint32_t *ev_start, *out_pairs, *cl_rank;
+    float *ev_mean;
+    double *cl_signal;
+    uint64_t *et_start;
+    float *et_length, *et_mean, *et_stdv;
+};
+
+}  // namespace
 
 struct dnb_batch {
     dnb_ctx *ctx = nullptr;
     size_t R = 0;
     cudaStream_t stream = nullptr;
     bool want_table = false;     // dnb_detect_events: keep the full scrappie table, segmentation only
-    bool uploaded = false, ran = false, fetched = false;
+    bool uploaded = false, ran = false, fetched = false, have_work = false;
     // ---- host-side shapes ----
-    std::vector<uint64_t> raw_off, q_off, r_off, ev_off, band_off, al_off, cl_off, out_off;
-    std::vector<uint32_t> n_samples, order;
-    std::vector<uint32_t> qlen, rlen;
+    std::vector<uint64_t> raw_off, q_off, r_off, ev_off, band_off, al_off, cl_off, out_off, ck_off;
+    std::vector<uint32_t> n_samples, order, qlen, rlen, tile_off, tile_read;
+    std::vector<double> lp;
     bool i16 = false;
     uint64_t tot_raw = 0, tot_q = 0, tot_r = 0, tot_ev = 0, tot_bands = 0, tot_al = 0, tot_cl = 0, tot_out = 0;
-    // ---- device: inputs ----
+    // ---- device: resident inputs ----
     void *d_raw = nullptr;
     float *d_dac_off = nullptr, *d_dac_scl = nullptr;
     char *d_query = nullptr, *d_ref = nullptr;
     int32_t *d_q2r = nullptr;
-    uint64_t *d_raw_off = nullptr, *d_q_off = nullptr, *d_r_off = nullptr, *d_ev_off = nullptr;
-    uint32_t *d_n_samples = nullptr, *d_order = nullptr;
-    // ---- device: phase A outputs ----
-    uint32_t *d_et_n = nullptr, *d_n_events = nullptr, *d_ev_start = nullptr;
-    float *d_ev_mean = nullptr;
-    int *d_status = nullptr;
-    uint64_t *d_et_start = nullptr;
-    float *d_et_length = nullptr, *d_et_mean = nullptr, *d_et_stdv = nullptr;
-    double *d_mu_q = nullptr, *d_x_e = nullptr, *d_rough_shift = nullptr, *d_rough_scale = nullptr;
-    uint32_t *d_rank_ref = nullptr;
-    // ---- device: phase B ----
-    double *d_lp = nullptr;
-    uint64_t *d_band_off = nullptr, *d_al_off = nullptr, *d_cl_off = nullptr, *d_out_off = nullptr;
-    uint8_t *d_trace = nullptr;
-    int32_t *d_end_event = nullptr, *d_end_ll = nullptr;
-    float *d_end_score = nullptr;
-    unsigned long long *d_cells = nullptr;
-    uint32_t *d_al_rev = nullptr, *d_n_align = nullptr, *d_cl_rank = nullptr, *d_n_cleaned = nullptr, *d_out_pairs = nullptr;
-    double *d_cl_signal = nullptr, *d_avg = nullptr, *d_shift = nullptr, *d_scale = nullptr;
-    int *d_spanned = nullptr, *d_max_gap = nullptr;
-    // ---- host results (pinned where they are DMA targets) ----
-    uint32_t *h_et_n = nullptr, *h_n_events = nullptr, *h_n_align = nullptr, *h_n_cleaned = nullptr;
-    int *h_status = nullptr, *h_spanned = nullptr, *h_max_gap = nullptr;
-    double *h_rough_shift = nullptr, *h_rough_scale = nullptr, *h_shift = nullptr, *h_scale = nullptr, *h_avg = nullptr;
-    uint32_t *h_ev_start = nullptr, *h_out_pairs = nullptr, *h_cl_rank = nullptr;
-    float *h_ev_mean = nullptr;
-    double *h_cl_signal = nullptr;
-    uint64_t *h_et_start = nullptr;
-    float *h_et_length = nullptr, *h_et_mean = nullptr, *h_et_stdv = nullptr;
-    std::vector<double> lp;
-    // ---- tiled segmentation workspace ----
-    std::vector<uint32_t> tile_off, tile_read;
-    std::vector<uint64_t> ck_off;
-    DnbSegTiles seg = {};
-    uint32_t *d_tile_off = nullptr, *d_tile_read = nullptr;
-    uint64_t *d_ck_off = nullptr;
+    uint64_t *d_raw_off = nullptr, *d_q_off = nullptr, *d_r_off = nullptr, *d_ev_off = nullptr, *d_ck_off = nullptr;
+    uint32_t *d_n_samples = nullptr, *d_order = nullptr, *d_tile_off = nullptr, *d_tile_read = nullptr;
+    Work w = {};
+    HostRes h = {};
     // ---- timings ----
     cudaEvent_t ev[8] = {};
     double ms[6] = {};
     uint64_t counts[8] = {};
-    std::vector<uint32_t> h_redo;
     unsigned long long h_cells = 0;
-    std::vector<void *> dev_allocs, host_allocs;
+    std::vector<void *> input_allocs, work_allocs, res_allocs;
 };
 
 namespace {
 
 template <class T>
-int dalloc(dnb_batch *b, T **p, size_t n) {
+int dev_alloc(dnb_batch *b, std::vector<void *> &owner, T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
     void *q = nullptr;
@@ -136,32 +176,21 @@ int dalloc(dnb_batch *b, T **p, size_t n) {
         cudaGetLastError();
         return e == cudaErrorMemoryAllocation ? DNB_ERR_NOMEM : DNB_ERR_CUDA;
     }
-    b->dev_allocs.push_back(q);
+    owner.push_back(q);
     *p = (T *)q;
     return DNB_OK;
 }
+template <class T> int ialloc(dnb_batch *b, T **p, size_t n) { return dev_alloc(b, b->input_allocs, p, n); }
+template <class T> int walloc(dnb_batch *b, T **p, size_t n) { return dev_alloc(b, b->work_allocs, p, n); }
 
 template <class T>
-int halloc(dnb_batch *b, T **p, size_t n) {
-    *p = nullptr;
-    if (n == 0) n = 1;
-    void *q = nullptr;
-    cudaError_t e = cudaMallocHost(&q, n * sizeof(T));
-    if (e != cudaSuccess) {
-        g_last_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
-        cudaGetLastError();
-        return DNB_ERR_NOMEM;
-    }
-    b->host_allocs.push_back(q);
+int ralloc(dnb_batch *b, T **p, size_t n) {   // pinned host, from the context pool
+    void *q = b->ctx->pinned.acquire(n * sizeof(T));
     *p = (T *)q;
+    if (!q) { g_last_error = "pinned host allocation failed"; return DNB_ERR_NOMEM; }
+    b->res_allocs.push_back(q);
     return DNB_OK;
 }
-
-#define TRY(x)                    \
-    do {                          \
-        int _rc = (x);            \
-        if (_rc != DNB_OK) return _rc; \
-    } while (0)
 
 template <class T>
 int h2d(dnb_batch *b, T *dst, const T *src, size_t n) {
@@ -192,24 +221,38 @@ DnbBatchView make_view(const dnb_batch *b) {
     v.q_off = b->d_q_off;
     v.r_off = b->d_r_off;
     v.q2r = b->d_q2r;
-    v.et_n = b->d_et_n;
-    v.n_events = b->d_n_events;
+    v.et_n = b->w.et_n;
+    v.n_events = b->w.n_events;
     v.ev_off = b->d_ev_off;
-    v.ev_start = b->d_ev_start;
-    v.ev_mean = b->d_ev_mean;
-    v.status = b->d_status;
-    v.et_start = b->d_et_start;
-    v.et_length = b->d_et_length;
-    v.et_mean = b->d_et_mean;
-    v.et_stdv = b->d_et_stdv;
+    v.ev_start = b->w.ev_start;
+    v.ev_mean = b->w.ev_mean;
+    v.status = b->w.status;
+    v.et_start = b->w.et_start;
+    v.et_length = b->w.et_length;
+    v.et_mean = b->w.et_mean;
+    v.et_stdv = b->w.et_stdv;
     return v;
+}
+
+void drop_work(dnb_batch *b) {
+    for (void *p : b->work_allocs) cudaFreeAsync(p, b->stream);
+    b->work_allocs.clear();
+    b->w = Work{};
+    b->have_work = false;
+}
+void drop_results(dnb_batch *b) {
+    for (void *p : b->res_allocs) b->ctx->pinned.release(p);
+    b->res_allocs.clear();
+    b->h = HostRes{};
+    b->fetched = false;
 }
 
 void free_batch(dnb_batch *b) {
     if (!b) return;
     if (b->stream) cudaStreamSynchronize(b->stream);
-    for (void *p : b->dev_allocs) cudaFreeAsync(p, b->stream);
-    for (void *p : b->host_allocs) cudaFreeHost(p);
+    drop_work(b);
+    drop_results(b);
+    for (void *p : b->input_allocs) cudaFreeAsync(p, b->stream);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
     if (b->stream) {
@@ -282,13 +325,17 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
 
     // ---- pinned staging + device inputs ----
     const size_t esz = b->i16 ? 2 : 4;
-    uint8_t *h_raw = nullptr; char *h_q = nullptr, *h_r = nullptr; int32_t *h_q2r = nullptr;
-    float *h_doff = nullptr, *h_dscl = nullptr;
     int rc = DNB_OK;
-#define TRYF(x) do { rc = (x); if (rc != DNB_OK) { free_batch(b); return rc; } } while (0)
-    TRYF(halloc(b, &h_raw, ro * esz));
-    TRYF(halloc(b, &h_q, qo)); TRYF(halloc(b, &h_r, fo)); TRYF(halloc(b, &h_q2r, qo));
-    TRYF(halloc(b, &h_doff, R)); TRYF(halloc(b, &h_dscl, R));
+    uint8_t *h_raw = (uint8_t *)ctx->pinned.acquire(ro * esz);
+    char *h_q = (char *)ctx->pinned.acquire(qo), *h_r = (char *)ctx->pinned.acquire(fo);
+    int32_t *h_q2r = (int32_t *)ctx->pinned.acquire(qo * 4);
+    float *h_doff = (float *)ctx->pinned.acquire(R * 4), *h_dscl = (float *)ctx->pinned.acquire(R * 4);
+    auto release_staging = [&]() {
+        for (void *p : {(void *)h_raw, (void *)h_q, (void *)h_r, (void *)h_q2r, (void *)h_doff, (void *)h_dscl})
+            if (p) ctx->pinned.release(p);
+    };
+#define TRYF(x) do { rc = (x); if (rc != DNB_OK) { cudaStreamSynchronize(b->stream); release_staging(); free_batch(b); return rc; } } while (0)
+    if (!h_raw || !h_q || !h_r || !h_q2r || !h_doff || !h_dscl) { g_last_error = "pinned staging allocation failed"; TRYF(DNB_ERR_NOMEM); }
 #pragma omp parallel for schedule(dynamic, 16)
     for (size_t i = 0; i < R; i++) {
         const dnb_read_desc &d = reads[i];
@@ -301,64 +348,53 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
         if (d.query_to_ref) memcpy(h_q2r + b->q_off[i], d.query_to_ref, (size_t)d.query_len * 4);
         h_doff[i] = d.dac_offset; h_dscl[i] = d.dac_scale;
     }
-    TRYF(dalloc(b, (uint8_t **)&b->d_raw, ro * esz));
-    TRYF(dalloc(b, &b->d_query, qo)); TRYF(dalloc(b, &b->d_ref, fo)); TRYF(dalloc(b, &b->d_q2r, qo));
-    TRYF(dalloc(b, &b->d_dac_off, R)); TRYF(dalloc(b, &b->d_dac_scl, R));
-    TRYF(dalloc(b, &b->d_raw_off, R + 1)); TRYF(dalloc(b, &b->d_q_off, R + 1)); TRYF(dalloc(b, &b->d_r_off, R + 1));
-    TRYF(dalloc(b, &b->d_ev_off, R + 1)); TRYF(dalloc(b, &b->d_n_samples, R)); TRYF(dalloc(b, &b->d_order, R));
+    TRYF(ialloc(b, (uint8_t **)&b->d_raw, ro * esz));
+    TRYF(ialloc(b, &b->d_query, qo)); TRYF(ialloc(b, &b->d_ref, fo)); TRYF(ialloc(b, &b->d_q2r, qo));
+    TRYF(ialloc(b, &b->d_dac_off, R)); TRYF(ialloc(b, &b->d_dac_scl, R));
+    TRYF(ialloc(b, &b->d_raw_off, R + 1)); TRYF(ialloc(b, &b->d_q_off, R + 1)); TRYF(ialloc(b, &b->d_r_off, R + 1));
+    TRYF(ialloc(b, &b->d_ev_off, R + 1)); TRYF(ialloc(b, &b->d_n_samples, R)); TRYF(ialloc(b, &b->d_order, R));
+    TRYF(ialloc(b, &b->d_tile_off, R + 1)); TRYF(ialloc(b, &b->d_tile_read, b->tile_read.size()));
+    TRYF(ialloc(b, &b->d_ck_off, R + 1));
     TRYF(h2d(b, (uint8_t *)b->d_raw, h_raw, ro * esz));
     TRYF(h2d(b, b->d_query, h_q, qo)); TRYF(h2d(b, b->d_ref, h_r, fo)); TRYF(h2d(b, b->d_q2r, h_q2r, qo));
     TRYF(h2d(b, b->d_dac_off, h_doff, R)); TRYF(h2d(b, b->d_dac_scl, h_dscl, R));
     TRYF(h2d(b, b->d_raw_off, b->raw_off.data(), R + 1)); TRYF(h2d(b, b->d_q_off, b->q_off.data(), R + 1));
     TRYF(h2d(b, b->d_r_off, b->r_off.data(), R + 1)); TRYF(h2d(b, b->d_ev_off, b->ev_off.data(), R + 1));
     TRYF(h2d(b, b->d_n_samples, b->n_samples.data(), R)); TRYF(h2d(b, b->d_order, b->order.data(), R));
-    if (!want_table) {
-        double *d_tot = nullptr; uint32_t *d_redo = nullptr;
-        TRYF(dalloc(b, &b->d_tile_off, R + 1)); TRYF(dalloc(b, &b->d_tile_read, b->tile_read.size()));
-        TRYF(dalloc(b, &b->d_ck_off, R + 1)); TRYF(dalloc(b, &d_tot, R)); TRYF(dalloc(b, &d_redo, R));
-        TRYF(h2d(b, b->d_tile_off, b->tile_off.data(), R + 1));
-        TRYF(h2d(b, b->d_tile_read, b->tile_read.data(), b->tile_read.size()));
-        TRYF(h2d(b, b->d_ck_off, b->ck_off.data(), R + 1));
-        b->seg.n_tiles = b->tile_off[R]; b->seg.tile_off = b->d_tile_off; b->seg.tile_read = b->d_tile_read;
-        b->seg.ck_off = b->d_ck_off; b->seg.tot_sum = d_tot; b->seg.redo = d_redo;
-    }
-
-    // ---- phase A outputs + small per-read arrays ----
-    TRYF(dalloc(b, &b->d_et_n, R)); TRYF(dalloc(b, &b->d_n_events, R)); TRYF(dalloc(b, &b->d_status, R));
-    TRYF(dalloc(b, &b->d_ev_start, eo + R)); TRYF(dalloc(b, &b->d_ev_mean, eo));
-    TRYF(halloc(b, &b->h_et_n, R)); TRYF(halloc(b, &b->h_n_events, R)); TRYF(halloc(b, &b->h_status, R));
-    if (want_table) {
-        TRYF(dalloc(b, &b->d_et_start, eo + R)); TRYF(dalloc(b, &b->d_et_length, eo + R));
-        TRYF(dalloc(b, &b->d_et_mean, eo + R)); TRYF(dalloc(b, &b->d_et_stdv, eo + R));
-        TRYF(halloc(b, &b->h_et_start, eo + R)); TRYF(halloc(b, &b->h_et_length, eo + R));
-        TRYF(halloc(b, &b->h_et_mean, eo + R)); TRYF(halloc(b, &b->h_et_stdv, eo + R));
-    } else {
-        TRYF(dalloc(b, &b->d_mu_q, qo)); TRYF(dalloc(b, &b->d_rank_ref, fo)); TRYF(dalloc(b, &b->d_x_e, eo));
-        TRYF(dalloc(b, &b->d_rough_shift, R)); TRYF(dalloc(b, &b->d_rough_scale, R));
-        TRYF(dalloc(b, &b->d_lp, 4 * R));
-        TRYF(dalloc(b, &b->d_band_off, R + 1)); TRYF(dalloc(b, &b->d_al_off, R + 1)); TRYF(dalloc(b, &b->d_cl_off, R + 1));
-        TRYF(dalloc(b, &b->d_out_off, R + 1));
-        TRYF(dalloc(b, &b->d_end_event, R)); TRYF(dalloc(b, &b->d_end_ll, R)); TRYF(dalloc(b, &b->d_end_score, R));
-        TRYF(dalloc(b, &b->d_cells, 1));
-        TRYF(dalloc(b, &b->d_n_align, R)); TRYF(dalloc(b, &b->d_n_cleaned, R)); TRYF(dalloc(b, &b->d_avg, R));
-        TRYF(dalloc(b, &b->d_shift, R)); TRYF(dalloc(b, &b->d_scale, R));
-        TRYF(dalloc(b, &b->d_spanned, R)); TRYF(dalloc(b, &b->d_max_gap, R));
-        TRYF(halloc(b, &b->h_n_align, R)); TRYF(halloc(b, &b->h_n_cleaned, R)); TRYF(halloc(b, &b->h_spanned, R));
-        TRYF(halloc(b, &b->h_max_gap, R)); TRYF(halloc(b, &b->h_rough_shift, R)); TRYF(halloc(b, &b->h_rough_scale, R));
-        TRYF(halloc(b, &b->h_shift, R)); TRYF(halloc(b, &b->h_scale, R)); TRYF(halloc(b, &b->h_avg, R));
-    }
-    TRYF(halloc(b, &b->h_ev_start, eo + R)); TRYF(halloc(b, &b->h_ev_mean, eo));
+    TRYF(h2d(b, b->d_tile_off, b->tile_off.data(), R + 1));
+    TRYF(h2d(b, b->d_tile_read, b->tile_read.data(), b->tile_read.size()));
+    TRYF(h2d(b, b->d_ck_off, b->ck_off.data(), R + 1));
     e = cudaStreamSynchronize(b->stream);
+    release_staging();
     if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); free_batch(b); return DNB_ERR_CUDA; }
-    // staging buffers for the inputs are no longer needed
-    for (void *p : {(void *)h_raw, (void *)h_q, (void *)h_r, (void *)h_q2r, (void *)h_doff, (void *)h_dscl}) {
-        cudaFreeHost(p);
-        b->host_allocs.erase(std::find(b->host_allocs.begin(), b->host_allocs.end(), p));
-    }
     b->uploaded = true;
     *out = b;
     return DNB_OK;
 #undef TRYF
+}
+
+// workspace that does not depend on the event counts
+int alloc_work_a(dnb_batch *b) {
+    const size_t R = b->R, eo = b->tot_ev, qo = b->tot_q, fo = b->tot_r;
+    Work &w = b->w;
+    TRY(walloc(b, &w.et_n, R)); TRY(walloc(b, &w.n_events, R)); TRY(walloc(b, &w.status, R));
+    TRY(walloc(b, &w.ev_start, eo + R)); TRY(walloc(b, &w.ev_mean, eo));
+    TRY(walloc(b, &w.tot_sum, R)); TRY(walloc(b, &w.redo, R));
+    if (b->want_table) {
+        TRY(walloc(b, &w.et_start, eo + R)); TRY(walloc(b, &w.et_length, eo + R));
+        TRY(walloc(b, &w.et_mean, eo + R)); TRY(walloc(b, &w.et_stdv, eo + R));
+    } else {
+        TRY(walloc(b, &w.mu_q, qo)); TRY(walloc(b, &w.rank_ref, fo)); TRY(walloc(b, &w.x_e, eo));
+        TRY(walloc(b, &w.rough_shift, R)); TRY(walloc(b, &w.rough_scale, R)); TRY(walloc(b, &w.lp, 4 * R));
+        TRY(walloc(b, &w.band_off, R + 1)); TRY(walloc(b, &w.al_off, R + 1)); TRY(walloc(b, &w.cl_off, R + 1));
+        TRY(walloc(b, &w.out_off, R + 1));
+        TRY(walloc(b, &w.end_event, R)); TRY(walloc(b, &w.end_ll, R)); TRY(walloc(b, &w.end_score, R));
+        TRY(walloc(b, &w.cells, 1));
+        TRY(walloc(b, &w.n_align, R)); TRY(walloc(b, &w.n_cleaned, R)); TRY(walloc(b, &w.avg, R));
+        TRY(walloc(b, &w.shift, R)); TRY(walloc(b, &w.scale, R)); TRY(walloc(b, &w.spanned, R)); TRY(walloc(b, &w.max_gap, R));
+    }
+    b->have_work = true;
+    return DNB_OK;
 }
 
 int run(dnb_batch *b) {
@@ -367,58 +403,66 @@ int run(dnb_batch *b) {
     CK(cudaSetDevice(ctx->cfg.device));
     const size_t R = b->R;
     cudaStream_t s = b->stream;
+    drop_work(b);
+    drop_results(b);
+    TRY(alloc_work_a(b));
+    // the few per-read counters the host reads in the middle of the pipeline
+    TRY(ralloc(b, &b->h.n_events, R)); TRY(ralloc(b, &b->h.et_n, R)); TRY(ralloc(b, &b->h.status, R));
+    TRY(ralloc(b, &b->h.redo, R));
     DnbBatchView v = make_view(b);
     DnbDetector det = {ctx->cfg.window_length1, ctx->cfg.window_length2, ctx->cfg.threshold1, ctx->cfg.threshold2,
                        ctx->cfg.peak_height};
     uint64_t launches = 0;
-    // phase-B buffers of a previous run are released first
     CK(cudaEventRecord(b->ev[0], s));
     if (b->want_table) {
         dnb_launch_segmentation_serial(v, det, nullptr, s); launches++;
     } else {
-        // per-run scratch of the tiled segmentation (returned to the pool before the DP workspace is taken)
-        const size_t nt = b->seg.n_tiles, nck = b->ck_off[R];
+        // per-run scratch of the tiled segmentation (back in the pool before the DP workspace is taken)
+        const size_t nt = b->tile_off[R], nck = b->ck_off[R];
         void *scratch[10] = {};
         auto sal = [&](int i, size_t bytes) -> cudaError_t { return cudaMallocAsync(&scratch[i], bytes ? bytes : 1, s); };
         CK(sal(0, nck * 8)); CK(sal(1, nck * 8)); CK(sal(2, nt * DNB_SEG_PEAK_CAP * 4)); CK(sal(3, nt * DNB_SEG_PEAK_CAP * 8));
         CK(sal(4, nt * 4)); CK(sal(5, nt * DNB_SEG_BOUNDARY_BYTES)); CK(sal(6, nt * DNB_SEG_BOUNDARY_BYTES));
         CK(sal(7, nt * 4)); CK(sal(8, nt * 4)); CK(sal(9, nt * 8));
-        DnbSegTiles t = b->seg;
+        DnbSegTiles t;
+        memset(&t, 0, sizeof(t));
+        t.n_tiles = (uint32_t)nt; t.tile_off = b->d_tile_off; t.tile_read = b->d_tile_read; t.ck_off = b->d_ck_off;
+        t.tot_sum = b->w.tot_sum; t.redo = b->w.redo;
         t.ck_sum = (double *)scratch[0]; t.ck_sq = (double *)scratch[1]; t.pk_pos = (uint32_t *)scratch[2];
         t.pk_sum = (double *)scratch[3]; t.pk_count = (uint32_t *)scratch[4]; t.b_start = (SegBoundary *)scratch[5];
         t.b_end = (SegBoundary *)scratch[6]; t.tile_prefix = (uint32_t *)scratch[7]; t.tile_prev_pos = (uint32_t *)scratch[8];
         t.tile_prev_sum = (double *)scratch[9];
-        dnb_launch_segmentation_tiled(v, det, t, s); launches += 6;
+        dnb_launch_segmentation_tiled(v, det, t, s); launches += 5;
         for (void *p : scratch) CK(cudaFreeAsync(p, s));
     }
     CK(cudaEventRecord(b->ev[1], s));
-    CK(cudaMemcpyAsync(b->h_n_events, b->d_n_events, R * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(b->h_et_n, b->d_et_n, R * 4, cudaMemcpyDeviceToHost, s));
+    TRY(d2h(b, b->h.n_events, b->w.n_events, R));
+    TRY(d2h(b, b->h.et_n, b->w.et_n, R));
     if (b->want_table) {
-        CK(cudaMemcpyAsync(b->h_status, b->d_status, R * 4, cudaMemcpyDeviceToHost, s));
+        TRY(d2h(b, b->h.status, b->w.status, R));
         CK(cudaStreamSynchronize(s));
         CK(cudaGetLastError());
         b->ran = true;
         return DNB_OK;
     }
+    TRY(d2h(b, b->h.redo, b->w.redo, R));
     const DnbModelDev pore = ctx->model[DNB_MODEL_PORE].dev();
-    dnb_launch_ranks(v, pore, b->d_mu_q, b->d_rank_ref, s); launches++;
-    dnb_launch_quantile_scaling(v, pore, b->d_rank_ref, b->d_rough_shift, b->d_rough_scale, s); launches++;
-    dnb_launch_scale_events(v, b->d_rough_shift, b->d_rough_scale, b->d_x_e, s); launches++;
-    b->h_redo.resize(R);
-    CK(cudaMemcpyAsync(b->h_redo.data(), b->seg.redo, R * 4, cudaMemcpyDeviceToHost, s));
+    dnb_launch_ranks(v, pore, b->w.mu_q, b->w.rank_ref, s); launches++;
+    dnb_launch_quantile_scaling(v, pore, b->w.rank_ref, b->w.rough_shift, b->w.rough_scale, s); launches++;
+    dnb_launch_scale_events(v, b->w.rough_shift, b->w.rough_scale, b->w.x_e, s); launches++;
     CK(cudaEventRecord(b->ev[2], s));
-    CK(cudaStreamSynchronize(s));   // n_events is on the host (copy was enqueued before the prep kernels)
+    CK(cudaStreamSynchronize(s));   // n_events is on the host (its copy was enqueued before the prep kernels)
     CK(cudaGetLastError());
 
     // ---- host step: transition constants with glibc (event_handling.cpp:174-183) + workspace shapes ----
     b->lp.resize(4 * R);
     b->band_off.assign(R + 1, 0); b->al_off.assign(R + 1, 0); b->cl_off.assign(R + 1, 0);
-    uint64_t bo = 0, ao = 0, co = 0, n_ev = 0, n_km = 0;
+    uint64_t bo = 0, ao = 0, co = 0, n_ev = 0, n_km = 0, n_redo = 0;
     for (size_t i = 0; i < R; i++) {
-        const uint32_t E = b->h_n_events[i];
+        const uint32_t E = b->h.n_events[i];
         const int64_t K = (int64_t)b->qlen[i] - DNB_K + 1;
         b->band_off[i] = bo; b->al_off[i] = ao; b->cl_off[i] = co;
+        n_redo += b->h.redo[i] ? 1 : 0;
         if (K >= 1 && E >= 1) {
             const double epk = (double)E / (double)K;
             const double p_stay = 1 - (1 / (epk + 1));
@@ -432,36 +476,35 @@ int run(dnb_batch *b) {
     }
     b->band_off[R] = bo; b->al_off[R] = ao; b->cl_off[R] = co;
     b->tot_bands = bo; b->tot_al = ao; b->tot_cl = co;
-    if (!b->d_trace) {
-        TRY(dalloc(b, &b->d_trace, bo * DNB_TRACE_ROW + 64));
-        TRY(dalloc(b, &b->d_al_rev, 2 * ao)); TRY(dalloc(b, &b->d_cl_signal, co)); TRY(dalloc(b, &b->d_cl_rank, co));
-    }
-    TRY(h2d(b, b->d_lp, b->lp.data(), 4 * R));
-    TRY(h2d(b, b->d_band_off, b->band_off.data(), R + 1));
-    TRY(h2d(b, b->d_al_off, b->al_off.data(), R + 1));
-    TRY(h2d(b, b->d_cl_off, b->cl_off.data(), R + 1));
-    CK(cudaMemsetAsync(b->d_cells, 0, sizeof(unsigned long long), s));
+    Work &w = b->w;
+    TRY(walloc(b, &w.trace, bo * DNB_TRACE_ROW + 64));
+    TRY(walloc(b, &w.al_rev, 2 * ao)); TRY(walloc(b, &w.cl_signal, co)); TRY(walloc(b, &w.cl_rank, co));
+    TRY(h2d(b, w.lp, b->lp.data(), 4 * R));
+    TRY(h2d(b, w.band_off, b->band_off.data(), R + 1));
+    TRY(h2d(b, w.al_off, b->al_off.data(), R + 1));
+    TRY(h2d(b, w.cl_off, b->cl_off.data(), R + 1));
+    CK(cudaMemsetAsync(w.cells, 0, sizeof(unsigned long long), s));
 
     DnbDpArgs dp;
-    dp.x_e = b->d_x_e; dp.mu_q = b->d_mu_q; dp.lp = b->d_lp; dp.emit_const = ctx->emit_const; dp.inv_sigma = 1.0 / 0.14;
-    dp.band_off = b->d_band_off; dp.trace = b->d_trace; dp.end_event = b->d_end_event; dp.end_ll_event = b->d_end_ll;
-    dp.end_score = b->d_end_score; dp.cells = b->d_cells;
+    dp.x_e = w.x_e; dp.mu_q = w.mu_q; dp.lp = w.lp; dp.emit_const = ctx->emit_const; dp.inv_sigma = 1.0 / 0.14;
+    dp.band_off = w.band_off; dp.trace = w.trace; dp.end_event = w.end_event; dp.end_ll_event = w.end_ll;
+    dp.end_score = w.end_score; dp.cells = w.cells;
     CK(cudaEventRecord(b->ev[3], s));
     dnb_launch_banded_dp(v, dp, s); launches++;
     CK(cudaEventRecord(b->ev[4], s));
     DnbBtArgs bt;
-    bt.dp = dp; bt.rank_ref = b->d_rank_ref; bt.al_off = b->d_al_off; bt.al_pairs_rev = b->d_al_rev; bt.n_align = b->d_n_align;
-    bt.cl_off = b->d_cl_off; bt.cl_signal = b->d_cl_signal; bt.cl_rank = b->d_cl_rank; bt.n_cleaned = b->d_n_cleaned;
-    bt.avg_log_emission = b->d_avg; bt.spanned = b->d_spanned; bt.max_gap = b->d_max_gap;
+    bt.dp = dp; bt.rank_ref = w.rank_ref; bt.al_off = w.al_off; bt.al_pairs_rev = w.al_rev; bt.n_align = w.n_align;
+    bt.cl_off = w.cl_off; bt.cl_signal = w.cl_signal; bt.cl_rank = w.cl_rank; bt.n_cleaned = w.n_cleaned;
+    bt.avg_log_emission = w.avg; bt.spanned = w.spanned; bt.max_gap = w.max_gap;
     bt.min_avg_log_emission = ctx->cfg.min_average_log_emission; bt.max_gap_threshold = ctx->cfg.max_gap_threshold;
     dnb_launch_backtrace(v, bt, s); launches++;
     CK(cudaEventRecord(b->ev[5], s));
     DnbTsArgs ts;
-    ts.cl_off = b->d_cl_off; ts.cl_signal = b->d_cl_signal; ts.cl_rank = b->d_cl_rank; ts.n_cleaned = b->d_n_cleaned;
-    ts.rough_shift = b->d_rough_shift; ts.rough_scale = b->d_rough_scale; ts.shift = b->d_shift; ts.scale = b->d_scale;
+    ts.cl_off = w.cl_off; ts.cl_signal = w.cl_signal; ts.cl_rank = w.cl_rank; ts.n_cleaned = w.n_cleaned;
+    ts.rough_shift = w.rough_shift; ts.rough_scale = w.rough_scale; ts.shift = w.shift; ts.scale = w.scale;
     dnb_launch_theil_sen(v, pore, ts, s); launches++;
     CK(cudaEventRecord(b->ev[6], s));
-    CK(cudaMemcpyAsync(&b->h_cells, b->d_cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&b->h_cells, w.cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     float t;
@@ -474,53 +517,61 @@ int run(dnb_batch *b) {
     uint64_t n_samp = 0;
     for (size_t i = 0; i < R; i++) n_samp += b->n_samples[i];
     b->counts[0] = n_samp; b->counts[1] = n_ev; b->counts[2] = n_km; b->counts[3] = bo; b->counts[4] = b->h_cells;
-    b->counts[5] = launches;
-    b->counts[6] = 0;
-    for (size_t i = 0; i < R; i++) b->counts[6] += b->h_redo[i] ? 1 : 0;
+    b->counts[5] = launches; b->counts[6] = n_redo; b->counts[7] = 0;
     b->ran = true;
     b->fetched = false;
     return DNB_OK;
 }
 
 int fetch(dnb_batch *b) {
-    if (!b || !b->ran) return DNB_ERR_STATE;
+    if (!b || !b->ran || !b->have_work) return DNB_ERR_STATE;
     if (b->fetched) return DNB_OK;
     dnb_ctx *ctx = b->ctx;
     CK(cudaSetDevice(ctx->cfg.device));
     const size_t R = b->R;
     cudaStream_t s = b->stream;
-    TRY(d2h(b, b->h_ev_start, b->d_ev_start, b->tot_ev + R));
-    TRY(d2h(b, b->h_ev_mean, b->d_ev_mean, b->tot_ev));
+    HostRes &h = b->h;
+    Work &w = b->w;
+    TRY(ralloc(b, &h.ev_start, b->tot_ev + R)); TRY(ralloc(b, &h.ev_mean, b->tot_ev));
+    TRY(d2h(b, h.ev_start, w.ev_start, b->tot_ev + R));
+    TRY(d2h(b, h.ev_mean, w.ev_mean, b->tot_ev));
     if (b->want_table) {
-        TRY(d2h(b, b->h_et_start, b->d_et_start, b->tot_ev + R)); TRY(d2h(b, b->h_et_length, b->d_et_length, b->tot_ev + R));
-        TRY(d2h(b, b->h_et_mean, b->d_et_mean, b->tot_ev + R)); TRY(d2h(b, b->h_et_stdv, b->d_et_stdv, b->tot_ev + R));
+        TRY(ralloc(b, &h.et_start, b->tot_ev + R)); TRY(ralloc(b, &h.et_length, b->tot_ev + R));
+        TRY(ralloc(b, &h.et_mean, b->tot_ev + R)); TRY(ralloc(b, &h.et_stdv, b->tot_ev + R));
+        TRY(d2h(b, h.et_start, w.et_start, b->tot_ev + R)); TRY(d2h(b, h.et_length, w.et_length, b->tot_ev + R));
+        TRY(d2h(b, h.et_mean, w.et_mean, b->tot_ev + R)); TRY(d2h(b, h.et_stdv, w.et_stdv, b->tot_ev + R));
         CK(cudaStreamSynchronize(s));
         b->fetched = true;
         return DNB_OK;
     }
-    TRY(d2h(b, b->h_status, b->d_status, R)); TRY(d2h(b, b->h_n_align, b->d_n_align, R));
-    TRY(d2h(b, b->h_n_cleaned, b->d_n_cleaned, R)); TRY(d2h(b, b->h_spanned, b->d_spanned, R));
-    TRY(d2h(b, b->h_max_gap, b->d_max_gap, R)); TRY(d2h(b, b->h_rough_shift, b->d_rough_shift, R));
-    TRY(d2h(b, b->h_rough_scale, b->d_rough_scale, R)); TRY(d2h(b, b->h_shift, b->d_shift, R));
-    TRY(d2h(b, b->h_scale, b->d_scale, R)); TRY(d2h(b, b->h_avg, b->d_avg, R));
+    TRY(ralloc(b, &h.n_align, R)); TRY(ralloc(b, &h.n_cleaned, R)); TRY(ralloc(b, &h.spanned, R));
+    TRY(ralloc(b, &h.max_gap, R)); TRY(ralloc(b, &h.rough_shift, R)); TRY(ralloc(b, &h.rough_scale, R));
+    TRY(ralloc(b, &h.shift, R)); TRY(ralloc(b, &h.scale, R)); TRY(ralloc(b, &h.avg, R));
+    TRY(d2h(b, h.status, w.status, R)); TRY(d2h(b, h.n_align, w.n_align, R));
+    TRY(d2h(b, h.n_cleaned, w.n_cleaned, R)); TRY(d2h(b, h.spanned, w.spanned, R));
+    TRY(d2h(b, h.max_gap, w.max_gap, R)); TRY(d2h(b, h.rough_shift, w.rough_shift, R));
+    TRY(d2h(b, h.rough_scale, w.rough_scale, R)); TRY(d2h(b, h.shift, w.shift, R));
+    TRY(d2h(b, h.scale, w.scale, R)); TRY(d2h(b, h.avg, w.avg, R));
     CK(cudaStreamSynchronize(s));
     // alignment compaction: reversed, capacity-strided device layout -> dense forward pairs
     b->out_off.assign(R + 1, 0);
-    uint64_t oo = 0;
-    for (size_t i = 0; i < R; i++) { b->out_off[i] = oo; oo += b->h_n_align[i]; }
-    b->out_off[R] = oo;
-    if (!b->d_out_pairs || oo > b->tot_out) {
-        TRY(dalloc(b, &b->d_out_pairs, 2 * oo));
-        TRY(halloc(b, &b->h_out_pairs, 2 * oo));
-        b->tot_out = oo;
+    uint64_t oo = 0, n_fail = 0;
+    for (size_t i = 0; i < R; i++) {
+        b->out_off[i] = oo; oo += h.n_align[i];
+        n_fail += h.status[i] != DNB_READ_OK;
     }
-    TRY(h2d(b, b->d_out_off, b->out_off.data(), R + 1));
-    dnb_launch_compact_alignment(make_view(b), b->d_al_off, b->d_al_rev, b->d_n_align, b->d_out_off, b->d_out_pairs, s);
-    TRY(d2h(b, b->h_out_pairs, b->d_out_pairs, 2 * oo));
+    b->out_off[R] = oo;
+    b->tot_out = oo;
+    b->counts[7] = n_fail;
+    TRY(walloc(b, &w.out_pairs, 2 * oo));
+    TRY(ralloc(b, &h.out_pairs, 2 * oo));
+    TRY(h2d(b, w.out_off, b->out_off.data(), R + 1));
+    dnb_launch_compact_alignment(make_view(b), w.al_off, w.al_rev, w.n_align, w.out_off, w.out_pairs, s);
+    TRY(d2h(b, h.out_pairs, w.out_pairs, 2 * oo));
     if (ctx->cfg.keep_debug) {
-        if (!b->h_cl_signal) { TRY(halloc(b, &b->h_cl_signal, b->tot_cl)); TRY(halloc(b, &b->h_cl_rank, b->tot_cl)); }
-        TRY(d2h(b, b->h_cl_signal, b->d_cl_signal, b->tot_cl));
-        TRY(d2h(b, b->h_cl_rank, b->d_cl_rank, b->tot_cl));
+        TRY(ralloc(b, &h.cl_signal, b->tot_cl)); TRY(ralloc(b, &h.cl_rank, b->tot_cl));
+        TRY(d2h(b, h.cl_signal, w.cl_signal, b->tot_cl));
+        TRY(d2h(b, h.cl_rank, w.cl_rank, b->tot_cl));
     }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
@@ -599,6 +650,7 @@ void dnb_destroy(dnb_ctx *ctx) {
     for (auto &m : ctx->model) {
         cudaFree(m.d_mean); cudaFree(m.d_stdv); cudaFree(m.d_sorted); cudaFree(m.d_order);
     }
+    ctx->pinned.destroy();
     delete ctx;
 }
 
@@ -630,6 +682,12 @@ int dnb_batch_upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, d
 }
 int dnb_batch_run(dnb_batch *batch) { return run(batch); }
 int dnb_batch_fetch(dnb_batch *batch) { return fetch(batch); }
+int dnb_batch_drop_workspace(dnb_batch *b) {
+    if (!b) return DNB_ERR_ARG;
+    CK(cudaSetDevice(b->ctx->cfg.device));
+    drop_work(b);
+    return DNB_OK;
+}
 
 int dnb_submit(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch) {
     dnb_batch *b = nullptr;
@@ -637,6 +695,7 @@ int dnb_submit(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_bat
     int rc = run(b);
     if (rc == DNB_OK) rc = fetch(b);
     if (rc != DNB_OK) { free_batch(b); return rc; }
+    drop_work(b);   // results are on the host: give the HBM workspace back to the pool for the next batch
     *batch = b;
     return DNB_OK;
 }
@@ -651,24 +710,25 @@ int dnb_wait(dnb_batch *b) {
 int dnb_result(dnb_batch *b, size_t i, dnb_read_result *o) {
     if (!b || !o || i >= b->R) return DNB_ERR_ARG;
     if (!b->fetched || b->want_table) return DNB_ERR_STATE;
+    const HostRes &h = b->h;
     memset(o, 0, sizeof(*o));
-    o->status = b->h_status[i];
-    o->et_n = b->h_et_n[i];
-    o->n_events = b->h_n_events[i];
+    o->status = h.status[i];
+    o->et_n = h.et_n[i];
+    o->n_events = h.n_events[i];
     if (o->status == DNB_READ_OVERFLOW) o->n_events = 0;
-    o->event_start = b->h_ev_start + b->ev_off[i] + i;
-    o->event_mean = b->h_ev_mean + b->ev_off[i];
-    o->n_align = o->status == DNB_READ_OK ? b->h_n_align[i] : 0;
-    o->align_pairs = b->h_out_pairs + 2 * b->out_off[i];
-    o->rough_shift = b->h_rough_shift[i]; o->rough_scale = b->h_rough_scale[i];
-    o->shift = b->h_shift[i]; o->scale = b->h_scale[i];
+    o->event_start = h.ev_start + b->ev_off[i] + i;
+    o->event_mean = h.ev_mean + b->ev_off[i];
+    o->n_align = o->status == DNB_READ_OK ? h.n_align[i] : 0;
+    o->align_pairs = h.out_pairs + 2 * b->out_off[i];
+    o->rough_shift = h.rough_shift[i]; o->rough_scale = h.rough_scale[i];
+    o->shift = h.shift[i]; o->scale = h.scale[i];
     const int64_t denom = (int64_t)b->qlen[i] - DNB_K;
     o->events_per_base = (double)o->et_n / (double)denom;                      // event_handling.cpp:606 (quirk Q4)
-    o->avg_log_emission = b->h_avg[i]; o->spanned = b->h_spanned[i]; o->max_gap = b->h_max_gap[i];
-    if (b->ctx->cfg.keep_debug && b->h_cl_signal) {
-        o->n_cleaned = b->h_n_cleaned[i];
-        o->cleaned_signal = b->h_cl_signal + b->cl_off[i];
-        o->cleaned_rank = b->h_cl_rank + b->cl_off[i];
+    o->avg_log_emission = h.avg[i]; o->spanned = h.spanned[i]; o->max_gap = h.max_gap[i];
+    if (b->ctx->cfg.keep_debug && h.cl_signal) {
+        o->n_cleaned = h.n_cleaned[i];
+        o->cleaned_signal = h.cl_signal + b->cl_off[i];
+        o->cleaned_rank = h.cl_rank + b->cl_off[i];
     }
     return DNB_OK;
 }
@@ -696,12 +756,12 @@ int dnb_detect_events(dnb_ctx *ctx, const float *raw_pA, size_t n, dnb_event_t *
     int rc = run(b);
     if (rc == DNB_OK) rc = fetch(b);
     if (rc == DNB_OK) {
-        const size_t ne = b->h_et_n[0];
+        const size_t ne = b->h.et_n[0];
         *n_events = ne;
-        if (b->h_status[0] == DNB_READ_OVERFLOW) rc = DNB_ERR_NOMEM;
+        if (b->h.status[0] == DNB_READ_OVERFLOW) rc = DNB_ERR_NOMEM;
         for (size_t i = 0; rc == DNB_OK && i < ne && i < cap; i++) {
-            events[i].start = b->h_et_start[i]; events[i].length = b->h_et_length[i];
-            events[i].mean = b->h_et_mean[i]; events[i].stdv = b->h_et_stdv[i];
+            events[i].start = b->h.et_start[i]; events[i].length = b->h.et_length[i];
+            events[i].mean = b->h.et_mean[i]; events[i].stdv = b->h.et_stdv[i];
             events[i].pos = -1; events[i].state = -1;                         // event_detection.c:219-220
         }
     }

@@ -140,6 +140,9 @@ DNB_API void dnb_release(dnb_batch *batch);
 DNB_API int dnb_batch_upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch);
 DNB_API int dnb_batch_run(dnb_batch *batch);     /* device pipeline only; blocks until done */
 DNB_API int dnb_batch_fetch(dnb_batch *batch);   /* device -> pinned host results */
+/* returns the batch's device workspace (~27 B/sample) to the pool; the inputs stay resident, results already
+ * fetched stay valid.  dnb_submit does this itself once the results are on the host. */
+DNB_API int dnb_batch_drop_workspace(dnb_batch *batch);
 /* device-time breakdown of the last dnb_batch_run, milliseconds, measured with CUDA events on the
  * pipeline stream: [0]=segmentation [1]=ranks+scaling+prep [2]=banded DP [3]=backtrace+QC [4]=Theil-Sen [5]=total;
  * counts: [0]=samples [1]=events [2]=k-mers [3]=bands [4]=DP cells [5]=kernel launches

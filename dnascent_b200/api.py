@@ -285,3 +285,56 @@ def normalPDF(mu: float, sigma: float, x: float) -> float:
 
 def cauchyPDF(loc: float, scale: float, x: float) -> float:
     return _lib.lib().dnb_cauchyPDF(loc, scale, x)
+
+
+# ---- llAcrossRead helper: the event gathering around every T of the reference (host side) -----------------------
+def gather_sites(refseq: bytes, ref_to_query, is_reverse: bool, event_alignment, event_mean, window: int = 12):
+    """Per T site of `referenceSeqMappedTo`, the events sequenceProbability is called on: a transcription of the
+    gathering loop of llAcrossRead (src/detect.cpp:381-390, 399-510).  Returns [(posOnRef, events, snippet)].
+    The forward passes themselves run on the device (Context.sequence_probability_batch)."""
+    k = 9
+    n = len(refseq)
+    out = []
+    if n < 4 * window + 1 or len(event_alignment) == 0:
+        return out
+    r2q = np.asarray(ref_to_query)
+    al_e = np.asarray(event_alignment)[:, 0]
+    al_k = np.asarray(event_alignment)[:, 1]
+    pois = [i for i in range(2 * window, n - 2 * window) if refseq[i:i + 1] == b"T"]
+    read_head = 0
+    if is_reverse:
+        read_head = len(al_e) - 1
+        pois.reverse()
+    for p in pois:
+        sn = refseq[p - window:p + window + k]
+        if len(sn) != 2 * window + k or any(c not in b"ATGC" for c in sn):
+            continue
+        lo, hi = int(r2q[p - window]) & 0xFFFFFFFF, int(r2q[p + window]) & 0xFFFFFFFF
+        ev, first = [], True
+        if is_reverse:
+            j = read_head
+            while j >= 0:
+                if lo <= al_k[j] < hi:
+                    if first:
+                        read_head, first = j, False
+                    m = float(event_mean[al_e[j]])
+                    if 0.0 < m < 250.0:
+                        ev.append(m)
+                if al_k[j] < lo:
+                    ev.reverse()
+                    break
+                j -= 1
+        else:
+            for j in range(read_head, len(al_e)):
+                if lo <= al_k[j] < hi:
+                    if first:
+                        read_head, first = j, False
+                    m = float(event_mean[al_e[j]])
+                    if 0.0 < m < 250.0:
+                        ev.append(m)
+                if al_k[j] >= hi:
+                    break
+        if len(ev) < 2 * window - k:
+            continue
+        out.append((p, np.array(ev), sn))
+    return out

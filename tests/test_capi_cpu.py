@@ -1,0 +1,83 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol the header declares, refuses to compute
+without a GPU (no CPU fallback), and its scalar probability.h drop-ins match the reference's known answers."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    from dnascent_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dnascent_b200.h")).read()
+    declared = sorted(set(re.findall(r"DNB_API\s+[\w\s\*]+?\b(dnb_\w+)\s*\(", hdr)))
+    assert len(declared) >= 24
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/dnascent_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_struct_layouts_match_header():
+    from dnascent_b200 import _lib
+    assert C.sizeof(_lib.ReadDesc) == 72 and _lib.READ_DESC_DTYPE.itemsize == 72
+    assert C.sizeof(_lib.EventT) == 32
+    cfg = _lib.Config()
+    _lib.lib().dnb_default_config(C.byref(cfg))
+    # event_detection.h:19-25 and config.h:41
+    assert (cfg.window_length1, cfg.window_length2) == (3, 6)
+    assert (cfg.threshold1, cfg.threshold2, cfg.peak_height) == (np.float32(1.4), np.float32(9.0), np.float32(0.2))
+    assert (cfg.min_average_log_emission, cfg.max_gap_threshold, cfg.bandwidth) == (-2.0, 5, 100)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from dnascent_b200 import api
+    with pytest.raises(api.DnbError) as e:
+        api.Context(device=0)
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+
+
+def test_probability_drop_ins_known_answers():
+    from dnascent_b200 import api
+    k = np.load(os.path.join(GOLDEN, "probability_v1.npz"))
+    for x, e in zip(k["xs"], k["eexp"]):
+        assert api.eexp(float(x)) == e
+    for x, e in zip(k["xs"], k["eln"]):
+        if np.isinf(e):
+            with pytest.raises(api.NegativeLog):
+                api.eln(float(x))
+        elif np.isnan(e):
+            assert math.isnan(api.eln(float(x)))
+        else:
+            assert api.eln(float(x)) == e
+    for (a, b), s, pr, gt in zip(k["pairs"], k["lnSum"], k["lnProd"], k["lnGreaterThan"]):
+        for got, want in ((api.lnSum(float(a), float(b)), s), (api.lnProd(float(a), float(b)), pr)):
+            assert (math.isnan(got) and math.isnan(want)) or got == want
+        assert api.lnGreaterThan(float(a), float(b)) == bool(gt)
+    for t, u, n, c in zip(k["triples"], k["uniformPDF"], k["normalPDF"], k["cauchyPDF"]):
+        t = [float(v) for v in t]
+        assert api.uniformPDF(*t) == u and api.normalPDF(*t) == n and api.cauchyPDF(*t) == c
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under dnascent_b200/ may import or link it."""
+    pkg = os.path.join(ROOT, "dnascent_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle" not in text and "dnb_oracle" not in text, f

@@ -118,3 +118,66 @@ def test_segmentation_edge_shapes(ctx, port, pore_mean):
             np.testing.assert_array_equal(st, p["et_start"], err_msg=name)
             np.testing.assert_array_equal(mn, p["et_mean"], err_msg=name)
             np.testing.assert_array_equal(sd, p["et_stdv"], err_msg=name)
+
+
+def _hmm_tables():
+    import os
+    h = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hmm_v1.npz"))
+    tabs = []
+    for name in ("unl_mean", "unl_stdv", "ana_mean", "ana_stdv"):
+        t = np.zeros(4 ** 9)
+        t[h["ranks"]] = h[name]
+        tabs.append(t)
+    return h, tabs
+
+
+def test_sequence_probability_golden(ctx):
+    """Analogue / thymidine forward probabilities vs the reference's sequenceProbability (detect.cpp:235-378).
+    Tolerance 1e-4 relative (BASELINE.json north_star) -- CUDA log/exp instead of glibc."""
+    h, (um, us, am, as_) = _hmm_tables()
+    ctx.load_model(api.MODEL_UNLABELLED, um, us)
+    ctx.load_model(api.MODEL_ANALOGUE, am, as_)
+    off = h["sp_obs_off"]
+    n = h["sp_out"].shape[0]
+    obs = [h["sp_obs"][off[j]:off[j + 1]] for j in range(n)]
+    snips = [h["sp_seq"][j].tobytes() for j in range(n)]
+    la, lt = ctx.sequence_probability_batch(obs, snips, h["sp_par"][:, 0], h["sp_par"][:, 1], h["sp_par"][:, 2], window=12)
+    np.testing.assert_allclose(la, h["sp_out"][:, 0], rtol=1e-4)
+    np.testing.assert_allclose(lt, h["sp_out"][:, 1], rtol=1e-4)
+
+
+def test_ll_across_read_golden(ctx, golden_reads):
+    """llAcrossRead (detect.cpp:393-574) on golden read 4: the host gathers each T site's events exactly like the
+    reference (port of the gathering is checked on CPU); the device computes both forward passes per site."""
+    from oracle import portbind  # the checker: provides the per-site event snippets the reference would build
+    h, (um, us, am, as_) = _hmm_tables()
+    ctx.load_model(api.MODEL_UNLABELLED, um, us)
+    ctx.load_model(api.MODEL_ANALOGUE, am, as_)
+    g = golden_reads[int(h["read_index"])]
+    res = ctx.normaliseEvents([api.Read(g.raw, g.basecall, g.refseq, g.query_to_ref)])[0]
+    sites = api.gather_sites(g.refseq, h["ref_to_query"], bool(h["is_reverse"]), res.eventAlignment,
+                             res.event_mean.astype(np.float64), window=12)
+    la, lt = ctx.sequence_probability_batch([s[1] for s in sites], [s[2] for s in sites], res.shift, res.scale,
+                                            res.eventsPerBase, window=12)
+    pos = np.array([s[0] for s in sites], dtype=np.int64)
+    glob = (int(h["ref_end"]) - pos - 1) if bool(h["is_reverse"]) else int(h["ref_start"]) + pos
+    order = np.argsort(glob)
+    np.testing.assert_array_equal(glob[order], h["pos_global"])
+    np.testing.assert_allclose((la - lt)[order], h["llr"], rtol=1e-4, atol=1e-6)
+    del portbind
+
+
+def test_large_batch_vs_oracle_statistics(ctx, port, pore_mean):
+    """A few hundred reads in one batch (exercises ordering, tiling, workspace offsets); a random subset is checked
+    bit-for-bit against the oracle, every read must come back with a definite status."""
+    ref = synth.make_reference(600_000, 21)
+    rng = np.random.default_rng(22)
+    lengths = synth.lognormal_lengths(300, 6000, rng, lo=1100, hi=40_000)
+    reads = synth.simulate_batch(ref, lengths, pore_mean, seed=23, sub_rate=0.01)
+    out = ctx.normaliseEvents([api.Read.from_synth(r, use_dac=True) for r in reads])
+    assert all(o.status in (0, 1, 2, 3) for o in out)
+    assert sum(o.status == 0 for o in out) > 0.9 * len(out)
+    for i in rng.choice(len(reads), size=40, replace=False):
+        r = reads[i]
+        p = port.normalise(r.raw, r.basecall, r.refseq, r.query_to_ref, pore_mean)
+        _compare_with_port(out[i], p, tag=f"read {i}")

@@ -1,0 +1,99 @@
+"""CPU tests of the host-side logic: the synthetic generator, length-balanced sharding/binning and the
+world_size-2 shard plan (gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from dnascent_b200 import sharding, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synth_is_deterministic_and_pod5_shaped(pore_mean):
+    ref = synth.make_reference(30_000, 5)
+    a = synth.simulate_batch(ref, [1500, 2500], pore_mean, seed=9)
+    b = synth.simulate_batch(ref, [1500, 2500], pore_mean, seed=9)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x.dac, y.dac)
+        assert x.basecall == y.basecall and x.flag == y.flag
+    r = a[0]
+    # float32-exact pA, the expression shape of pod5.cpp:60
+    np.testing.assert_array_equal(r.raw, (r.dac.astype(np.float32) + np.float32(-240.0)) * np.float32(0.1465))
+    assert r.raw.dtype == np.float32 and 8 < r.raw.size / len(r.basecall) < 16
+    if r.flag == 16:
+        assert r.basecall == synth.revcomp(r.seq_bam)
+    np.testing.assert_array_equal(r.query_to_ref, np.arange(len(r.basecall)))
+
+
+def test_lognormal_n50():
+    L = synth.lognormal_lengths(200_000, 30_000, np.random.default_rng(1))
+    s = np.sort(L)[::-1]
+    n50 = s[np.searchsorted(np.cumsum(s), s.sum() / 2)]
+    assert abs(n50 - 30_000) / 30_000 < 0.03
+
+
+def test_shard_reads_balanced_and_complete():
+    rng = np.random.default_rng(3)
+    n = synth.lognormal_lengths(20_000, 30_000, rng) * 12
+    for ranks in (1, 2, 4, 8):
+        sh = sharding.shard_reads(n, ranks)
+        allidx = np.sort(np.concatenate(sh))
+        np.testing.assert_array_equal(allidx, np.arange(n.size))           # every read exactly once
+        loads = np.array([n[s].sum() for s in sh], dtype=np.float64)
+        assert loads.max() / loads.mean() < 1.01                           # length-balanced
+    assert sharding.shard_reads([], 2)[0].size == 0
+
+
+def test_make_bins_respects_budget_and_orders_longest_first():
+    rng = np.random.default_rng(4)
+    n = synth.lognormal_lengths(5_000, 30_000, rng) * 12
+    bins = sharding.make_bins(n, 20_000_000)
+    np.testing.assert_array_equal(np.sort(np.concatenate(bins)), np.arange(n.size))
+    for b in bins:
+        assert n[b].sum() <= 20_000_000 or b.size == 1
+    firsts = [n[b[0]] for b in bins]
+    assert firsts == sorted(firsts, reverse=True)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch
+    sys.path.insert(0, ROOT)
+    from dnascent_b200 import sharding as sh, synth as sy
+    lengths = sy.lognormal_lengths(4000, 30_000, np.random.default_rng(11))      # same seed on every rank
+    mine = sh.shard_reads(lengths, world)[rank]
+    # what bench.py reduces: per-rank sample counts (SUM) and step times (MAX)
+    load = torch.tensor([float(lengths[mine].sum()), float(mine.size)], dtype=torch.float64)
+    tot = load.clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    t = torch.tensor([1.0 + rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine.tolist())
+    q.put((rank, load.tolist(), tot.tolist(), float(t.item()), gathered))
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_plan_gloo():
+    """world_size 2 over gloo: ranks derive disjoint, complete, balanced shards from the same seed with no data-path
+    collective; only the scalar reductions of bench.py (SUM of samples, MAX of time) cross ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, l0, tot0, t0, g0), (r1, l1, tot1, t1, g1) = out
+    assert tot0 == tot1 and tot0[1] == 4000 and t0 == t1 == 2.0
+    assert abs(l0[0] - l1[0]) / tot0[0] < 0.01
+    assert g0 == g1 and sorted(g0[0] + g0[1]) == list(range(4000)) and not set(g0[0]) & set(g0[1])

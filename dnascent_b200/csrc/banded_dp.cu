@@ -7,13 +7,23 @@
 //   backtrace, cleaned (signal,rank) vectors, QC src/event_handling.cpp:347-443
 //
 // Layout.  The reference allocates n_bands x 100 floats + n_bands x 100 bytes per read.  Here a band lives in
-// registers: lane L of the warp owns offsets 4L..4L+3 (lanes 25..31 own nothing and stay at -inf), with the two
-// previous bands, the scaled event level x_e and the model level mu_k of each owned cell.  A band step is
-// warp-uniform: Suzuki's rule is evaluated from cells 0 and 99 (two shuffles), then either the k-mer registers
-// shift one cell down (right move) or the event registers shift one cell up (down move) -- one lane-to-lane
-// shuffle each -- and the three neighbours of every cell are register moves plus one edge shuffle.  Only
-// 2 bits of trace per cell and 1 move bit per band go to HBM (one 32-byte row per band), plus the running
-// end-cell maximum; the band scores themselves are never stored.
+// registers, indexed by EVENT, not by band offset: the cell of the current band whose event index is e sits in slot
+// e mod 128 = (lane, register) = ((e >> 2) & 31, e & 3).  With that indexing the three neighbours of a cell are at
+// fixed places whatever the band did -- left = same slot of band b-1, up = slot-1 of band b-1, diag = slot-1 of
+// band b-2 -- so a band step needs no register shuffling of scores: one lane-to-lane shuffle per band array for the
+// slot-1 edge, the two previous bands swap roles (loop unrolled by two).  The scaled event level x_e of a slot never
+// moves (a new event is dropped into its slot on a down move); the model level mu_k moves one slot per band like a
+// conveyor (a new k-mer is dropped in on a right move).  Suzuki's rule reads the two end cells with two shuffles.
+//
+// Arithmetic.  Scores are kept as doubles that hold float values.  The reference's `float = double expression`
+// roundings are done with the exponent-aligned magic-constant add (exact round-to-nearest-even at 24 bits, 2 integer
+// + 2 FP64 instructions) instead of F2F conversions, which run at quarter rate on the XU pipe (50 % busy in the
+// first version, profiles/r1_captureA).  (x - mu)/0.14 is a multiply by the correctly rounded reciprocal, guarded:
+// if the product lies within 8 ulps of a float rounding boundary the whole band redoes its four quotients with
+// the IEEE division (probability ~3e-6 per band).  -inf is represented by -FLT_MAX, which is a fixed point of every
+// update and compares like -inf does.
+//
+// HBM traffic per band: one 32-byte row (2-bit trace code per slot) + 1 move bit; scores never leave registers.
 #include <cfloat>
 #include <cmath>
 #include "dnb_internal.cuh"
@@ -21,19 +31,142 @@
 
 #define DP_WARPS 4
 #define FULL 0xffffffffu
+#define NEG_SENT (-3.4028234663852886e38)   /* (double)(-FLT_MAX): stands for -INFINITY */
 
 namespace {
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
-__device__ __forceinline__ double shfl_down_d(double v) { return __shfl_down_sync(FULL, v, 1); }
-__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(FULL, v, 1); }
 
-// event_handling.cpp:133-136 with sigma == 0.14 (import_poreModel_staticStdv, data_IO.cpp:170)
+// event_handling.cpp:133-136 with sigma == 0.14 (import_poreModel_staticStdv, data_IO.cpp:170): literal form
 __device__ __forceinline__ float emission_static(double x, double mu, double emit_const) {
     float a = d2f(dDiv(dSub(x, mu), 0.14));
     float t = fMul(fMul(-0.5f, a), a);
     return d2f(dAdd(emit_const, (double)t));
 }
+
+// (double)(float)v for |v| in the normal float range (or 0, or the sentinel): round to nearest even at 24 bits by
+// adding and subtracting 1.5 * 2^(exponent(v) + 29), built from v's own sign and exponent field
+__device__ __forceinline__ double rn24(double v) {
+    const int mhi = (__double2hiint(v) & 0xFFF00000) + 0x01D80000;
+    const double M = __hiloint2double(mhi, 0);
+    return __dsub_rn(__dadd_rn(v, M), M);
+}
+
+__device__ __forceinline__ double pick4(const double (&p)[4], int j) {
+    return j == 0 ? p[0] : j == 1 ? p[1] : j == 2 ? p[2] : p[3];
+}
+
+struct DpConst {
+    double lp_skip, lp_stay, lp_step, lp_trim, emit_const, inv_sigma;
+};
+
+// one cell: returns the new score, sets `from`
+__device__ __forceinline__ double cell_update(double diag, double up, double left, double a, const DpConst &c, uint32_t &from) {
+    const double r = rn24(dMul(a, a));                                   // float(a*a); (-0.5f*a)*a == -0.5f*float(a*a)
+    const double em = rn24(__fma_rn(r, -0.5, c.emit_const));            // product exact: one rounding, as C + (double)t
+    const double sd = rn24(dAdd(dAdd(diag, c.lp_step), em));            // event_handling.cpp:296
+    const double su = rn24(dAdd(dAdd(up, c.lp_stay), em));              // :297
+    const double sl = rn24(dAdd(left, c.lp_skip));                      // :298
+    double m = sd;                                                       // :300-306, ties: L over U over D
+    from = DNB_FROM_D;
+    if (su >= m) { m = su; from = DNB_FROM_U; }
+    if (sl >= m) { m = sl; from = DNB_FROM_L; }
+    return m;
+}
+
+// One band.  P1 = band b-1, P2 = band b-2 (overwritten with band b).
+#define DP_BAND_STEP(P1, P2)                                                                                      \
+    {                                                                                                             \
+        /* Suzuki's rule on cells 0 and 99 of band b-1 (event_handling.cpp:237-253) */                            \
+        const int s_ll = ll_e & 127, s_ur = (ll_e - (DNB_BW - 1)) & 127;                                          \
+        const double ur = shfl_d(pick4(P1, s_ur & 3), s_ur >> 2);                                                 \
+        const double llv = pick4(P1, s_ll & 3);                                                                   \
+        const int r0 = (llv == NEG_SENT && ur == NEG_SENT) ? (b & 1) : (llv < ur ? 1 : 0);                        \
+        const bool right = __shfl_sync(FULL, r0, s_ll >> 2) != 0;                                                 \
+        /* the k-mer level conveyor advances one slot every band */                                              \
+        {                                                                                                         \
+            const double in = shfl_d(mk[3], (lane + 31) & 31);                                                    \
+            mk[3] = mk[2]; mk[2] = mk[1]; mk[1] = mk[0]; mk[0] = in;                                              \
+        }                                                                                                         \
+        if (right) {                                                                                              \
+            ll_k++;                                                                                               \
+            const int need = ll_k + DNB_BW - 1;                                                                   \
+            if (need - mbase == 32) {                                                                             \
+                mbuf = mnxt; mbase += 32;                                                                         \
+                mnxt = (mbase + 32 + lane < K) ? mu[mbase + 32 + lane] : 0.0;                                     \
+            }                                                                                                     \
+            const double fresh = shfl_d(mbuf, need - mbase);                                                      \
+            const int s99 = (ll_e - (DNB_BW - 1)) & 127;                                                          \
+            if (lane == (s99 >> 2)) {                                                                             \
+                const int jj = s99 & 3;                                                                           \
+                if (jj == 0) mk[0] = fresh; else if (jj == 1) mk[1] = fresh; else if (jj == 2) mk[2] = fresh; else mk[3] = fresh; \
+            }                                                                                                     \
+            mvword |= 1u << (b & 31);                                                                             \
+        } else {                                                                                                  \
+            ll_e++;                                                                                               \
+            const int need = ll_e;                                                                                \
+            if (need - xbase == 32) {                                                                             \
+                xbuf = xnxt; xbase += 32;                                                                         \
+                xnxt = (xbase + 32 + lane < E) ? x[xbase + 32 + lane] : 0.0;                                      \
+            }                                                                                                     \
+            const double fresh = shfl_d(xbuf, need - xbase);                                                      \
+            const int s0 = ll_e & 127;                                                                            \
+            if (lane == (s0 >> 2)) {                                                                              \
+                const int jj = s0 & 3;                                                                            \
+                if (jj == 0) xe[0] = fresh; else if (jj == 1) xe[1] = fresh; else if (jj == 2) xe[2] = fresh; else xe[3] = fresh; \
+            }                                                                                                     \
+        }                                                                                                         \
+        /* slot-1 edges of the two previous bands */                                                             \
+        const double e1 = shfl_d(P1[3], (lane + 31) & 31);                                                        \
+        const double e2 = shfl_d(P2[3], (lane + 31) & 31);                                                        \
+        /* fill range (event_handling.cpp:269-278) and trim cell (:256-265), as band offsets o = ll_e - event */ \
+        const int lo = max(max(-ll_k, ll_e - (E - 1)), 0);                                                        \
+        const int hi = min(min(K - ll_k, ll_e + 1), DNB_BW);                                                      \
+        const unsigned span = hi > lo ? (unsigned)(hi - lo) : 0u;                                                 \
+        const int o_trim = -1 - ll_k;                                                                             \
+        const int ev_trim = ll_e - o_trim;                                                                        \
+        const bool trim_ok = o_trim >= 0 && o_trim < DNB_BW && ev_trim >= 0 && ev_trim < E;                       \
+        const double trim_val = rn24(dMul(c.lp_trim, (double)((uint32_t)ev_trim + 1u)));   /* :260 */             \
+        fills += span;                                                                                            \
+        /* emissions: a = float((x - mu) / 0.14) via the guarded reciprocal multiply */                          \
+        double q[4];                                                                                              \
+        bool near = false;                                                                                        \
+        _Pragma("unroll") for (int j = 0; j < 4; j++) {                                                           \
+            q[j] = dMul(dSub(xe[j], mk[j]), c.inv_sigma);                                                         \
+            near |= (((unsigned)__double2loint(q[j]) & 0x1FFFFFFFu) - 0x0FFFFFF8u) <= 16u;                         \
+        }                                                                                                         \
+        if (__any_sync(FULL, near)) {                                                                             \
+            _Pragma("unroll") for (int j = 0; j < 4; j++) q[j] = dDiv(dSub(xe[j], mk[j]), 0.14);                  \
+        }                                                                                                         \
+        uint32_t tb = 0;                                                                                          \
+        _Pragma("unroll") for (int j = 3; j >= 0; j--) {                                                          \
+            const int o = (ll_e - (lane * 4 + j)) & 127;                                                          \
+            uint32_t from;                                                                                        \
+            double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24(q[j]), c, from); \
+            const bool valid = (unsigned)(o - lo) < span;                                                         \
+            const bool trim = (o == o_trim) && trim_ok;                                                           \
+            m = valid ? m : (trim ? trim_val : NEG_SENT);                                                         \
+            from = valid ? from : (trim ? (uint32_t)DNB_FROM_U : 0u);                                             \
+            P2[j] = m;                                                                                            \
+            tb |= from << (2 * j);                                                                                \
+        }                                                                                                         \
+        rows[(size_t)b * DNB_TRACE_ROW + lane] = (uint8_t)tb;                                                     \
+        if ((b & 31) == 31) { if (lane == 0) moves[b >> 5] = mvword; mvword = 0; }                                \
+        /* end-cell candidate of this band: (event b-K-1, last k-mer) (event_handling.cpp:329-340) */            \
+        {                                                                                                         \
+            const int e = b - K - 1;                                                                              \
+            const int o = ll_e - e;                                                                               \
+            if (e >= 0 && e < E && o >= 0 && o < DNB_BW) {                                                        \
+                const int sl_ = e & 127;                                                                          \
+                if (lane == (sl_ >> 2)) {                                                                         \
+                    const double val = pick4(P2, sl_ & 3);                                                        \
+                    const double s = rn24(dAdd(val, dMul((double)(unsigned long long)(E - e), c.lp_trim)));       \
+                    if (s > best_s) { best_s = s; best_e = e; best_lle = ll_e; }                                  \
+                }                                                                                                 \
+            }                                                                                                     \
+        }                                                                                                         \
+        b++;                                                                                                      \
+    }
 
 __global__ void __launch_bounds__(DP_WARPS * 32) banded_dp_kernel(DnbBatchView v, DnbDpArgs a) {
     const int lane = threadIdx.x & 31;
@@ -48,149 +181,54 @@ __global__ void __launch_bounds__(DP_WARPS * 32) banded_dp_kernel(DnbBatchView v
     const int K = (int)(v.q_off[r + 1] - v.q_off[r]) - DNB_K + 1;
     const double *__restrict__ x = a.x_e + v.ev_off[r];
     const double *__restrict__ mu = a.mu_q + v.q_off[r];
-    const double lp_skip = a.lp[4 * r + 0], lp_stay = a.lp[4 * r + 1], lp_step = a.lp[4 * r + 2], lp_trim = a.lp[4 * r + 3];
-    const double emit_const = a.emit_const;
+    DpConst c;
+    c.lp_skip = a.lp[4 * r + 0]; c.lp_stay = a.lp[4 * r + 1]; c.lp_step = a.lp[4 * r + 2]; c.lp_trim = a.lp[4 * r + 3];
+    c.emit_const = a.emit_const; c.inv_sigma = a.inv_sigma;
     uint8_t *rows = a.trace + a.band_off[r] * DNB_TRACE_ROW;
+    uint32_t *moves = a.moves + (a.band_off[r] >> 5) + r;
     const int n_bands = E + K + 2;
-    const float NINF = -INFINITY;
 
-    // ---- bands 0 and 1 (event_handling.cpp:213-228) ----
-    float p1[4], p2[4];
-    double xe[4], mk[4];
+    // ---- bands 0 and 1 (event_handling.cpp:213-228): A = band 0, B = band 1 ----
+    double A[4], B[4], xe[4], mk[4];
     int ll_e = DNB_BW / 2, ll_k = -1 - DNB_BW / 2;     // lower-left of band 1 = move_down(band 0)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int o = lane * 4 + j;
-        p2[j] = (o == DNB_BW / 2) ? 0.0f : NINF;                 // bands[0][50] = 0
-        p1[j] = (o == DNB_BW / 2) ? d2f(lp_trim) : NINF;         // bands[1][50] = lp_trim
+        const int s = lane * 4 + j;
+        A[j] = (s == 127) ? 0.0 : NEG_SENT;                        // bands[0][50] = 0: event -1 -> slot 127
+        B[j] = (s == 0) ? rn24(c.lp_trim) : NEG_SENT;              // bands[1][50] = lp_trim: event 0 -> slot 0
+        const int o = (ll_e - s) & 127;
         const int e = ll_e - o, km = ll_k + o;
         xe[j] = (e >= 0 && e < E) ? x[e] : 0.0;
         mk[j] = (km >= 0 && km < K) ? mu[km] : 0.0;
     }
-    rows[lane] = 0;                                                               // band 0: no trace, move 0
-    rows[DNB_TRACE_ROW + lane] = (lane == 12) ? (uint8_t)(DNB_FROM_U << 4) : 0;   // trace[1][50] = FROM_U
+    rows[lane] = 0;                                                            // band 0: no trace
+    rows[DNB_TRACE_ROW + lane] = (lane == 0) ? (uint8_t)DNB_FROM_U : 0;       // trace[1][50] = FROM_U (slot 0)
 
     // coalesced 32-wide look-ahead of the next events / k-mers entering the band (double buffered)
-    int xbase = ll_e + 1, mbase = ll_k + DNB_BW;     // next event index on a down move / next k-mer on a right move
+    int xbase = ll_e + 1, mbase = ll_k + DNB_BW;
     double xbuf = (xbase + lane < E) ? x[xbase + lane] : 0.0;
     double xnxt = (xbase + 32 + lane < E) ? x[xbase + 32 + lane] : 0.0;
     double mbuf = (mbase + lane < K) ? mu[mbase + lane] : 0.0;
     double mnxt = (mbase + 32 + lane < K) ? mu[mbase + 32 + lane] : 0.0;
 
-    bool prev_right = false;
-    float best_s = NINF;
+    double best_s = NEG_SENT;
     int best_e = 0x7fffffff, best_lle = 0;
     unsigned long long fills = 0;
+    uint32_t mvword = 0;
 
-    for (int b = 2; b < n_bands; b++) {
-        // Suzuki's rule (event_handling.cpp:237-253)
-        const float ll = __shfl_sync(FULL, p1[0], 0);
-        const float ur = __shfl_sync(FULL, p1[3], (DNB_BW - 1) / 4);
-        const bool right = (ll == NINF && ur == NINF) ? ((b & 1) == 1) : (ll < ur);
-
-        float up[4], left[4], diag[4];
-        if (right) {
-            ll_k++;
-            // k-mer at offset o becomes the old k-mer at o+1; cell 99 receives k-mer ll_k+99
-            const double in = shfl_down_d(mk[0]);
-            mk[0] = mk[1]; mk[1] = mk[2]; mk[2] = mk[3]; mk[3] = in;
-            const int need = ll_k + DNB_BW - 1;
-            if (need - mbase == 32) {
-                mbuf = mnxt; mbase += 32;
-                mnxt = (mbase + 32 + lane < K) ? mu[mbase + 32 + lane] : 0.0;
-            }
-            const double fresh = shfl_d(mbuf, need - mbase);
-            if (lane == (DNB_BW - 1) / 4) mk[3] = fresh;
-            // up = band[b-1][o+1], left = band[b-1][o]
-            const float e1 = __shfl_down_sync(FULL, p1[0], 1);
-            up[0] = p1[1]; up[1] = p1[2]; up[2] = p1[3]; up[3] = e1;
-            left[0] = p1[0]; left[1] = p1[1]; left[2] = p1[2]; left[3] = p1[3];
-        } else {
-            ll_e++;
-            // event at offset o becomes the old event at o-1; cell 0 receives event ll_e
-            const double in = shfl_up_d(xe[3]);
-            xe[3] = xe[2]; xe[2] = xe[1]; xe[1] = xe[0]; xe[0] = in;
-            const int need = ll_e;
-            if (need - xbase == 32) {
-                xbuf = xnxt; xbase += 32;
-                xnxt = (xbase + 32 + lane < E) ? x[xbase + 32 + lane] : 0.0;
-            }
-            const double fresh = shfl_d(xbuf, need - xbase);
-            if (lane == 0) xe[0] = fresh;
-            // up = band[b-1][o], left = band[b-1][o-1]
-            float e1 = __shfl_up_sync(FULL, p1[3], 1);
-            if (lane == 0) e1 = NINF;
-            up[0] = p1[0]; up[1] = p1[1]; up[2] = p1[2]; up[3] = p1[3];
-            left[0] = e1; left[1] = p1[0]; left[2] = p1[1]; left[3] = p1[2];
-        }
-        // diag = band[b-2][o + d], d = +1 (right,right), 0 (mixed), -1 (down,down)
-        if (prev_right && right) {
-            const float e2 = __shfl_down_sync(FULL, p2[0], 1);
-            diag[0] = p2[1]; diag[1] = p2[2]; diag[2] = p2[3]; diag[3] = e2;
-        } else if (!prev_right && !right) {
-            float e2 = __shfl_up_sync(FULL, p2[3], 1);
-            if (lane == 0) e2 = NINF;
-            diag[0] = e2; diag[1] = p2[0]; diag[2] = p2[1]; diag[3] = p2[2];
-        } else {
-            diag[0] = p2[0]; diag[1] = p2[1]; diag[2] = p2[2]; diag[3] = p2[3];
-        }
-
-        // fill range (event_handling.cpp:269-278) and trim cell (:256-265)
-        int lo = max(max(-ll_k, ll_e - (E - 1)), 0);
-        int hi = min(min(K - ll_k, ll_e + 1), DNB_BW);
-        const int o_trim = -1 - ll_k;
-        const int ev_trim = ll_e - o_trim;
-        const bool trim_ok = o_trim >= 0 && o_trim < DNB_BW && ev_trim >= 0 && ev_trim < E;
-        if (lane == 0 && hi > lo) fills += (unsigned long long)(hi - lo);
-
-        float nb[4];
-        uint32_t tb = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int o = lane * 4 + j;
-            float m = NINF;
-            uint32_t from = 0;
-            if (o >= lo && o < hi) {
-                const float em = emission_static(xe[j], mk[j], emit_const);
-                const float sd = d2f(dAdd(dAdd((double)diag[j], lp_step), (double)em));   // :296
-                const float su = d2f(dAdd(dAdd((double)up[j], lp_stay), (double)em));     // :297
-                const float sl = d2f(dAdd((double)left[j], lp_skip));                     // :298
-                m = sd; from = DNB_FROM_D;                                                // :300-306
-                m = su > m ? su : m; from = (m == su) ? DNB_FROM_U : from;
-                m = sl > m ? sl : m; from = (m == sl) ? DNB_FROM_L : from;
-            } else if (o == o_trim && trim_ok) {
-                m = d2f(dMul(lp_trim, (double)((uint32_t)ev_trim + 1u)));                 // :260
-                from = DNB_FROM_U;
-            }
-            nb[j] = m;
-            tb |= from << (2 * j);
-        }
-        uint32_t rowbyte = tb;
-        if (lane == 25) rowbyte = right ? 1u : 0u;
-        if (lane > 25) rowbyte = 0;
-        rows[(size_t)b * DNB_TRACE_ROW + lane] = (uint8_t)rowbyte;
-
-        // end-cell candidate of this band: cell (event b-K-1, last k-mer) (event_handling.cpp:329-340)
-        {
-            const int e = b - K - 1;
-            const int o = (K - 1) - ll_k;
-            if (e >= 0 && e < E && o >= 0 && o < DNB_BW && (o >> 2) == lane) {
-                const int j = o & 3;
-                const float val = j == 0 ? nb[0] : j == 1 ? nb[1] : j == 2 ? nb[2] : nb[3];
-                const float s = d2f(dAdd((double)val, dMul((double)(unsigned long long)(E - e), lp_trim)));
-                if (s > best_s) { best_s = s; best_e = e; best_lle = ll_e; }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) { p2[j] = p1[j]; p1[j] = nb[j]; }
-        prev_right = right;
+    int b = 2;
+    while (b + 1 < n_bands) {
+        DP_BAND_STEP(B, A)      // band b   : P1 = B (b-1), P2 = A (b-2) -> A becomes band b
+        DP_BAND_STEP(A, B)      // band b+1 : P1 = A,       P2 = B       -> B becomes band b+1
     }
+    if (b < n_bands) DP_BAND_STEP(B, A)
+    if (lane == 0 && (b & 31) != 0) moves[b >> 5] = mvword;
 
     // first event index attaining the maximum (strict '>' in ascending event order, :335)
-    float gmax = best_s;
+    double gmax = best_s;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(FULL, gmax, d));
-    int cand = (best_s == gmax && gmax != NINF) ? best_e : 0x7fffffff;
+    for (int d = 16; d > 0; d >>= 1) gmax = fmax(gmax, shfl_d(gmax, lane ^ d));
+    int cand = (best_s == gmax && gmax != NEG_SENT) ? best_e : 0x7fffffff;
     int gmin = cand;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) gmin = min(gmin, __shfl_xor_sync(FULL, gmin, d));
@@ -199,10 +237,10 @@ __global__ void __launch_bounds__(DP_WARPS * 32) banded_dp_kernel(DnbBatchView v
     if (who) lle = __shfl_sync(FULL, best_lle, __ffs(who) - 1);
     if (lane == 0) {
         if (gmin == 0x7fffffff) {
-            a.end_event[r] = -1; a.end_ll_event[r] = 0; a.end_score[r] = NINF;
+            a.end_event[r] = -1; a.end_ll_event[r] = 0; a.end_score[r] = -INFINITY;
             v.status[r] = DNB_READ_UNDEFINED;   // the reference would backtrace from an out-of-band cell
         } else {
-            a.end_event[r] = gmin; a.end_ll_event[r] = lle; a.end_score[r] = gmax;
+            a.end_event[r] = gmin; a.end_ll_event[r] = lle; a.end_score[r] = (float)gmax;
         }
         atomicAdd(a.cells, fills);
     }
@@ -237,6 +275,7 @@ __global__ void __launch_bounds__(BT_WARPS * 32) backtrace_kernel(DnbBatchView v
     const int32_t *__restrict__ q2r = v.q2r + v.q_off[r];
     const uint32_t *__restrict__ rr = a.rank_ref + v.r_off[r];
     const uint8_t *rows = a.dp.trace + a.dp.band_off[r] * DNB_TRACE_ROW;
+    const uint32_t *moves = a.dp.moves + (a.dp.band_off[r] >> 5) + r;
     uint32_t *pairs = a.al_pairs_rev + 2 * a.al_off[r];
     double *cls = a.cl_signal + a.cl_off[r];
     uint32_t *clr = a.cl_rank + a.cl_off[r];
@@ -248,6 +287,8 @@ __global__ void __launch_bounds__(BT_WARPS * 32) backtrace_kernel(DnbBatchView v
     uint32_t buf_n = 0, na = 0, nc = 0;
     int gap = 0, max_gap = 0, last_k = -1;
     bool bad = false, done = false;
+    int mv_idx = -1;
+    uint32_t mv_cur = 0;
 
     while (!done) {
         const int hi = e + k + 2;
@@ -275,8 +316,10 @@ __global__ void __launch_bounds__(BT_WARPS * 32) backtrace_kernel(DnbBatchView v
                 const int off = lle - e;
                 if (off < 0 || off >= DNB_BW) { bad = true; break; }
                 const uint8_t *row = wb + (size_t)(b - lo) * DNB_TRACE_ROW;
-                const uint32_t from = (row[off >> 2] >> (2 * (off & 3))) & 3u;
-                const int down_b = row[25] ? 0 : 1;            // band b was placed by a down move
+                const int sl = e & 127;                        // rows are indexed by event slot
+                const uint32_t from = (row[sl >> 2] >> (2 * (sl & 3))) & 3u;
+                if ((b >> 5) != mv_idx) { mv_idx = b >> 5; mv_cur = moves[mv_idx]; }
+                const int down_b = ((mv_cur >> (b & 31)) & 1u) ? 0 : 1;   // band b was placed by a down move
                 if (from == DNB_FROM_D) {
                     buf_total = dAdd(buf_total, (double)evm[e]); buf_n++;
                     const int32_t qr = q2r[k];
@@ -286,7 +329,8 @@ __global__ void __launch_bounds__(BT_WARPS * 32) backtrace_kernel(DnbBatchView v
                         nc++;
                     }
                     buf_total = 0.0; buf_n = 0;
-                    const int down_b1 = (wb + (size_t)(b - 1 - lo) * DNB_TRACE_ROW)[25] ? 0 : 1;
+                    const uint32_t w1 = ((b - 1) >> 5) == mv_idx ? mv_cur : moves[(b - 1) >> 5];
+                    const int down_b1 = ((w1 >> ((b - 1) & 31)) & 1u) ? 0 : 1;
                     lle -= down_b + down_b1;
                     k--; e--; gap = 0;
                 } else if (from == DNB_FROM_U) {

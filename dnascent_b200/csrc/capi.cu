@@ -112,6 +112,7 @@ struct Work {
     uint32_t *rank_ref, *redo;
     uint64_t *band_off, *al_off, *cl_off, *out_off;
     uint8_t *trace;
+    uint32_t *moves;
     int32_t *end_event, *end_ll;
     float *end_score;
     unsigned long long *cells;
@@ -478,6 +479,7 @@ int run(dnb_batch *b) {
     b->tot_bands = bo; b->tot_al = ao; b->tot_cl = co;
     Work &w = b->w;
     TRY(walloc(b, &w.trace, bo * DNB_TRACE_ROW + 64));
+    TRY(walloc(b, &w.moves, (bo >> 5) + R + 2));
     TRY(walloc(b, &w.al_rev, 2 * ao)); TRY(walloc(b, &w.cl_signal, co)); TRY(walloc(b, &w.cl_rank, co));
     TRY(h2d(b, w.lp, b->lp.data(), 4 * R));
     TRY(h2d(b, w.band_off, b->band_off.data(), R + 1));
@@ -487,7 +489,7 @@ int run(dnb_batch *b) {
 
     DnbDpArgs dp;
     dp.x_e = w.x_e; dp.mu_q = w.mu_q; dp.lp = w.lp; dp.emit_const = ctx->emit_const; dp.inv_sigma = 1.0 / 0.14;
-    dp.band_off = w.band_off; dp.trace = w.trace; dp.end_event = w.end_event; dp.end_ll_event = w.end_ll;
+    dp.band_off = w.band_off; dp.trace = w.trace; dp.moves = w.moves; dp.end_event = w.end_event; dp.end_ll_event = w.end_ll;
     dp.end_score = w.end_score; dp.cells = w.cells;
     CK(cudaEventRecord(b->ev[3], s));
     dnb_launch_banded_dp(v, dp, s); launches++;

@@ -12,7 +12,7 @@
 
 #define DNB_BW 100          // AdaptiveBanded_Params.bandwidth, src/config.h:41
 #define DNB_K 9
-#define DNB_TRACE_ROW 32    // bytes per band in HBM: 25 B of 2-bit trace codes, byte 25 = move bit, rest 0
+#define DNB_TRACE_ROW 32    // bytes per band in HBM: 128 event slots x 2-bit trace code
 #define DNB_CELLS_PER_LANE 4
 
 enum { DNB_FROM_D = 0, DNB_FROM_U = 1, DNB_FROM_L = 2 };   // event_handling.cpp:160-162
@@ -117,9 +117,10 @@ struct DnbDpArgs {
     const double *mu_q;           // indexed like query (K entries used per read)
     const double *lp;             // [R][4] lp_skip, lp_stay, lp_step, lp_trim (host glibc, event_handling.cpp:174-183)
     double emit_const;            // (double)(float)log(1/sqrt(2pi)) - log(0.14)
-    double inv_sigma;             // unused by the exact path (kept for the guarded fast path)
+    double inv_sigma;             // correctly rounded 1/0.14 for the guarded reciprocal multiply
     const uint64_t *band_off;     // [R+1] band-row offsets
-    uint8_t *trace;               // [band_off[R]] rows of DNB_TRACE_ROW bytes
+    uint8_t *trace;               // [band_off[R]] rows of DNB_TRACE_ROW bytes: 2-bit code of slot s at bits 2*(s&3) of byte s>>2
+    uint32_t *moves;              // [band_off[R]/32 + R + 1] move bits (1 = right), read r starts at band_off[r]/32 + r
     int32_t *end_event;           // [R] event index of the best end cell, -1 if none
     int32_t *end_ll_event;        // [R] band_lower_left.event_idx of that band
     float *end_score;             // [R]

@@ -1,0 +1,352 @@
+// dnascent_shim.cpp -- the reference's C++ symbols for the detect signal hot path, on top of libdnascent_b200.
+// See dnascent_shim.h for what it replaces and INTEGRATION.md for how it is linked into the reference.
+//
+// This file is compiled against the REFERENCE's headers (reads.h, config.h, probability.h, event_detection.h):
+// the data contract is DNAscent::read itself (src/reads.h:178-208).  All arithmetic happens on the GPU behind the
+// C ABI; this layer only marshals:  r.raw (double, float32-exact: src/pod5.cpp:60) -> float32 staging,
+// r.queryToRef (std::map) -> dense int32, and the results back into r.events / r.eventAlignment / r.scalings /
+// r.alignmentQCs.  There is no CPU fallback: any library error aborts with the library's message, like the
+// reference's own `assert(et.n > 0)` (src/event_handling.cpp:547).
+#include "dnascent_shim.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "config.h"
+#include "event_handling.h"
+#include "probability.h"
+#include "scrappie/event_detection.h"
+#include "dnascent_b200.h"
+
+namespace {
+
+std::mutex g_mu;
+dnb_ctx *g_ctx = nullptr;
+int g_device = -1;
+
+[[noreturn]] void die(const char *where, int rc) {
+    std::fprintf(stderr, "dnascent_b200 shim: %s failed: %s (%s)\n", where, dnb_strerror(rc), dnb_last_error());
+    std::abort();
+}
+
+void load_table(dnb_ctx *ctx, int which, const std::vector<std::pair<double, double>> &t) {
+    if (t.empty()) return;   // table not configured (e.g. a tool that never scores analogues)
+    std::vector<double> mean(t.size()), stdv(t.size());
+    for (size_t i = 0; i < t.size(); i++) {
+        mean[i] = t[i].first;
+        stdv[i] = t[i].second;
+    }
+    int rc = dnb_load_model(ctx, which, mean.data(), stdv.data(), t.size());
+    if (rc != DNB_OK) die("dnb_load_model", rc);
+}
+
+// r.raw is vector<double> but every value is a float (pod5.cpp:60, fast5.cpp:103-107): narrowing is lossless
+void narrow_signal(const std::vector<double> &raw, std::vector<float> &out) {
+    out.resize(raw.size());
+    for (size_t i = 0; i < raw.size(); i++) {
+        const float f = (float)raw[i];
+        if ((double)f != raw[i]) {
+            std::fprintf(stderr, "dnascent_b200 shim: raw[%zu] = %.17g is not float32-exact\n", i, raw[i]);
+            std::abort();
+        }
+        out[i] = f;
+    }
+}
+
+struct Staged {
+    std::vector<float> raw;
+    std::vector<int32_t> q2r;
+};
+
+void stage_read(const DNAscent::read &r, Staged &s, dnb_read_desc &d) {
+    narrow_signal(r.raw, s.raw);
+    s.q2r.assign(r.basecall.size(), -1);
+    for (const auto &kv : r.queryToRef)
+        if (kv.first < s.q2r.size()) s.q2r[kv.first] = (int32_t)kv.second;
+    std::memset(&d, 0, sizeof(d));
+    d.raw_pA = s.raw.data();
+    d.n_samples = s.raw.size();
+    d.query = r.basecall.data();
+    d.query_len = (uint32_t)r.basecall.size();
+    d.ref = r.referenceSeqMappedTo.data();
+    d.ref_len = (uint32_t)r.referenceSeqMappedTo.size();
+    d.query_to_ref = s.q2r.data();
+}
+
+// what src/event_handling.cpp:549-606 leaves in the read
+void unpack_result(DNAscent::read &r, const dnb_read_result &o) {
+    if (o.status == DNB_READ_UNDEFINED || o.status == DNB_READ_OVERFLOW) {
+        // inputs on which the reference itself aborts or indexes out of range: fail the read the reference's way
+        r.events.clear();
+        r.eventAlignment.clear();
+        return;
+    }
+    r.events.clear();
+    r.events.resize(o.n_events);
+    for (uint32_t j = 0; j < o.n_events; j++) {
+        event &e = r.events[j];
+        e.mean = (double)o.event_mean[j];
+        e.raw.assign(r.raw.begin() + o.event_start[j], r.raw.begin() + o.event_start[j + 1]);
+    }
+    r.eventAlignment.clear();
+    r.eventAlignment.reserve(o.n_align);
+    for (uint32_t j = 0; j < o.n_align; j++)
+        r.eventAlignment.push_back(std::make_pair(o.align_pairs[2 * j], o.align_pairs[2 * j + 1]));
+    r.alignmentQCs.recordQCs(o.avg_log_emission, o.spanned != 0, (unsigned int)o.max_gap);
+    r.scalings.shift = o.shift;
+    r.scalings.scale = o.scale;
+    r.scalings.eventsPerBase = o.events_per_base;
+}
+
+}  // namespace
+
+namespace dnb_shim {
+
+void set_device(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_device = device;
+}
+
+dnb_ctx *context() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx) return g_ctx;
+    dnb_config cfg;
+    dnb_default_config(&cfg);
+    if (g_device < 0) {
+        const char *e = std::getenv("DNB_DEVICE");
+        g_device = e ? std::atoi(e) : 0;
+    }
+    cfg.device = g_device;
+    cfg.min_average_log_emission = Pore_Substrate_Config.AdaptiveBanded_config.min_average_log_emission;
+    cfg.max_gap_threshold = Pore_Substrate_Config.AdaptiveBanded_config.max_gap_threshold;
+    cfg.bandwidth = Pore_Substrate_Config.AdaptiveBanded_config.bandwidth;
+    dnb_ctx *ctx = nullptr;
+    int rc = dnb_create(&ctx, &cfg);
+    if (rc != DNB_OK) die("dnb_create", rc);
+    load_table(ctx, DNB_MODEL_PORE, Pore_Substrate_Config.pore_model);
+    load_table(ctx, DNB_MODEL_UNLABELLED, Pore_Substrate_Config.unlabelled_model);
+    load_table(ctx, DNB_MODEL_ANALOGUE, Pore_Substrate_Config.analogue_model);
+    g_ctx = ctx;
+    return g_ctx;
+}
+
+void shutdown() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx) dnb_destroy(g_ctx);
+    g_ctx = nullptr;
+}
+
+void normaliseEvents_batch(const std::vector<DNAscent::read *> &reads, bool useFitPoreModel) {
+    if (reads.empty()) return;
+    if (useFitPoreModel) {
+        // every caller in the reference passes false (detect.cpp:875, alignment.cpp:855, trainCNN.cpp:318)
+        std::fprintf(stderr, "dnascent_b200 shim: normaliseEvents(useFitPoreModel=true) is not supported\n");
+        std::abort();
+    }
+    dnb_ctx *ctx = context();
+    const size_t n = reads.size();
+    std::vector<Staged> staged(n);
+    std::vector<dnb_read_desc> descs(n);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < n; i++) stage_read(*reads[i], staged[i], descs[i]);
+    dnb_batch *b = nullptr;
+    int rc = dnb_submit(ctx, descs.data(), n, &b);
+    if (rc != DNB_OK) die("dnb_submit", rc);
+    rc = dnb_wait(b);
+    if (rc != DNB_OK) die("dnb_wait", rc);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < n; i++) {
+        dnb_read_result o;
+        int rc2 = dnb_result(b, i, &o);
+        if (rc2 != DNB_OK) die("dnb_result", rc2);
+        unpack_result(*reads[i], o);
+    }
+    dnb_release(b);
+}
+
+}  // namespace dnb_shim
+
+// ---- src/event_handling.h:13 ---------------------------------------------------------------------------------------
+void normaliseEvents(DNAscent::read &r, bool useFitPoreModel) {
+    std::vector<DNAscent::read *> one(1, &r);
+    dnb_shim::normaliseEvents_batch(one, useFitPoreModel);
+}
+
+// ---- src/scrappie/event_detection.h:35 -------------------------------------------------------------------------------
+extern "C" event_table detect_events(double *raw, size_t raw_size, detector_param const edparam) {
+    const detector_param &d = event_detection_defaults;
+    if (edparam.window_length1 != d.window_length1 || edparam.window_length2 != d.window_length2 ||
+        edparam.threshold1 != d.threshold1 || edparam.threshold2 != d.threshold2 || edparam.peak_height != d.peak_height) {
+        std::fprintf(stderr, "dnascent_b200 shim: detect_events supports event_detection_defaults only\n");
+        std::abort();
+    }
+    event_table et = {0, 0, 0, nullptr};
+    if (!raw || raw_size == 0) return et;
+    std::vector<double> rv(raw, raw + raw_size);
+    std::vector<float> f;
+    narrow_signal(rv, f);
+    // the caller frees et.event with free() (event_handling.cpp:575)
+    dnb_event_t *ev = (dnb_event_t *)std::calloc(raw_size + 2, sizeof(dnb_event_t));
+    size_t n = 0;
+    int rc = dnb_detect_events(dnb_shim::context(), f.data(), raw_size, ev, raw_size + 2, &n);
+    if (rc != DNB_OK) die("dnb_detect_events", rc);
+    static_assert(sizeof(dnb_event_t) == sizeof(event_t), "event_t layout");
+    et.n = n;
+    et.start = 0;
+    et.end = n;
+    et.event = (event_t *)ev;
+    return et;
+}
+
+// ---- src/probability.h:26-33 ------------------------------------------------------------------------------------------
+double eexp(double x) { return dnb_eexp(x); }
+double eln(double x) {
+    double o = 0.0;
+    if (dnb_eln(x, &o) == DNB_ERR_NEGATIVE_LOG) throw NegativeLog();   // src/probability.cpp:45
+    return o;
+}
+double lnSum(double ln_x, double ln_y) { return dnb_lnSum(ln_x, ln_y); }
+double lnProd(double ln_x, double ln_y) { return dnb_lnProd(ln_x, ln_y); }
+bool lnGreaterThan(double ln_x, double ln_y) { return dnb_lnGreaterThan(ln_x, ln_y) != 0; }
+double uniformPDF(double lb, double ub, double x) { return dnb_uniformPDF(lb, ub, x); }
+double normalPDF(double mu, double sigma, double x) { return dnb_normalPDF(mu, sigma, x); }
+double cauchyPDF(double location, double scale, double x) { return dnb_cauchyPDF(location, scale, x); }
+
+#ifdef DNB_SHIM_WITH_HMM
+// ---- src/detect.h:119,121 ------------------------------------------------------------------------------------------------
+#include "detect.h"
+
+namespace {
+
+struct Site {
+    size_t read;
+    unsigned int posOnRef;
+    std::vector<double> events;
+};
+
+// The event gathering of llAcrossRead for one read (src/detect.cpp:381-390, 399-510): which T positions are
+// scored and with which events.  It uses the read's own refToQuery map with the reference's operators ([] inserts
+// a zero for a missing key, at() throws), so gaps in the CIGAR behave identically.
+void gather_sites(DNAscent::read &r, size_t read_idx, unsigned int w, std::vector<Site> &out) {
+    const unsigned int k = Pore_Substrate_Config.kmer_len;
+    const std::string &refSeq = r.referenceSeqMappedTo;
+    std::vector<unsigned int> pois;
+    for (unsigned int i = 2 * w; i < refSeq.length() - 2 * w; i++)
+        if (refSeq[i] == 'T') pois.push_back(i);
+    const auto &al = r.eventAlignment;
+    size_t head = 0;
+    if (r.isReverse) {
+        head = al.size() - 1;
+        std::reverse(pois.begin(), pois.end());
+    }
+    for (unsigned int p : pois) {
+        (void)r.refToQuery.at(p);
+        bool defined = true;
+        for (size_t c = p - w; c < (size_t)p + w + k; c++) {
+            const char ch = c < refSeq.size() ? refSeq[c] : 'N';
+            if (ch != 'A' && ch != 'T' && ch != 'G' && ch != 'C') defined = false;
+        }
+        if (!defined || (size_t)p + w + k > refSeq.size()) continue;
+        const unsigned int lo = r.refToQuery[p - w], hi = r.refToQuery[p + w];
+        Site s;
+        s.read = read_idx;
+        s.posOnRef = p;
+        bool first = true;
+        auto consider = [&](size_t j) {
+            if (lo <= al[j].second && al[j].second < hi) {
+                if (first) { head = j; first = false; }
+                const double ev = r.events[al[j].first].mean;
+                if (ev > 0. && ev < 250.0) s.events.push_back(ev);
+            }
+        };
+        if (r.isReverse) {
+            for (long j = (long)head; j >= 0; j--) {
+                consider((size_t)j);
+                if (al[j].second < lo) { std::reverse(s.events.begin(), s.events.end()); break; }
+            }
+        } else {
+            for (size_t j = head; j < al.size(); j++) {
+                consider(j);
+                if (al[j].second >= hi) break;
+            }
+        }
+        if (s.events.size() < 2 * w - k) continue;
+        out.push_back(std::move(s));
+    }
+}
+
+}  // namespace
+
+namespace dnb_shim {
+
+void llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, unsigned int w) {
+    const unsigned int k = Pore_Substrate_Config.kmer_len;
+    std::vector<Site> sites;
+    for (size_t i = 0; i < reads.size(); i++) {
+        DNAscent::read &r = *reads[i];
+        r.humanReadable_detectOut = ">" + r.readID + " " + r.referenceMappedTo + " " + std::to_string(r.refStart) + " " +
+                                    std::to_string(r.refEnd) + " " + (r.isReverse ? "rev" : "fwd") + "\n";
+        if (!r.eventAlignment.empty()) gather_sites(r, i, w, sites);
+    }
+    const size_t n = sites.size();
+    if (n == 0) return;
+    const size_t snip = 2 * (size_t)w + k;
+    std::vector<uint64_t> off(n + 1, 0);
+    for (size_t s = 0; s < n; s++) off[s + 1] = off[s] + sites[s].events.size();
+    std::vector<double> obs(off[n]), shift(n), scale(n), epb(n), la(n), lt(n);
+    std::string seq(n * snip, 'A');
+    for (size_t s = 0; s < n; s++) {
+        const DNAscent::read &r = *reads[sites[s].read];
+        std::copy(sites[s].events.begin(), sites[s].events.end(), obs.begin() + off[s]);
+        std::memcpy(&seq[s * snip], r.referenceSeqMappedTo.data() + sites[s].posOnRef - w, snip);
+        shift[s] = r.scalings.shift;
+        scale[s] = r.scalings.scale;
+        epb[s] = r.scalings.eventsPerBase;
+    }
+    int rc = dnb_sequence_probability_batch(context(), obs.data(), off.data(), seq.data(), shift.data(), scale.data(),
+                                            epb.data(), n, w, la.data(), lt.data());
+    if (rc != DNB_OK) die("dnb_sequence_probability_batch", rc);
+    for (size_t s = 0; s < n; s++) {
+        DNAscent::read &r = *reads[sites[s].read];
+        const unsigned int p = sites[s].posOnRef, q = r.refToQuery.at(p);
+        std::string kmerQuery = r.basecall.substr(q - k / 2, k), kmerRef = r.referenceSeqMappedTo.substr(p - k / 2, k);
+        int globalPos = r.refStart + (int)p;
+        if (r.isReverse) {
+            globalPos = r.refEnd - (int)p - 1;
+            kmerQuery = reverseComplement(kmerQuery);
+            kmerRef = reverseComplement(kmerRef);
+        }
+        const double llr = la[s] - lt[s];   // detect.cpp:548
+        r.humanReadable_detectOut += std::to_string(globalPos) + "\t" + std::to_string(llr) + "\t" + kmerRef + "\t" + kmerQuery + "\n";
+        r.refCoordToCalls[globalPos] = std::make_pair(llr, 0.);
+    }
+}
+
+}  // namespace dnb_shim
+
+void llAcrossRead(DNAscent::read &r, unsigned int windowLength) {
+    std::vector<DNAscent::read *> one(1, &r);
+    dnb_shim::llAcrossRead_batch(one, windowLength);
+}
+
+double sequenceProbability(std::vector<double> &observations, std::string &sequence, size_t windowSize, bool useBrdU,
+                           PoreParameters scalings, size_t BrdUStart, size_t BrdUEnd) {
+    const size_t k = Pore_Substrate_Config.kmer_len;
+    // the device kernel scores the analogue span llAcrossRead uses (detect.cpp:544-545)
+    if (useBrdU && (BrdUStart != windowSize - k / 2 || BrdUEnd != windowSize + k / 2))
+        throw std::invalid_argument("dnascent_b200 shim: sequenceProbability supports BrdUStart/End = window -/+ k/2 only");
+    if (sequence.size() != 2 * windowSize + k)
+        throw std::invalid_argument("dnascent_b200 shim: sequence must hold 2*windowSize + k bases");
+    uint64_t off[2] = {0, observations.size()};
+    double la = 0., lt = 0.;
+    int rc = dnb_sequence_probability_batch(dnb_shim::context(), observations.data(), off, sequence.data(), &scalings.shift,
+                                            &scalings.scale, &scalings.eventsPerBase, 1, (uint32_t)windowSize, &la, &lt);
+    if (rc != DNB_OK) die("dnb_sequence_probability_batch", rc);
+    return useBrdU ? la : lt;
+}
+#endif  // DNB_SHIM_WITH_HMM

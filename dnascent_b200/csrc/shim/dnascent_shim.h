@@ -1,0 +1,37 @@
+// dnascent_shim.h -- C++ drop-in layer: the reference's own symbols for the detect signal hot path, re-implemented
+// on top of the C ABI of libdnascent_b200 (include/dnascent_b200.h).
+//
+// Compiled INSIDE the reference tree (it includes the reference's reads.h / config.h) in place of
+//   src/event_handling.cpp     normaliseEvents                         (decl. src/event_handling.h:13)
+//   src/scrappie/event_detection.c   detect_events                     (decl. src/scrappie/event_detection.h:35)
+//   src/probability.cpp        eexp eln lnSum lnProd lnGreaterThan uniformPDF normalPDF cauchyPDF   (src/probability.h:26-33)
+// and, with -DDNB_SHIM_WITH_HMM, of the two hot functions of src/detect.cpp
+//   sequenceProbability, llAcrossRead                                  (decl. src/detect.h:119,121)
+// so that detect.cpp / alignment.cpp / trainCNN.cpp link unchanged (call sites detect.cpp:876, alignment.cpp:856,
+// trainCNN.cpp:319).  The batched entry points below are what the patched read loop of detect.cpp:850-908 calls
+// (INTEGRATION.md shows the patch); the one-read signatures are kept for every other caller.
+#pragma once
+#include <vector>
+
+#include "reads.h"   // DNAscent::read, PoreParameters (reference header)
+
+struct dnb_ctx;
+
+namespace dnb_shim {
+
+// Process-wide context on `device` (default: $DNB_DEVICE or 0).  Created on first use; loads the three tables of
+// Pore_Substrate_Config (pore_model, unlabelled_model, analogue_model) into HBM.  Thread-safe.
+dnb_ctx *context();
+void set_device(int device);   // call before the first use
+void shutdown();               // destroys the context (optional; e.g. before pod5_terminate at detect.cpp:917)
+
+// Batched normaliseEvents(r, false): one GPU submission for the whole buffer of reads (the reference's
+// `buffer`, detect.cpp:819).  Leaves each read exactly as the reference would: r.events, r.eventAlignment (empty ==
+// failed read, detect.cpp:879), r.scalings, r.alignmentQCs.  Reads must have r.raw filled (pod5_getSignal).
+void normaliseEvents_batch(const std::vector<DNAscent::read *> &reads, bool useFitPoreModel);
+
+// Batched llAcrossRead (detect.cpp:393-574): the per-site event gathering stays on the host, every forward pass of
+// every site of every read runs in one device launch.
+void llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, unsigned int windowLength);
+
+}  // namespace dnb_shim

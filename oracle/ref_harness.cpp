@@ -232,6 +232,7 @@ int dnbref_normalise(void *hv, int useFit) {
     return 0;
 }
 
+#ifndef DNB_SHIM_BUILD
 // normaliseEvents, then re-derivation of the intermediate stages through the reference's own helper
 // functions so that per-stage goldens exist: rough (quantile) scaling, cleaned (signal,rank) vectors.
 // Returns 0 if the re-derived alignment equals the one normaliseEvents produced, 1 otherwise.
@@ -269,6 +270,8 @@ int dnbref_normalise_staged(void *hv, int useFitI) {
     r.alignmentQCs = savedQC;
     return same ? 0 : 1;
 }
+
+#endif  // !DNB_SHIM_BUILD
 
 size_t dnbref_n_events(void *hv) { return ((Handle *)hv)->r->events.size(); }
 // means[j] = r.events[j].mean ; raw_len[j] = r.events[j].raw.size()
@@ -340,6 +343,7 @@ size_t dnbref_detect_events(const float *raw_pA, size_t n, uint64_t *start, floa
     return n_ev;
 }
 
+#ifndef DNB_SHIM_BUILD
 // Theil-Sen alone (src/event_handling.cpp:24)
 void dnbref_theil_sen(const double *sig, const uint32_t *ranks, size_t n, double shift, double scale, int useFit,
                       double *out_shift, double *out_scale) {
@@ -352,6 +356,8 @@ void dnbref_theil_sen(const double *sig, const uint32_t *ranks, size_t n, double
     *out_shift = o.shift;
     *out_scale = o.scale;
 }
+
+#endif  // !DNB_SHIM_BUILD
 
 // ---- analogue likelihood path (src/detect.cpp:235-574) ---------------------------------------
 double dnbref_sequence_probability(const double *obs, size_t n_obs, const char *seq, size_t windowSize, int useBrdU,
@@ -414,6 +420,39 @@ double dnbref_bench_normalise(void **handles, size_t n, int threads, int useFit,
     if (failed) *failed = nfail;
     return std::chrono::duration<double>(t1 - t0).count();
 }
+
+#ifdef DNB_SHIM_BUILD
+}  // extern "C"
+#include "dnascent_shim.h"
+extern "C" {
+// shim build only: the batched entry points the patched read loop of detect.cpp would call
+int dnbshim_normalise_batch(void **handles, size_t n) {
+    std::vector<DNAscent::read *> reads(n);
+    for (size_t i = 0; i < n; i++) reads[i] = ((Handle *)handles[i])->r;
+    dnb_shim::normaliseEvents_batch(reads, false);
+    return 0;
+}
+int dnbshim_ll_across_read_batch(void **handles, size_t n, unsigned int windowLength) {
+    std::vector<DNAscent::read *> reads(n);
+    for (size_t i = 0; i < n; i++) {
+        reads[i] = ((Handle *)handles[i])->r;
+        reads[i]->refCoordToCalls.clear();
+    }
+    dnb_shim::llAcrossRead_batch(reads, windowLength);
+    return 0;
+}
+// calls recorded by (batched) llAcrossRead, as dnbref_ll_across_read returns them
+size_t dnbshim_calls(void *hv, int32_t *pos, double *llr, size_t cap) {
+    DNAscent::read *r = ((Handle *)hv)->r;
+    size_t n = 0;
+    for (auto &kv : r->refCoordToCalls) {
+        if (n < cap) { pos[n] = (int32_t)kv.first; llr[n] = kv.second.first; }
+        n++;
+    }
+    return n;
+}
+void dnbshim_shutdown(void) { dnb_shim::shutdown(); }
+#endif  // DNB_SHIM_BUILD
 
 int dnbref_max_threads(void) { return omp_get_max_threads(); }
 

@@ -10,6 +10,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "libdnascent_ref.so")
+# same harness + reference objects, but the hot-path symbols come from the product's C++ shim over the CUDA library
+SHIM_LIB_PATH = os.path.join(HERE, "_ref", "libdnascent_shim.so")
 
 PORE, UNLABELLED, ANALOGUE = 0, 1, 2
 NKMER = 4 ** 9
@@ -19,6 +21,10 @@ def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
+def shim_available() -> bool:
+    return os.path.exists(SHIM_LIB_PATH)
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -26,11 +32,19 @@ def _p(a):
 class Ref:
     """One process-wide instance (the reference keeps its tables in a global)."""
 
-    def __init__(self):
-        if not available():
-            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
-        L = self.L = C.CDLL(LIB_PATH)
+    def __init__(self, shim: bool = False):
+        path = SHIM_LIB_PATH if shim else LIB_PATH
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make -C oracle {'shim' if shim else 'ref'}` where /root/reference exists")
+        self.is_shim = shim
+        L = self.L = C.CDLL(path)
         sz, vp, d = C.c_size_t, C.c_void_p, C.c_double
+        if shim:
+            L.dnbshim_normalise_batch.argtypes = [vp, sz]
+            L.dnbshim_ll_across_read_batch.argtypes = [vp, sz, C.c_uint]
+            L.dnbshim_calls.restype = sz
+            L.dnbshim_calls.argtypes = [vp, vp, vp, sz]
+            L.dnbshim_shutdown.restype = None
         L.dnbref_get_model.restype = sz
         L.dnbref_get_model.argtypes = [C.c_int, vp, vp, sz]
         L.dnbref_set_model.argtypes = [C.c_int, vp, vp, sz]
@@ -44,7 +58,8 @@ class Ref:
         for f in ("dnbref_read_is_reverse", "dnbref_read_ref_start", "dnbref_read_ref_end"):
             getattr(L, f).argtypes = [vp]
         L.dnbref_normalise.argtypes = [vp, C.c_int]
-        L.dnbref_normalise_staged.argtypes = [vp, C.c_int]
+        if not shim:
+            L.dnbref_normalise_staged.argtypes = [vp, C.c_int]
         L.dnbref_n_events.restype = sz
         L.dnbref_n_events.argtypes = [vp]
         L.dnbref_events.restype = sz
@@ -58,7 +73,8 @@ class Ref:
         L.dnbref_cleaned.argtypes = [vp, vp, vp, sz]
         L.dnbref_detect_events.restype = sz
         L.dnbref_detect_events.argtypes = [vp, sz, vp, vp, vp, vp, sz]
-        L.dnbref_theil_sen.argtypes = [vp, vp, sz, d, d, C.c_int, vp, vp]
+        if not shim:
+            L.dnbref_theil_sen.argtypes = [vp, vp, sz, d, d, C.c_int, vp, vp]
         L.dnbref_sequence_probability.restype = d
         L.dnbref_sequence_probability.argtypes = [vp, sz, C.c_char_p, sz, C.c_int, d, d, d, sz, sz]
         L.dnbref_ll_across_read.restype = sz
@@ -139,6 +155,27 @@ class Ref:
         if self.L.dnbref_eln(x, _p(o)):
             raise ValueError("NegativeLog")
         return float(o[0])
+
+    # -- shim build only: the batched entry points ---------------------------------------
+    def normalise_batch(self, reads):
+        arr = (C.c_void_p * len(reads))(*[r.h for r in reads])
+        self.L.dnbshim_normalise_batch(arr, len(reads))
+
+    def ll_across_read_batch(self, reads, window: int = 12):
+        arr = (C.c_void_p * len(reads))(*[r.h for r in reads])
+        self.L.dnbshim_ll_across_read_batch(arr, len(reads), window)
+        out = []
+        for r in reads:
+            cap = len(r.refseq) + 1
+            pos = np.zeros(cap, dtype=np.int32)
+            llr = np.zeros(cap)
+            n = self.L.dnbshim_calls(r.h, _p(pos), _p(llr), cap)
+            out.append((pos[:n].copy(), llr[:n].copy()))
+        return out
+
+    def shutdown(self):
+        if self.is_shim:
+            self.L.dnbshim_shutdown()
 
     def bench_normalise(self, reads, threads: int, use_fit=False):
         arr = (C.c_void_p * len(reads))(*[r.h for r in reads])

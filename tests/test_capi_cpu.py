@@ -81,3 +81,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text and "dnb_oracle" not in text, f
+
+
+def test_shim_exports_the_reference_symbols():
+    """The C++ drop-in layer defines, with the reference's exact (mangled) signatures, every symbol of the hot path
+    that detect.cpp / alignment.cpp / trainCNN.cpp link against (event_handling.h:13, event_detection.h:35,
+    probability.h:26-33, detect.h:119,121).  Built only where the reference headers are mounted."""
+    import subprocess
+    from oracle import refbind
+    if not refbind.shim_available():
+        pytest.skip("oracle/_ref/libdnascent_shim.so not built (needs /root/reference at build time)")
+    out = subprocess.run(["nm", "-D", "--defined-only", refbind.SHIM_LIB_PATH], capture_output=True, text=True).stdout
+    defined = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    for sym in ("_Z15normaliseEventsRN8DNAscent4readEb", "detect_events", "_Z4eexpd", "_Z3elnd", "_Z5lnSumdd", "_Z6lnProddd",
+                "_Z13lnGreaterThandd", "_Z10uniformPDFddd", "_Z9normalPDFddd", "_Z9cauchyPDFddd",
+                "_Z12llAcrossReadRN8DNAscent4readEj"):
+        assert sym in defined, sym
+    assert any(s.startswith("_Z19sequenceProbabilityRSt6vectorIdSaIdEE") for s in defined)
+    refbind.Ref(shim=True)          # loads (resolves libdnascent_b200.so through its rpath) without a GPU

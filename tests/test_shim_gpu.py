@@ -1,0 +1,113 @@
+"""Drop-in test of the C++ shim (dnascent_b200/csrc/shim): the reference's own objects (read constructor, parseCigar,
+kmer2index, ...) linked against OUR normaliseEvents / detect_events / probability / llAcrossRead symbols must leave a
+DNAscent::read exactly as the unmodified reference does.  Both libraries are prebuilt by oracle/Makefile where the
+reference is mounted and travel to the GPU box; nothing here reads /root/reference at run time."""
+import numpy as np
+import pytest
+
+from dnascent_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def shim(pore_mean):
+    from oracle import refbind
+    if not refbind.shim_available():
+        pytest.skip("oracle/_ref/libdnascent_shim.so not built (needs /root/reference at build time)")
+    S = refbind.Ref(shim=True)
+    S.set_model(refbind.PORE, pore_mean, np.full(pore_mean.size, 0.14))
+    yield S
+    S.shutdown()
+
+
+def _reads(pore_mean, ref, n, seed, lo=1500, hi=9000):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        L = int(rng.integers(lo, hi))
+        out.append(synth.simulate_read(ref, int(rng.integers(0, len(ref) - L)), L, bool(i % 2), pore_mean, rng,
+                                       name=f"s{i}", sub_rate=0.02 if i % 3 == 0 else 0.0))
+    return out
+
+
+def _same(a: dict, b: dict, tag):
+    np.testing.assert_array_equal(a["event_mean"], b["event_mean"], err_msg=tag)
+    np.testing.assert_array_equal(a["event_raw_len"], b["event_raw_len"], err_msg=tag)
+    np.testing.assert_array_equal(a["align_event"], b["align_event"], err_msg=tag)
+    np.testing.assert_array_equal(a["align_kmer"], b["align_kmer"], err_msg=tag)
+    for k in ("shift", "scale", "events_per_base", "avg_log_emission", "spanned", "max_gap", "qc_set"):
+        assert a[k] == b[k], (tag, k, a[k], b[k])
+
+
+def test_shim_normalise_events_matches_reference(shim, ref_oracle, pore_mean):
+    ref = synth.make_reference(200_000, 31)
+    shim.set_reference(ref)
+    ref_oracle.set_reference(ref)
+    reads = _reads(pore_mean, ref, 12, 32)
+    hs = [shim.read_new(r) for r in reads]
+    hr = [ref_oracle.read_new(r) for r in reads]
+    shim.normalise_batch(hs)                       # one GPU submission for the whole buffer
+    n_ok = 0
+    for i, (a, b) in enumerate(zip(hs, hr)):
+        want = b.normalise(staged=False)
+        got = a.outputs(staged=False)
+        _same(got, want, f"read {i}")
+        # r.events[j].raw concatenated == the reference's
+        na = a.L.dnbref_events_raw_concat(a.h, None, 0)
+        nb = b.L.dnbref_events_raw_concat(b.h, None, 0)
+        assert na == nb
+        n_ok += want["align_event"].size > 0
+    assert n_ok >= 10
+    # the one-read signature (what alignment.cpp:856 / trainCNN.cpp:319 call) gives the same answer
+    h1 = shim.read_new(reads[0])
+    _same(h1.normalise(staged=False), hr[0].outputs(staged=False), "single-read call")
+
+
+def test_shim_detect_events_and_probability(shim, ref_oracle, pore_mean):
+    ref = synth.make_reference(50_000, 33)
+    r = _reads(pore_mean, ref, 1, 34)[0]
+    for x, y in zip(shim.detect_events(r.raw), ref_oracle.detect_events(r.raw)):
+        np.testing.assert_array_equal(x, y)
+    L, R = shim.L, ref_oracle.L
+    for a, b in [(0.5, -3.0), (float("nan"), 1.0), (2.0, float("nan")), (float("nan"), float("nan")), (-700.0, 3.0)]:
+        for f in ("dnbref_lnSum", "dnbref_lnProd"):
+            x, y = getattr(L, f)(a, b), getattr(R, f)(a, b)
+            assert (np.isnan(x) and np.isnan(y)) or x == y
+        assert L.dnbref_lnGreaterThan(a, b) == R.dnbref_lnGreaterThan(a, b)
+    with pytest.raises(ValueError):
+        shim.eln(-1.0)                              # NegativeLog crosses the shim as the reference's exception
+    assert np.isnan(shim.eln(0.0)) and shim.eln(2.0) == ref_oracle.eln(2.0)
+    assert L.dnbref_normalPDF(0.1, 0.14, 0.3) == R.dnbref_normalPDF(0.1, 0.14, 0.3)
+
+
+def test_shim_ll_across_read_matches_reference(shim, ref_oracle, pore_mean):
+    import os
+    h = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hmm_v1.npz"))
+    from oracle import refbind
+    for name_m, name_s, which in (("unl_mean", "unl_stdv", refbind.UNLABELLED), ("ana_mean", "ana_stdv", refbind.ANALOGUE)):
+        m, s = np.zeros(4 ** 9), np.zeros(4 ** 9)
+        m[h["ranks"]] = h[name_m]
+        s[h["ranks"]] = h[name_s]
+        shim.set_model(which, m, s)
+        ref_oracle.set_model(which, m, s)
+    shim.shutdown()                                  # context reloads the tables on next use
+    ref = synth.make_reference(120_000, 35)
+    shim.set_reference(ref)
+    ref_oracle.set_reference(ref)
+    reads = _reads(pore_mean, ref, 4, 36, lo=3000, hi=6000)
+    hs = [shim.read_new(r) for r in reads]
+    hr = [ref_oracle.read_new(r) for r in reads]
+    shim.normalise_batch(hs)
+    calls = shim.ll_across_read_batch(hs, 12)
+    n_sites = 0
+    for (pos, llr), b in zip(calls, hr):
+        b.normalise(staged=False)
+        if b.outputs(staged=False)["align_event"].size == 0:
+            assert pos.size == 0
+            continue
+        rpos, rllr = b.ll_across_read(12)
+        np.testing.assert_array_equal(pos, rpos)
+        np.testing.assert_allclose(llr, rllr, rtol=1e-4, atol=1e-6)    # BASELINE.json tolerance for the HMM path
+        n_sites += pos.size
+    assert n_sites > 500

@@ -102,7 +102,7 @@ def lib():
     L.dnb_result.argtypes = [vp, sz, C.POINTER(ReadResult)]
     L.dnb_release.argtypes = [vp]
     L.dnb_release.restype = None
-    L.dnb_batch_timings.argtypes = [vp, C.POINTER(d * 6), C.POINTER(C.c_uint64 * 8)]
+    L.dnb_batch_timings.argtypes = [vp, C.POINTER(d * 8), C.POINTER(C.c_uint64 * 8)]
     L.dnb_detect_events.argtypes = [vp, vp, sz, C.POINTER(EventT), sz, C.POINTER(sz)]
     L.dnb_eexp.restype = d
     L.dnb_eexp.argtypes = [d]

@@ -90,10 +90,10 @@ class Batch:
         _lib.check(self.ctx.L.dnb_batch_drop_workspace(self.h), "dnb_batch_drop_workspace")
 
     def timings(self):
-        ms = (C.c_double * 6)()
+        ms = (C.c_double * 8)()
         cnt = (C.c_uint64 * 8)()
         _lib.check(self.ctx.L.dnb_batch_timings(self.h, C.byref(ms), C.byref(cnt)), "dnb_batch_timings")
-        names = ("segmentation", "prep", "banded_dp", "backtrace", "theil_sen", "total")
+        names = ("segmentation", "prep", "banded_dp", "backtrace", "theil_sen", "total", "host_step", "wall")
         cn = ("samples", "events", "kmers", "bands", "cells", "launches", "seg_serial_reads", "failed_reads")
         return dict(zip(names, ms)), dict(zip(cn, (int(x) for x in cnt)))
 

@@ -89,6 +89,59 @@ struct PinnedPool {
     }
 };
 
+// Device blocks are cached per context as whole cudaMalloc allocations, sizes rounded up to a coarse grid (1/16 of
+// the next power of two, at least 2 MiB) so that bins of similar size map to identical block sizes and are reused
+// without touching the driver.  (The stream-ordered pool fragmented under the 10-20 GB trace buffers: profiles/
+// r1 host trace showed 0.1-1.1 s stalls in cudaMallocAsync.)  Blocks are only released after their stream has been
+// synchronised, so reuse by another batch/stream is safe.
+struct DevCache {
+    struct Block { void *p; size_t n; bool used; };
+    std::vector<Block> blocks;
+    std::mutex mu;
+    static size_t grid(size_t n) {
+        size_t g = (size_t)2 << 20;
+        while (g * 16 < n) g <<= 1;
+        return (n + g - 1) / g * g;
+    }
+    void *acquire(size_t n, cudaError_t *err) {
+        n = grid(n ? n : 1);
+        *err = cudaSuccess;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (auto &b : blocks)
+                if (!b.used && b.n == n) { b.used = true; return b.p; }
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaErrorMemoryAllocation) {   // give cached-but-idle blocks back and retry once
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(&p, n);
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); *err = e; return nullptr; }
+        std::lock_guard<std::mutex> lk(mu);
+        blocks.push_back({p, n, true});
+        return p;
+    }
+    void release(void *p) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        size_t k = 0;
+        for (auto &b : blocks) {
+            if (b.used) blocks[k++] = b;
+            else cudaFree(b.p);
+        }
+        blocks.resize(k);
+    }
+    void destroy() {
+        for (auto &b : blocks) cudaFree(b.p);
+        blocks.clear();
+    }
+};
+
 }  // namespace
 
 struct dnb_ctx {
@@ -97,6 +150,7 @@ struct dnb_ctx {
     double emit_const = 0.0;
     std::mutex mu;
     PinnedPool pinned;
+    DevCache dev;
 };
 
 namespace {
@@ -158,7 +212,7 @@ struct dnb_batch {
     HostRes h = {};
     // ---- timings ----
     cudaEvent_t ev[8] = {};
-    double ms[6] = {};
+    double ms[8] = {};
     uint64_t counts[8] = {};
     unsigned long long h_cells = 0;
     std::vector<void *> input_allocs, work_allocs, res_allocs;
@@ -170,11 +224,10 @@ template <class T>
 int dev_alloc(dnb_batch *b, std::vector<void *> &owner, T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    void *q = nullptr;
-    cudaError_t e = cudaMallocAsync(&q, n * sizeof(T), b->stream);
-    if (e != cudaSuccess) {
-        g_last_error = std::string("cudaMallocAsync(") + std::to_string(n * sizeof(T)) + " B): " + cudaGetErrorString(e);
-        cudaGetLastError();
+    cudaError_t e;
+    void *q = b->ctx->dev.acquire(n * sizeof(T), &e);
+    if (!q) {
+        g_last_error = std::string("cudaMalloc(") + std::to_string(n * sizeof(T)) + " B): " + cudaGetErrorString(e);
         return e == cudaErrorMemoryAllocation ? DNB_ERR_NOMEM : DNB_ERR_CUDA;
     }
     owner.push_back(q);
@@ -235,8 +288,9 @@ DnbBatchView make_view(const dnb_batch *b) {
     return v;
 }
 
+// callers make sure the batch's stream is idle (every run/fetch ends with a synchronize)
 void drop_work(dnb_batch *b) {
-    for (void *p : b->work_allocs) cudaFreeAsync(p, b->stream);
+    for (void *p : b->work_allocs) b->ctx->dev.release(p);
     b->work_allocs.clear();
     b->w = Work{};
     b->have_work = false;
@@ -253,7 +307,7 @@ void free_batch(dnb_batch *b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     drop_work(b);
     drop_results(b);
-    for (void *p : b->input_allocs) cudaFreeAsync(p, b->stream);
+    for (void *p : b->input_allocs) b->ctx->dev.release(p);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
     if (b->stream) {
@@ -404,27 +458,43 @@ int run(dnb_batch *b) {
     CK(cudaSetDevice(ctx->cfg.device));
     const size_t R = b->R;
     cudaStream_t s = b->stream;
+    const double wall0 = omp_get_wtime();
+    static const bool trace_host = getenv("DNB_TRACE_HOST") != nullptr;
+    double tick_prev = wall0;
+    auto tick = [&](const char *what) {
+        if (!trace_host) return;
+        const double now = omp_get_wtime();
+        fprintf(stderr, "[dnb host] %-28s %8.2f ms\n", what, 1e3 * (now - tick_prev));
+        tick_prev = now;
+    };
     drop_work(b);
     drop_results(b);
     TRY(alloc_work_a(b));
     // the few per-read counters the host reads in the middle of the pipeline
     TRY(ralloc(b, &b->h.n_events, R)); TRY(ralloc(b, &b->h.et_n, R)); TRY(ralloc(b, &b->h.status, R));
     TRY(ralloc(b, &b->h.redo, R));
+    tick("drop + alloc A + pinned");
     DnbBatchView v = make_view(b);
     DnbDetector det = {ctx->cfg.window_length1, ctx->cfg.window_length2, ctx->cfg.threshold1, ctx->cfg.threshold2,
                        ctx->cfg.peak_height};
     uint64_t launches = 0;
+    // scratch of the tiled segmentation: back in the cache at the mid-pipeline sync, before the DP workspace is taken
+    std::vector<void *> seg_scratch;
+    struct ScratchGuard {
+        dnb_batch *b; std::vector<void *> &v;
+        ~ScratchGuard() { if (!v.empty()) { cudaStreamSynchronize(b->stream); for (void *p : v) b->ctx->dev.release(p); v.clear(); } }
+    } scratch_guard{b, seg_scratch};
     CK(cudaEventRecord(b->ev[0], s));
     if (b->want_table) {
         dnb_launch_segmentation_serial(v, det, nullptr, s); launches++;
     } else {
         // per-run scratch of the tiled segmentation (back in the pool before the DP workspace is taken)
         const size_t nt = b->tile_off[R], nck = b->ck_off[R];
-        void *scratch[10] = {};
-        auto sal = [&](int i, size_t bytes) -> cudaError_t { return cudaMallocAsync(&scratch[i], bytes ? bytes : 1, s); };
-        CK(sal(0, nck * 8)); CK(sal(1, nck * 8)); CK(sal(2, nt * DNB_SEG_PEAK_CAP * 4)); CK(sal(3, nt * DNB_SEG_PEAK_CAP * 8));
-        CK(sal(4, nt * 4)); CK(sal(5, nt * DNB_SEG_BOUNDARY_BYTES)); CK(sal(6, nt * DNB_SEG_BOUNDARY_BYTES));
-        CK(sal(7, nt * 4)); CK(sal(8, nt * 4)); CK(sal(9, nt * 8));
+        uint8_t *scratch[10] = {};
+        auto sal = [&](int i, size_t bytes) -> int { return dev_alloc(b, seg_scratch, &scratch[i], bytes); };
+        TRY(sal(0, nck * 8)); TRY(sal(1, nck * 8)); TRY(sal(2, nt * DNB_SEG_PEAK_CAP * 4)); TRY(sal(3, nt * DNB_SEG_PEAK_CAP * 8));
+        TRY(sal(4, nt * 4)); TRY(sal(5, nt * DNB_SEG_BOUNDARY_BYTES)); TRY(sal(6, nt * DNB_SEG_BOUNDARY_BYTES));
+        TRY(sal(7, nt * 4)); TRY(sal(8, nt * 4)); TRY(sal(9, nt * 8));
         DnbSegTiles t;
         memset(&t, 0, sizeof(t));
         t.n_tiles = (uint32_t)nt; t.tile_off = b->d_tile_off; t.tile_read = b->d_tile_read; t.ck_off = b->d_ck_off;
@@ -434,7 +504,7 @@ int run(dnb_batch *b) {
         t.b_end = (SegBoundary *)scratch[6]; t.tile_prefix = (uint32_t *)scratch[7]; t.tile_prev_pos = (uint32_t *)scratch[8];
         t.tile_prev_sum = (double *)scratch[9];
         dnb_launch_segmentation_tiled(v, det, t, s); launches += 5;
-        for (void *p : scratch) CK(cudaFreeAsync(p, s));
+        tick("seg scratch + launches");
     }
     CK(cudaEventRecord(b->ev[1], s));
     TRY(d2h(b, b->h.n_events, b->w.n_events, R));
@@ -454,6 +524,10 @@ int run(dnb_batch *b) {
     CK(cudaEventRecord(b->ev[2], s));
     CK(cudaStreamSynchronize(s));   // n_events is on the host (its copy was enqueued before the prep kernels)
     CK(cudaGetLastError());
+    for (void *p : seg_scratch) ctx->dev.release(p);
+    seg_scratch.clear();
+    const double wall_gap0 = omp_get_wtime();
+    tick("phase A sync (GPU wait)");
 
     // ---- host step: transition constants with glibc (event_handling.cpp:174-183) + workspace shapes ----
     b->lp.resize(4 * R);
@@ -478,9 +552,11 @@ int run(dnb_batch *b) {
     b->band_off[R] = bo; b->al_off[R] = ao; b->cl_off[R] = co;
     b->tot_bands = bo; b->tot_al = ao; b->tot_cl = co;
     Work &w = b->w;
+    tick("host loop (lp, offsets)");
     TRY(walloc(b, &w.trace, bo * DNB_TRACE_ROW + 64));
     TRY(walloc(b, &w.moves, (bo >> 5) + R + 2));
     TRY(walloc(b, &w.al_rev, 2 * ao)); TRY(walloc(b, &w.cl_signal, co)); TRY(walloc(b, &w.cl_rank, co));
+    tick("alloc B");
     TRY(h2d(b, w.lp, b->lp.data(), 4 * R));
     TRY(h2d(b, w.band_off, b->band_off.data(), R + 1));
     TRY(h2d(b, w.al_off, b->al_off.data(), R + 1));
@@ -492,6 +568,8 @@ int run(dnb_batch *b) {
     dp.band_off = w.band_off; dp.trace = w.trace; dp.moves = w.moves; dp.end_event = w.end_event; dp.end_ll_event = w.end_ll;
     dp.end_score = w.end_score; dp.cells = w.cells;
     CK(cudaEventRecord(b->ev[3], s));
+    const double wall_gap1 = omp_get_wtime();
+    tick("h2d B + memset");
     dnb_launch_banded_dp(v, dp, s); launches++;
     CK(cudaEventRecord(b->ev[4], s));
     DnbBtArgs bt;
@@ -509,6 +587,7 @@ int run(dnb_batch *b) {
     CK(cudaMemcpyAsync(&b->h_cells, w.cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    tick("phase B launches + sync");
     float t;
     cudaEventElapsedTime(&t, b->ev[0], b->ev[1]); b->ms[0] = t;
     cudaEventElapsedTime(&t, b->ev[1], b->ev[2]); b->ms[1] = t;
@@ -516,6 +595,8 @@ int run(dnb_batch *b) {
     cudaEventElapsedTime(&t, b->ev[4], b->ev[5]); b->ms[3] = t;
     cudaEventElapsedTime(&t, b->ev[5], b->ev[6]); b->ms[4] = t;
     cudaEventElapsedTime(&t, b->ev[0], b->ev[6]); b->ms[5] = t;
+    b->ms[6] = 1e3 * (wall_gap1 - wall_gap0);
+    b->ms[7] = 1e3 * (omp_get_wtime() - wall0);
     uint64_t n_samp = 0;
     for (size_t i = 0; i < R; i++) n_samp += b->n_samples[i];
     b->counts[0] = n_samp; b->counts[1] = n_ev; b->counts[2] = n_km; b->counts[3] = bo; b->counts[4] = b->h_cells;
@@ -653,6 +734,7 @@ void dnb_destroy(dnb_ctx *ctx) {
         cudaFree(m.d_mean); cudaFree(m.d_stdv); cudaFree(m.d_sorted); cudaFree(m.d_order);
     }
     ctx->pinned.destroy();
+    ctx->dev.destroy();
     delete ctx;
 }
 
@@ -741,9 +823,9 @@ void dnb_release(dnb_batch *b) {
     free_batch(b);
 }
 
-int dnb_batch_timings(dnb_batch *b, double ms[6], uint64_t counts[8]) {
+int dnb_batch_timings(dnb_batch *b, double ms[8], uint64_t counts[8]) {
     if (!b || !b->ran) return DNB_ERR_STATE;
-    for (int i = 0; i < 6; i++) if (ms) ms[i] = b->ms[i];
+    for (int i = 0; i < 8; i++) if (ms) ms[i] = b->ms[i];
     for (int i = 0; i < 8; i++) if (counts) counts[i] = b->counts[i];
     return DNB_OK;
 }

@@ -144,10 +144,12 @@ DNB_API int dnb_batch_fetch(dnb_batch *batch);   /* device -> pinned host result
  * fetched stay valid.  dnb_submit does this itself once the results are on the host. */
 DNB_API int dnb_batch_drop_workspace(dnb_batch *batch);
 /* device-time breakdown of the last dnb_batch_run, milliseconds, measured with CUDA events on the
- * pipeline stream: [0]=segmentation [1]=ranks+scaling+prep [2]=banded DP [3]=backtrace+QC [4]=Theil-Sen [5]=total;
+ * pipeline stream: [0]=segmentation [1]=ranks+scaling+prep [2]=banded DP [3]=backtrace+QC [4]=Theil-Sen [5]=total
+ * (first to last kernel, host step included); host wall clock: [6]=the mid-pipeline host step (transition constants,
+ * workspace sizing) [7]=the whole dnb_batch_run call;
  * counts: [0]=samples [1]=events [2]=k-mers [3]=bands [4]=DP cells [5]=kernel launches
  *         [6]=reads the tiled segmentation handed to its serial kernel [7]=reads with status != DNB_READ_OK */
-DNB_API int dnb_batch_timings(dnb_batch *batch, double ms[6], uint64_t counts[8]);
+DNB_API int dnb_batch_timings(dnb_batch *batch, double ms[8], uint64_t counts[8]);
 
 /* ---- detect_events drop-in (src/scrappie/event_detection.h:35) ------------------------------ */
 /* raw_pA: n float32-exact samples.  events: caller array of capacity cap; *n_events receives event_table.n. */

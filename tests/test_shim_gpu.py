@@ -81,33 +81,28 @@ def test_shim_detect_events_and_probability(shim, ref_oracle, pore_mean):
     assert L.dnbref_normalPDF(0.1, 0.14, 0.3) == R.dnbref_normalPDF(0.1, 0.14, 0.3)
 
 
-def test_shim_ll_across_read_matches_reference(shim, ref_oracle, pore_mean):
+def test_shim_ll_across_read_matches_reference(shim, golden_reads, golden_reference):
+    """llAcrossRead through the shim on golden read `read_index` (built by the reference's own read constructor from the
+    SAM fields) against the LLRs the unmodified reference produced for it (tests/golden/hmm_v1.npz; the fixture holds
+    the unlabelled / BrdU table rows this read touches)."""
     import os
-    h = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hmm_v1.npz"))
     from oracle import refbind
+    h = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hmm_v1.npz"))
     for name_m, name_s, which in (("unl_mean", "unl_stdv", refbind.UNLABELLED), ("ana_mean", "ana_stdv", refbind.ANALOGUE)):
         m, s = np.zeros(4 ** 9), np.zeros(4 ** 9)
         m[h["ranks"]] = h[name_m]
         s[h["ranks"]] = h[name_s]
         shim.set_model(which, m, s)
-        ref_oracle.set_model(which, m, s)
-    shim.shutdown()                                  # context reloads the tables on next use
-    ref = synth.make_reference(120_000, 35)
-    shim.set_reference(ref)
-    ref_oracle.set_reference(ref)
-    reads = _reads(pore_mean, ref, 4, 36, lo=3000, hi=6000)
-    hs = [shim.read_new(r) for r in reads]
-    hr = [ref_oracle.read_new(r) for r in reads]
+    shim.shutdown()                                  # the context reloads the three tables on next use
+    shim.set_reference(golden_reference)
+    g = golden_reads[int(h["read_index"])]
+    hs = [shim.read_new(g)]
     shim.normalise_batch(hs)
-    calls = shim.ll_across_read_batch(hs, 12)
-    n_sites = 0
-    for (pos, llr), b in zip(calls, hr):
-        b.normalise(staged=False)
-        if b.outputs(staged=False)["align_event"].size == 0:
-            assert pos.size == 0
-            continue
-        rpos, rllr = b.ll_across_read(12)
-        np.testing.assert_array_equal(pos, rpos)
-        np.testing.assert_allclose(llr, rllr, rtol=1e-4, atol=1e-6)    # BASELINE.json tolerance for the HMM path
-        n_sites += pos.size
-    assert n_sites > 500
+    np.testing.assert_array_equal(hs[0].outputs(staged=False)["align_event"], g.align[:, 0])
+    (pos, llr), = shim.ll_across_read_batch(hs, 12)
+    np.testing.assert_array_equal(pos, h["pos_global"])
+    np.testing.assert_allclose(llr, h["llr"], rtol=1e-4, atol=1e-6)     # BASELINE.json tolerance for the HMM path
+    # the one-read signature llAcrossRead(r, 12) (detect.cpp:883) gives the same calls
+    pos1, llr1 = hs[0].ll_across_read(12)
+    np.testing.assert_array_equal(pos1, pos)
+    np.testing.assert_array_equal(llr1, llr)

@@ -1,4 +1,4 @@
-// banded_dp.cu -- adaptive banded event-to-k-mer alignment: band fill (one warp per read) and backtrace/QC.
+// banded_dp.cu -- adaptive banded event-to-k-mer alignment: band fill and backtrace/QC, one warp per read, one kernel.
 //
 // Replaces (reference, paths relative to /root/reference):
 //   logProbabilityMatch                          src/event_handling.cpp:116-137
@@ -151,7 +151,10 @@ __device__ __forceinline__ double cell_update(double diag, double up, double lef
             tb |= from << (2 * j);                                                                                \
         }                                                                                                         \
         rows[(size_t)b * DNB_TRACE_ROW + lane] = (uint8_t)tb;                                                     \
-        if ((b & 31) == 31) { if (lane == 0) moves[b >> 5] = mvword; mvword = 0; }                                \
+        if ((b & 31) == 31) {                                                                                     \
+            if (lane == 0) { moves[b >> 5] = mvword; rcum[b >> 5] = rights; }                                     \
+            rights += __popc(mvword); mvword = 0;                                                                 \
+        }                                                                                                         \
         /* end-cell candidate of this band: (event b-K-1, last k-mer) (event_handling.cpp:329-340) */            \
         {                                                                                                         \
             const int e = b - K - 1;                                                                              \
@@ -168,15 +171,14 @@ __device__ __forceinline__ double cell_update(double diag, double up, double lef
         b++;                                                                                                      \
     }
 
-__global__ void __launch_bounds__(DP_WARPS * 32) banded_dp_kernel(DnbBatchView v, DnbDpArgs a) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t slot = blockIdx.x * DP_WARPS + (threadIdx.x >> 5);
-    if (slot >= v.n_reads) return;
-    const uint32_t r = v.order[slot];
-    if (v.status[r] != 0) {
-        if (lane == 0) { a.end_event[r] = -1; a.end_ll_event[r] = 0; a.end_score[r] = -INFINITY; }
-        return;
-    }
+struct DpEnd {
+    int event;        // event index of the best end cell, -1 if none
+    int ll_event;     // band_lower_left.event_idx of that band
+    float score;
+};
+
+// Band fill of one read by one warp (event_handling.cpp:213-312 and the end-cell scan :321-340).
+__device__ __forceinline__ DpEnd dp_fill_warp(const DnbBatchView &v, const DnbDpArgs &a, uint32_t r, int lane) {
     const int E = (int)v.n_events[r];
     const int K = (int)(v.q_off[r + 1] - v.q_off[r]) - DNB_K + 1;
     const double *__restrict__ x = a.x_e + v.ev_off[r];
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32) banded_dp_kernel(DnbBatchView v
     c.emit_const = a.emit_const; c.inv_sigma = a.inv_sigma;
     uint8_t *rows = a.trace + a.band_off[r] * DNB_TRACE_ROW;
     uint32_t *moves = a.moves + (a.band_off[r] >> 5) + r;
+    uint32_t *rcum = a.rcum + (a.band_off[r] >> 5) + r;
     const int n_bands = E + K + 2;
 
     // ---- bands 0 and 1 (event_handling.cpp:213-228): A = band 0, B = band 1 ----
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32) banded_dp_kernel(DnbBatchView v
     double best_s = NEG_SENT;
     int best_e = 0x7fffffff, best_lle = 0;
     unsigned long long fills = 0;
-    uint32_t mvword = 0;
+    uint32_t mvword = 0, rights = 0;
 
     int b = 2;
     while (b + 1 < n_bands) {
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32) banded_dp_kernel(DnbBatchView v
         DP_BAND_STEP(A, B)      // band b+1 : P1 = A,       P2 = B       -> B becomes band b+1
     }
     if (b < n_bands) DP_BAND_STEP(B, A)
-    if (lane == 0 && (b & 31) != 0) moves[b >> 5] = mvword;
+    if (lane == 0 && (b & 31) != 0) { moves[b >> 5] = mvword; rcum[b >> 5] = rights; }
 
     // first event index attaining the maximum (strict '>' in ascending event order, :335)
     double gmax = best_s;
@@ -235,38 +238,37 @@ __global__ void __launch_bounds__(DP_WARPS * 32) banded_dp_kernel(DnbBatchView v
     const unsigned who = __ballot_sync(FULL, cand == gmin && gmin != 0x7fffffff);
     int lle = 0;
     if (who) lle = __shfl_sync(FULL, best_lle, __ffs(who) - 1);
-    if (lane == 0) {
-        if (gmin == 0x7fffffff) {
-            a.end_event[r] = -1; a.end_ll_event[r] = 0; a.end_score[r] = -INFINITY;
-            v.status[r] = DNB_READ_UNDEFINED;   // the reference would backtrace from an out-of-band cell
-        } else {
-            a.end_event[r] = gmin; a.end_ll_event[r] = lle; a.end_score[r] = (float)gmax;
-        }
-        atomicAdd(a.cells, fills);
-    }
+    if (lane == 0) atomicAdd(a.cells, fills);
+    DpEnd end;
+    if (gmin == 0x7fffffff) { end.event = -1; end.ll_event = 0; end.score = -INFINITY; }
+    else { end.event = gmin; end.ll_event = lle; end.score = (float)gmax; }
+    return end;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Backtrace + QC.  One warp per read: all lanes stage a 64-row window of the trace into shared memory with
-// 16-byte loads, lane 0 walks it (the walk is a serial pointer chase; the accumulations must keep the
-// reference's order: sum_emission adds floats into a double in walk order, vectorMean sums in push order).
+// Backtrace + QC of one read by one warp (event_handling.cpp:347-443).
+//
+// The walk itself is a serial pointer chase, but it only needs the 2-bit trace codes: lane 0 follows them through
+// a 64-band window of the trace staged in shared memory (<= 32 steps per round, nothing else on its dependency
+// chain).  Everything that hangs off the path is done by all lanes afterwards, one step per lane: the (event,
+// k-mer) coordinates come from prefix counts of the codes (D: -1,-1  U: -1,0  L: 0,-1), then the alignment pairs,
+// the emission of every aligned event, and for every diagonal step the k-mer's cleaned signal (mean of the event
+// means buffered since the previous diagonal step, summed in push order) and its reference rank.  Only two
+// quantities depend on the walk order through floating-point rounding or state, and both stay with lane 0:
+// sum_emission (float emissions added into a double in walk order; added one round late, from shared memory, in
+// the shadow of the next round's pointer chase) and the running gap length.
 // ---------------------------------------------------------------------------------------------------------------
-#define BT_WARPS 4
 #define BT_ROWS 64
+#define BT_STEPS 32
 
-__global__ void __launch_bounds__(BT_WARPS * 32) backtrace_kernel(DnbBatchView v, DnbBtArgs a) {
-    __shared__ __align__(16) uint8_t win[BT_WARPS][BT_ROWS * DNB_TRACE_ROW];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t slot = blockIdx.x * BT_WARPS + w;
-    if (slot >= v.n_reads) return;
-    const uint32_t r = v.order[slot];
-    if (v.status[r] != 0) {
-        if (lane == 0) {
-            a.n_align[r] = 0; a.n_cleaned[r] = 0; a.avg_log_emission[r] = 0.0; a.spanned[r] = 0; a.max_gap[r] = 0;
-        }
-        return;
-    }
-    const int E = (int)v.n_events[r];
+struct BtSmem {
+    __align__(16) uint8_t win[BT_ROWS * DNB_TRACE_ROW];
+    float lp[BT_STEPS];
+    uint8_t code[BT_STEPS];
+};
+
+__device__ __forceinline__ void backtrace_warp(const DnbBatchView &v, const DnbBtArgs &a, uint32_t r, int lane,
+                                               int end_event, BtSmem &sm) {
     const int K = (int)(v.q_off[r + 1] - v.q_off[r]) - DNB_K + 1;
     const uint32_t Kref = (uint32_t)((v.r_off[r + 1] - v.r_off[r]) - DNB_K + 1);
     const double *__restrict__ x = a.dp.x_e + v.ev_off[r];
@@ -276,87 +278,107 @@ __global__ void __launch_bounds__(BT_WARPS * 32) backtrace_kernel(DnbBatchView v
     const uint32_t *__restrict__ rr = a.rank_ref + v.r_off[r];
     const uint8_t *rows = a.dp.trace + a.dp.band_off[r] * DNB_TRACE_ROW;
     const uint32_t *moves = a.dp.moves + (a.dp.band_off[r] >> 5) + r;
-    uint32_t *pairs = a.al_pairs_rev + 2 * a.al_off[r];
+    const uint32_t *rcum = a.dp.rcum + (a.dp.band_off[r] >> 5) + r;
+    uint2 *pairs = reinterpret_cast<uint2 *>(a.al_pairs_rev) + a.al_off[r];
     double *cls = a.cl_signal + a.cl_off[r];
     uint32_t *clr = a.cl_rank + a.cl_off[r];
     const double emit_const = a.dp.emit_const;
-    (void)E;
+    const unsigned lt = (1u << lane) - 1u;
 
-    int e = a.dp.end_event[r], k = K - 1, lle = a.dp.end_ll_event[r];
-    double sum_em = 0.0, n_aligned = 0.0, buf_total = 0.0;
-    uint32_t buf_n = 0, na = 0, nc = 0;
-    int gap = 0, max_gap = 0, last_k = -1;
-    bool bad = false, done = false;
-    int mv_idx = -1;
-    uint32_t mv_cur = 0;
+    int e = end_event, k = K - 1;          // warp-uniform position of the walk
+    int e_prev_d = e + 1;                  // event of the previous diagonal step (+1 before the first: empty buffer)
+    uint32_t na = 0, nc = 0;
+    int last_k = -1;
+    bool bad = false;
+    // lane 0 only
+    double sum_em = 0.0;
+    int gap = 0, max_gap = 0, n_prev = 0;
 
-    while (!done) {
+    while (k >= 0 && e >= 0) {
         const int hi = e + k + 2;
         const int lo = max(hi - (BT_ROWS - 1), 0);
-        const int nrows = hi - lo + 1;
-        // stage rows [lo, hi]
-        const uint4 *src = reinterpret_cast<const uint4 *>(rows + (size_t)lo * DNB_TRACE_ROW);
-        uint4 *dst = reinterpret_cast<uint4 *>(win[w]);
+        {   // stage rows [lo, hi]
+            const uint4 *src = reinterpret_cast<const uint4 *>(rows + (size_t)lo * DNB_TRACE_ROW);
+            uint4 *dst = reinterpret_cast<uint4 *>(sm.win);
+            const int n16 = (hi - lo + 1) * (DNB_TRACE_ROW / 16);
 #pragma unroll
-        for (int i = 0; i < (BT_ROWS * DNB_TRACE_ROW / 16) / 32; i++) {
-            const int c = lane + 32 * i;
-            if ((c >> 1) < nrows) dst[c] = src[c];
+            for (int i = 0; i < (BT_ROWS * DNB_TRACE_ROW / 16) / 32; i++) {
+                const int q = lane + 32 * i;
+                if (q < n16) dst[q] = src[q];
+            }
         }
         __syncwarp();
+        int ns = 0;
         if (lane == 0) {
-            const uint8_t *wb = win[w];
-            while (k >= 0 && e >= 0) {
-                const int b = e + k + 2;
-                if (b - 1 < lo) break;                         // next window
-                pairs[2 * na] = (uint32_t)e; pairs[2 * na + 1] = (uint32_t)k; na++;       // :359
-                last_k = k;
-                const float lp = emission_static(x[e], mu[k], emit_const);                // :363
-                sum_em = dAdd(sum_em, (double)lp);
-                n_aligned = dAdd(n_aligned, 1.0);
-                const int off = lle - e;
-                if (off < 0 || off >= DNB_BW) { bad = true; break; }
-                const uint8_t *row = wb + (size_t)(b - lo) * DNB_TRACE_ROW;
-                const int sl = e & 127;                        // rows are indexed by event slot
-                const uint32_t from = (row[sl >> 2] >> (2 * (sl & 3))) & 3u;
-                if ((b >> 5) != mv_idx) { mv_idx = b >> 5; mv_cur = moves[mv_idx]; }
-                const int down_b = ((mv_cur >> (b & 31)) & 1u) ? 0 : 1;   // band b was placed by a down move
-                if (from == DNB_FROM_D) {
-                    buf_total = dAdd(buf_total, (double)evm[e]); buf_n++;
-                    const int32_t qr = q2r[k];
-                    if (qr >= 0 && (uint32_t)qr < Kref) {                                 // :386-393
-                        clr[nc] = rr[qr];
-                        cls[nc] = dDiv(buf_total, (double)buf_n);                         // vectorMean, common.h:184
-                        nc++;
-                    }
-                    buf_total = 0.0; buf_n = 0;
-                    const uint32_t w1 = ((b - 1) >> 5) == mv_idx ? mv_cur : moves[(b - 1) >> 5];
-                    const int down_b1 = ((w1 >> ((b - 1) & 31)) & 1u) ? 0 : 1;
-                    lle -= down_b + down_b1;
-                    k--; e--; gap = 0;
-                } else if (from == DNB_FROM_U) {
-                    buf_total = dAdd(buf_total, (double)evm[e]); buf_n++;
-                    lle -= down_b;
-                    e--; gap = 0;
-                } else {
-                    lle -= down_b;
-                    k--; gap++;
-                    max_gap = max(max_gap, gap);
-                }
+            int ee = e, kk = k;
+            while (ns < BT_STEPS && kk >= 0 && ee >= 0) {
+                const int bb = ee + kk + 2;
+                const uint32_t code = (sm.win[(bb - lo) * DNB_TRACE_ROW + ((ee & 127) >> 2)] >> (2 * (ee & 3))) & 3u;
+                sm.code[ns] = (uint8_t)code;
+                if (ns < n_prev) sum_em = dAdd(sum_em, (double)sm.lp[ns]);     // previous round's emissions, in order
+                ee -= (code != DNB_FROM_L);
+                kk -= (code != DNB_FROM_U);
+                gap = (code == DNB_FROM_L) ? gap + 1 : 0;
+                max_gap = max(max_gap, gap);
+                ns++;
             }
-            if (bad || k < 0 || e < 0) done = true;
+            for (int t = ns; t < n_prev; t++) sum_em = dAdd(sum_em, (double)sm.lp[t]);
+            n_prev = ns;
         }
-        done = __shfl_sync(FULL, done, 0);
-        e = __shfl_sync(FULL, e, 0);
-        k = __shfl_sync(FULL, k, 0);
+        ns = __shfl_sync(FULL, ns, 0);
+        __syncwarp();
+
+        // ---- one step per lane ----
+        const bool act = lane < ns;
+        const uint32_t code = act ? sm.code[lane] : 3u;
+        const unsigned m_e = __ballot_sync(FULL, act && code != DNB_FROM_L);
+        const unsigned m_k = __ballot_sync(FULL, act && code != DNB_FROM_U);
+        const unsigned m_d = __ballot_sync(FULL, act && code == DNB_FROM_D);
+        const int ei = e - __popc(m_e & lt), ki = k - __popc(m_k & lt);
+        if (act) {
+            // the cell must lie inside its band (the reference would index trace[][] out of range otherwise)
+            const int bi = ei + ki + 2;
+            const uint32_t w = moves[bi >> 5];
+            const int rights = (int)rcum[bi >> 5] + __popc(w & ((2u << (bi & 31)) - 1u));
+            const int off = DNB_BW / 2 + (bi - 1) - rights - ei;
+            if (off < 0 || off >= DNB_BW) bad = true;
+            pairs[na + lane] = make_uint2((uint32_t)ei, (uint32_t)ki);                         // :359
+            sm.lp[lane] = emission_static(x[ei], mu[ki], emit_const);                          // :363
+        }
+        // previous diagonal step: inside this round or carried over
+        const unsigned pm = m_d & lt;
+        const int e_round = __shfl_sync(FULL, ei, pm ? 31 - __clz(pm) : 0);
+        const int e_p = pm ? e_round : e_prev_d;
+        const bool is_d = act && code == DNB_FROM_D;
+        int32_t qr = -1;
+        if (is_d) qr = q2r[ki];
+        const bool emit = is_d && qr >= 0 && (uint32_t)qr < Kref;                              // :386-393
+        const unsigned m_out = __ballot_sync(FULL, emit);
+        if (emit) {
+            double tot = 0.0;
+            for (int j = e_p - 1; j >= ei; j--) tot = dAdd(tot, (double)evm[j]);               // push order
+            const uint32_t idx = nc + __popc(m_out & lt);
+            cls[idx] = dDiv(tot, (double)(uint32_t)(e_p - ei));                                // vectorMean, common.h:184
+            clr[idx] = rr[qr];
+        }
+        nc += __popc(m_out);
+        if (m_d) e_prev_d = __shfl_sync(FULL, ei, 31 - __clz(m_d));
+        if (ns > 0) last_k = __shfl_sync(FULL, ki, ns - 1);
+        na += ns;
+        e -= __popc(m_e);
+        k -= __popc(m_k);
+        if (__any_sync(FULL, bad)) { bad = true; break; }
         __syncwarp();
     }
+    __syncwarp();
     if (lane == 0) {
         if (bad) {
             v.status[r] = DNB_READ_UNDEFINED;
             a.n_align[r] = 0; a.n_cleaned[r] = 0; a.avg_log_emission[r] = 0.0; a.spanned[r] = 0; a.max_gap[r] = 0;
             return;
         }
-        const double avg = dDiv(sum_em, n_aligned);                                        // :420
+        for (int t = 0; t < n_prev; t++) sum_em = dAdd(sum_em, (double)sm.lp[t]);
+        const double avg = dDiv(sum_em, (double)na);                                       // :420 (n_aligned counts steps)
         const bool spanned = na > 0 && last_k == 0;     // front().second == 0; back().second == K-1 holds by construction
         a.avg_log_emission[r] = avg;
         a.spanned[r] = spanned ? 1 : 0;
@@ -366,6 +388,47 @@ __global__ void __launch_bounds__(BT_WARPS * 32) backtrace_kernel(DnbBatchView v
         if (!fail && nc < 1000) fail = true;                                                // :438
         if (fail) { v.status[r] = DNB_READ_QC_FAIL; a.n_align[r] = 0; }
         else a.n_align[r] = na;
+    }
+}
+
+// kMode 0: fill + backtrace (production)   1: fill only   2: backtrace only (the split pair is for profiling the two
+// phases as separate launches; same device code)
+template <int kMode>
+__global__ void __launch_bounds__(DP_WARPS * 32) align_kernel(DnbBatchView v, DnbBtArgs a) {
+    __shared__ BtSmem sm[kMode == 1 ? 1 : DP_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t slot = blockIdx.x * DP_WARPS + w;
+    if (slot >= v.n_reads) return;
+    const uint32_t r = v.order[slot];
+    if (v.status[r] != 0) {
+        if (lane == 0 && kMode != 2) { a.dp.end_event[r] = -1; a.dp.end_ll_event[r] = 0; a.dp.end_score[r] = -INFINITY; }
+        if (lane == 0 && kMode != 1) {
+            a.n_align[r] = 0; a.n_cleaned[r] = 0; a.avg_log_emission[r] = 0.0; a.spanned[r] = 0; a.max_gap[r] = 0;
+        }
+        return;
+    }
+    int end_event;
+    if (kMode != 2) {
+        const long long t0 = clock64();
+        const DpEnd end = dp_fill_warp(v, a.dp, r, lane);
+        if (lane == 0) {
+            a.dp.end_event[r] = end.event; a.dp.end_ll_event[r] = end.ll_event; a.dp.end_score[r] = end.score;
+            if (end.event < 0) v.status[r] = DNB_READ_UNDEFINED;   // the reference would backtrace from an out-of-band cell
+            atomicAdd(&a.phase_cycles[0], (unsigned long long)(clock64() - t0));
+        }
+        end_event = end.event;
+        __syncwarp();      // the trace rows written above are read back by other lanes below
+    } else {
+        end_event = a.dp.end_event[r];
+    }
+    if (kMode != 1) {
+        if (end_event < 0) {
+            if (lane == 0) { a.n_align[r] = 0; a.n_cleaned[r] = 0; a.avg_log_emission[r] = 0.0; a.spanned[r] = 0; a.max_gap[r] = 0; }
+            return;
+        }
+        const long long t1 = clock64();
+        backtrace_warp(v, a, r, lane, end_event, sm[kMode == 1 ? 0 : w]);
+        if (lane == 0) atomicAdd(&a.phase_cycles[1], (unsigned long long)(clock64() - t1));
     }
 }
 
@@ -380,14 +443,12 @@ __global__ void compact_alignment_kernel(DnbBatchView v, const uint64_t *al_off,
 
 }  // namespace
 
-void dnb_launch_banded_dp(const DnbBatchView &v, const DnbDpArgs &a, cudaStream_t s) {
+void dnb_launch_align(const DnbBatchView &v, const DnbBtArgs &a, int mode, cudaStream_t s) {
     if (v.n_reads == 0) return;
-    banded_dp_kernel<<<(v.n_reads + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, s>>>(v, a);
-}
-
-void dnb_launch_backtrace(const DnbBatchView &v, const DnbBtArgs &a, cudaStream_t s) {
-    if (v.n_reads == 0) return;
-    backtrace_kernel<<<(v.n_reads + BT_WARPS - 1) / BT_WARPS, BT_WARPS * 32, 0, s>>>(v, a);
+    const unsigned grid = (v.n_reads + DP_WARPS - 1) / DP_WARPS;
+    if (mode == 0) align_kernel<0><<<grid, DP_WARPS * 32, 0, s>>>(v, a);
+    else if (mode == 1) align_kernel<1><<<grid, DP_WARPS * 32, 0, s>>>(v, a);
+    else align_kernel<2><<<grid, DP_WARPS * 32, 0, s>>>(v, a);
 }
 
 void dnb_launch_compact_alignment(const DnbBatchView &v, const uint64_t *al_off, const uint32_t *al_pairs_rev,

@@ -121,12 +121,12 @@ struct DnbDpArgs {
     const uint64_t *band_off;     // [R+1] band-row offsets
     uint8_t *trace;               // [band_off[R]] rows of DNB_TRACE_ROW bytes: 2-bit code of slot s at bits 2*(s&3) of byte s>>2
     uint32_t *moves;              // [band_off[R]/32 + R + 1] move bits (1 = right), read r starts at band_off[r]/32 + r
+    uint32_t *rcum;               // same indexing: right moves in the bands before each 32-band word
     int32_t *end_event;           // [R] event index of the best end cell, -1 if none
     int32_t *end_ll_event;        // [R] band_lower_left.event_idx of that band
     float *end_score;             // [R]
     unsigned long long *cells;    // [1] total DP cells filled (the reference's `fills`)
 };
-void dnb_launch_banded_dp(const DnbBatchView &v, const DnbDpArgs &a, cudaStream_t s);
 
 struct DnbBtArgs {
     DnbDpArgs dp;
@@ -142,8 +142,10 @@ struct DnbBtArgs {
     int *spanned, *max_gap;       // [R]
     double min_avg_log_emission;
     int max_gap_threshold;
+    unsigned long long *phase_cycles;   // [2] summed warp cycles spent in the band fill / in the backtrace
 };
-void dnb_launch_backtrace(const DnbBatchView &v, const DnbBtArgs &a, cudaStream_t s);
+// mode 0: band fill + backtrace in one launch; 1: band fill only; 2: backtrace only
+void dnb_launch_align(const DnbBatchView &v, const DnbBtArgs &a, int mode, cudaStream_t s);
 
 struct DnbTsArgs {
     const uint64_t *cl_off;

@@ -331,6 +331,31 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_serial_kernel(DnbBatchView v,
 }
 
 // ---- K1: exact (sum, sumsq) checkpoints every DNB_SEG_CK samples, one lane per read ------------------------------------
+// The two chains cost 3 flops per sample but are serial, so this kernel is a latency machine: a lane may not wait
+// for memory.  Samples come in 16-byte vectors, one group (32 samples) ahead in registers, and the lines of the
+// groups after that are pulled into L2 with prefetch instructions ~2 KB ahead of the chain.
+#define CK_GROUP 32   // samples per register group
+
+template <bool kI16>
+struct CkGroup {
+    uint4 q[kI16 ? CK_GROUP / 8 : CK_GROUP / 4];
+    __device__ __forceinline__ void load(const SampleReader<kI16> &rd, uint64_t idx) {
+        const uint4 *p = kI16 ? reinterpret_cast<const uint4 *>(rd.i16 + idx) : reinterpret_cast<const uint4 *>(rd.f32 + idx);
+#pragma unroll
+        for (int i = 0; i < (kI16 ? CK_GROUP / 8 : CK_GROUP / 4); i++) q[i] = __ldg(p + i);
+    }
+    __device__ __forceinline__ float get(const SampleReader<kI16> &rd, int i) const {
+        if (kI16) {
+            const uint32_t w = (&q[i >> 3].x)[(i >> 1) & 3];
+            const short sv = (short)((i & 1) ? (w >> 16) : (w & 0xffffu));
+            return fMul(fAdd((float)sv, rd.dac_off), rd.dac_scl);                       // src/pod5.cpp:60
+        }
+        return __uint_as_float((&q[i >> 2].x)[i & 3]);
+    }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <bool kI16>
 __global__ void __launch_bounds__(128) seg_checkpoint_kernel(DnbBatchView v, DnbSegTiles t) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,22 +366,32 @@ __global__ void __launch_bounds__(128) seg_checkpoint_kernel(DnbBatchView v, Dnb
     SampleReader<kI16> rd{v.raw_f32, v.raw_i16, 0.f, 1.f};
     if (kI16) { rd.dac_off = v.dac_offset[r]; rd.dac_scl = v.dac_scale[r]; }
     double *cs = t.ck_sum + t.ck_off[r], *cq = t.ck_sq + t.ck_off[r];
+    const char *bytes = kI16 ? reinterpret_cast<const char *>(rd.i16 + base) : reinterpret_cast<const char *>(rd.f32 + base);
+    const uint32_t group_bytes = CK_GROUP * (kI16 ? 2 : 4);
+    const uint64_t total_bytes = (uint64_t)N * (kI16 ? 2 : 4);
+    const uint32_t pf_ahead = 2048;
     double sum = 0.0, sumsq = 0.0;
-    const uint32_t n4 = N & ~3u;
-    float cur[4], nxt[4] = {0.f, 0.f, 0.f, 0.f};
-    if (n4) rd.four(base, cur);
-    for (uint32_t j = 0; j < n4; j += 4) {
-        if (j + 4 < n4) rd.four(base + j + 4, nxt);
+    const uint32_t ng = N / CK_GROUP;
+    for (uint32_t o = 0; o < pf_ahead && o < total_bytes; o += 128) prefetch_l2(bytes + o);
+    CkGroup<kI16> cur, nxt;
+    if (ng) cur.load(rd, base);
+    for (uint32_t g = 0; g < ng; g++) {
+        if (g + 1 < ng) nxt.load(rd, base + (uint64_t)(g + 1) * CK_GROUP);
+        {
+            const uint64_t o = (uint64_t)g * group_bytes + pf_ahead;
+            if ((o & 127) == 0 && o < total_bytes) prefetch_l2(bytes + o);
+        }
+        const uint32_t j = g * CK_GROUP;
         if ((j & (DNB_SEG_CK - 1)) == 0) { cs[j / DNB_SEG_CK] = sum; cq[j / DNB_SEG_CK] = sumsq; }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const double x = (double)cur[u];
-            sum = dAdd(sum, x);
-            sumsq = dAdd(sumsq, dMul(x, x));
+        for (int u = 0; u < CK_GROUP; u++) {
+            const double x = (double)cur.get(rd, u);
+            sum = dAdd(sum, x);                  // event_detection.c:45
+            sumsq = dAdd(sumsq, dMul(x, x));     // :46 (x*x is exact for a float-valued x)
         }
-        cur[0] = nxt[0]; cur[1] = nxt[1]; cur[2] = nxt[2]; cur[3] = nxt[3];
+        cur = nxt;
     }
-    for (uint32_t j = n4; j < N; j++) {
+    for (uint32_t j = ng * CK_GROUP; j < N; j++) {
         if ((j & (DNB_SEG_CK - 1)) == 0) { cs[j / DNB_SEG_CK] = sum; cq[j / DNB_SEG_CK] = sumsq; }
         const double x = (double)rd.one(base + j);
         sum = dAdd(sum, x);
@@ -404,29 +439,59 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_tile_kernel(DnbBatchView v, D
     t.b_end[g] = en.boundary(t1);
 }
 
-// ---- K3: stitch the tiles of a read -----------------------------------------------------------------------------------
+// ---- K3: stitch the tiles of a read, one warp per read ---------------------------------------------------------------
 __global__ void __launch_bounds__(128) seg_stitch_kernel(DnbBatchView v, DnbSegTiles t) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (slot >= v.n_reads) return;
     const uint32_t r = v.order[slot];
     const uint32_t g0 = t.tile_off[r], g1 = t.tile_off[r + 1];
     bool bad = false;
     uint32_t prefix = 0, last_pos = 0;
     double last_sum = 0.0;
-    for (uint32_t g = g0; g < g1; g++) {
-        if (g > g0 && !same_boundary(t.b_start[g], t.b_end[g - 1])) bad = true;
-        const uint32_t c = t.pk_count[g];
-        if (c > DNB_SEG_PEAK_CAP) bad = true;
-        if (bad) break;
-        t.tile_prefix[g] = prefix;
-        t.tile_prev_pos[g] = last_pos;
-        t.tile_prev_sum[g] = last_sum;
-        if (c > 0) {
-            last_pos = t.pk_pos[(size_t)g * DNB_SEG_PEAK_CAP + c - 1];
-            last_sum = t.pk_sum[(size_t)g * DNB_SEG_PEAK_CAP + c - 1];
+    for (uint32_t gb = g0; gb < g1 && !bad; gb += 32) {
+        const uint32_t g = gb + lane;
+        const bool ok = g < g1;
+        uint32_t c = 0;
+        bool mism = false;
+        if (ok) {
+            c = t.pk_count[g];
+            if (g > g0 && !same_boundary(t.b_start[g], t.b_end[g - 1])) mism = true;
+            if (c > DNB_SEG_PEAK_CAP) mism = true;
         }
-        prefix += c;
+        if (__any_sync(0xffffffffu, mism)) { bad = true; break; }
+        // exclusive prefix of the peak counts; last peak (pos, sum) before each tile = that of the nearest earlier
+        // tile with a peak
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const unsigned has = __ballot_sync(0xffffffffu, ok && c > 0);
+        uint32_t my_pos = 0;
+        double my_sum = 0.0;
+        if (ok && c > 0) {
+            my_pos = t.pk_pos[(size_t)g * DNB_SEG_PEAK_CAP + c - 1];
+            my_sum = t.pk_sum[(size_t)g * DNB_SEG_PEAK_CAP + c - 1];
+        }
+        const unsigned before = has & ((1u << lane) - 1u);
+        const int src = before ? 31 - __clz(before) : 0;
+        const uint32_t p_pos = __shfl_sync(0xffffffffu, my_pos, src);
+        const double p_sum = __shfl_sync(0xffffffffu, my_sum, src);
+        if (ok) {
+            t.tile_prefix[g] = prefix + incl - c;
+            t.tile_prev_pos[g] = before ? p_pos : last_pos;
+            t.tile_prev_sum[g] = before ? p_sum : last_sum;
+        }
+        if (has) {
+            const int top = 31 - __clz(has);
+            last_pos = __shfl_sync(0xffffffffu, my_pos, top);
+            last_sum = __shfl_sync(0xffffffffu, my_sum, top);
+        }
+        prefix += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane != 0) return;
     const uint32_t cap = (uint32_t)(v.ev_off[r + 1] - v.ev_off[r]);
     int status = DNB_READ_OK;
     t.redo[r] = bad ? 1u : 0u;
@@ -505,7 +570,7 @@ void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const
         seg_checkpoint_kernel<false><<<gr, 128, 0, s>>>(v, t);
         seg_tile_kernel<false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
     }
-    seg_stitch_kernel<<<gr, 128, 0, s>>>(v, t);
+    seg_stitch_kernel<<<(v.n_reads + 3) / 4, 128, 0, s>>>(v, t);
     seg_events_kernel<<<(t.n_tiles + 3) / 4, 128, 0, s>>>(v, t);
     dnb_launch_segmentation_serial(v, det, t.redo, s);
 }

@@ -2,15 +2,22 @@
 //
 // Replaces estimateScaling_theilSen, /root/reference/src/event_handling.cpp:24-110.
 // The reference materialises <= 499 500 slopes and std::sorts them (4 MB, 58 ms per read).  Here the <= 1000
-// (x, y) points sit in shared memory and the median is found by an exact 8 x 8-bit radix select over the
-// order-preserving 64-bit image of the slopes, recomputing the IEEE divisions in every pass; nothing is
-// spilled to HBM.  A pass votes per warp first (in the leading passes every slope shares its digit), so the
-// shared-memory histogram sees one atomic per warp instead of 32 on the same address.
+// (x, y) points sit in shared memory and nothing is spilled to HBM.  The median is an exact order statistic, found
+// by narrowing the order-preserving 64-bit image of the slopes 12 bits at a time:
+//   level 0   histogram of the top 12 bits (sign + exponent) over all pairs        -> the bin holding rank ns/2
+//   level 1   histogram of the next 12 bits, over the pairs inside that bin         -> a bin of a few hundred slopes
+//   collect   the slopes of that bin are gathered into shared memory and the wanted rank is picked by counting
+// Further 12-bit levels are run only while the bin still holds more slopes than the candidate buffer (ties by the
+// thousand), so a read costs three sweeps over its pairs (IEEE divisions recomputed in each) instead of the eight
+// 8-bit sweeps of the first version (profiles/r1_captureA: 10 us per read).  Pairs are enumerated circulantly
+// (round d pairs point i with point i+d), which keeps the shared-memory reads of a warp on consecutive addresses.
 #include "dnb_internal.cuh"
 #include "../../include/dnascent_b200.h"
 
 #define TS_THREADS 256
 #define TS_MAXP 1000
+#define TS_BINS 4096            // 12-bit digits
+#define TS_CAND 2048            // candidate buffer (64-bit keys); shares storage with the histogram
 #define FULL 0xffffffffu
 
 namespace {
@@ -26,7 +33,8 @@ __device__ __forceinline__ double key_to_double(unsigned long long k) {
 }
 
 __device__ __forceinline__ void hist_add(uint32_t *hist, uint32_t d, bool active) {
-    // warp-aggregated increment for the digit of the first active lane, plain atomics for the rest
+    // warp-aggregated increment for the digit of the first active lane (at level 0 every slope shares it), plain
+    // shared-memory atomics for the rest
     const unsigned act = __ballot_sync(FULL, active);
     if (act == 0) return;
     const int leader = __ffs(act) - 1;
@@ -36,83 +44,127 @@ __device__ __forceinline__ void hist_add(uint32_t *hist, uint32_t d, bool active
     if (active && d != d0) atomicAdd(&hist[d], 1u);
 }
 
-// k-th smallest (0-based) of a multiset enumerated cooperatively by the CTA: `make()` returns a per-thread
-// enumerator whose next(key) yields this thread's items (every thread is stepped `rounds` times so the
-// warp votes in hist_add stay convergent).
-template <class Make>
-__device__ unsigned long long radix_select64(Make make, uint32_t rounds, uint32_t kth, uint32_t *hist,
-                                             unsigned long long *sh_prefix, uint32_t *sh_rem) {
-    const int tid = threadIdx.x;
-    if (tid == 0) { *sh_prefix = 0ull; *sh_rem = kth; }
-    __syncthreads();
-    for (int level = 0; level < 8; level++) {
-        const int shift = 56 - 8 * level;
-        const unsigned long long himask = level == 0 ? 0ull : (~0ull << (shift + 8));
-        const unsigned long long prefix = *sh_prefix;
-        hist[tid] = 0;   // TS_THREADS == 256 bins
-        __syncthreads();
-        auto en = make();
-        for (uint32_t it = 0; it < rounds; it++) {
+struct TsShared {
+    double x[TS_MAXP], y[TS_MAXP];
+    union {
+        uint32_t hist[TS_BINS];
+        unsigned long long cand[TS_CAND];
+    } u;
+    unsigned long long prefix;   // key bits decided so far
+    uint32_t rank;               // wanted rank inside the current bin
+    uint32_t count;              // slopes inside the current bin
+    uint32_t n_cand;
+    unsigned long long answer;
+};
+
+// visits every unordered pair once; f(key) is called by all lanes of a warp together (ok == false for padding lanes)
+template <class F>
+__device__ __forceinline__ void for_each_slope(const TsShared &sm, uint32_t np, F f) {
+    const uint32_t full_rounds = (np - 1) / 2;
+    const uint32_t lane_base = threadIdx.x;
+    for (uint32_t d = 1; d <= full_rounds; d++) {
+        for (uint32_t base = 0; base < np; base += TS_THREADS) {
+            const uint32_t i = base + lane_base;
+            const bool ok = i < np;
             unsigned long long key = 0;
-            bool active = en.next(key);
-            active = active && (key & himask) == prefix;
-            hist_add(hist, (uint32_t)(key >> shift) & 0xFFu, active);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t rem = *sh_rem, d = 0;
-            for (; d < 255; d++) {
-                const uint32_t c = hist[d];
-                if (rem < c) break;
-                rem -= c;
+            if (ok) {
+                uint32_t j = i + d;
+                if (j >= np) j -= np;
+                // oriented lower index first, exactly as the reference's nested loop (:67-75): dx, dy and the signed
+                // zero of dy/dx are the reference's
+                const uint32_t lo = min(i, j), hi = max(i, j);
+                key = order_key(dDiv(dSub(sm.y[lo], sm.y[hi]), dSub(sm.x[lo], sm.x[hi])));
             }
-            *sh_prefix = prefix | ((unsigned long long)d << shift);
-            *sh_rem = rem;
+            f(key, ok);
         }
-        __syncthreads();
     }
-    return *sh_prefix;
+    if ((np & 1u) == 0) {   // even np: the half round d = np/2 pairs i < np/2 with i + np/2
+        const uint32_t d = np / 2;
+        for (uint32_t base = 0; base < d; base += TS_THREADS) {
+            const uint32_t i = base + lane_base;
+            const bool ok = i < d;
+            unsigned long long key = 0;
+            if (ok) key = order_key(dDiv(dSub(sm.y[i], sm.y[i + d]), dSub(sm.x[i], sm.x[i + d])));
+            f(key, ok);
+        }
+    }
 }
 
-// All unordered pairs {i, j} of np points, circulant order: round d = 1..(np-1)/2 pairs i with (i+d) mod np; for even
-// np a final half round d = np/2 with i < np/2.  Each pair is oriented (lower index first) exactly as the reference's
-// nested loop (event_handling.cpp:67-75), so dx, dy and the signed zero of dy/dx are the reference's.
-struct PairEnum {
-    const double *x, *y;
-    uint32_t np, d, i, full_rounds;
-    __device__ bool next(unsigned long long &key) {
-        while (i >= np) { i -= np; d++; }
-        const bool in_full = d <= full_rounds;
-        const bool in_half = (np % 2 == 0) && d == np / 2 && i < np / 2;
-        bool ok = in_full || in_half;
-        if (ok) {
-            uint32_t j = i + d;
-            if (j >= np) j -= np;
-            const uint32_t lo = min(i, j), hi = max(i, j);
-            key = order_key(dDiv(dSub(y[lo], y[hi]), dSub(x[lo], x[hi])));
+// rank-th smallest (0-based) of the n keys in sm.u.cand: every thread ranks its candidates by counting
+__device__ __forceinline__ void select_among_candidates(TsShared &sm, uint32_t n, uint32_t rank) {
+    for (uint32_t c = threadIdx.x; c < n; c += TS_THREADS) {
+        const unsigned long long mine = sm.u.cand[c];
+        uint32_t less = 0, equal = 0;
+        for (uint32_t t = 0; t < n; t++) {
+            const unsigned long long o = sm.u.cand[t];
+            less += o < mine;
+            equal += o == mine;
         }
-        i += TS_THREADS;
-        return ok;
+        if (less <= rank && rank < less + equal) sm.answer = mine;   // every writer holds the same value
     }
-};
+    __syncthreads();
+}
 
-struct IcptEnum {
-    const double *x, *y;
-    double slope;
-    uint32_t np, i;
-    __device__ bool next(unsigned long long &key) {
-        const bool ok = i < np;
-        if (ok) key = order_key(dSub(y[i], dMul(slope, x[i])));   // :83, not fused
-        i += TS_THREADS;
-        return ok;
+// exact k-th smallest slope over all pairs
+__device__ unsigned long long select_slope(TsShared &sm, uint32_t np, uint32_t kth) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { sm.prefix = 0ull; sm.rank = kth; sm.count = np * (np - 1) / 2; }
+    __syncthreads();
+    for (int level = 0; level < 6; level++) {
+        const int shift = level < 5 ? 52 - 12 * level : 0;            // digits: bits 63-52, 51-40, 39-28, 27-16, 15-4, 3-0
+        const uint32_t dmask = level < 5 ? 0xFFFu : 0xFu;
+        const unsigned long long himask = level == 0 ? 0ull : (~0ull << (level < 5 ? shift + 12 : 4));
+        const unsigned long long prefix = sm.prefix;
+        if (level > 0 && sm.count <= TS_CAND) {
+            // few enough slopes share the decided bits: gather them and finish
+            if (tid == 0) sm.n_cand = 0;
+            __syncthreads();
+            for_each_slope(sm, np, [&](unsigned long long key, bool ok) {
+                if (ok && (key & himask) == prefix) sm.u.cand[atomicAdd(&sm.n_cand, 1u)] = key;
+            });
+            __syncthreads();
+            select_among_candidates(sm, sm.n_cand, sm.rank);
+            return sm.answer;
+        }
+        for (int i = tid; i < TS_BINS; i += TS_THREADS) sm.u.hist[i] = 0;
+        __syncthreads();
+        for_each_slope(sm, np, [&](unsigned long long key, bool ok) {
+            hist_add(sm.u.hist, (uint32_t)(key >> shift) & dmask, ok && (key & himask) == prefix);
+        });
+        __syncthreads();
+        if (tid < 32) {
+            // warp 0 finds the bin holding the wanted rank: per-lane partial sums over 128-bin stripes, then a scan
+            const uint32_t per = TS_BINS / 32;
+            uint32_t sum = 0;
+            for (uint32_t q = 0; q < per; q++) sum += sm.u.hist[tid * per + q];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (tid >= o) incl += t;
+            }
+            const uint32_t excl = incl - sum, rank = sm.rank;
+            const bool mine = rank >= excl && rank < incl;
+            if (mine) {
+                uint32_t rem = rank - excl, q = 0;
+                for (; q < per - 1; q++) {
+                    const uint32_t c = sm.u.hist[tid * per + q];
+                    if (rem < c) break;
+                    rem -= c;
+                }
+                const uint32_t digit = tid * per + q;
+                sm.prefix = prefix | ((unsigned long long)digit << shift);
+                sm.rank = rem;
+                sm.count = sm.u.hist[digit];
+            }
+        }
+        __syncthreads();
     }
-};
+    return sm.prefix;   // all 64 bits decided: the bin holds copies of one value
+}
 
 __global__ void __launch_bounds__(TS_THREADS) theil_sen_kernel(DnbBatchView v, DnbModelDev m, DnbTsArgs a) {
-    __shared__ double sx[TS_MAXP], sy[TS_MAXP];
-    __shared__ uint32_t hist[256];
-    __shared__ unsigned long long sh_prefix;
-    __shared__ uint32_t sh_rem;
+    __shared__ TsShared sm;
     const uint32_t r = v.order[blockIdx.x];
     const int tid = threadIdx.x;
     const int st = v.status[r];
@@ -131,24 +183,22 @@ __global__ void __launch_bounds__(TS_THREADS) theil_sen_kernel(DnbBatchView v, D
     if (eff > maxPoints) { skip = eff / maxPoints; np = maxPoints; }
     for (uint32_t j = tid; j < np; j += TS_THREADS) {
         const uint32_t i = trim + j * skip;
-        sx[j] = dDiv(dSub(sig[i], shift), scale);          // :51
-        sy[j] = m.mean[rk[i]];                              // :58
+        sm.x[j] = dDiv(dSub(sig[i], shift), scale);        // :51
+        sm.y[j] = m.mean[rk[i]];                            // :58
     }
     __syncthreads();
 
     // median slope: element ns/2 of the ascending sort of dy/dx over all i<j (:67-78)
     const uint32_t ns = np * (np - 1) / 2;
-    const uint32_t full_rounds = (np - 1) / 2;
-    const uint32_t items = full_rounds * np + ((np % 2 == 0) ? np : 0);   // enumeration span incl. the padded half round
-    auto make_pairs = [&]() { return PairEnum{sx, sy, np, 1u, (uint32_t)tid, full_rounds}; };
-    const double slope = key_to_double(
-        radix_select64(make_pairs, (items + TS_THREADS - 1) / TS_THREADS, ns / 2, hist, &sh_prefix, &sh_rem));
+    const double slope = key_to_double(select_slope(sm, np, ns / 2));
     __syncthreads();
 
-    // median intercept: element np/2 of y - slope*x (:81-87)
-    auto make_icpt = [&]() { return IcptEnum{sx, sy, slope, np, (uint32_t)tid}; };
-    const double icpt = key_to_double(
-        radix_select64(make_icpt, (np + TS_THREADS - 1) / TS_THREADS, np / 2, hist, &sh_prefix, &sh_rem));
+    // median intercept: element np/2 of y - slope*x (:81-87); np <= TS_MAXP <= TS_CAND
+    for (uint32_t i = tid; i < np; i += TS_THREADS)
+        sm.u.cand[i] = order_key(dSub(sm.y[i], dMul(slope, sm.x[i])));   // :83, not fused
+    __syncthreads();
+    select_among_candidates(sm, np, np / 2);
+    const double icpt = key_to_double(sm.answer);
 
     if (tid == 0) {
         double o_shift, o_scale;

@@ -247,15 +247,17 @@ def main():
     if os.path.exists(pj):
         with open(pj) as f:
             prof = json.load(f)
-    i_cell = prof.get("banded_dp_thread_instr_per_cell")
+    i_cell = prof.get("align_thread_instr_per_cell")
     dp_s = per_step["banded_dp"] / 1e3
     cells = cnt_step["cells"]
     issue_peak = 148 * 4 * 32 * f_clk                       # thread-instructions/s at 1 warp-instr/clk/scheduler
     roofline = {
-        "kernel": "banded_dp_kernel", "bound": "issue",
+        "kernel": "align_kernel (band fill phase; duration = its warp-cycle share of the fused fill+backtrace launch)",
+        "bound": "issue",
         "achieved": (cells * i_cell / dp_s / 1e12) if i_cell else None, "peak": issue_peak / 1e12,
         "unit": "T thread-instr/s", "frac": (cells * i_cell / dp_s / issue_peak) if i_cell else None,
-        "traffic": prof.get("banded_dp_dram_bytes_per_cell", None) and prof["banded_dp_dram_bytes_per_cell"] * cells,
+        "traffic": prof.get("align_dram_bytes_per_cell", None) and prof["align_dram_bytes_per_cell"] * cells,
+        "constants_source": prof.get("source"),
         "cells_per_s": cells / dp_s, "thread_instr_per_cell": i_cell, "sm_clock_used_mhz": f_clk / 1e6,
         "hbm_view": {"bound": "hbm", "achieved": 0.29 * cells / dp_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": 0.29 * cells / dp_s / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_cell": 0.29},

@@ -74,174 +74,229 @@ __device__ __forceinline__ double cell_update(double diag, double up, double lef
     return m;
 }
 
-// One band.  P1 = band b-1, P2 = band b-2 (overwritten with band b).
-#define DP_BAND_STEP(P1, P2)                                                                                      \
-    {                                                                                                             \
-        /* Suzuki's rule on cells 0 and 99 of band b-1 (event_handling.cpp:237-253) */                            \
-        const int s_ll = ll_e & 127, s_ur = (ll_e - (DNB_BW - 1)) & 127;                                          \
-        const double ur = shfl_d(pick4(P1, s_ur & 3), s_ur >> 2);                                                 \
-        const double llv = pick4(P1, s_ll & 3);                                                                   \
-        const int r0 = (llv == NEG_SENT && ur == NEG_SENT) ? (b & 1) : (llv < ur ? 1 : 0);                        \
-        const bool right = __shfl_sync(FULL, r0, s_ll >> 2) != 0;                                                 \
-        /* the k-mer level conveyor advances one slot every band */                                              \
-        {                                                                                                         \
-            const double in = shfl_d(mk[3], (lane + 31) & 31);                                                    \
-            mk[3] = mk[2]; mk[2] = mk[1]; mk[1] = mk[0]; mk[0] = in;                                              \
-        }                                                                                                         \
-        if (right) {                                                                                              \
-            ll_k++;                                                                                               \
-            const int need = ll_k + DNB_BW - 1;                                                                   \
-            if (need - mbase == 32) {                                                                             \
-                mbuf = mnxt; mbase += 32;                                                                         \
-                mnxt = (mbase + 32 + lane < K) ? mu[mbase + 32 + lane] : 0.0;                                     \
-            }                                                                                                     \
-            const double fresh = shfl_d(mbuf, need - mbase);                                                      \
-            const int s99 = (ll_e - (DNB_BW - 1)) & 127;                                                          \
-            if (lane == (s99 >> 2)) {                                                                             \
-                const int jj = s99 & 3;                                                                           \
-                if (jj == 0) mk[0] = fresh; else if (jj == 1) mk[1] = fresh; else if (jj == 2) mk[2] = fresh; else mk[3] = fresh; \
-            }                                                                                                     \
-            mvword |= 1u << (b & 31);                                                                             \
-        } else {                                                                                                  \
-            ll_e++;                                                                                               \
-            const int need = ll_e;                                                                                \
-            if (need - xbase == 32) {                                                                             \
-                xbuf = xnxt; xbase += 32;                                                                         \
-                xnxt = (xbase + 32 + lane < E) ? x[xbase + 32 + lane] : 0.0;                                      \
-            }                                                                                                     \
-            const double fresh = shfl_d(xbuf, need - xbase);                                                      \
-            const int s0 = ll_e & 127;                                                                            \
-            if (lane == (s0 >> 2)) {                                                                              \
-                const int jj = s0 & 3;                                                                            \
-                if (jj == 0) xe[0] = fresh; else if (jj == 1) xe[1] = fresh; else if (jj == 2) xe[2] = fresh; else xe[3] = fresh; \
-            }                                                                                                     \
-        }                                                                                                         \
-        /* slot-1 edges of the two previous bands */                                                             \
-        const double e1 = shfl_d(P1[3], (lane + 31) & 31);                                                        \
-        const double e2 = shfl_d(P2[3], (lane + 31) & 31);                                                        \
-        /* fill range (event_handling.cpp:269-278) and trim cell (:256-265), as band offsets o = ll_e - event */ \
-        const int lo = max(max(-ll_k, ll_e - (E - 1)), 0);                                                        \
-        const int hi = min(min(K - ll_k, ll_e + 1), DNB_BW);                                                      \
-        const unsigned span = hi > lo ? (unsigned)(hi - lo) : 0u;                                                 \
-        const int o_trim = -1 - ll_k;                                                                             \
-        const int ev_trim = ll_e - o_trim;                                                                        \
-        const bool trim_ok = o_trim >= 0 && o_trim < DNB_BW && ev_trim >= 0 && ev_trim < E;                       \
-        const double trim_val = rn24(dMul(c.lp_trim, (double)((uint32_t)ev_trim + 1u)));   /* :260 */             \
-        fills += span;                                                                                            \
-        /* emissions: a = float((x - mu) / 0.14) via the guarded reciprocal multiply */                          \
-        double q[4];                                                                                              \
-        bool near = false;                                                                                        \
-        _Pragma("unroll") for (int j = 0; j < 4; j++) {                                                           \
-            q[j] = dMul(dSub(xe[j], mk[j]), c.inv_sigma);                                                         \
-            near |= (((unsigned)__double2loint(q[j]) & 0x1FFFFFFFu) - 0x0FFFFFF8u) <= 16u;                         \
-        }                                                                                                         \
-        if (__any_sync(FULL, near)) {                                                                             \
-            _Pragma("unroll") for (int j = 0; j < 4; j++) q[j] = dDiv(dSub(xe[j], mk[j]), 0.14);                  \
-        }                                                                                                         \
-        uint32_t tb = 0;                                                                                          \
-        _Pragma("unroll") for (int j = 3; j >= 0; j--) {                                                          \
-            const int o = (ll_e - (lane * 4 + j)) & 127;                                                          \
-            uint32_t from;                                                                                        \
-            double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24(q[j]), c, from); \
-            const bool valid = (unsigned)(o - lo) < span;                                                         \
-            const bool trim = (o == o_trim) && trim_ok;                                                           \
-            m = valid ? m : (trim ? trim_val : NEG_SENT);                                                         \
-            from = valid ? from : (trim ? (uint32_t)DNB_FROM_U : 0u);                                             \
-            P2[j] = m;                                                                                            \
-            tb |= from << (2 * j);                                                                                \
-        }                                                                                                         \
-        rows[(size_t)b * DNB_TRACE_ROW + lane] = (uint8_t)tb;                                                     \
-        if ((b & 31) == 31) {                                                                                     \
-            if (lane == 0) { moves[b >> 5] = mvword; rcum[b >> 5] = rights; }                                     \
-            rights += __popc(mvword); mvword = 0;                                                                 \
-        }                                                                                                         \
-        /* end-cell candidate of this band: (event b-K-1, last k-mer) (event_handling.cpp:329-340) */            \
-        {                                                                                                         \
-            const int e = b - K - 1;                                                                              \
-            const int o = ll_e - e;                                                                               \
-            if (e >= 0 && e < E && o >= 0 && o < DNB_BW) {                                                        \
-                const int sl_ = e & 127;                                                                          \
-                if (lane == (sl_ >> 2)) {                                                                         \
-                    const double val = pick4(P2, sl_ & 3);                                                        \
-                    const double s = rn24(dAdd(val, dMul((double)(unsigned long long)(E - e), c.lp_trim)));       \
-                    if (s > best_s) { best_s = s; best_e = e; best_lle = ll_e; }                                  \
-                }                                                                                                 \
-            }                                                                                                     \
-        }                                                                                                         \
-        b++;                                                                                                      \
-    }
-
+// ---------------------------------------------------------------------------------------------------------------
+// Band fill of one read by one warp (event_handling.cpp:213-312 and the end-cell scan :321-340).
+// ---------------------------------------------------------------------------------------------------------------
 struct DpEnd {
     int event;        // event index of the best end cell, -1 if none
     int ll_event;     // band_lower_left.event_idx of that band
     float score;
 };
 
-// Band fill of one read by one warp (event_handling.cpp:213-312 and the end-cell scan :321-340).
-__device__ __forceinline__ DpEnd dp_fill_warp(const DnbBatchView &v, const DnbDpArgs &a, uint32_t r, int lane) {
-    const int E = (int)v.n_events[r];
-    const int K = (int)(v.q_off[r + 1] - v.q_off[r]) - DNB_K + 1;
-    const double *__restrict__ x = a.x_e + v.ev_off[r];
-    const double *__restrict__ mu = a.mu_q + v.q_off[r];
+struct DpWarp {
+    // per read
+    int E, K, lane;
+    const double *__restrict__ x;
+    const double *__restrict__ mu;
     DpConst c;
-    c.lp_skip = a.lp[4 * r + 0]; c.lp_stay = a.lp[4 * r + 1]; c.lp_step = a.lp[4 * r + 2]; c.lp_trim = a.lp[4 * r + 3];
-    c.emit_const = a.emit_const; c.inv_sigma = a.inv_sigma;
-    uint8_t *rows = a.trace + a.band_off[r] * DNB_TRACE_ROW;
-    uint32_t *moves = a.moves + (a.band_off[r] >> 5) + r;
-    uint32_t *rcum = a.rcum + (a.band_off[r] >> 5) + r;
+    uint8_t *rows;
+    uint32_t *moves, *rcum;
+    double *sc;                 // shared memory, 128 doubles: the band just computed, by event slot
+    // state
+    double xe[4], mk[4];        // event level / k-mer level of this lane's four slots
+    int ll_e, ll_k;             // lower-left cell of the newest band
+    int xbase, mbase;           // coalesced 32-wide look-ahead of the events / k-mers entering the band
+    double xbuf, xnxt, mbuf, mnxt;
+    double v_ll, v_ur;          // cells 0 and 99 of the newest band (Suzuki's rule reads them), warp-uniform
+    double best_s;              // end-cell scan, warp-uniform
+    int best_e, best_lle;
+    unsigned long long fills;
+    uint32_t mvword, rights;
+};
+
+// value of slot s (warp-uniform) in the four registers of lane s >> 2; only that lane's result is meaningful
+__device__ __forceinline__ void put4(double (&p)[4], int lane, int s, double v) {
+    const bool mine = lane == (s >> 2);
+    const int j = s & 3;
+    p[0] = (mine && j == 0) ? v : p[0];
+    p[1] = (mine && j == 1) ? v : p[1];
+    p[2] = (mine && j == 2) ? v : p[2];
+    p[3] = (mine && j == 3) ? v : p[3];
+}
+
+// One band b.  P1 = band b-1, P2 = band b-2 (overwritten with band b).
+//
+// Out-of-band neighbours must read as -inf (event_handling.cpp:283-294).  With event-indexed slots the only
+// out-of-band slots a band can read are the one just above its top cell (as `up`, after a right move; as `diag`
+// after two) and the one its new bottom cell enters (as `left`, after a down move; as `diag` after two).  Both
+// belong to band b-1's array and are set to the sentinel here, once per band, which also covers the diagonal
+// reads of band b+1.  Away from the ends of the read (kSteady) every one of the 100 cells is inside the event and
+// k-mer ranges, so nothing else needs masking: the 28 slots outside the band compute garbage nobody reads.
+template <bool kSteady>
+__device__ __forceinline__ void dp_cells(DpWarp &w, double (&P1)[4], double (&P2)[4], const int b) {
+    const int lane = w.lane;
+    const DpConst &c = w.c;
+    // slot-1 edges of the two previous bands
+    const double e1 = shfl_d(P1[3], (lane + 31) & 31);
+    const double e2 = shfl_d(P2[3], (lane + 31) & 31);
+    // emissions: a = float((x - mu) / 0.14) via the guarded reciprocal multiply
+    double q[4];
+    bool near = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        q[j] = dMul(dSub(w.xe[j], w.mk[j]), c.inv_sigma);
+        near |= (((unsigned)__double2loint(q[j]) & 0x1FFFFFFFu) - 0x0FFFFFF8u) <= 16u;
+    }
+    if (__any_sync(FULL, near)) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) q[j] = dDiv(dSub(w.xe[j], w.mk[j]), 0.14);
+    }
+    uint32_t tb = 0;
+    if (kSteady) {
+#pragma unroll
+        for (int j = 3; j >= 0; j--) {
+            uint32_t from;
+            const double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24(q[j]), c, from);
+            P2[j] = m;
+            tb |= from << (2 * j);
+        }
+        w.fills += DNB_BW;
+    } else {
+        // fill range (event_handling.cpp:269-278) and trim cell (:256-265), as band offsets o = ll_e - event
+        const int lo = max(max(-w.ll_k, w.ll_e - (w.E - 1)), 0);
+        const int hi = min(min(w.K - w.ll_k, w.ll_e + 1), DNB_BW);
+        const unsigned span = hi > lo ? (unsigned)(hi - lo) : 0u;
+        const int o_trim = -1 - w.ll_k;
+        const int ev_trim = w.ll_e - o_trim;
+        const bool trim_ok = o_trim >= 0 && o_trim < DNB_BW && ev_trim >= 0 && ev_trim < w.E;
+        const double trim_val = rn24(dMul(c.lp_trim, (double)((uint32_t)ev_trim + 1u)));   // :260
+        w.fills += span;
+#pragma unroll
+        for (int j = 3; j >= 0; j--) {
+            const int o = (w.ll_e - (lane * 4 + j)) & 127;
+            uint32_t from;
+            double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24(q[j]), c, from);
+            const bool valid = (unsigned)(o - lo) < span;
+            const bool trim = (o == o_trim) && trim_ok;
+            m = valid ? m : (trim ? trim_val : NEG_SENT);
+            from = valid ? from : (trim ? (uint32_t)DNB_FROM_U : 0u);
+            P2[j] = m;
+            tb |= from << (2 * j);
+        }
+    }
+    // publish the band by event slot: the next move decision and the end-cell scan read single cells from it
+    __syncwarp();
+    *reinterpret_cast<double2 *>(w.sc + 4 * lane) = make_double2(P2[0], P2[1]);
+    *reinterpret_cast<double2 *>(w.sc + 4 * lane + 2) = make_double2(P2[2], P2[3]);
+    __syncwarp();
+    w.v_ll = w.sc[w.ll_e & 127];
+    w.v_ur = w.sc[(w.ll_e - (DNB_BW - 1)) & 127];
+    w.rows[(size_t)b * DNB_TRACE_ROW + lane] = (uint8_t)tb;
+    if ((b & 31) == 31) {
+        if (lane == 0) { w.moves[b >> 5] = w.mvword; w.rcum[b >> 5] = w.rights; }
+        w.rights += __popc(w.mvword);
+        w.mvword = 0;
+    }
+    // end-cell candidate of this band: (event b-K-1, last k-mer) (event_handling.cpp:329-340); strict '>' in
+    // ascending event order keeps the first maximum
+    {
+        const int e = b - w.K - 1;
+        const int o = w.ll_e - e;
+        if (e >= 0 && e < w.E && o >= 0 && o < DNB_BW) {
+            const double val = w.sc[e & 127];
+            const double s = rn24(dAdd(val, dMul((double)(unsigned long long)(w.E - e), c.lp_trim)));
+            if (s > w.best_s) { w.best_s = s; w.best_e = e; w.best_lle = w.ll_e; }
+        }
+    }
+}
+
+__device__ __forceinline__ void dp_band(DpWarp &w, double (&P1)[4], double (&P2)[4], const int b) {
+    const int lane = w.lane;
+    // Suzuki's rule on cells 0 and 99 of band b-1 (event_handling.cpp:237-253)
+    const bool right = (w.v_ll == NEG_SENT && w.v_ur == NEG_SENT) ? ((b & 1) != 0) : (w.v_ll < w.v_ur);
+    // the k-mer level conveyor advances one slot every band
+    {
+        const double in = shfl_d(w.mk[3], (lane + 31) & 31);
+        w.mk[3] = w.mk[2]; w.mk[2] = w.mk[1]; w.mk[1] = w.mk[0]; w.mk[0] = in;
+    }
+    if (right) {
+        w.ll_k++;
+        const int need = w.ll_k + DNB_BW - 1;
+        if (need - w.mbase == 32) {
+            w.mbuf = w.mnxt; w.mbase += 32;
+            w.mnxt = (w.mbase + 32 + lane < w.K) ? w.mu[w.mbase + 32 + lane] : 0.0;
+        }
+        const double fresh = shfl_d(w.mbuf, need - w.mbase);
+        put4(w.mk, lane, (w.ll_e - (DNB_BW - 1)) & 127, fresh);       // the new top cell's k-mer
+        put4(P1, lane, (w.ll_e - DNB_BW) & 127, NEG_SENT);            // above the top: out of band b-1
+        w.mvword |= 1u << (b & 31);
+    } else {
+        w.ll_e++;
+        const int need = w.ll_e;
+        if (need - w.xbase == 32) {
+            w.xbuf = w.xnxt; w.xbase += 32;
+            w.xnxt = (w.xbase + 32 + lane < w.E) ? w.x[w.xbase + 32 + lane] : 0.0;
+        }
+        const double fresh = shfl_d(w.xbuf, need - w.xbase);
+        const int s0 = w.ll_e & 127;
+        const bool mine = lane == (s0 >> 2);
+        const int j0 = s0 & 3;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                                  // the new bottom cell: its event level enters,
+            const bool hit = mine && j0 == j;                          // and its slot was out of band b-1
+            w.xe[j] = hit ? fresh : w.xe[j];
+            P1[j] = hit ? NEG_SENT : P1[j];
+        }
+    }
+    const bool steady = w.ll_k >= 0 && w.ll_e >= DNB_BW - 1 && w.ll_e <= w.E - 1 && w.ll_k + DNB_BW <= w.K;
+    if (steady) dp_cells<true>(w, P1, P2, b);
+    else dp_cells<false>(w, P1, P2, b);
+}
+
+__device__ __forceinline__ DpEnd dp_fill_warp(const DnbBatchView &v, const DnbDpArgs &a, uint32_t r, int lane, double *sc) {
+    DpWarp w;
+    w.lane = lane;
+    w.E = (int)v.n_events[r];
+    w.K = (int)(v.q_off[r + 1] - v.q_off[r]) - DNB_K + 1;
+    w.x = a.x_e + v.ev_off[r];
+    w.mu = a.mu_q + v.q_off[r];
+    w.c.lp_skip = a.lp[4 * r + 0]; w.c.lp_stay = a.lp[4 * r + 1]; w.c.lp_step = a.lp[4 * r + 2]; w.c.lp_trim = a.lp[4 * r + 3];
+    w.c.emit_const = a.emit_const; w.c.inv_sigma = a.inv_sigma;
+    w.rows = a.trace + a.band_off[r] * DNB_TRACE_ROW;
+    w.moves = a.moves + (a.band_off[r] >> 5) + r;
+    w.rcum = a.rcum + (a.band_off[r] >> 5) + r;
+    w.sc = sc;
+    const int E = w.E, K = w.K;
     const int n_bands = E + K + 2;
 
     // ---- bands 0 and 1 (event_handling.cpp:213-228): A = band 0, B = band 1 ----
-    double A[4], B[4], xe[4], mk[4];
-    int ll_e = DNB_BW / 2, ll_k = -1 - DNB_BW / 2;     // lower-left of band 1 = move_down(band 0)
+    double A[4], B[4];
+    w.ll_e = DNB_BW / 2; w.ll_k = -1 - DNB_BW / 2;     // lower-left of band 1 = move_down(band 0)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int s = lane * 4 + j;
         A[j] = (s == 127) ? 0.0 : NEG_SENT;                        // bands[0][50] = 0: event -1 -> slot 127
-        B[j] = (s == 0) ? rn24(c.lp_trim) : NEG_SENT;              // bands[1][50] = lp_trim: event 0 -> slot 0
-        const int o = (ll_e - s) & 127;
-        const int e = ll_e - o, km = ll_k + o;
-        xe[j] = (e >= 0 && e < E) ? x[e] : 0.0;
-        mk[j] = (km >= 0 && km < K) ? mu[km] : 0.0;
+        B[j] = (s == 0) ? rn24(w.c.lp_trim) : NEG_SENT;            // bands[1][50] = lp_trim: event 0 -> slot 0
+        const int o = (w.ll_e - s) & 127;
+        const int e = w.ll_e - o, km = w.ll_k + o;
+        w.xe[j] = (e >= 0 && e < E) ? w.x[e] : 0.0;
+        w.mk[j] = (km >= 0 && km < K) ? w.mu[km] : 0.0;
     }
-    rows[lane] = 0;                                                            // band 0: no trace
-    rows[DNB_TRACE_ROW + lane] = (lane == 0) ? (uint8_t)DNB_FROM_U : 0;       // trace[1][50] = FROM_U (slot 0)
+    w.rows[lane] = 0;                                                            // band 0: no trace
+    w.rows[DNB_TRACE_ROW + lane] = (lane == 0) ? (uint8_t)DNB_FROM_U : 0;       // trace[1][50] = FROM_U (slot 0)
+    // cells 0 and 99 of band 1: offsets 0 and 99 are events 50 and -49 -> both -inf (only offset 50 is set)
+    w.v_ll = NEG_SENT; w.v_ur = NEG_SENT;
 
-    // coalesced 32-wide look-ahead of the next events / k-mers entering the band (double buffered)
-    int xbase = ll_e + 1, mbase = ll_k + DNB_BW;
-    double xbuf = (xbase + lane < E) ? x[xbase + lane] : 0.0;
-    double xnxt = (xbase + 32 + lane < E) ? x[xbase + 32 + lane] : 0.0;
-    double mbuf = (mbase + lane < K) ? mu[mbase + lane] : 0.0;
-    double mnxt = (mbase + 32 + lane < K) ? mu[mbase + 32 + lane] : 0.0;
+    w.xbase = w.ll_e + 1; w.mbase = w.ll_k + DNB_BW;
+    w.xbuf = (w.xbase + lane < E) ? w.x[w.xbase + lane] : 0.0;
+    w.xnxt = (w.xbase + 32 + lane < E) ? w.x[w.xbase + 32 + lane] : 0.0;
+    w.mbuf = (w.mbase + lane < K) ? w.mu[w.mbase + lane] : 0.0;
+    w.mnxt = (w.mbase + 32 + lane < K) ? w.mu[w.mbase + 32 + lane] : 0.0;
 
-    double best_s = NEG_SENT;
-    int best_e = 0x7fffffff, best_lle = 0;
-    unsigned long long fills = 0;
-    uint32_t mvword = 0, rights = 0;
+    w.best_s = NEG_SENT; w.best_e = 0x7fffffff; w.best_lle = 0;
+    w.fills = 0; w.mvword = 0; w.rights = 0;
 
     int b = 2;
-    while (b + 1 < n_bands) {
-        DP_BAND_STEP(B, A)      // band b   : P1 = B (b-1), P2 = A (b-2) -> A becomes band b
-        DP_BAND_STEP(A, B)      // band b+1 : P1 = A,       P2 = B       -> B becomes band b+1
+    for (; b + 1 < n_bands; b += 2) {
+        dp_band(w, B, A, b);          // band b   : P1 = B (b-1), P2 = A (b-2) -> A becomes band b
+        dp_band(w, A, B, b + 1);      // band b+1 : P1 = A,       P2 = B       -> B becomes band b+1
     }
-    if (b < n_bands) DP_BAND_STEP(B, A)
-    if (lane == 0 && (b & 31) != 0) { moves[b >> 5] = mvword; rcum[b >> 5] = rights; }
-
-    // first event index attaining the maximum (strict '>' in ascending event order, :335)
-    double gmax = best_s;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) gmax = fmax(gmax, shfl_d(gmax, lane ^ d));
-    int cand = (best_s == gmax && gmax != NEG_SENT) ? best_e : 0x7fffffff;
-    int gmin = cand;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) gmin = min(gmin, __shfl_xor_sync(FULL, gmin, d));
-    const unsigned who = __ballot_sync(FULL, cand == gmin && gmin != 0x7fffffff);
-    int lle = 0;
-    if (who) lle = __shfl_sync(FULL, best_lle, __ffs(who) - 1);
-    if (lane == 0) atomicAdd(a.cells, fills);
+    if (b < n_bands) { dp_band(w, B, A, b); b++; }
+    if (lane == 0 && (b & 31) != 0) { w.moves[b >> 5] = w.mvword; w.rcum[b >> 5] = w.rights; }
+    if (lane == 0) atomicAdd(a.cells, w.fills);
     DpEnd end;
-    if (gmin == 0x7fffffff) { end.event = -1; end.ll_event = 0; end.score = -INFINITY; }
-    else { end.event = gmin; end.ll_event = lle; end.score = (float)gmax; }
+    if (w.best_e == 0x7fffffff) { end.event = -1; end.ll_event = 0; end.score = -INFINITY; }
+    else { end.event = w.best_e; end.ll_event = w.best_lle; end.score = (float)w.best_s; }
     return end;
 }
 
@@ -395,7 +450,7 @@ __device__ __forceinline__ void backtrace_warp(const DnbBatchView &v, const DnbB
 // phases as separate launches; same device code)
 template <int kMode>
 __global__ void __launch_bounds__(DP_WARPS * 32) align_kernel(DnbBatchView v, DnbBtArgs a) {
-    __shared__ BtSmem sm[kMode == 1 ? 1 : DP_WARPS];
+    __shared__ BtSmem sm[DP_WARPS];      // the band fill's 1 KB slot copy aliases the backtrace window (used after it)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t slot = blockIdx.x * DP_WARPS + w;
     if (slot >= v.n_reads) return;
@@ -410,7 +465,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32) align_kernel(DnbBatchView v, Dn
     int end_event;
     if (kMode != 2) {
         const long long t0 = clock64();
-        const DpEnd end = dp_fill_warp(v, a.dp, r, lane);
+        const DpEnd end = dp_fill_warp(v, a.dp, r, lane, reinterpret_cast<double *>(sm[w].win));
         if (lane == 0) {
             a.dp.end_event[r] = end.event; a.dp.end_ll_event[r] = end.ll_event; a.dp.end_score[r] = end.score;
             if (end.event < 0) v.status[r] = DNB_READ_UNDEFINED;   // the reference would backtrace from an out-of-band cell
@@ -427,7 +482,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32) align_kernel(DnbBatchView v, Dn
             return;
         }
         const long long t1 = clock64();
-        backtrace_warp(v, a, r, lane, end_event, sm[kMode == 1 ? 0 : w]);
+        backtrace_warp(v, a, r, lane, end_event, sm[w]);
         if (lane == 0) atomicAdd(&a.phase_cycles[1], (unsigned long long)(clock64() - t1));
     }
 }

@@ -273,27 +273,24 @@ def main():
     # ---- e2e leg: host buffers through dnb_submit, H2D + D2H inside the timed region ----
     e2e_bins = sharding.make_bins(W.n_samples, int(args.e2e_bin_samples))
     descs = [W.descs(b) for b in e2e_bins]
-    h2d_bytes = int(2 * n_samples + 6 * int(W.seq_off[-1]) + 8 * 4 * W.n_reads)
-    d2h_acc = [0]
+    io_acc = [0, 0]
 
     def one(d):
         b = ctx.submit_descs(d)
         b.wait()
-        _, cnt = b.timings()
-        # what fetch copied back: event slots (capacity-strided), alignment pairs, per-read scalars
-        cap = int(np.sum((0.4 * d["n_samples"]).astype(np.int64) + 16))
         res0 = b.result(0)                      # touch a result: the step's outcome is read on the host
         assert res0.status in (0, 1, 2, 3, 4)
-        nbytes = 8 * cap + 4 * d.size + 84 * d.size
+        io = b.io_bytes()                       # counted by the library from the copies it made
         b.release()
-        return nbytes, cnt
+        return io
 
     def e2e_step():
-        tot = 0
+        hb = db = 0
         with ThreadPoolExecutor(max_workers=args.e2e_inflight) as ex:
-            for nb, _ in ex.map(one, descs):
-                tot += nb
-        d2h_acc[0] = tot
+            for h2d, d2h in ex.map(one, descs):
+                hb += h2d
+                db += d2h
+        io_acc[0], io_acc[1] = hb, db
 
     for _ in range(min(args.warmup, 3)):
         e2e_step()
@@ -304,8 +301,7 @@ def main():
     barrier()
     dt_e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_samples * args.steps / dt_e / 1e6
-    # alignment pairs copied back: 8 B per aligned event (~ n_events)
-    d2h_bytes = d2h_acc[0] + 8 * cnt_step["events"]
+    h2d_bytes, d2h_bytes = io_acc
 
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None

@@ -69,6 +69,7 @@ EXPORTS = [
     "dnb_default_config", "dnb_create", "dnb_destroy", "dnb_strerror", "dnb_last_error", "dnb_load_model",
     "dnb_submit", "dnb_wait", "dnb_result", "dnb_release",
     "dnb_batch_upload", "dnb_batch_run", "dnb_batch_fetch", "dnb_batch_drop_workspace", "dnb_batch_timings",
+    "dnb_batch_io_bytes",
     "dnb_detect_events",
     "dnb_eexp", "dnb_eln", "dnb_lnSum", "dnb_lnProd", "dnb_lnGreaterThan", "dnb_uniformPDF", "dnb_normalPDF",
     "dnb_cauchyPDF", "dnb_sequence_probability_batch",
@@ -103,6 +104,7 @@ def lib():
     L.dnb_release.argtypes = [vp]
     L.dnb_release.restype = None
     L.dnb_batch_timings.argtypes = [vp, C.POINTER(d * 8), C.POINTER(C.c_uint64 * 8)]
+    L.dnb_batch_io_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.dnb_detect_events.argtypes = [vp, vp, sz, C.POINTER(EventT), sz, C.POINTER(sz)]
     L.dnb_eexp.restype = d
     L.dnb_eexp.argtypes = [d]

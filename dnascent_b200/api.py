@@ -97,6 +97,12 @@ class Batch:
         cn = ("samples", "events", "kmers", "bands", "cells", "launches", "seg_serial_reads", "failed_reads")
         return dict(zip(names, ms)), dict(zip(cn, (int(x) for x in cnt)))
 
+    def io_bytes(self):
+        """(host->device, device->host) bytes this batch moved over PCIe, counted by the library."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _lib.check(self.ctx.L.dnb_batch_io_bytes(self.h, C.byref(a), C.byref(b)), "dnb_batch_io_bytes")
+        return a.value, b.value
+
     def result(self, i: int) -> Normalised:
         r = ReadResult()
         _lib.check(self.ctx.L.dnb_result(self.h, i, C.byref(r)), "dnb_result")

@@ -30,6 +30,9 @@
 #include "../../include/dnascent_b200.h"
 
 #define DP_WARPS 4
+#ifndef DP_MIN_BLOCKS
+#define DP_MIN_BLOCKS 4      // resident CTAs per SM the register allocation must allow (4 warps each)
+#endif
 #define FULL 0xffffffffu
 #define NEG_SENT (-3.4028234663852886e38)   /* (double)(-FLT_MAX): stands for -INFINITY */
 
@@ -449,7 +452,7 @@ __device__ __forceinline__ void backtrace_warp(const DnbBatchView &v, const DnbB
 // kMode 0: fill + backtrace (production)   1: fill only   2: backtrace only (the split pair is for profiling the two
 // phases as separate launches; same device code)
 template <int kMode>
-__global__ void __launch_bounds__(DP_WARPS * 32) align_kernel(DnbBatchView v, DnbBtArgs a) {
+__global__ void __launch_bounds__(DP_WARPS * 32, DP_MIN_BLOCKS) align_kernel(DnbBatchView v, DnbBtArgs a) {
     __shared__ BtSmem sm[DP_WARPS];      // the band fill's 1 KB slot copy aliases the backtrace window (used after it)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t slot = blockIdx.x * DP_WARPS + w;
@@ -496,7 +499,27 @@ __global__ void compact_alignment_kernel(DnbBatchView v, const uint64_t *al_off,
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[n - 1 - i];   // std::reverse, :413
 }
 
+__global__ void compact_events_kernel(DnbBatchView v, const uint64_t *dense_off, uint32_t *out_start, float *out_mean) {
+    const uint32_t r = blockIdx.x;
+    const uint32_t n = (uint32_t)(dense_off[r + 1] - dense_off[r]);
+    if (n == 0) return;
+    const uint32_t *ss = v.ev_start + v.ev_off[r] + r;
+    const float *ms = v.ev_mean + v.ev_off[r];
+    uint32_t *ds = out_start + dense_off[r] + r;
+    float *dm = out_mean + dense_off[r];
+    for (uint32_t i = threadIdx.x; i <= n; i += blockDim.x) {
+        ds[i] = ss[i];
+        if (i < n) dm[i] = ms[i];
+    }
+}
+
 }  // namespace
+
+void dnb_launch_compact_events(const DnbBatchView &v, const uint64_t *dense_off, uint32_t *out_start, float *out_mean,
+                               cudaStream_t s) {
+    if (v.n_reads == 0) return;
+    compact_events_kernel<<<v.n_reads, 256, 0, s>>>(v, dense_off, out_start, out_mean);
+}
 
 void dnb_launch_align(const DnbBatchView &v, const DnbBtArgs &a, int mode, cudaStream_t s) {
     if (v.n_reads == 0) return;

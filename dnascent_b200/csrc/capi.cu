@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -53,6 +54,24 @@ thread_local std::string g_last_error;
         if (_rc != DNB_OK) return _rc; \
     } while (0)
 
+// DNB_TRACE_HOST=1 prints the host wall time of every pipeline phase to stderr (diagnostics only)
+struct HostTrace {
+    bool on;
+    double prev;
+    const char *who;
+    explicit HostTrace(const char *w) : who(w) {
+        static const bool enabled = getenv("DNB_TRACE_HOST") != nullptr;
+        on = enabled;
+        prev = on ? omp_get_wtime() : 0.0;
+    }
+    void tick(const char *what) {
+        if (!on) return;
+        const double now = omp_get_wtime();
+        fprintf(stderr, "[dnb host] %-6s %-28s %8.2f ms  (t=%.3f)\n", who, what, 1e3 * (now - prev), now);
+        prev = now;
+    }
+};
+
 struct ModelHost {
     bool loaded = false;
     double *d_mean = nullptr, *d_stdv = nullptr, *d_sorted = nullptr;
@@ -75,7 +94,10 @@ struct PinnedPool {
         const size_t gran = 1u << 20;
         const size_t sz = (n + gran - 1) / gran * gran;
         void *p = nullptr;
+        static const bool trace = getenv("DNB_TRACE_HOST") != nullptr;
+        const double t0 = trace ? omp_get_wtime() : 0.0;
         if (cudaMallocHost(&p, sz) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (trace) fprintf(stderr, "[dnb host] cudaMallocHost %.1f MB took %.2f ms (t=%.3f)\n", sz / 1e6, 1e3 * (omp_get_wtime() - t0), omp_get_wtime());
         blocks.push_back({p, sz, true});
         return p;
     }
@@ -112,7 +134,10 @@ struct DevCache {
                 if (!b.used && b.n == n) { b.used = true; return b.p; }
         }
         void *p = nullptr;
+        static const bool trace = getenv("DNB_TRACE_HOST") != nullptr;
+        const double t0 = trace ? omp_get_wtime() : 0.0;
         cudaError_t e = cudaMalloc(&p, n);
+        if (trace) fprintf(stderr, "[dnb host] cudaMalloc %.1f MB took %.2f ms (t=%.3f)\n", n / 1e6, 1e3 * (omp_get_wtime() - t0), omp_get_wtime());
         if (e == cudaErrorMemoryAllocation) {   // give cached-but-idle blocks back and retry once
             cudaGetLastError();
             trim();
@@ -144,6 +169,54 @@ struct DevCache {
 
 }  // namespace
 
+// counting semaphore: how many batches may be in one pipeline stage of dnb_submit at a time
+struct StageGate {
+    std::mutex mu;
+    std::condition_variable cv;
+    int free_slots;
+    explicit StageGate(int n) : free_slots(n) {}
+    void enter() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return free_slots > 0; }); free_slots--; }
+    void leave() { { std::lock_guard<std::mutex> lk(mu); free_slots++; } cv.notify_one(); }
+};
+struct StageHold {
+    StageGate &g;
+    explicit StageHold(StageGate &gate) : g(gate) { g.enter(); }
+    ~StageHold() { g.leave(); }
+};
+
+// streams and events are recycled: creating them per batch cost ~30 ms per dnb_submit under load (driver lock)
+struct StreamSet {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+};
+struct StreamPool {
+    std::vector<StreamSet> idle;
+    std::mutex mu;
+    bool acquire(StreamSet *out) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!idle.empty()) { *out = idle.back(); idle.pop_back(); return true; }
+        }
+        StreamSet s;
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+        for (auto &e : s.ev)
+            if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return false; }
+        *out = s;
+        return true;
+    }
+    void release(const StreamSet &s) {
+        std::lock_guard<std::mutex> lk(mu);
+        idle.push_back(s);
+    }
+    void destroy() {
+        for (auto &s : idle) {
+            for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+        idle.clear();
+    }
+};
+
 struct dnb_ctx {
     dnb_config cfg;
     ModelHost model[3];
@@ -151,6 +224,11 @@ struct dnb_ctx {
     std::mutex mu;
     PinnedPool pinned;
     DevCache dev;
+    // dnb_submit from several host threads forms a software pipeline: one batch packing + copying in, up to two
+    // computing, one copying out.  Without the gates concurrent callers fall into lockstep (all upload, then all
+    // compute, then all fetch) and the GPU idles during the copy phases.
+    StageGate gate_pack{1}, gate_h2d{1}, gate_compute{2}, gate_fetch{1};
+    StreamPool streams;
 };
 
 namespace {
@@ -170,7 +248,8 @@ struct Work {
     int32_t *end_event, *end_ll;
     float *end_score;
     unsigned long long *cells;   // [3]: DP cells filled, warp cycles in the band fill, warp cycles in the backtrace
-    uint32_t *al_rev, *n_align, *cl_rank, *n_cleaned, *out_pairs;
+    uint32_t *al_rev, *n_align, *cl_rank, *n_cleaned, *out_pairs, *cev_start;
+    float *cev_mean;
     double *cl_signal, *avg, *shift, *scale;
     int *spanned, *max_gap;
 };
@@ -196,7 +275,8 @@ struct dnb_batch {
     bool want_table = false;     // dnb_detect_events: keep the full scrappie table, segmentation only
     bool uploaded = false, ran = false, fetched = false, have_work = false;
     // ---- host-side shapes ----
-    std::vector<uint64_t> raw_off, q_off, r_off, ev_off, band_off, al_off, cl_off, out_off, ck_off;
+    std::vector<uint64_t> raw_off, q_off, r_off, ev_off, cev_off, band_off, al_off, cl_off, out_off, ck_off;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;   // PCIe payload of the last upload / fetch
     std::vector<uint32_t> n_samples, order, qlen, rlen, tile_off, tile_read;
     std::vector<double> lp;
     bool i16 = false;
@@ -308,16 +388,16 @@ void free_batch(dnb_batch *b) {
     drop_work(b);
     drop_results(b);
     for (void *p : b->input_allocs) b->ctx->dev.release(p);
-    for (auto &e : b->ev)
-        if (e) cudaEventDestroy(e);
     if (b->stream) {
-        cudaStreamSynchronize(b->stream);
-        cudaStreamDestroy(b->stream);
+        StreamSet ss;
+        ss.stream = b->stream;
+        for (int i = 0; i < 8; i++) ss.ev[i] = b->ev[i];
+        b->ctx->streams.release(ss);
     }
     delete b;
 }
 
-int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, dnb_batch **out) {
+int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, dnb_batch **out, bool gated = false) {
     if (!ctx || (!reads && R) || !out) return DNB_ERR_ARG;
     if (!ctx->model[DNB_MODEL_PORE].loaded && !want_table) return DNB_ERR_MODEL;
     if (ctx->cfg.use_fit_pore_model) {
@@ -325,13 +405,26 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
         return DNB_ERR_ARG;
     }
     CK(cudaSetDevice(ctx->cfg.device));
+    // dnb_submit pipelines concurrent callers: one batch packs on the host cores while another one's copy is on the bus
+    struct Gate {
+        StageGate *g = nullptr;
+        void enter(StageGate *gate) { leave(); g = gate; if (g) g->enter(); }
+        void leave() { if (g) g->leave(); g = nullptr; }
+        ~Gate() { leave(); }
+    } gate;
+    if (gated) gate.enter(&ctx->gate_pack);
+    HostTrace ht("upload");
     dnb_batch *b = new dnb_batch();
     b->ctx = ctx;
     b->R = R;
     b->want_table = want_table;
-    cudaError_t e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); delete b; return DNB_ERR_CUDA; }
-    for (auto &ev : b->ev) cudaEventCreate(&ev);
+    cudaError_t e = cudaSuccess;
+    {
+        StreamSet ss;
+        if (!ctx->streams.acquire(&ss)) { g_last_error = "stream/event creation failed"; delete b; return DNB_ERR_CUDA; }
+        b->stream = ss.stream;
+        for (int i = 0; i < 8; i++) b->ev[i] = ss.ev[i];
+    }
 
     // ---- shapes ----
     b->raw_off.resize(R + 1); b->q_off.resize(R + 1); b->r_off.resize(R + 1); b->ev_off.resize(R + 1);
@@ -378,19 +471,25 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
             for (uint32_t g = b->tile_off[i]; g < b->tile_off[i + 1]; g++) b->tile_read[g] = (uint32_t)i;
     }
 
+    ht.tick("shapes");
     // ---- pinned staging + device inputs ----
     const size_t esz = b->i16 ? 2 : 4;
     int rc = DNB_OK;
     uint8_t *h_raw = (uint8_t *)ctx->pinned.acquire(ro * esz);
     char *h_q = (char *)ctx->pinned.acquire(qo), *h_r = (char *)ctx->pinned.acquire(fo);
     int32_t *h_q2r = (int32_t *)ctx->pinned.acquire(qo * 4);
-    float *h_doff = (float *)ctx->pinned.acquire(R * 4), *h_dscl = (float *)ctx->pinned.acquire(R * 4);
+    // per-read tables travel in one pinned block (pageable sources would make every copy synchronous)
+    const size_t nt = b->tile_read.size();
+    const size_t meta_bytes = 8 * (R + 1) * 5 + 4 * R * 2 + 4 * (R + 1) + 4 * nt + 4 * R * 2 + 256;
+    uint8_t *h_meta = (uint8_t *)ctx->pinned.acquire(meta_bytes);
     auto release_staging = [&]() {
-        for (void *p : {(void *)h_raw, (void *)h_q, (void *)h_r, (void *)h_q2r, (void *)h_doff, (void *)h_dscl})
+        for (void *p : {(void *)h_raw, (void *)h_q, (void *)h_r, (void *)h_q2r, (void *)h_meta})
             if (p) ctx->pinned.release(p);
     };
 #define TRYF(x) do { rc = (x); if (rc != DNB_OK) { cudaStreamSynchronize(b->stream); release_staging(); free_batch(b); return rc; } } while (0)
-    if (!h_raw || !h_q || !h_r || !h_q2r || !h_doff || !h_dscl) { g_last_error = "pinned staging allocation failed"; TRYF(DNB_ERR_NOMEM); }
+    if (!h_raw || !h_q || !h_r || !h_q2r || !h_meta) { g_last_error = "pinned staging allocation failed"; TRYF(DNB_ERR_NOMEM); }
+    float *h_doff = (float *)h_meta, *h_dscl = h_doff + R;
+    size_t meta_used = 8 * R;
 #pragma omp parallel for schedule(dynamic, 16)
     for (size_t i = 0; i < R; i++) {
         const dnb_read_desc &d = reads[i];
@@ -403,23 +502,43 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
         if (d.query_to_ref) memcpy(h_q2r + b->q_off[i], d.query_to_ref, (size_t)d.query_len * 4);
         h_doff[i] = d.dac_offset; h_dscl[i] = d.dac_scale;
     }
+    ht.tick("pack into pinned staging");
+    if (gated) gate.enter(&ctx->gate_h2d);
     TRYF(ialloc(b, (uint8_t **)&b->d_raw, ro * esz));
     TRYF(ialloc(b, &b->d_query, qo)); TRYF(ialloc(b, &b->d_ref, fo)); TRYF(ialloc(b, &b->d_q2r, qo));
     TRYF(ialloc(b, &b->d_dac_off, R)); TRYF(ialloc(b, &b->d_dac_scl, R));
     TRYF(ialloc(b, &b->d_raw_off, R + 1)); TRYF(ialloc(b, &b->d_q_off, R + 1)); TRYF(ialloc(b, &b->d_r_off, R + 1));
     TRYF(ialloc(b, &b->d_ev_off, R + 1)); TRYF(ialloc(b, &b->d_n_samples, R)); TRYF(ialloc(b, &b->d_order, R));
-    TRYF(ialloc(b, &b->d_tile_off, R + 1)); TRYF(ialloc(b, &b->d_tile_read, b->tile_read.size()));
+    TRYF(ialloc(b, &b->d_tile_off, R + 1)); TRYF(ialloc(b, &b->d_tile_read, nt));
     TRYF(ialloc(b, &b->d_ck_off, R + 1));
-    TRYF(h2d(b, (uint8_t *)b->d_raw, h_raw, ro * esz));
-    TRYF(h2d(b, b->d_query, h_q, qo)); TRYF(h2d(b, b->d_ref, h_r, fo)); TRYF(h2d(b, b->d_q2r, h_q2r, qo));
-    TRYF(h2d(b, b->d_dac_off, h_doff, R)); TRYF(h2d(b, b->d_dac_scl, h_dscl, R));
-    TRYF(h2d(b, b->d_raw_off, b->raw_off.data(), R + 1)); TRYF(h2d(b, b->d_q_off, b->q_off.data(), R + 1));
-    TRYF(h2d(b, b->d_r_off, b->r_off.data(), R + 1)); TRYF(h2d(b, b->d_ev_off, b->ev_off.data(), R + 1));
-    TRYF(h2d(b, b->d_n_samples, b->n_samples.data(), R)); TRYF(h2d(b, b->d_order, b->order.data(), R));
-    TRYF(h2d(b, b->d_tile_off, b->tile_off.data(), R + 1));
-    TRYF(h2d(b, b->d_tile_read, b->tile_read.data(), b->tile_read.size()));
-    TRYF(h2d(b, b->d_ck_off, b->ck_off.data(), R + 1));
+    uint64_t sent = 0;
+    auto send = [&](void *dst, const void *src, size_t bytes) -> int {
+        if (bytes == 0) return DNB_OK;
+        sent += bytes;
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, b->stream));
+        return DNB_OK;
+    };
+    auto send_table = [&](void *dst, const void *src, size_t bytes) -> int {   // through the pinned meta block
+        if (bytes == 0) return DNB_OK;
+        meta_used = (meta_used + 15) & ~(size_t)15;
+        memcpy(h_meta + meta_used, src, bytes);
+        const int rc2 = send(dst, h_meta + meta_used, bytes);
+        meta_used += bytes;
+        return rc2;
+    };
+    TRYF(send(b->d_raw, h_raw, ro * esz));
+    TRYF(send(b->d_query, h_q, qo)); TRYF(send(b->d_ref, h_r, fo)); TRYF(send(b->d_q2r, h_q2r, qo * 4));
+    TRYF(send(b->d_dac_off, h_doff, R * 4)); TRYF(send(b->d_dac_scl, h_dscl, R * 4));
+    TRYF(send_table(b->d_raw_off, b->raw_off.data(), 8 * (R + 1))); TRYF(send_table(b->d_q_off, b->q_off.data(), 8 * (R + 1)));
+    TRYF(send_table(b->d_r_off, b->r_off.data(), 8 * (R + 1))); TRYF(send_table(b->d_ev_off, b->ev_off.data(), 8 * (R + 1)));
+    TRYF(send_table(b->d_n_samples, b->n_samples.data(), 4 * R)); TRYF(send_table(b->d_order, b->order.data(), 4 * R));
+    TRYF(send_table(b->d_tile_off, b->tile_off.data(), 4 * (R + 1)));
+    TRYF(send_table(b->d_tile_read, b->tile_read.data(), 4 * nt));
+    TRYF(send_table(b->d_ck_off, b->ck_off.data(), 8 * (R + 1)));
+    b->h2d_bytes = sent;
+    ht.tick("alloc + enqueue H2D");
     e = cudaStreamSynchronize(b->stream);
+    ht.tick("H2D wait");
     release_staging();
     if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); free_batch(b); return DNB_ERR_CUDA; }
     b->uploaded = true;
@@ -459,14 +578,8 @@ int run(dnb_batch *b) {
     const size_t R = b->R;
     cudaStream_t s = b->stream;
     const double wall0 = omp_get_wtime();
-    static const bool trace_host = getenv("DNB_TRACE_HOST") != nullptr;
-    double tick_prev = wall0;
-    auto tick = [&](const char *what) {
-        if (!trace_host) return;
-        const double now = omp_get_wtime();
-        fprintf(stderr, "[dnb host] %-28s %8.2f ms\n", what, 1e3 * (now - tick_prev));
-        tick_prev = now;
-    };
+    HostTrace ht("run");
+    auto tick = [&](const char *what) { ht.tick(what); };
     drop_work(b);
     drop_results(b);
     TRY(alloc_work_a(b));
@@ -631,10 +744,12 @@ int fetch(dnb_batch *b) {
     cudaStream_t s = b->stream;
     HostRes &h = b->h;
     Work &w = b->w;
-    TRY(ralloc(b, &h.ev_start, b->tot_ev + R)); TRY(ralloc(b, &h.ev_mean, b->tot_ev));
-    TRY(d2h(b, h.ev_start, w.ev_start, b->tot_ev + R));
-    TRY(d2h(b, h.ev_mean, w.ev_mean, b->tot_ev));
+    HostTrace ht("fetch");
     if (b->want_table) {
+        TRY(ralloc(b, &h.ev_start, b->tot_ev + R)); TRY(ralloc(b, &h.ev_mean, b->tot_ev));
+        TRY(d2h(b, h.ev_start, w.ev_start, b->tot_ev + R));
+        TRY(d2h(b, h.ev_mean, w.ev_mean, b->tot_ev));
+        b->cev_off = b->ev_off;
         TRY(ralloc(b, &h.et_start, b->tot_ev + R)); TRY(ralloc(b, &h.et_length, b->tot_ev + R));
         TRY(ralloc(b, &h.et_mean, b->tot_ev + R)); TRY(ralloc(b, &h.et_stdv, b->tot_ev + R));
         TRY(d2h(b, h.et_start, w.et_start, b->tot_ev + R)); TRY(d2h(b, h.et_length, w.et_length, b->tot_ev + R));
@@ -643,6 +758,7 @@ int fetch(dnb_batch *b) {
         b->fetched = true;
         return DNB_OK;
     }
+    // per-read scalars first: the host sizes the dense result arrays from them
     TRY(ralloc(b, &h.n_align, R)); TRY(ralloc(b, &h.n_cleaned, R)); TRY(ralloc(b, &h.spanned, R));
     TRY(ralloc(b, &h.max_gap, R)); TRY(ralloc(b, &h.rough_shift, R)); TRY(ralloc(b, &h.rough_scale, R));
     TRY(ralloc(b, &h.shift, R)); TRY(ralloc(b, &h.scale, R)); TRY(ralloc(b, &h.avg, R));
@@ -652,19 +768,29 @@ int fetch(dnb_batch *b) {
     TRY(d2h(b, h.rough_scale, w.rough_scale, R)); TRY(d2h(b, h.shift, w.shift, R));
     TRY(d2h(b, h.scale, w.scale, R)); TRY(d2h(b, h.avg, w.avg, R));
     CK(cudaStreamSynchronize(s));
-    // alignment compaction: reversed, capacity-strided device layout -> dense forward pairs
+    ht.tick("scalars D2H");
+    // dense layouts: events (the device slots are capacity-strided) and forward alignment pairs (the device list is
+    // in backtrace order): only what dnb_result hands out crosses PCIe
     b->out_off.assign(R + 1, 0);
-    uint64_t oo = 0, n_fail = 0;
+    b->cev_off.assign(R + 1, 0);
+    uint64_t oo = 0, ce = 0, n_fail = 0;
     for (size_t i = 0; i < R; i++) {
         b->out_off[i] = oo; oo += h.n_align[i];
+        b->cev_off[i] = ce; ce += h.status[i] == DNB_READ_OVERFLOW ? 0 : h.n_events[i];
         n_fail += h.status[i] != DNB_READ_OK;
     }
-    b->out_off[R] = oo;
+    b->out_off[R] = oo; b->cev_off[R] = ce;
     b->tot_out = oo;
     b->counts[7] = n_fail;
-    TRY(walloc(b, &w.out_pairs, 2 * oo));
-    TRY(ralloc(b, &h.out_pairs, 2 * oo));
+    uint64_t *d_cev_off = nullptr;
+    TRY(walloc(b, &w.out_pairs, 2 * oo)); TRY(walloc(b, &w.cev_start, ce + R)); TRY(walloc(b, &w.cev_mean, ce));
+    TRY(walloc(b, &d_cev_off, R + 1));
+    TRY(ralloc(b, &h.out_pairs, 2 * oo)); TRY(ralloc(b, &h.ev_start, ce + R)); TRY(ralloc(b, &h.ev_mean, ce));
     TRY(h2d(b, w.out_off, b->out_off.data(), R + 1));
+    TRY(h2d(b, d_cev_off, b->cev_off.data(), R + 1));
+    dnb_launch_compact_events(make_view(b), d_cev_off, w.cev_start, w.cev_mean, s);
+    TRY(d2h(b, h.ev_start, w.cev_start, ce + R));
+    TRY(d2h(b, h.ev_mean, w.cev_mean, ce));
     dnb_launch_compact_alignment(make_view(b), w.al_off, w.al_rev, w.n_align, w.out_off, w.out_pairs, s);
     TRY(d2h(b, h.out_pairs, w.out_pairs, 2 * oo));
     if (ctx->cfg.keep_debug) {
@@ -672,8 +798,10 @@ int fetch(dnb_batch *b) {
         TRY(d2h(b, h.cl_signal, w.cl_signal, b->tot_cl));
         TRY(d2h(b, h.cl_rank, w.cl_rank, b->tot_cl));
     }
+    b->d2h_bytes = 8 * ce + 4 * R + 8 * oo + 84 * R;
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    ht.tick("compact + D2H events, pairs");
     b->fetched = true;
     return DNB_OK;
 }
@@ -751,6 +879,7 @@ void dnb_destroy(dnb_ctx *ctx) {
     }
     ctx->pinned.destroy();
     ctx->dev.destroy();
+    ctx->streams.destroy();
     delete ctx;
 }
 
@@ -791,9 +920,17 @@ int dnb_batch_drop_workspace(dnb_batch *b) {
 
 int dnb_submit(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch) {
     dnb_batch *b = nullptr;
-    TRY(upload(ctx, reads, n_reads, false, &b));
-    int rc = run(b);
-    if (rc == DNB_OK) rc = fetch(b);
+    if (!ctx) return DNB_ERR_ARG;
+    TRY(upload(ctx, reads, n_reads, false, &b, /*gated=*/true));
+    int rc;
+    {
+        StageHold hold(ctx->gate_compute);
+        rc = run(b);
+    }
+    if (rc == DNB_OK) {
+        StageHold hold(ctx->gate_fetch);
+        rc = fetch(b);
+    }
     if (rc != DNB_OK) { free_batch(b); return rc; }
     drop_work(b);   // results are on the host: give the HBM workspace back to the pool for the next batch
     *batch = b;
@@ -816,8 +953,8 @@ int dnb_result(dnb_batch *b, size_t i, dnb_read_result *o) {
     o->et_n = h.et_n[i];
     o->n_events = h.n_events[i];
     if (o->status == DNB_READ_OVERFLOW) o->n_events = 0;
-    o->event_start = h.ev_start + b->ev_off[i] + i;
-    o->event_mean = h.ev_mean + b->ev_off[i];
+    o->event_start = h.ev_start + b->cev_off[i] + i;
+    o->event_mean = h.ev_mean + b->cev_off[i];
     o->n_align = o->status == DNB_READ_OK ? h.n_align[i] : 0;
     o->align_pairs = h.out_pairs + 2 * b->out_off[i];
     o->rough_shift = h.rough_shift[i]; o->rough_scale = h.rough_scale[i];
@@ -843,6 +980,13 @@ int dnb_batch_timings(dnb_batch *b, double ms[8], uint64_t counts[8]) {
     if (!b || !b->ran) return DNB_ERR_STATE;
     for (int i = 0; i < 8; i++) if (ms) ms[i] = b->ms[i];
     for (int i = 0; i < 8; i++) if (counts) counts[i] = b->counts[i];
+    return DNB_OK;
+}
+
+int dnb_batch_io_bytes(dnb_batch *b, uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+    if (!b) return DNB_ERR_ARG;
+    if (h2d_bytes) *h2d_bytes = b->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = b->d2h_bytes;
     return DNB_OK;
 }
 

@@ -161,6 +161,10 @@ void dnb_launch_compact_alignment(const DnbBatchView &v, const uint64_t *al_off,
                                   const uint32_t *n_align, const uint64_t *out_off, uint32_t *out_pairs,
                                   cudaStream_t s);
 
+// capacity-strided event slots -> dense (start[n+1], mean[n]) per read at dense_off[r] (+ r for the starts)
+void dnb_launch_compact_events(const DnbBatchView &v, const uint64_t *dense_off, uint32_t *out_start, float *out_mean,
+                               cudaStream_t s);
+
 void dnb_launch_hmm_forward(const double *obs, const uint64_t *obs_off, const char *seq, const double *shift,
                             const double *scale, const double *epb, size_t n_sites, uint32_t window,
                             const DnbModelDev &unl, const DnbModelDev &ana, double *out_analogue, double *out_thymidine,

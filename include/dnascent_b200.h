@@ -150,6 +150,9 @@ DNB_API int dnb_batch_drop_workspace(dnb_batch *batch);
  * counts: [0]=samples [1]=events [2]=k-mers [3]=bands [4]=DP cells [5]=kernel launches
  *         [6]=reads the tiled segmentation handed to its serial kernel [7]=reads with status != DNB_READ_OK */
 DNB_API int dnb_batch_timings(dnb_batch *batch, double ms[8], uint64_t counts[8]);
+/* PCIe payload of this batch, counted from the copies made: host->device bytes of the upload (signal, sequences,
+ * queryToRef, offset tables) and device->host bytes of the fetch (dense events, alignment pairs, per-read scalars) */
+DNB_API int dnb_batch_io_bytes(dnb_batch *batch, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 /* ---- detect_events drop-in (src/scrappie/event_detection.h:35) ------------------------------ */
 /* raw_pA: n float32-exact samples.  events: caller array of capacity cap; *n_events receives event_table.n. */

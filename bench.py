@@ -80,7 +80,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_reads = max(2 * cores, 8)
+    n_reads = max(16 * cores, 64)
     reads, ref, mean = cpu_sample_reads(n_reads, args.n50, args.seed)
     n_samp = sum(r.raw.size for r in reads)
     for _ in range(args.warmup):
@@ -149,7 +149,7 @@ def main():
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--bin-samples", type=float, default=2.5e9, help="samples per device bin (value leg)")
     ap.add_argument("--e2e-bin-samples", type=float, default=4.0e8, help="samples per dnb_submit call (e2e leg)")
-    ap.add_argument("--e2e-inflight", type=int, default=3)
+    ap.add_argument("--e2e-inflight", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -307,7 +307,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        reads, ref, mean_c = cpu_sample_reads(max(2 * cores, 8), args.n50, args.seed)
+        reads, ref, mean_c = cpu_sample_reads(max(16 * cores, 64), args.n50, args.seed)
         t, failed, kind = run_cpu_reference(reads, ref, mean_c, cores)
         ns = sum(r.raw.size for r in reads)
         cpu = {"value": ns / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,

@@ -22,8 +22,13 @@ WANT = [
 
 
 def short(name):
-    m = re.search(r"(\w+_kernel)", name)
-    return m.group(1) if m else name[:40]
+    m = re.search(r"(\w+_kernel)(<(?:\(int\))?(\d)>)?", name)
+    if not m:
+        return name[:40]
+    k = m.group(1)
+    if k == "align_kernel" and m.group(3):
+        k += {"0": "", "1": "_fill_only", "2": "_backtrace_only"}[m.group(3)]
+    return k
 
 
 def to_bytes(v, unit):
@@ -57,13 +62,13 @@ def main():
         if "dram__bytes_read.sum" in vals:
             tr = to_bytes(*vals["dram__bytes_read.sum"]) + to_bytes(*vals["dram__bytes_write.sum"])
             md.append(f"DRAM traffic per launch: {tr / 1e9:.3f} GB")
-            if a.cells and k in ("align_kernel", "banded_dp_kernel"):
+            if a.cells and k in ("align_kernel_fill_only", "banded_dp_kernel"):
                 consts["align_dram_bytes_per_cell"] = tr / a.cells
                 md.append(f"-> {tr / a.cells:.3f} B per DP cell (algorithmic floor 0.29 B/cell)")
             if a.samples and k == "seg_tile_kernel":
                 consts["seg_tile_dram_bytes_per_sample"] = tr / a.samples
                 md.append(f"-> {tr / a.samples:.2f} B per sample")
-        if a.cells and k in ("align_kernel", "banded_dp_kernel") and "smsp__thread_inst_executed.sum" in vals:
+        if a.cells and k in ("align_kernel_fill_only", "banded_dp_kernel") and "smsp__thread_inst_executed.sum" in vals:
             ti = float(vals["smsp__thread_inst_executed.sum"][0])
             wi = float(vals["smsp__inst_executed.sum"][0])
             consts["align_thread_instr_per_cell"] = ti / a.cells

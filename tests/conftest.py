@@ -54,6 +54,48 @@ def golden_reads():
     return [GoldenRead(d, i) for i in range(int(d["n_reads"]))]
 
 
+class GoldenReadV2(GoldenRead):
+    """reads_v2.npz: analogue-substituted reads (a*) and reads with indel / soft-clip CIGARs (i*)."""
+
+    def __init__(self, d, tag):
+        from dnascent_b200 import synth
+        p = tag + "_"
+        self.index = tag
+        self.name = tag
+        self.seq_bam = d[p + "seq_bam"].tobytes()
+        self.flag = int(d[p + "flag"])
+        self.pos = int(d[p + "pos"])
+        self.cigar = d[p + "cigar"]
+        self.dac = d[p + "dac"]
+        self.raw = synth.dac_to_pa(self.dac)
+        self.basecall = d[p + "basecall"].tobytes()
+        self.refseq = d[p + "refseq"].tobytes()
+        self.query_to_ref = d[p + "query_to_ref"]
+        self.et_n = int(d[p + "et_n"])
+        self.event_mean = d[p + "event_mean"]
+        self.event_raw_len = d[p + "event_raw_len"]
+        self.align = d[p + "align"]
+        (self.shift, self.scale, self.events_per_base, self.rough_shift, self.rough_scale, self.avg_log_emission,
+         sp, mg) = d[p + "scalars"]
+        self.spanned, self.max_gap = bool(sp), int(mg)
+        self.cleaned_signal = d[p + "cleaned_signal"]
+        self.cleaned_rank = d[p + "cleaned_rank"]
+        if p + "llr" in d:
+            self.pos_global, self.llr = d[p + "pos_global"], d[p + "llr"]
+
+
+@pytest.fixture(scope="session")
+def golden_v2():
+    d = np.load(os.path.join(GOLDEN, "reads_v2.npz"))
+    reads = {t: GoldenReadV2(d, t) for t in ("a0", "a1", "i0", "i1")}
+    tables = []
+    for name in ("unl_mean", "unl_stdv", "ana_mean", "ana_stdv"):
+        t = np.zeros(4 ** 9)
+        t[d["ranks"]] = d[name]
+        tables.append(t)
+    return reads, tables, d["reference"].tobytes()
+
+
 @pytest.fixture(scope="session")
 def golden_reference():
     return np.load(os.path.join(GOLDEN, "reads_v1.npz"))["reference"].tobytes()

@@ -181,3 +181,64 @@ def test_large_batch_vs_oracle_statistics(ctx, port, pore_mean):
         r = reads[i]
         p = port.normalise(r.raw, r.basecall, r.refseq, r.query_to_ref, pore_mean)
         _compare_with_port(out[i], p, tag=f"read {i}")
+
+
+def _check_v2(res, g, tag):
+    assert res.status == api.READ_OK, tag
+    assert res.et_n == g.et_n, tag
+    np.testing.assert_array_equal(res.event_mean, g.event_mean, err_msg=tag)
+    np.testing.assert_array_equal(np.diff(res.event_start.astype(np.int64)), g.event_raw_len.astype(np.int64), err_msg=tag)
+    np.testing.assert_array_equal(res.eventAlignment, g.align, err_msg=tag)
+    assert (res.rough_shift, res.rough_scale, res.shift, res.scale) == (g.rough_shift, g.rough_scale, g.shift, g.scale), tag
+    assert res.eventsPerBase == g.events_per_base and res.avg_log_emission == g.avg_log_emission, tag
+    assert res.spanned == g.spanned and res.maxGap == g.max_gap, tag
+    np.testing.assert_array_equal(res.cleaned_signal, g.cleaned_signal, err_msg=tag)
+    np.testing.assert_array_equal(res.cleaned_rank, g.cleaned_rank, err_msg=tag)
+
+
+def test_golden_v2_indel_cigars_and_analogue_reads(ctx, golden_v2):
+    """reads_v2.npz: queryToRef from CIGARs with insertions / deletions / soft clips (duplicate and out-of-range
+    entries, as parseCigar produces them) and BrdU-substituted signal; bit-exact against the reference's outputs."""
+    reads, _, _ = golden_v2
+    tags = list(reads)
+    out = ctx.normaliseEvents([api.Read(reads[t].raw, reads[t].basecall, reads[t].refseq, reads[t].query_to_ref) for t in tags])
+    for t, res in zip(tags, out):
+        _check_v2(res, reads[t], t)
+
+
+def test_analogue_llr_configs3(golden_v2, pore_mean):
+    """BASELINE.json configs[3]: analogue log-likelihood ratios of BrdU-substituted reads, through the C++ shim
+    (reference read constructor + our normaliseEvents + our llAcrossRead) against the reference's LLRs, 1e-4 relative."""
+    from oracle import refbind
+    if not refbind.shim_available():
+        pytest.skip("oracle/_ref/libdnascent_shim.so not built")
+    reads, (um, us, am, as_), reference = golden_v2
+    S = refbind.Ref(shim=True)
+    S.set_model(refbind.PORE, pore_mean, np.full(pore_mean.size, 0.14))
+    S.set_model(refbind.UNLABELLED, um, us)
+    S.set_model(refbind.ANALOGUE, am, as_)
+    S.shutdown()
+    S.set_reference(reference)
+    hs = [S.read_new(reads[t]) for t in ("a0", "a1")]
+    S.normalise_batch(hs)
+    calls = S.ll_across_read_batch(hs, 12)
+    for t, h, (pos, llr) in zip(("a0", "a1"), hs, calls):
+        g = reads[t]
+        np.testing.assert_array_equal(h.outputs(staged=False)["align_event"], g.align[:, 0], err_msg=t)
+        np.testing.assert_array_equal(pos, g.pos_global, err_msg=t)
+        np.testing.assert_allclose(llr, g.llr, rtol=1e-4, atol=1e-6, err_msg=t)
+    S.shutdown()
+
+
+def test_ultra_long_read_configs2(ctx, port, pore_mean):
+    """BASELINE.json configs[2] (100 kb - 1 Mb reads): long band walks, >1000 segmentation tiles per read, trace
+    windows far apart.  One 130-kb and one 260-kb read against the CPU oracle, bit-exact."""
+    ref = synth.make_reference(400_000, 41)
+    rng = np.random.default_rng(42)
+    reads = [synth.simulate_read(ref, 1000, 130_000, False, pore_mean, rng, name="u0"),
+             synth.simulate_read(ref, 90_000, 260_000, True, pore_mean, rng, name="u1", sub_rate=0.01)]
+    out = ctx.normaliseEvents([api.Read.from_synth(r, use_dac=True) for r in reads])
+    for r, o in zip(reads, out):
+        p = port.normalise(r.raw, r.basecall, r.refseq, r.query_to_ref, pore_mean)
+        _compare_with_port(o, p, tag=r.name)
+        assert o.status == api.READ_OK and o.eventAlignment.shape[0] > len(r.basecall)

@@ -190,6 +190,23 @@ def main():
     peaks, peak_src = load_peaks()
     mean = pore_model()
 
+    # ---- host-memory guard: every rank keeps its shard's signal in host RAM for the e2e leg (~2.6 B/sample + staging); never let N ranks on one box run the host out of memory
+    reads_per_gpu = args.reads
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        need = 1.3 * 2.6 * SAMPLES_PER_BASE * 25_100.0 * reads_per_gpu * world      # mean read ~25.1 kb at N50 30 kb
+        if need > 0.8 * avail:
+            reads_per_gpu = max(int(reads_per_gpu * 0.8 * avail / need), 1000)
+    except Exception:  # noqa: BLE001
+        pass
+    if world > 1:
+        t = torch.tensor([reads_per_gpu], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        reads_per_gpu = int(t.item())
+    reduced = reads_per_gpu != args.reads
+    args.reads = reads_per_gpu
+
     # ---- workload: one N*reads batch, length-balanced across ranks (no data-path collective) ----
     lengths_all = workload_lengths(world * args.reads, args.n50, args.seed)
     mine = sharding.shard_reads(lengths_all, world)[rank]
@@ -322,6 +339,7 @@ def main():
                 "workload": f"configs[1]: {args.reads} synthetic R10.4.1 reads per GPU, N50 {int(args.n50)} b, "
                             f"int16 DAC input, generated on device (seed {args.seed})",
                 "reads_per_gpu": args.reads, "samples_per_gpu": n_samples, "bins": len(bins),
+                "reads_per_gpu_reduced_for_host_ram": reduced,
                 "l2": "inputs (>= 60 GB per step) exceed the 126 MB L2; no flush needed",
                 "parallelism": f"read-sharded x{world}, length-balanced, no collective",
                 "reads_per_s": total_samples and (world * args.reads * args.steps / dt),

@@ -124,5 +124,18 @@ def generate(lengths, model_mean: np.ndarray, seed: int, device: str = "cuda:0",
     seq_off = np.zeros(R + 1, dtype=np.int64)
     seq_off[1:] = np.cumsum(lengths)
     torch.cuda.empty_cache()
-    return Workload(dac=np.concatenate(dac_parts), raw_off=raw_off, seq=np.concatenate(seq_parts), seq_off=seq_off,
+
+    def join(parts, total, dtype):
+        # assemble without ever holding two full copies (np.empty pages are not resident until written)
+        out = np.empty(total, dtype=dtype)
+        pos = 0
+        for i in range(len(parts)):
+            p = parts[i]
+            out[pos:pos + p.size] = p
+            pos += p.size
+            parts[i] = None
+        return out
+
+    return Workload(dac=join(dac_parts, int(raw_off[-1]), np.int16), raw_off=raw_off,
+                    seq=join(seq_parts, int(seq_off[-1]), np.uint8), seq_off=seq_off,
                     q2r=np.arange(int(lengths.max()) if R else 1, dtype=np.int32))

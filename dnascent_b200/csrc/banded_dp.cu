@@ -55,6 +55,20 @@ __device__ __forceinline__ double rn24(double v) {
     return __dsub_rn(__dadd_rn(v, M), M);
 }
 
+// The same rounding by Veltkamp's split with C = 2^29 + 1: p = v*C, result = p - (p - v).  Three FP64 instructions
+// and no integer ones (the magic-constant form is 2 FP64 + 3 integer), so the two forms trade FP64-pipe cycles
+// against issue slots; DP_VELTKAMP picks how many of a cell's six roundings use this one.  Exact RN-even on 24 bits
+// including ties (checked against the (float) cast on 2*10^8 doubles, 2.5*10^7 of them exact ties).
+#ifndef DP_VELTKAMP
+#define DP_VELTKAMP 6
+#endif
+__device__ __forceinline__ double rn24v(double v) {
+    const double p = __dmul_rn(v, 536870913.0);
+    return __dsub_rn(p, __dsub_rn(p, v));
+}
+template <int kSite>
+__device__ __forceinline__ double rn24s(double v) { return kSite < DP_VELTKAMP ? rn24v(v) : rn24(v); }
+
 __device__ __forceinline__ double pick4(const double (&p)[4], int j) {
     return j == 0 ? p[0] : j == 1 ? p[1] : j == 2 ? p[2] : p[3];
 }
@@ -65,11 +79,11 @@ struct DpConst {
 
 // one cell: returns the new score, sets `from`
 __device__ __forceinline__ double cell_update(double diag, double up, double left, double a, const DpConst &c, uint32_t &from) {
-    const double r = rn24(dMul(a, a));                                   // float(a*a); (-0.5f*a)*a == -0.5f*float(a*a)
-    const double em = rn24(__fma_rn(r, -0.5, c.emit_const));            // product exact: one rounding, as C + (double)t
-    const double sd = rn24(dAdd(dAdd(diag, c.lp_step), em));            // event_handling.cpp:296
-    const double su = rn24(dAdd(dAdd(up, c.lp_stay), em));              // :297
-    const double sl = rn24(dAdd(left, c.lp_skip));                      // :298
+    const double r = rn24s<1>(dMul(a, a));                                 // float(a*a); (-0.5f*a)*a == -0.5f*float(a*a)
+    const double em = rn24s<2>(__fma_rn(r, -0.5, c.emit_const));            // product exact: one rounding, as C + (double)t
+    const double sd = rn24s<4>(dAdd(dAdd(diag, c.lp_step), em));            // event_handling.cpp:296
+    const double su = rn24s<5>(dAdd(dAdd(up, c.lp_stay), em));              // :297
+    const double sl = rn24s<3>(dAdd(left, c.lp_skip));                      // :298
     double m = sd;                                                       // :300-306, ties: L over U over D
     from = DNB_FROM_D;
     if (su >= m) { m = su; from = DNB_FROM_U; }
@@ -149,7 +163,7 @@ __device__ __forceinline__ void dp_cells(DpWarp &w, double (&P1)[4], double (&P2
 #pragma unroll
         for (int j = 3; j >= 0; j--) {
             uint32_t from;
-            const double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24(q[j]), c, from);
+            const double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24s<0>(q[j]), c, from);
             P2[j] = m;
             tb |= from << (2 * j);
         }
@@ -168,7 +182,7 @@ __device__ __forceinline__ void dp_cells(DpWarp &w, double (&P1)[4], double (&P2
         for (int j = 3; j >= 0; j--) {
             const int o = (w.ll_e - (lane * 4 + j)) & 127;
             uint32_t from;
-            double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24(q[j]), c, from);
+            double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24s<0>(q[j]), c, from);
             const bool valid = (unsigned)(o - lo) < span;
             const bool trim = (o == o_trim) && trim_ok;
             m = valid ? m : (trim ? trim_val : NEG_SENT);

@@ -29,6 +29,7 @@
 // The signal is read twice (K1, K2 + halo) and only the event table is written: algorithmic traffic is
 // 4 B/sample + 8 B/event (2 B/sample for int16 DAC input).
 #include <cfloat>
+#include <cmath>
 #include "dnb_internal.cuh"
 #include "../../include/dnascent_b200.h"
 
@@ -124,18 +125,73 @@ __device__ __forceinline__ float tstat_at(double sm, double qm, double s0, doubl
     return d2f(dDiv(fabs((double)dm), __dsqrt_rn((double)fDiv(cv, wf))));
 }
 
+// ---- the same t-statistic without IEEE division / square-root subroutines (tile kernel only) ----------------------
+// Bit-identical to tstat_at for every read that passes the sample precondition checked by the checkpoint kernel
+// (every sample 0 or 2^-20 <= |x| < 2^30; other reads go to the literal serial kernel):
+//  * x / w with w a small integer constant: q0 = x*r, rem = fma(-q0, w, x), q = fma(rem, r, q0), r = RN(1/w)
+//    (Markstein's correction step).  It returns the correctly rounded quotient when |1 - w*r| <= 2^-54 (double;
+//    checked on the host for the configured windows, DnbDetector::fast_div) resp. for every finite float with
+//    |x| >= 2^-124 and w = 2..7 (checked exhaustively, tests/test_host_logic.py::test_constant_divisor_sequences).
+//  * |dm| / sqrt(v): rsqrt.approx (2^-22) + one cubic correction gives |dm| * v^-1/2 to < 8 ulp of the reference's
+//    RN(|dm| / RN(sqrt v)); if that double lies within 64 ulp of a float rounding boundary, or the seed was worse than
+//    2^-20, or cv is near the subnormal range, the lane recomputes the tail with the IEEE operations.
+struct FastDiv {
+    double wd, rd;
+    float wf, rf;
+};
+__device__ __forceinline__ double div_const(double x, const FastDiv &f) {
+    const double q0 = dMul(x, f.rd);
+    const double rem = __fma_rn(-q0, f.wd, x);      // exact remainder
+    return __fma_rn(rem, f.rd, q0);
+}
+__device__ __forceinline__ float div_const(float x, const FastDiv &f) {
+    const float q0 = fMul(x, f.rf);
+    const float rem = __fmaf_rn(-q0, f.wf, x);
+    return __fmaf_rn(rem, f.rf, q0);
+}
+__device__ __forceinline__ double rsqrt_seed(double v) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+    return y;
+}
+__device__ __forceinline__ float tstat_fast(double sm, double qm, double s0, double q0, double sp, double qp, const FastDiv &f) {
+    const double sum1 = dSub(s0, sm);
+    const double sumsq1 = dSub(q0, qm);
+    const float sum2 = d2f(dSub(sp, s0));
+    const float sumsq2 = d2f(dSub(qp, q0));
+    const float mean1 = d2f(div_const(sum1, f));
+    const float mean2 = div_const(sum2, f);
+    const float m1sq = fMul(mean1, mean1);
+    const float q2 = div_const(sumsq2, f);
+    const float m2sq = fMul(mean2, mean2);
+    float cv = d2f(dSub(dAdd(dSub(div_const(sumsq1, f), (double)m1sq), (double)q2), (double)m2sq));
+    cv = fmaxf(cv, FLT_MIN);
+    const double adm = fabs((double)fSub(mean2, mean1));
+    const double v = (double)div_const(cv, f);
+    const double y = rsqrt_seed(v);
+    const double e = __fma_rn(-dMul(v, y), y, 1.0);                    // 1 - v*y^2
+    const double y1 = __fma_rn(dMul(y, e), __fma_rn(e, 0.375, 0.5), y);   // y * (1 + e/2 + 3e^2/8)
+    const double t = dMul(adm, y1);
+    bool slow = !(cv >= 7.888609052210118e-31f);                           // 2^-100 (also catches NaN)
+    slow |= ((uint32_t)__double2hiint(e) & 0x7ff00000u) > 0x3eb00000u;    // |e| >= 2^-20: seed not as accurate as assumed
+    slow |= (((uint32_t)__double2loint(t) & 0x1fffffffu) - (0x10000000u - 64u)) <= 128u;
+    if (slow) return d2f(dDiv(adm, __dsqrt_rn((double)fDiv(cv, f.wf))));
+    return d2f(t);
+}
+
 __device__ __forceinline__ bool same_boundary(const SegBoundary &a, const SegBoundary &b) {
     return a.s_pos == b.s_pos && a.l_pos == b.l_pos && __float_as_uint(a.s_val) == __float_as_uint(b.s_val) &&
            __float_as_uint(a.l_val) == __float_as_uint(b.l_val) && a.masked == b.masked && a.valid == b.valid;
 }
 
 // ---- the streaming engine: serial chains + t-statistics + detector pair over positions [first_pos, end_pos) ------
-template <class Sink>
+template <class Sink, bool kFast = false>
 struct SegEngine {
     uint32_t N;
     DnbDetector det;
     int w1, w2;
     float w1f, w2f;
+    FastDiv f1, f2;
     bool t1_on, t2_on;
     double *rs, *rq;            // this thread's column of the shared-memory rings (stride SEG_THREADS)
     Detector ds, dl;
@@ -151,6 +207,8 @@ struct SegEngine {
 
     __device__ void init(uint32_t n, const DnbDetector &d, double *ring_s, double *ring_q, int chain_start, double s0, double q0) {
         N = n; det = d; w1 = (int)d.w1; w2 = (int)d.w2; w1f = (float)d.w1; w2f = (float)d.w2;
+        f1 = {(double)d.w1, dDiv(1.0, (double)d.w1), w1f, fDiv(1.0f, w1f)};
+        f2 = {(double)d.w2, dDiv(1.0, (double)d.w2), w2f, fDiv(1.0f, w2f)};
         t1_on = (n >= 2u * d.w1) && d.w1 >= 2; t2_on = (n >= 2u * d.w2) && d.w2 >= 2;
         rs = ring_s; rq = ring_q;
         ds = {-1, FLT_MAX, false, 0.0, 0.0}; dl = {-1, FLT_MAX, false, 0.0, 0.0};
@@ -215,9 +273,11 @@ struct SegEngine {
         float t1 = 0.0f, t2 = 0.0f;
         const double s0 = RS(i), q0 = RQ(i);
         if (t1_on && i >= w1 && (uint32_t)i <= N - det.w1)
-            t1 = tstat_at(RS(i - w1), RQ(i - w1), s0, q0, RS(i + w1), RQ(i + w1), w1f);
+            t1 = kFast ? tstat_fast(RS(i - w1), RQ(i - w1), s0, q0, RS(i + w1), RQ(i + w1), f1)
+                       : tstat_at(RS(i - w1), RQ(i - w1), s0, q0, RS(i + w1), RQ(i + w1), w1f);
         if (t2_on && i >= w2 && (uint32_t)i <= N - det.w2)
-            t2 = tstat_at(RS(i - w2), RQ(i - w2), s0, q0, RS(i + w2), RQ(i + w2), w2f);
+            t2 = kFast ? tstat_fast(RS(i - w2), RQ(i - w2), s0, q0, RS(i + w2), RQ(i + w2), f2)
+                       : tstat_at(RS(i - w2), RQ(i - w2), s0, q0, RS(i + w2), RQ(i + w2), w2f);
         fsm(i, t1, t2);
     }
 
@@ -371,6 +431,7 @@ __global__ void __launch_bounds__(128) seg_checkpoint_kernel(DnbBatchView v, Dnb
     const uint64_t total_bytes = (uint64_t)N * (kI16 ? 2 : 4);
     const uint32_t pf_ahead = 2048;
     double sum = 0.0, sumsq = 0.0;
+    uint32_t out_of_range = 0;     // precondition of tstat_fast: every sample is 0 or 2^-20 <= |x| < 2^30
     const uint32_t ng = N / CK_GROUP;
     for (uint32_t o = 0; o < pf_ahead && o < total_bytes; o += 128) prefetch_l2(bytes + o);
     CkGroup<kI16> cur, nxt;
@@ -385,7 +446,10 @@ __global__ void __launch_bounds__(128) seg_checkpoint_kernel(DnbBatchView v, Dnb
         if ((j & (DNB_SEG_CK - 1)) == 0) { cs[j / DNB_SEG_CK] = sum; cq[j / DNB_SEG_CK] = sumsq; }
 #pragma unroll
         for (int u = 0; u < CK_GROUP; u++) {
-            const double x = (double)cur.get(rd, u);
+            const float xf = cur.get(rd, u);
+            const double x = (double)xf;
+            const uint32_t ax = __float_as_uint(xf) & 0x7fffffffu;
+            out_of_range |= (ax - 0x35800000u >= 0x19000000u) && ax != 0u;
             sum = dAdd(sum, x);                  // event_detection.c:45
             sumsq = dAdd(sumsq, dMul(x, x));     // :46 (x*x is exact for a float-valued x)
         }
@@ -393,15 +457,19 @@ __global__ void __launch_bounds__(128) seg_checkpoint_kernel(DnbBatchView v, Dnb
     }
     for (uint32_t j = ng * CK_GROUP; j < N; j++) {
         if ((j & (DNB_SEG_CK - 1)) == 0) { cs[j / DNB_SEG_CK] = sum; cq[j / DNB_SEG_CK] = sumsq; }
-        const double x = (double)rd.one(base + j);
+        const float xf = rd.one(base + j);
+        const double x = (double)xf;
+        const uint32_t ax = __float_as_uint(xf) & 0x7fffffffu;
+        out_of_range |= (ax - 0x35800000u >= 0x19000000u) && ax != 0u;
         sum = dAdd(sum, x);
         sumsq = dAdd(sumsq, dMul(x, x));
     }
     t.tot_sum[r] = sum;
+    t.redo[r] = out_of_range;      // the stitch kernel ORs its own verdict into this
 }
 
 // ---- K2: one lane per tile ------------------------------------------------------------------------------------------
-template <bool kI16>
+template <bool kI16, bool kFast>
 __global__ void __launch_bounds__(SEG_THREADS) seg_tile_kernel(DnbBatchView v, DnbDetector det, DnbSegTiles t) {
     __shared__ double ring_s[SEG_RING][SEG_THREADS];
     __shared__ double ring_q[SEG_RING][SEG_THREADS];
@@ -421,7 +489,7 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_tile_kernel(DnbBatchView v, D
     const int c0 = tile == 0 ? 0 : ((s0 - w2) / DNB_SEG_CK) * DNB_SEG_CK;   // chains restart at this checkpoint
     const uint64_t ck = t.ck_off[r] + (uint32_t)c0 / DNB_SEG_CK;
 
-    SegEngine<PeakSink> en;
+    SegEngine<PeakSink, kFast> en;
     en.init(N, det, &ring_s[0][tid], &ring_q[0][tid], c0, t.ck_sum[ck], t.ck_sq[ck]);
     en.next_pos = s0; en.end_pos = t1;
     en.capture_at = tile == 0 ? -1 : t0;
@@ -494,6 +562,7 @@ __global__ void __launch_bounds__(128) seg_stitch_kernel(DnbBatchView v, DnbSegT
     if (lane != 0) return;
     const uint32_t cap = (uint32_t)(v.ev_off[r + 1] - v.ev_off[r]);
     int status = DNB_READ_OK;
+    if (t.redo[r]) bad = true;                     // sample precondition of the fast t-statistic failed (checkpoint kernel)
     t.redo[r] = bad ? 1u : 0u;
     if (!bad) {
         const uint32_t m = prefix;                 // peaks; scrappie events n = m + 1; r.events (all means > 0) = m
@@ -559,16 +628,26 @@ void dnb_launch_segmentation_serial(const DnbBatchView &v, DnbDetector det, cons
         seg_serial_kernel<false><<<grid, SEG_THREADS, 0, s>>>(v, det, only_flagged);
 }
 
+// Markstein's correction returns the correctly rounded x/w when RN(1/w) is within 2^-54 (relative) of 1/w
+static bool fast_div_ok(uint32_t w) {
+    if (w < 2 || w > 7) return false;
+    const double wd = (double)w, r = 1.0 / wd;
+    return std::fabs(std::fma(-wd, r, 1.0)) <= 0x1p-54;
+}
+
 void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s) {
     if (v.n_reads == 0) return;
     const unsigned gr = (v.n_reads + 127) / 128;
     const unsigned gt = (t.n_tiles + SEG_THREADS - 1) / SEG_THREADS;
+    const bool fast = fast_div_ok(det.w1) && fast_div_ok(det.w2);
     if (v.raw_i16) {
         seg_checkpoint_kernel<true><<<gr, 128, 0, s>>>(v, t);
-        seg_tile_kernel<true><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
+        if (fast) seg_tile_kernel<true, true><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
+        else seg_tile_kernel<true, false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
     } else {
         seg_checkpoint_kernel<false><<<gr, 128, 0, s>>>(v, t);
-        seg_tile_kernel<false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
+        if (fast) seg_tile_kernel<false, true><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
+        else seg_tile_kernel<false, false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
     }
     seg_stitch_kernel<<<(v.n_reads + 3) / 4, 128, 0, s>>>(v, t);
     seg_events_kernel<<<(t.n_tiles + 3) / 4, 128, 0, s>>>(v, t);

@@ -105,9 +105,94 @@ __device__ __forceinline__ void select_among_candidates(TsShared &sm, uint32_t n
     __syncthreads();
 }
 
+// Windowed shortcut (two sweeps instead of three).  The median of one circulant round of slopes (np of them) places
+// a window of 2^53 keys -- about one binade either side of it -- whose 4096 linear bins are histogrammed in one
+// sweep while the slopes below the window are counted; if the wanted rank falls inside the window, the slopes of
+// its bin are gathered and ranked.  Every decision is made on exact keys, so the answer is the exact order
+// statistic; when the window misses (or the bin overflows the candidate buffer) the caller runs the general
+// digit-by-digit search.
+__device__ bool select_slope_windowed(TsShared &sm, uint32_t np, uint32_t kth, unsigned long long *out) {
+    const int tid = threadIdx.x;
+    const uint32_t d = (np - 1) / 2;                  // a full round: every point paired with the one d places on
+    for (uint32_t i = tid; i < np; i += TS_THREADS) {
+        uint32_t j = i + d;
+        if (j >= np) j -= np;
+        const uint32_t lo = min(i, j), hi = max(i, j);
+        sm.u.cand[i] = order_key(dDiv(dSub(sm.y[lo], sm.y[hi]), dSub(sm.x[lo], sm.x[hi])));
+    }
+    __syncthreads();
+    select_among_candidates(sm, np, np / 2);
+    const unsigned long long centre = sm.answer;
+    const unsigned long long half = 1ull << 52;
+    const unsigned long long k0 = centre < half ? 0ull : (centre > ~0ull - half ? ~0ull - 2 * half + 1 : centre - half);
+    __syncthreads();
+    for (int i = tid; i < TS_BINS; i += TS_THREADS) sm.u.hist[i] = 0;
+    if (tid == 0) { sm.count = 0; sm.n_cand = 0; }
+    __syncthreads();
+    uint32_t below = 0;
+    for_each_slope(sm, np, [&](unsigned long long key, bool ok) {
+        const unsigned long long off = key - k0;
+        below += (ok && key < k0) ? 1u : 0u;
+        if (ok && key >= k0 && (off >> 53) == 0) atomicAdd(&sm.u.hist[(uint32_t)(off >> 41)], 1u);
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(FULL, below, o);
+    if ((tid & 31) == 0) atomicAdd(&sm.count, below);
+    __syncthreads();
+    below = sm.count;
+    __syncthreads();
+    if (tid < 32) {
+        const uint32_t per = TS_BINS / 32;
+        uint32_t sum = 0;
+        for (uint32_t q = 0; q < per; q++) sum += sm.u.hist[tid * per + q];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (tid >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        const bool inside = kth >= below && kth - below < total;
+        if (tid == 0) sm.rank = 0xffffffffu;
+        __syncwarp();
+        if (inside) {
+            const uint32_t excl = incl - sum, rank = kth - below;
+            if (rank >= excl && rank < incl) {
+                uint32_t rem = rank - excl, q = 0;
+                for (; q < per - 1; q++) {
+                    const uint32_t c = sm.u.hist[tid * per + q];
+                    if (rem < c) break;
+                    rem -= c;
+                }
+                const uint32_t bin = tid * per + q;
+                sm.prefix = bin;
+                sm.rank = rem;
+                sm.count = sm.u.hist[bin];
+            }
+        }
+    }
+    __syncthreads();
+    if (sm.rank == 0xffffffffu || sm.count > TS_CAND) return false;
+    const uint32_t bin = (uint32_t)sm.prefix, rank = sm.rank;
+    __syncthreads();
+    for_each_slope(sm, np, [&](unsigned long long key, bool ok) {
+        const unsigned long long off = key - k0;
+        if (ok && key >= k0 && (off >> 53) == 0 && (uint32_t)(off >> 41) == bin) sm.u.cand[atomicAdd(&sm.n_cand, 1u)] = key;
+    });
+    __syncthreads();
+    select_among_candidates(sm, sm.n_cand, rank);
+    *out = sm.answer;
+    return true;
+}
+
 // exact k-th smallest slope over all pairs
 __device__ unsigned long long select_slope(TsShared &sm, uint32_t np, uint32_t kth) {
     const int tid = threadIdx.x;
+    {
+        unsigned long long fast;
+        if (select_slope_windowed(sm, np, kth, &fast)) return fast;
+        __syncthreads();
+    }
     if (tid == 0) { sm.prefix = 0ull; sm.rank = kth; sm.count = np * (np - 1) / 2; }
     __syncthreads();
     for (int level = 0; level < 6; level++) {

@@ -77,14 +77,41 @@ struct DpConst {
     double lp_skip, lp_stay, lp_step, lp_trim, emit_const, inv_sigma;
 };
 
-// one cell: returns the new score, sets `from`
-__device__ __forceinline__ double cell_update(double diag, double up, double left, double a, const DpConst &c, uint32_t &from) {
-    const double r = rn24s<1>(dMul(a, a));                                 // float(a*a); (-0.5f*a)*a == -0.5f*float(a*a)
+// Which of a cell's six float roundings go through the conversion unit (F2F on the XU pipe: one instruction, but an
+// eighth of the FP64 rate) instead of three FP64 instructions: bit 0 = the emission's a and a*a (a*a is then a
+// native FP32 multiply), bit 1 = the three candidate scores (the maximum and the tie rule are then FP32 compares and
+// single-register selects, and the winner is widened once).  The kernel is issue-bound, so what counts is the
+// instruction total as long as no single pipe saturates (XU: 8 cycles per warp instruction and scheduler).
+// DP_XU holds one such 2-bit choice per register slot j (nibble j), so the XU load can be set in steps of one cell.
+#ifndef DP_XU
+#define DP_XU 0x3333
+#endif
+
+// one cell: q = (x - mu)/sigma still in double; returns the new score, sets `from`
+template <int kXU>
+__device__ __forceinline__ double cell_update(double diag, double up, double left, double q, const DpConst &c, uint32_t &from) {
+    double r;
+    if (kXU & 1) {
+        const float a = d2f(q);                                             // event_handling.cpp:133
+        r = (double)fMul(a, a);                                             // (-0.5f*a)*a == -0.5f*float(a*a)
+    } else {
+        const double a = rn24s<0>(q);
+        r = rn24s<1>(dMul(a, a));
+    }
     const double em = rn24s<2>(__fma_rn(r, -0.5, c.emit_const));            // product exact: one rounding, as C + (double)t
-    const double sd = rn24s<4>(dAdd(dAdd(diag, c.lp_step), em));            // event_handling.cpp:296
-    const double su = rn24s<5>(dAdd(dAdd(up, c.lp_stay), em));              // :297
-    const double sl = rn24s<3>(dAdd(left, c.lp_skip));                      // :298
-    double m = sd;                                                       // :300-306, ties: L over U over D
+    const double xd = dAdd(dAdd(diag, c.lp_step), em);                      // event_handling.cpp:296
+    const double xu = dAdd(dAdd(up, c.lp_stay), em);                        // :297
+    const double xl = dAdd(left, c.lp_skip);                                // :298
+    if (kXU & 2) {
+        const float sd = d2f(xd), su = d2f(xu), sl = d2f(xl);
+        float m = sd;                                                       // :300-306, ties: L over U over D
+        from = DNB_FROM_D;
+        if (su >= m) { m = su; from = DNB_FROM_U; }
+        if (sl >= m) { m = sl; from = DNB_FROM_L; }
+        return (double)m;
+    }
+    const double sd = rn24s<4>(xd), su = rn24s<5>(xu), sl = rn24s<3>(xl);
+    double m = sd;
     from = DNB_FROM_D;
     if (su >= m) { m = su; from = DNB_FROM_U; }
     if (sl >= m) { m = sl; from = DNB_FROM_L; }
@@ -160,13 +187,16 @@ __device__ __forceinline__ void dp_cells(DpWarp &w, double (&P1)[4], double (&P2
     }
     uint32_t tb = 0;
     if (kSteady) {
-#pragma unroll
-        for (int j = 3; j >= 0; j--) {
-            uint32_t from;
-            const double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24s<0>(q[j]), c, from);
-            P2[j] = m;
-            tb |= from << (2 * j);
+#define DP_CELL(j)                                                                                                  \
+        {                                                                                                           \
+            uint32_t from;                                                                                          \
+            const double m = cell_update<(DP_XU >> (4 * (j))) & 3>((j) ? P2[(j) ? (j) - 1 : 0] : e2,                \
+                                                                   (j) ? P1[(j) ? (j) - 1 : 0] : e1, P1[j], q[j], c, from); \
+            P2[j] = m;                                                                                              \
+            tb |= from << (2 * (j));                                                                                \
         }
+        DP_CELL(3) DP_CELL(2) DP_CELL(1) DP_CELL(0)
+#undef DP_CELL
         w.fills += DNB_BW;
     } else {
         // fill range (event_handling.cpp:269-278) and trim cell (:256-265), as band offsets o = ll_e - event
@@ -182,7 +212,7 @@ __device__ __forceinline__ void dp_cells(DpWarp &w, double (&P1)[4], double (&P2
         for (int j = 3; j >= 0; j--) {
             const int o = (w.ll_e - (lane * 4 + j)) & 127;
             uint32_t from;
-            double m = cell_update(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], rn24s<0>(q[j]), c, from);
+            double m = cell_update<DP_XU & 3>(j ? P2[j ? j - 1 : 0] : e2, j ? P1[j ? j - 1 : 0] : e1, P1[j], q[j], c, from);
             const bool valid = (unsigned)(o - lo) < span;
             const bool trim = (o == o_trim) && trim_ok;
             m = valid ? m : (trim ? trim_val : NEG_SENT);

@@ -632,6 +632,206 @@ double dnbo_sequence_probability(const double *obs, size_t n_obs, const char *se
     return fwd;
 }
 
+/* ------------------------------------------------------------------------------------------------------------
+ * SURVEY s.8 row f1: builtinViterbi (src/alignment.cpp:193-516) and eventalign (src/alignment.cpp:547-744)
+ * ------------------------------------------------------------------------------------------------------------ */
+static int gt_(double a, double b) { return dnbo_lnGreaterThan(a, b); }
+
+/* alignment.cpp:193-516 with flip == false.  Backtrace codes instead of the two size_t matrices:
+ *   I: 0 = from I(i)   1 = from M(i)   2 = from start (i == 0 only)
+ *   M: 0 = from I(i-1) 1 = from M(i-1) 2 = from M(i)  3 = from D(i-1);  for i == 0: 0 = from M(0), 1 = from start
+ *   D: 0 = from M(i-1) 1 = from D(i-1);  D(0) always comes from start */
+size_t dnbo_builtin_viterbi(const double *obs, size_t T, const char *seq, size_t seq_len, double shift, double scale,
+                            double events_per_base, const double *model_mean, const double *model_stdv, double *score,
+                            int32_t *idx, uint8_t *type, size_t cap) {
+    const double externalD2D = eln_(0.3), externalD2M1 = eln_(0.7), externalI2M1 = eln_(0.999), externalM12D = eln_(0.0025);
+    const double internalM12I = eln_(0.001), internalI2I = eln_(0.001);
+    const double internalM12M1 = eln_(1. - (1. / events_per_base));                                   /* :208 */
+    const double externalM12M1 = eln_(1.0 - externalM12D - internalM12I - internalM12M1);             /* :209 (Q10) */
+    const double externalM12M1orD = dnbo_lnSum(externalM12M1, externalM12D);
+    const double externalOrInternalM12M1 = dnbo_lnSum(externalM12M1, internalM12M1);
+    const size_t n = seq_len - KLEN + 1;
+    double *buf = (double *)malloc(8 * n * sizeof(double));
+    double *Ip = buf, *Mp = buf + n, *Dp = buf + 2 * n, *Ic = buf + 3 * n, *Mc = buf + 4 * n, *Dc = buf + 5 * n;
+    double *mu = buf + 6 * n, *sg = buf + 7 * n;
+    uint8_t *bI = (uint8_t *)calloc(3 * n * (T + 1), 1), *bM = bI + n * (T + 1), *bD = bM + n * (T + 1);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t rk = dnbo_kmer2index(seq + i, KLEN);
+        mu[i] = model_mean[rk];
+        sg[i] = model_stdv ? model_stdv[rk] : 0.14;
+        Ip[i] = Mp[i] = Dp[i] = Ic[i] = Mc[i] = Dc[i] = NAN;
+    }
+    double start_prev = 0.0;
+    const double start_curr = NAN;
+    Dp[0] = dnbo_lnProd(start_prev, externalM12D);                                                    /* :241 */
+    for (size_t i = 1; i < n; i++) Dp[i] = Dp[i - 1] + externalD2D;                                   /* :248 */
+    for (size_t t = 0; t < T; t++) {
+        for (size_t i = 0; i < n; i++) Ic[i] = Mc[i] = Dc[i] = NAN;
+        const double x = (obs[t] - shift) / scale;
+        uint8_t *cI = bI + (t + 1) * n, *cM = bM + (t + 1) * n, *cD = bD + (t + 1) * n;
+        double mp = eln_(dnbo_normalPDF(mu[0], sg[0], x));
+        {   /* base 1 insertion :276-300 */
+            const double v0 = Ip[0] + internalI2I + 0.0, v1 = Mp[0] + internalM12I + 0.0, v2 = start_prev + internalM12I + 0.0;
+            double m = v0; int a = 0;
+            if (gt_(v1, m)) { m = v1; a = 1; }
+            if (gt_(v2, m)) { m = v2; a = 2; }
+            Ic[0] = m; cI[0] = (uint8_t)a;
+        }
+        {   /* base 1 match :303-322 */
+            const double v0 = Mp[0] + internalM12M1 + mp, v1 = start_prev + externalOrInternalM12M1 + mp;
+            double m = v0; int a = 0;
+            if (gt_(v1, m)) { m = v1; a = 1; }
+            Mc[0] = m; cM[0] = (uint8_t)a;
+        }
+        Dc[0] = dnbo_lnProd(NAN, externalM12D);                                                       /* :325 */
+        for (size_t i = 1; i < n; i++) {
+            mp = eln_(dnbo_normalPDF(mu[i], sg[i], x));
+            {
+                const double v0 = Ip[i] + internalI2I + 0.0, v1 = Mp[i] + internalM12I + 0.0;         /* :350-356 */
+                double m = v0; int a = 0;
+                if (gt_(v1, m)) { m = v1; a = 1; }
+                Ic[i] = m; cI[i] = (uint8_t)a;
+            }
+            {
+                const double v0 = Ip[i - 1] + externalI2M1 + mp, v1 = Mp[i - 1] + externalM12M1 + mp;  /* :372-381 */
+                const double v2 = Mp[i] + internalM12M1 + mp, v3 = Dp[i - 1] + externalD2M1 + mp;
+                double m = v0; int a = 0;
+                if (gt_(v1, m)) { m = v1; a = 1; }
+                if (gt_(v2, m)) { m = v2; a = 2; }
+                if (gt_(v3, m)) { m = v3; a = 3; }
+                Mc[i] = m; cM[i] = (uint8_t)a;
+            }
+        }
+        for (size_t i = 1; i < n; i++) {                                                              /* :405-428 */
+            const double v0 = Mc[i - 1] + externalM12D, v1 = Dc[i - 1] + externalD2D;
+            double m = v0; int a = 0;
+            if (gt_(v1, m)) { m = v1; a = 1; }
+            Dc[i] = m; cD[i] = (uint8_t)a;
+        }
+        memcpy(Ip, Ic, n * sizeof(double)); memcpy(Mp, Mc, n * sizeof(double)); memcpy(Dp, Dc, n * sizeof(double));
+        start_prev = start_curr;
+    }
+    /* termination :447-474.  T == 0 leaves the *_curr vectors NaN: D wins by default (index 0) */
+    double v0 = Dc[n - 1], v1 = Mc[n - 1] + externalM12M1orD, v2 = Ic[n - 1] + externalI2M1;
+    double m = v0; int a = 0;
+    if (gt_(v1, m)) { m = v1; a = 1; }
+    if (gt_(v2, m)) { m = v2; a = 2; }
+    *score = m;
+    /* traceback :476-505; state space: type (0 D, 1 M, 2 I), index i, time t */
+    int ty = a == 0 ? 0 : a == 1 ? 1 : 2;
+    long i = (long)n - 1, t = (long)T;
+    size_t np = 0;
+    while (1) {
+        if (np < cap) { idx[np] = (int32_t)i; type[np] = (uint8_t)ty; }
+        np++;
+        int nty; long ni = i, nt = t;
+        if (ty == 0) {                       /* D: backtraceT = t (same column) */
+            if (t == 0) { if (i == 0) break; nty = 0; ni = i - 1; }                     /* :242-250 */
+            else if (i == 0) break;                                                     /* :326 */
+            else { const int c = bD[t * n + i]; nty = c == 0 ? 1 : 0; ni = i - 1; }
+        } else if (ty == 1) {                /* M: consumed observation t-1 */
+            /* column 0 of an M or I row is never written: the zero-initialised matrices say "D state 0, t = 0" */
+            if (t == 0) { ty = 0; i = 0; continue; }
+            const int c = bM[t * n + i]; nt = t - 1;
+            if (i == 0) { if (c == 1) break; nty = 1; }
+            else if (c == 0) { nty = 2; ni = i - 1; } else if (c == 1) { nty = 1; ni = i - 1; }
+            else if (c == 2) { nty = 1; } else { nty = 0; ni = i - 1; }
+        } else {
+            if (t == 0) { ty = 0; i = 0; continue; }
+            const int c = bI[t * n + i]; nt = t - 1;
+            if (c == 0) nty = 2; else if (c == 1) nty = 1; else break;
+        }
+        ty = nty; i = ni; t = nt;
+    }
+    /* reverse into path order */
+    const size_t nn = np < cap ? np : cap;
+    for (size_t q = 0; q < nn / 2; q++) {
+        int32_t ti = idx[q]; idx[q] = idx[nn - 1 - q]; idx[nn - 1 - q] = ti;
+        uint8_t tt = type[q]; type[q] = type[nn - 1 - q]; type[nn - 1 - q] = tt;
+    }
+    free(buf); free(bI);
+    return np;
+}
+
+static int defined_acgt(const char *s, size_t n) {                                                    /* :519-544 */
+    for (size_t i = 0; i < n; i++)
+        if (!(s[i] == 'A' || s[i] == 'T' || s[i] == 'G' || s[i] == 'C')) return 0;
+    return 1;
+}
+
+/* alignment.cpp:547-744 up to (not including) the text formatting: one record per event the reference prints lines
+ * for -- (index into r.events, position on referenceSeqMappedTo = reference_index + pos, label 1 = M / 2 = I, the
+ * window's indelScore).  The printed coordinate is refStart + ref_pos + k/2 (fwd) or refEnd - ref_pos - k/2 - 1 (rev).
+ * Returns the number of records (may exceed cap; only cap are stored). */
+size_t dnbo_eventalign(const char *ref, size_t rlen, const int32_t *r2q, const uint32_t *al_e, const uint32_t *al_k,
+                       size_t n_align, const double *ev_mean, double shift, double scale, double events_per_base,
+                       unsigned total_window, const double *model_mean, uint32_t *rec_event, uint32_t *rec_refpos,
+                       uint8_t *rec_label, int32_t *rec_indel, size_t cap) {
+    const unsigned k = KLEN;
+    size_t nrec = 0;
+    long read_head = 0;
+    unsigned reference_index = 0;
+    double *snip = (double *)malloc((n_align + 1) * sizeof(double));
+    uint32_t *snip_ev = (uint32_t *)malloc((n_align + 1) * sizeof(uint32_t));
+    size_t path_cap = 4 * (n_align + 4 * (size_t)total_window) + 64;
+    int32_t *pidx = (int32_t *)malloc(path_cap * sizeof(int32_t));
+    uint8_t *ptyp = (uint8_t *)malloc(path_cap);
+    while (reference_index < rlen - k + 1) {
+        const unsigned bases_to_end = (unsigned)rlen - reference_index;
+        unsigned wl = bases_to_end < total_window ? bases_to_end : total_window;
+        if (bases_to_end > 1.5 * total_window) {                                                      /* :565-595 */
+            const size_t bl = (size_t)(1.5 * wl);
+            const char *bs = ref + reference_index;
+            if (!defined_acgt(bs, bl)) { reference_index += wl; continue; }
+            for (unsigned i = wl; i < 1.5 * wl - k - 1; i++) {
+                const double m = model_mean[dnbo_kmer2index(bs + i, k)];
+                const double mb = model_mean[dnbo_kmer2index(bs + i - 1, k)];
+                const double mf = model_mean[dnbo_kmer2index(bs + i + 1, k)];
+                if (fabs(m - mf) > 0.75 && fabs(m - mb) > 0.75) { wl = i + k; break; }
+            }
+        }
+        const char *rs = ref + reference_index;
+        if (!defined_acgt(rs, wl)) { reference_index += wl; continue; }
+        const uint32_t lo = (uint32_t)r2q[reference_index], hi = (uint32_t)r2q[reference_index + wl - k + 1];
+        size_t ns = 0;
+        int first = 1;
+        for (size_t j = (size_t)read_head; j < n_align; j++) {                                        /* :611-632 */
+            if (lo <= al_k[j] && al_k[j] < hi) {
+                if (first) { read_head = (long)j; first = 0; }
+                const double em = ev_mean[al_e[j]];
+                if (0. < em && em < 250.) { snip[ns] = em; snip_ev[ns] = al_e[j]; ns++; }
+            }
+            if (al_k[j] >= hi) break;
+        }
+        const int indel = ((int)hi - (int)lo) - (int)(wl - k + 1);                                    /* :635-638 */
+        if (ns < 2) { reference_index += wl; continue; }
+        double score;
+        const size_t np = dnbo_builtin_viterbi(snip, ns, rs, wl, shift, scale, events_per_base, model_mean, NULL, &score,
+                                               pidx, ptyp, path_cap);
+        size_t last_m_ev = 0, last_m_ref = 0, ev = 0;
+        for (size_t i = 0; i < np; i++) {                                                             /* :661-672 */
+            if (ptyp[i] == 1) { last_m_ev = ev; last_m_ref = (size_t)pidx[i]; }
+            if (ptyp[i] != 0) ev++;
+        }
+        ev = 0;
+        for (size_t i = 0; i < np; i++) {                                                             /* :676-736 */
+            if (ptyp[i] == 0) continue;
+            if (ptyp[i] == 1 || (ptyp[i] == 2 && ev < last_m_ev)) {
+                if (nrec < cap) {
+                    rec_event[nrec] = snip_ev[ev]; rec_refpos[nrec] = reference_index + (uint32_t)pidx[i];
+                    rec_label[nrec] = ptyp[i]; rec_indel[nrec] = indel;
+                }
+                nrec++;
+            }
+            ev++;
+        }
+        read_head += (long)last_m_ev + 1;                                                             /* :740-741 */
+        reference_index += (unsigned)last_m_ref + 1;
+    }
+    free(snip); free(snip_ev); free(pidx); free(ptyp);
+    return nrec;
+}
+
 /* detect.cpp:381-390 + 393-574 */
 size_t dnbo_ll_across_read(const char *ref, size_t rlen, const int32_t *r2q, int is_reverse,
                            const uint32_t *al_e, const uint32_t *al_k, size_t n_align, const double *ev_mean,

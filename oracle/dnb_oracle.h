@@ -110,6 +110,16 @@ size_t dnbo_ll_across_read(const char *ref, size_t rlen, const int32_t *ref_to_q
                            const double *unl_mean, const double *unl_stdv, const double *ana_mean,
                            const double *ana_stdv, uint32_t *pos, double *llr, size_t cap);
 
+/* f1: builtinViterbi (alignment.cpp:193-516); path in order, type 0 = D, 1 = M, 2 = I; model_stdv NULL = 0.14 */
+size_t dnbo_builtin_viterbi(const double *obs, size_t T, const char *seq, size_t seq_len, double shift, double scale,
+                            double events_per_base, const double *model_mean, const double *model_stdv, double *score,
+                            int32_t *idx, uint8_t *type, size_t cap);
+/* f1: eventalign (alignment.cpp:547-744) as records (event, ref_pos, label 1 = M / 2 = I, indelScore) */
+size_t dnbo_eventalign(const char *ref, size_t rlen, const int32_t *ref_to_query, const uint32_t *align_event,
+                       const uint32_t *align_kmer, size_t n_align, const double *ev_mean, double shift, double scale,
+                       double events_per_base, unsigned total_window, const double *model_mean, uint32_t *rec_event,
+                       uint32_t *rec_refpos, uint8_t *rec_label, int32_t *rec_indel, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,9 +89,41 @@ class Port:
             getattr(L, f).argtypes = [d, d, d]
         L.dnbo_sequence_probability.restype = d
         L.dnbo_sequence_probability.argtypes = [vp, sz, C.c_char_p, sz, sz, C.c_int, d, d, d, sz, sz, vp, vp, vp, vp]
+        L.dnbo_builtin_viterbi.restype = sz
+        L.dnbo_builtin_viterbi.argtypes = [vp, sz, C.c_char_p, sz, d, d, d, vp, vp, vp, vp, vp, sz]
+        L.dnbo_eventalign.restype = sz
+        L.dnbo_eventalign.argtypes = [C.c_char_p, sz, vp, vp, vp, sz, vp, d, d, d, C.c_uint, vp, vp, vp, vp, vp, sz]
         L.dnbo_ll_across_read.restype = sz
         L.dnbo_ll_across_read.argtypes = [C.c_char_p, sz, vp, C.c_int, vp, vp, sz, vp, d, d, d, C.c_uint, vp, vp, vp,
                                           vp, vp, vp, sz]
+
+    def builtin_viterbi(self, obs, seq: bytes, shift, scale, epb, model_mean, model_stdv=None):
+        """(score, state index[], state type[] 0=D 1=M 2=I) -- alignment.cpp:193-516"""
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        cap = 4 * (obs.size + len(seq)) + 16
+        idx = np.zeros(cap, dtype=np.int32)
+        typ = np.zeros(cap, dtype=np.uint8)
+        score = C.c_double(0.0)
+        n = self.L.dnbo_builtin_viterbi(_p(obs), obs.size, seq, len(seq), shift, scale, epb, _p(model_mean),
+                                        _p(model_stdv) if model_stdv is not None else None, C.byref(score), _p(idx),
+                                        _p(typ), cap)
+        return score.value, idx[:n].copy(), typ[:n].copy()
+
+    def eventalign(self, ref: bytes, r2q, align_event, align_kmer, ev_mean, shift, scale, epb, model_mean, window=50):
+        """records (event, ref_pos, label 1=M 2=I, indelScore) -- alignment.cpp:547-744"""
+        r2q = np.ascontiguousarray(r2q, dtype=np.int32)
+        ae = np.ascontiguousarray(align_event, dtype=np.uint32)
+        ak = np.ascontiguousarray(align_kmer, dtype=np.uint32)
+        ev_mean = np.ascontiguousarray(ev_mean, dtype=np.float64)
+        cap = ae.size + 16
+        ev = np.zeros(cap, dtype=np.uint32)
+        rp = np.zeros(cap, dtype=np.uint32)
+        lb = np.zeros(cap, dtype=np.uint8)
+        ind = np.zeros(cap, dtype=np.int32)
+        n = self.L.dnbo_eventalign(ref, len(ref), _p(r2q), _p(ae), _p(ak), ae.size, _p(ev_mean), shift, scale, epb,
+                                   window, _p(model_mean), _p(ev), _p(rp), _p(lb), _p(ind), cap)
+        assert n <= cap
+        return dict(event=ev[:n].copy(), ref_pos=rp[:n].copy(), label=lb[:n].copy(), indel=ind[:n].copy())
 
     def detect_events(self, raw, w1=3, w2=6, thr1=1.4, thr2=9.0, peak_height=0.2):
         raw = np.ascontiguousarray(raw, dtype=np.float32)

@@ -26,12 +26,16 @@
 #include "event_handling.h"
 #include "probability.h"
 #include "detect.h"
+#include "alignment.h"
 #include "data_IO.h"
 #include "scrappie/event_detection.h"
 
 // normally defined in src/main/DNAscent.cpp:61
 Global_Config Pore_Substrate_Config;
 
+// non-static in src/alignment.cpp:193, not declared in its header
+std::pair<double, std::vector<std::string>> builtinViterbi(std::vector<double> &observations, std::string &sequence,
+                                                           PoreParameters scalings, bool flip);
 // non-static helpers of src/event_handling.cpp (external linkage, not in its header)
 PoreParameters estimateScaling_quantiles(std::vector<double> &signal_means, std::string &sequence,
                                          std::vector<unsigned int> &kmer_ranks, bool useFitPoreModel);
@@ -386,6 +390,60 @@ size_t dnbref_ll_across_read(void *hv, unsigned int windowLength, int32_t *pos, 
     }
     return n;
 }
+
+// ---- eventalign / builtinViterbi (src/alignment.cpp:193-516, 547-744): SURVEY s.8 row f1 -------------------
+#ifndef DNB_SHIM_BUILD
+// one window: returns the number of states on the path; state i is (index[i], type[i]) with type 0=D 1=M 2=I
+size_t dnbref_builtin_viterbi(const double *obs, size_t n_obs, const char *seq, double shift, double scale,
+                              double eventsPerBase, double *score, int32_t *index, uint8_t *type, size_t cap) {
+    std::vector<double> o(obs, obs + n_obs);
+    std::string s(seq);
+    PoreParameters p;
+    p.shift = shift;
+    p.scale = scale;
+    p.eventsPerBase = eventsPerBase;
+    std::pair<double, std::vector<std::string>> res = builtinViterbi(o, s, p, false);
+    *score = res.first;
+    size_t n = 0;
+    for (const std::string &lab : res.second) {
+        if (n < cap) {
+            index[n] = std::stoi(lab.substr(0, lab.find('_')));
+            const char t = lab[lab.find('_') + 1];
+            type[n] = t == 'D' ? 0 : t == 'M' ? 1 : 2;
+        }
+        n++;
+    }
+    return n;
+}
+#endif  // !DNB_SHIM_BUILD
+
+// eventalign on a read that has been through normaliseEvents (the reference's own in the ref build, the shim's in the
+// shim build); returns strlen(humanReadable_eventalignOut) and copies up to cap bytes
+size_t dnbref_eventalign(void *hv, unsigned int windowLength, char *out, size_t cap) {
+    DNAscent::read *r = ((Handle *)hv)->r;
+    r->refCoordToAP.clear();
+    r->humanReadable_eventalignOut.clear();
+    eventalign(*r, windowLength);
+    const std::string &s = r->humanReadable_eventalignOut;
+    if (out && cap) memcpy(out, s.data(), s.size() < cap ? s.size() : cap);
+    return s.size();
+}
+
+// what eventalign left in r.refCoordToAP through r.addSignal (reads.h:288-372), as the DNN input builders see it:
+// signal tensor [P*RAWDEPTH], core / residual k-mer indices [P], reference coordinates [P]; returns P
+size_t dnbref_aligned_positions(void *hv, float *signal, float *core, float *residual, uint32_t *coords, size_t cap) {
+    DNAscent::read *r = ((Handle *)hv)->r;
+    const size_t P = r->refCoordToAP.size();
+    if (P == 0 || P > cap) return P;
+    std::vector<float> sg = r->makeSignalTensor(), co = r->makeCoreSequenceTensor(), re = r->makeResidualSequenceTensor();
+    std::vector<unsigned int> rc = r->getReferenceCoords();
+    memcpy(signal, sg.data(), sg.size() * sizeof(float));
+    memcpy(core, co.data(), co.size() * sizeof(float));
+    memcpy(residual, re.data(), re.size() * sizeof(float));
+    for (size_t i = 0; i < rc.size(); i++) coords[i] = rc[i];
+    return P;
+}
+size_t dnbref_rawdepth(void) { return RAWDEPTH; }
 
 // ---- probability.cpp helpers -----------------------------------------------------------------
 double dnbref_eexp(double x) { return eexp(x); }

@@ -92,6 +92,14 @@ class Ref:
         for f in ("dnbref_uniformPDF", "dnbref_normalPDF", "dnbref_cauchyPDF"):
             getattr(L, f).restype = d
             getattr(L, f).argtypes = [d, d, d]
+        L.dnbref_eventalign.restype = sz
+        L.dnbref_eventalign.argtypes = [vp, C.c_uint, vp, sz]
+        L.dnbref_aligned_positions.restype = sz
+        L.dnbref_aligned_positions.argtypes = [vp, vp, vp, vp, vp, sz]
+        L.dnbref_rawdepth.restype = sz
+        if not shim:
+            L.dnbref_builtin_viterbi.restype = sz
+            L.dnbref_builtin_viterbi.argtypes = [vp, sz, C.c_char_p, d, d, d, vp, vp, vp, sz]
         L.dnbref_bench_normalise.restype = d
         L.dnbref_bench_normalise.argtypes = [vp, sz, C.c_int, C.c_int, vp]
 
@@ -149,6 +157,17 @@ class Ref:
         obs = np.ascontiguousarray(obs, dtype=np.float64)
         return self.L.dnbref_sequence_probability(_p(obs), obs.size, seq, window, int(use_brdu), shift, scale,
                                                   events_per_base, start, end)
+
+    def builtin_viterbi(self, obs, seq: bytes, shift, scale, events_per_base):
+        """builtinViterbi (alignment.cpp:193-516) on one window: (score, state index[], state type[] 0=D 1=M 2=I)."""
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        cap = 4 * (obs.size + len(seq)) + 16
+        idx = np.zeros(cap, dtype=np.int32)
+        typ = np.zeros(cap, dtype=np.uint8)
+        score = C.c_double(0.0)
+        n = self.L.dnbref_builtin_viterbi(_p(obs), obs.size, seq, shift, scale, events_per_base, C.byref(score),
+                                          _p(idx), _p(typ), cap)
+        return score.value, idx[:n].copy(), typ[:n].copy()
 
     def eln(self, x: float):
         o = np.zeros(1)
@@ -258,6 +277,44 @@ class RefRead:
             out.update(rough_shift=sc[3], rough_scale=sc[4], cleaned_signal=csig[:nc].copy(),
                        cleaned_rank=crk[:nc].copy())
         return out
+
+    @property
+    def is_reverse(self) -> bool:
+        return bool(self.L.dnbref_read_is_reverse(self.h))
+
+    @property
+    def ref_start(self) -> int:
+        return self.L.dnbref_read_ref_start(self.h)
+
+    @property
+    def ref_end(self) -> int:
+        return self.L.dnbref_read_ref_end(self.h)
+
+    def events_raw_concat(self) -> np.ndarray:
+        """The raw pA slices of r.events, concatenated (lengths: outputs()['event_raw_len'])."""
+        n = self.L.dnbref_events_raw_concat(self.h, None, 0)
+        a = np.zeros(n)
+        self.L.dnbref_events_raw_concat(self.h, _p(a), n)
+        return a
+
+    def eventalign(self, window: int = 50) -> bytes:
+        """eventalign (alignment.cpp:547-744) on a normalised read: humanReadable_eventalignOut."""
+        n = self.L.dnbref_eventalign(self.h, window, None, 0)
+        b = C.create_string_buffer(n + 1)
+        self.L.dnbref_eventalign(self.h, window, b, n)
+        return b.raw[:n]
+
+    def aligned_positions(self) -> dict:
+        """What eventalign left in refCoordToAP, as the DNN tensor builders (reads.h:305-372) see it."""
+        P = self.L.dnbref_aligned_positions(self.h, None, None, None, None, 0)
+        depth = self.L.dnbref_rawdepth()
+        sig = np.zeros(P * depth, dtype=np.float32)
+        core = np.zeros(P, dtype=np.float32)
+        resid = np.zeros(P, dtype=np.float32)
+        coords = np.zeros(P, dtype=np.uint32)
+        if P:
+            self.L.dnbref_aligned_positions(self.h, _p(sig), _p(core), _p(resid), _p(coords), P)
+        return dict(signal=sig.reshape(P, depth), core=core, residual=resid, coords=coords)
 
     def ll_across_read(self, window: int = 12):
         cap = len(self.refseq) + 1

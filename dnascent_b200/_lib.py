@@ -59,6 +59,19 @@ class ReadResult(C.Structure):
     ]
 
 
+class EventalignDesc(C.Structure):
+    _fields_ = [
+        ("ref", C.c_void_p), ("ref_len", C.c_uint32), ("ref_to_query", C.c_void_p),
+        ("align_pairs", C.c_void_p), ("n_align", C.c_uint32),
+        ("event_mean", C.c_void_p), ("n_events", C.c_uint32),
+        ("shift", C.c_double), ("scale", C.c_double), ("events_per_base", C.c_double),
+    ]
+
+
+EVENTALIGN_REC_DTYPE = _np.dtype([("event", _np.uint32), ("ref_pos", _np.uint32), ("indel_score", _np.int32),
+                                  ("label", _np.uint32)])
+
+
 class EventT(C.Structure):
     _fields_ = [("start", C.c_uint64), ("length", C.c_float), ("mean", C.c_float), ("stdv", C.c_float),
                 ("pos", C.c_int), ("state", C.c_int)]
@@ -73,6 +86,7 @@ EXPORTS = [
     "dnb_detect_events",
     "dnb_eexp", "dnb_eln", "dnb_lnSum", "dnb_lnProd", "dnb_lnGreaterThan", "dnb_uniformPDF", "dnb_normalPDF",
     "dnb_cauchyPDF", "dnb_sequence_probability_batch",
+    "dnb_eventalign_batch", "dnb_eventalign_last_kernel_ms",
 ]
 
 
@@ -117,6 +131,8 @@ def lib():
         getattr(L, f).restype = d
         getattr(L, f).argtypes = [d, d, d]
     L.dnb_sequence_probability_batch.argtypes = [vp, vp, vp, C.c_char_p, vp, vp, vp, sz, C.c_uint32, vp, vp]
+    L.dnb_eventalign_batch.argtypes = [vp, vp, sz, C.c_uint32, vp, vp, vp, vp]
+    L.dnb_eventalign_last_kernel_ms.restype = d
     _lib = L
     return L
 

@@ -255,6 +255,46 @@ class Context:
         return oa, ot
 
 
+    # -- eventalign (src/alignment.cpp:547-744) -------------------------------------------------------------
+    def eventalign(self, reads, window: int = 50):
+        """Batched eventalign.  `reads`: dicts with refseq (bytes), ref_to_query (int32[ref_len]), eventAlignment
+        (uint32[n,2]), event_mean (float32[n_events]), shift, scale, events_per_base -- the fields eventalign reads
+        from DNAscent::read after normaliseEvents.  Returns per read a dict of record arrays (event, ref_pos, label
+        1 = M / 2 = I, indel) and a status; formatting the text / addSignal is the host's job (shim)."""
+        n = len(reads)
+        descs = (_lib.EventalignDesc * max(n, 1))()
+        keep = []
+        rec_off = np.zeros(n + 1, dtype=np.uint64)
+        for i, r in enumerate(reads):
+            ref = np.frombuffer(r["refseq"], dtype=np.uint8)
+            r2q = np.ascontiguousarray(r["ref_to_query"], dtype=np.int32)
+            al = np.ascontiguousarray(r["eventAlignment"], dtype=np.uint32).reshape(-1, 2)
+            evm = np.ascontiguousarray(r["event_mean"], dtype=np.float32)
+            assert r2q.size >= ref.size
+            keep += [ref, r2q, al, evm]
+            d = descs[i]
+            d.ref, d.ref_len, d.ref_to_query = ref.ctypes.data, ref.size, r2q.ctypes.data
+            d.align_pairs, d.n_align = al.ctypes.data, al.shape[0]
+            d.event_mean, d.n_events = evm.ctypes.data, evm.size
+            d.shift, d.scale, d.events_per_base = float(r["shift"]), float(r["scale"]), float(r["events_per_base"])
+            rec_off[i + 1] = rec_off[i] + al.shape[0] + 64
+        recs = np.zeros(int(rec_off[n]), dtype=_lib.EVENTALIGN_REC_DTYPE)
+        n_rec = np.zeros(max(n, 1), dtype=np.uint32)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        _lib.check(self.L.dnb_eventalign_batch(self.h, C.addressof(descs), n, window, recs.ctypes.data,
+                                               rec_off.ctypes.data, n_rec.ctypes.data, status.ctypes.data),
+                   "dnb_eventalign_batch")
+        out = []
+        for i in range(n):
+            rr = recs[int(rec_off[i]):int(rec_off[i]) + int(n_rec[i])]
+            out.append(dict(event=rr["event"].copy(), ref_pos=rr["ref_pos"].copy(), label=rr["label"].astype(np.uint8),
+                            indel=rr["indel_score"].copy(), status=int(status[i])))
+        return out
+
+    def eventalign_last_kernel_ms(self) -> float:
+        return float(self.L.dnb_eventalign_last_kernel_ms())
+
+
 # ---- probability.h drop-ins (scalar, host) ------------------------------------------------------------
 def eexp(x: float) -> float:
     return _lib.lib().dnb_eexp(x)

@@ -1085,4 +1085,124 @@ int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64
     return rc;
 }
 
+// ---- eventalign (SURVEY s.8 row f1) ------------------------------------------------------------------------------
+static thread_local double g_ea_kernel_ms = 0.0;
+double dnb_eventalign_last_kernel_ms(void) { return g_ea_kernel_ms; }
+
+int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t n_reads, uint32_t window,
+                         dnb_eventalign_rec *recs, const uint64_t *rec_off, uint32_t *n_recs, int *status) {
+    if (!ctx || (!reads && n_reads) || !rec_off || !n_recs || !status || (!recs && n_reads && rec_off[n_reads])) return DNB_ERR_ARG;
+    if (window < DNB_K + 2 || window > 60) { g_last_error = "eventalign window must be in [11, 60]"; return DNB_ERR_ARG; }
+    if (!ctx->model[DNB_MODEL_PORE].loaded) return DNB_ERR_MODEL;
+    if (n_reads == 0) return DNB_OK;
+    if (n_reads >= (1ull << 32)) return DNB_ERR_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const size_t R = n_reads;
+    // ---- pack (host) ----
+    std::vector<uint64_t> ref_off(R + 1, 0), al_off(R + 1, 0), ev_off(R + 1, 0);
+    for (size_t i = 0; i < R; i++) {
+        const dnb_eventalign_desc &d = reads[i];
+        if ((d.ref_len && (!d.ref || !d.ref_to_query)) || (d.n_align && !d.align_pairs) || (d.n_events && !d.event_mean)) {
+            g_last_error = "eventalign descriptor " + std::to_string(i) + " is incomplete";
+            return DNB_ERR_ARG;
+        }
+        ref_off[i + 1] = ref_off[i] + d.ref_len;
+        al_off[i + 1] = al_off[i] + d.n_align;
+        ev_off[i + 1] = ev_off[i] + d.n_events;
+    }
+    const uint64_t tot_ref = ref_off[R], tot_al = al_off[R], tot_ev = ev_off[R], tot_rec = rec_off[R];
+    std::vector<char> h_ref(tot_ref ? tot_ref : 1);
+    std::vector<int32_t> h_r2q(tot_ref ? tot_ref : 1);
+    std::vector<uint32_t> h_pairs(tot_al ? 2 * tot_al : 2);
+    std::vector<float> h_evm(tot_ev ? tot_ev : 1);
+    std::vector<double> h_shift(R), h_scale(R), h_trans(4 * R);
+    std::vector<int> h_status(R, DNB_READ_OK);
+    // eln() of HMM_TransitionProbs_DNA_R10 {0.3, 0.7, 0.999, 0.0025, 0.001, 0.001} (src/config.h:42, alignment.cpp:199-204)
+    const double d2d = log(0.3), d2m = log(0.7), i2m = log(0.999), m2d = log(0.0025), m2i = log(0.001), i2i = log(0.001);
+#pragma omp parallel for schedule(static)
+    for (long long ii = 0; ii < (long long)R; ii++) {
+        const size_t i = (size_t)ii;
+        const dnb_eventalign_desc &d = reads[i];
+        if (d.ref_len) { memcpy(&h_ref[ref_off[i]], d.ref, d.ref_len); memcpy(&h_r2q[ref_off[i]], d.ref_to_query, 4ull * d.ref_len); }
+        if (d.n_align) memcpy(&h_pairs[2 * al_off[i]], d.align_pairs, 8ull * d.n_align);
+        if (d.n_events) memcpy(&h_evm[ev_off[i]], d.event_mean, 4ull * d.n_events);
+        h_shift[i] = d.shift; h_scale[i] = d.scale;
+        // alignment.cpp:207-210.  eln throws NegativeLog for x < 0 and the next eln throws for a NaN argument (x == 0)
+        const double x = 1. - (1. / d.events_per_base);
+        bool ok = x > 0.0 && d.ref_len >= DNB_K;
+        // every (event, k-mer) the kernel dereferences must exist in the caller's arrays
+        for (uint32_t j = 0; ok && j < d.n_align; j++) ok = d.align_pairs[2 * j] < d.n_events;
+        if (!ok) { h_status[i] = DNB_READ_UNDEFINED; h_trans[4 * i] = h_trans[4 * i + 1] = h_trans[4 * i + 2] = h_trans[4 * i + 3] = 0.0; continue; }
+        const double m12m1_int = log(x);
+        const double m12m1_ext = eln_nothrow(1.0 - m2d - m2i - m12m1_int);        // quirk Q10: logs inside, on purpose
+        h_trans[4 * i + 0] = m12m1_int;
+        h_trans[4 * i + 1] = m12m1_ext;
+        h_trans[4 * i + 2] = dnb_lnSum(m12m1_ext, m12m1_int);                      // externalOrInternalM12M1
+        h_trans[4 * i + 3] = dnb_lnSum(m12m1_ext, m2d);                            // externalM12M1orD
+    }
+    // ---- device ----
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = DNB_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DNB_OK) { g_last_error = cudaGetErrorString(e); rc = DNB_ERR_CUDA; } };
+    std::vector<void *> owned;
+    auto dalloc = [&](size_t bytes) -> void * { void *p = nullptr; fail(cudaMallocAsync(&p, bytes ? bytes : 16, s)); if (p) owned.push_back(p); return p; };
+    DnbEaArgs a = {};
+    a.n_reads = (uint32_t)R; a.window = window; a.t_max = 4096;
+    unsigned grid = dnb_eventalign_grid(ctx->cfg.device);
+    const unsigned wpb = dnb_eventalign_warps_per_block();
+    if ((size_t)grid * wpb > R) grid = (unsigned)((R + wpb - 1) / wpb);
+    const size_t warps = (size_t)grid * wpb;
+    uint64_t *d_ref_off = (uint64_t *)dalloc((R + 1) * 8), *d_al_off = (uint64_t *)dalloc((R + 1) * 8);
+    uint64_t *d_ev_off = (uint64_t *)dalloc((R + 1) * 8), *d_rec_off = (uint64_t *)dalloc((R + 1) * 8);
+    char *d_ref = (char *)dalloc(tot_ref);
+    int32_t *d_r2q = (int32_t *)dalloc(tot_ref * 4);
+    uint32_t *d_pairs = (uint32_t *)dalloc(tot_al * 8);
+    float *d_evm = (float *)dalloc(tot_ev * 4);
+    double *d_shift = (double *)dalloc(R * 8), *d_scale = (double *)dalloc(R * 8), *d_trans = (double *)dalloc(R * 32);
+    dnb_eventalign_rec *d_recs = (dnb_eventalign_rec *)dalloc(tot_rec * sizeof(dnb_eventalign_rec));
+    uint32_t *d_nrec = (uint32_t *)dalloc(R * 4);
+    int *d_status = (int *)dalloc(R * 4);
+    unsigned int *d_next = (unsigned int *)dalloc(4);
+    a.scratch_obs = (double *)dalloc(warps * a.t_max * 8);
+    a.scratch_ev = (uint32_t *)dalloc(warps * a.t_max * 4);
+    a.scratch_bt = (uint8_t *)dalloc(warps * a.t_max * dnb_eventalign_bt_row_bytes());
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    fail(cudaEventCreate(&e0)); fail(cudaEventCreate(&e1));
+    if (rc == DNB_OK) {
+        auto up = [&](void *dst, const void *src, size_t bytes) { if (bytes) fail(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s)); };
+        up(d_ref_off, ref_off.data(), (R + 1) * 8); up(d_al_off, al_off.data(), (R + 1) * 8);
+        up(d_ev_off, ev_off.data(), (R + 1) * 8); up(d_rec_off, rec_off, (R + 1) * 8);
+        up(d_ref, h_ref.data(), tot_ref); up(d_r2q, h_r2q.data(), tot_ref * 4); up(d_pairs, h_pairs.data(), tot_al * 8);
+        up(d_evm, h_evm.data(), tot_ev * 4); up(d_shift, h_shift.data(), R * 8); up(d_scale, h_scale.data(), R * 8);
+        up(d_trans, h_trans.data(), R * 32); up(d_status, h_status.data(), R * 4);
+        fail(cudaMemsetAsync(d_next, 0, 4, s));
+        a.ref_off = d_ref_off; a.ref = d_ref; a.r2q = d_r2q; a.al_off = d_al_off; a.pairs = reinterpret_cast<const uint2 *>(d_pairs);
+        a.ev_off = d_ev_off; a.ev_mean = d_evm; a.shift = d_shift; a.scale = d_scale; a.trans = d_trans;
+        a.model_mean = ctx->model[DNB_MODEL_PORE].d_mean;
+        // normalPDF's constants for the static sigma of the ONT table (data_IO.cpp:170, probability.cpp:147), host libm
+        a.two_sigma2 = 2.0 * pow(0.14, 2.0);
+        a.c = 1.0 / sqrt(2.0 * pow(0.14, 2.0) * M_PI);
+        a.ln_c = log(a.c);
+        a.d2d = d2d; a.d2m = d2m; a.i2m = i2m; a.m2d = m2d; a.m2i = m2i; a.i2i = i2i;
+        a.rec_off = d_rec_off; a.recs = d_recs; a.n_rec = d_nrec; a.status = d_status; a.next_read = d_next;
+        fail(cudaEventRecord(e0, s));
+        dnb_launch_eventalign(a, grid, s);
+        fail(cudaEventRecord(e1, s));
+        fail(cudaGetLastError());
+        if (tot_rec) fail(cudaMemcpyAsync(recs, d_recs, tot_rec * sizeof(dnb_eventalign_rec), cudaMemcpyDeviceToHost, s));
+        fail(cudaMemcpyAsync(n_recs, d_nrec, R * 4, cudaMemcpyDeviceToHost, s));
+        fail(cudaMemcpyAsync(status, d_status, R * 4, cudaMemcpyDeviceToHost, s));
+        fail(cudaStreamSynchronize(s));
+        float ms = 0.f;
+        if (rc == DNB_OK && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) g_ea_kernel_ms = ms;
+    }
+    for (void *p : owned) cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+    return rc;
+}
+
 }  // extern "C"

@@ -169,3 +169,35 @@ void dnb_launch_hmm_forward(const double *obs, const uint64_t *obs_off, const ch
                             const double *scale, const double *epb, size_t n_sites, uint32_t window,
                             const DnbModelDev &unl, const DnbModelDev &ana, double *out_analogue, double *out_thymidine,
                             cudaStream_t s);
+
+// ---- eventalign (eventalign.cu): windowed Viterbi re-alignment, SURVEY s.8 row f1 -----------------------------------
+struct dnb_eventalign_rec;
+struct DnbEaArgs {
+    uint32_t n_reads;
+    uint32_t window;              // totalWindowLength (Global_Config.windowLength_align = 50)
+    uint32_t t_max;               // observations per window the scratch rows hold
+    const uint64_t *ref_off;      // [R+1] offsets into ref / r2q
+    const char *ref;              // concatenated referenceSeqMappedTo
+    const int32_t *r2q;           // dense refToQuery, indexed like ref
+    const uint64_t *al_off;       // [R+1] offsets into pairs
+    const uint2 *pairs;           // (event, k-mer) = r.eventAlignment
+    const uint64_t *ev_off;       // [R+1] offsets into ev_mean
+    const float *ev_mean;         // r.events[j].mean
+    const double *shift, *scale;  // [R] r.scalings
+    const double *trans;          // [R][4] host libm: internalM12M1, externalM12M1, lnSum(ext, int), lnSum(ext, M12D)
+    const double *model_mean;     // pore_model means [4^9]
+    double ln_c, c, two_sigma2;   // log(1/sqrt(2 sigma^2 pi)), that factor, 2 sigma^2 (sigma = 0.14), host libm
+    double d2d, d2m, i2m, m2d, m2i, i2i;   // eln() of HMM_TransitionProbs_DNA_R10 (src/config.h:42), host libm
+    const uint64_t *rec_off;      // [R+1] record capacity offsets
+    dnb_eventalign_rec *recs;
+    uint32_t *n_rec;              // [R]
+    int *status;                  // [R] in: DNB_READ_OK or a host-side rejection; out: DNB_READ_*
+    unsigned int *next_read;      // work counter (zeroed before the launch)
+    double *scratch_obs;          // [warps][t_max]
+    uint32_t *scratch_ev;         // [warps][t_max]
+    uint8_t *scratch_bt;          // [warps][t_max][96] backtrace codes: I (2 bits) | M (2 bits) << 2 | D (1 bit) << 4
+};
+unsigned dnb_eventalign_grid(int device);
+unsigned dnb_eventalign_warps_per_block(void);
+size_t dnb_eventalign_bt_row_bytes(void);
+void dnb_launch_eventalign(const DnbEaArgs &a, unsigned grid, cudaStream_t s);

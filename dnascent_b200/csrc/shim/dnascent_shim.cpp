@@ -19,6 +19,8 @@
 
 #include "config.h"
 #include "event_handling.h"
+#include "alignment.h"
+#include "common.h"
 #include "probability.h"
 #include "scrappie/event_detection.h"
 #include "dnascent_b200.h"
@@ -348,5 +350,106 @@ double sequenceProbability(std::vector<double> &observations, std::string &seque
                                             &scalings.scale, &scalings.eventsPerBase, 1, (uint32_t)windowSize, &la, &lt);
     if (rc != DNB_OK) die("dnb_sequence_probability_batch", rc);
     return useBrdU ? la : lt;
+}
+// ---- eventalign (src/alignment.h:22, src/alignment.cpp:547-744) ------------------------------------------------------
+// The window chain and every builtinViterbi run on the device (dnb_eventalign_batch); what stays here is what the
+// reference does with the resulting state labels: the text of humanReadable_eventalignOut (alignment.cpp:553, 676-736)
+// and r.addSignal (alignment.cpp:723), per raw sample of each recorded event.
+namespace dnb_shim {
+
+void eventalign_batch(const std::vector<DNAscent::read *> &reads, unsigned int totalWindowLength) {
+    const unsigned int k = Pore_Substrate_Config.kmer_len;
+    const size_t n = reads.size();
+    if (n == 0) return;
+    std::vector<dnb_eventalign_desc> descs(n);
+    std::vector<std::vector<int32_t>> r2q(n);
+    std::vector<std::vector<uint32_t>> pairs(n);
+    std::vector<std::vector<float>> evm(n);
+    std::vector<uint64_t> rec_off(n + 1, 0);
+    for (size_t i = 0; i < n; i++) {
+        DNAscent::read &r = *reads[i];
+        const size_t rl = r.referenceSeqMappedTo.size();
+        r2q[i].assign(rl, 0);                                    // std::map::operator[] reads an absent key as 0
+        for (const auto &kv : r.refToQuery)
+            if (kv.first < rl) r2q[i][kv.first] = (int32_t)kv.second;
+        pairs[i].resize(2 * r.eventAlignment.size());
+        for (size_t j = 0; j < r.eventAlignment.size(); j++) {
+            pairs[i][2 * j] = r.eventAlignment[j].first;
+            pairs[i][2 * j + 1] = r.eventAlignment[j].second;
+        }
+        evm[i].resize(r.events.size());
+        for (size_t j = 0; j < r.events.size(); j++) evm[i][j] = (float)r.events[j].mean;   // float32-exact (event_detection.c:226)
+        dnb_eventalign_desc &d = descs[i];
+        d.ref = r.referenceSeqMappedTo.data();
+        d.ref_len = (uint32_t)rl;
+        d.ref_to_query = r2q[i].data();
+        d.align_pairs = pairs[i].data();
+        d.n_align = (uint32_t)r.eventAlignment.size();
+        d.event_mean = evm[i].data();
+        d.n_events = (uint32_t)r.events.size();
+        d.shift = r.scalings.shift;
+        d.scale = r.scalings.scale;
+        d.events_per_base = r.scalings.eventsPerBase;
+        rec_off[i + 1] = rec_off[i] + r.eventAlignment.size() + 64;
+    }
+    std::vector<dnb_eventalign_rec> recs(rec_off[n]);
+    std::vector<uint32_t> n_rec(n);
+    std::vector<int> status(n);
+    int rc = dnb_eventalign_batch(context(), descs.data(), n, totalWindowLength, recs.data(), rec_off.data(), n_rec.data(),
+                                  status.data());
+    if (rc != DNB_OK) die("dnb_eventalign_batch", rc);
+    for (size_t i = 0; i < n; i++) {
+        DNAscent::read &r = *reads[i];
+        if (status[i] == DNB_READ_UNDEFINED) throw NegativeLog();          // what eln() does in the reference (alignment.cpp:208)
+        if (status[i] != DNB_READ_OK) die("dnb_eventalign_batch (per-read capacity)", DNB_ERR_NOMEM);
+        std::string &out = r.humanReadable_eventalignOut;
+        out = ">" + r.readID + " " + r.referenceMappedTo + " " + std::to_string(r.refStart) + " " + std::to_string(r.refEnd) + " " + r.strand + "\n";
+        const dnb_eventalign_rec *rr = recs.data() + rec_off[i];
+        for (uint32_t q = 0; q < n_rec[i]; q++) {
+            const unsigned int ref_pos = rr[q].ref_pos;
+            std::string kmerStrand = r.referenceSeqMappedTo.substr(ref_pos, k);   // kmer2index takes a non-const reference
+            unsigned int event_coord;
+            std::string kmerRef;
+            if (r.isReverse) {                                             // alignment.cpp:646-648, 690-697
+                event_coord = r.refEnd - ref_pos - k / 2 - 1;
+                kmerRef = reverseComplement(kmerStrand);
+            } else {
+                event_coord = r.refStart + ref_pos + k / 2;
+                kmerRef = kmerStrand;
+            }
+            const unsigned int event_indexRef = ref_pos + k / 2;
+            const unsigned int event_indexQuery = r.refToQuery.at(event_indexRef);
+            const std::vector<double> &raw = r.events[rr[q].event].raw;
+            if (rr[q].label == DNB_EA_MATCH) {
+                const std::pair<double, double> meanStd = Pore_Substrate_Config.pore_model[kmer2index(kmerStrand, k)];
+                const bool called = r.refCoordToCalls.count(event_coord) > 0;
+                for (size_t idx_raw = 0; idx_raw < raw.size(); idx_raw++) {
+                    const double scaledEvent = (raw[idx_raw] - r.scalings.shift) / r.scalings.scale;
+                    out += std::to_string(event_coord) + "\t" + kmerRef + "\t" + std::to_string(scaledEvent) + "\t" + kmerStrand + "\t" +
+                           std::to_string(meanStd.first);
+                    if (called) {
+                        out += "\t" + std::to_string(r.refCoordToCalls.at(event_coord).first) + "\t" +
+                               std::to_string(r.refCoordToCalls.at(event_coord).second) + "\n";
+                    } else {
+                        out += "\n";
+                        r.addSignal(kmerStrand, event_coord, event_indexQuery, event_indexRef, scaledEvent, rr[q].indel_score);
+                    }
+                }
+            } else {
+                for (size_t idx_raw = 0; idx_raw < raw.size(); idx_raw++) {
+                    const double scaledEvent = (raw[idx_raw] - r.scalings.shift) / r.scalings.scale;
+                    out += std::to_string(event_coord) + "\t" + kmerRef + "\t" + std::to_string(scaledEvent) + "\t" + std::string(k, 'N') + "\t" + "0" + "\n";
+                }
+            }
+        }
+        r.QCpassed = true;                                                 // alignment.cpp:743
+    }
+}
+
+}  // namespace dnb_shim
+
+void eventalign(DNAscent::read &r, unsigned int totalWindowLength) {
+    std::vector<DNAscent::read *> one{&r};
+    dnb_shim::eventalign_batch(one, totalWindowLength);
 }
 #endif  // DNB_SHIM_WITH_HMM

@@ -7,6 +7,8 @@
 //   src/probability.cpp        eexp eln lnSum lnProd lnGreaterThan uniformPDF normalPDF cauchyPDF   (src/probability.h:26-33)
 // and, with -DDNB_SHIM_WITH_HMM, of the two hot functions of src/detect.cpp
 //   sequenceProbability, llAcrossRead                                  (decl. src/detect.h:119,121)
+// and of the per-read stage of src/alignment.cpp
+//   eventalign (with builtinViterbi)                                   (decl. src/alignment.h:22)
 // so that detect.cpp / alignment.cpp / trainCNN.cpp link unchanged (call sites detect.cpp:876, alignment.cpp:856,
 // trainCNN.cpp:319).  The batched entry points below are what the patched read loop of detect.cpp:850-908 calls
 // (INTEGRATION.md shows the patch); the one-read signatures are kept for every other caller.
@@ -33,5 +35,9 @@ void normaliseEvents_batch(const std::vector<DNAscent::read *> &reads, bool useF
 // Batched llAcrossRead (detect.cpp:393-574): the per-site event gathering stays on the host, every forward pass of
 // every site of every read runs in one device launch.
 void llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, unsigned int windowLength);
+
+// Batched eventalign (alignment.cpp:547-744): all window chains and Viterbi passes of the buffer in one device
+// launch; humanReadable_eventalignOut and r.addSignal are produced on the host from the returned state records.
+void eventalign_batch(const std::vector<DNAscent::read *> &reads, unsigned int totalWindowLength);
 
 }  // namespace dnb_shim

@@ -179,6 +179,41 @@ DNB_API int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, cons
                                            size_t n_sites, uint32_t window, double *out_analogue,
                                            double *out_thymidine);
 
+/* ---- eventalign: windowed Viterbi re-alignment (src/alignment.h:22, src/alignment.cpp:193-516, 547-744) ---- */
+/* The stage that follows normaliseEvents in the read loop (src/detect.cpp:888, src/alignment.cpp:866,
+ * src/trainCNN.cpp:328): per read a serial chain of ~50-base reference windows, each re-aligned by builtinViterbi.
+ * One descriptor = the fields eventalign reads from DNAscent::read (src/reads.h:178-208). */
+typedef struct {
+    const char *ref;               /* r.referenceSeqMappedTo */
+    uint32_t ref_len;
+    const int32_t *ref_to_query;   /* dense r.refToQuery, ref_len entries; an absent key reads as 0 (std::map::operator[]) */
+    const uint32_t *align_pairs;   /* r.eventAlignment, interleaved (event_idx, kmer_idx) */
+    uint32_t n_align;
+    const float *event_mean;       /* r.events[j].mean (float32-exact), n_events entries */
+    uint32_t n_events;
+    double shift, scale, events_per_base;   /* r.scalings */
+} dnb_eventalign_desc;
+
+/* One record per event the reference prints lines for (alignment.cpp:676-736): the event (index into r.events), the
+ * position of its k-mer on referenceSeqMappedTo (reference_index + pos), the window's indelScore (alignment.cpp:638)
+ * and the state label.  Printed coordinate: refStart + ref_pos + 4 (fwd) / refEnd - ref_pos - 5 (rev). */
+enum { DNB_EA_MATCH = 1, DNB_EA_INSERTION = 2 };
+typedef struct dnb_eventalign_rec {
+    uint32_t event;
+    uint32_t ref_pos;
+    int32_t indel_score;
+    uint32_t label;                /* DNB_EA_MATCH / DNB_EA_INSERTION */
+} dnb_eventalign_rec;
+
+/* recs: caller array; read i owns recs[rec_off[i] .. rec_off[i+1]) (capacity; n_align + 64 always suffices on
+ * well-formed alignments); n_recs[i] receives the count, status[i] a DNB_READ_* code (DNB_READ_UNDEFINED where the
+ * reference itself throws or indexes out of range: events_per_base <= 1, ref_len < 9; DNB_READ_OVERFLOW when
+ * the record capacity or the per-window event capacity (4096) is exceeded).  Needs DNB_MODEL_PORE. */
+DNB_API int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t n_reads, uint32_t window,
+                                 dnb_eventalign_rec *recs, const uint64_t *rec_off, uint32_t *n_recs, int *status);
+/* device time (ms, CUDA events around the kernel) of the last dnb_eventalign_batch on this thread */
+DNB_API double dnb_eventalign_last_kernel_ms(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,79 @@
+"""SURVEY s.8 row f1 on the CPU: the oracle port of builtinViterbi / eventalign (oracle/dnb_oracle.c) against the
+fixtures produced by the unmodified reference (tests/golden/eventalign_v1.npz) and, where oracle/_ref is built,
+against the reference itself on fresh seeded reads (byte-identical text)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from helpers.eventalign_render import render
+from dnascent_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def ea_golden():
+    return np.load(os.path.join(GOLDEN, "eventalign_v1.npz"))
+
+
+def golden_eventalign_inputs(g, e, tag):
+    p = f"e_{tag}_"
+    return dict(refseq=g.refseq, ref_to_query=e[p + "ref_to_query"], eventAlignment=g.align, event_mean=g.event_mean,
+                shift=g.shift, scale=g.scale, events_per_base=g.events_per_base)
+
+
+def all_golden_reads(golden_reads, golden_v2):
+    out = [(f"g{g.index}", g) for g in golden_reads]
+    out += [(t, golden_v2[0][t]) for t in ("a0", "a1", "i0", "i1")]
+    return out
+
+
+def test_port_viterbi_matches_reference_paths(port, pore_mean, ea_golden):
+    e = ea_golden
+    for c in range(e["v_score"].size):
+        obs = e["v_obs"][int(e["v_obs_off"][c]):int(e["v_obs_off"][c + 1])]
+        seq = e["v_seq"][int(e["v_seq_off"][c]):int(e["v_seq_off"][c + 1])].tobytes()
+        shift, scale, epb = e["v_par"][c]
+        score, idx, typ = port.builtin_viterbi(obs, seq, shift, scale, epb, pore_mean)
+        lo, hi = int(e["v_path_off"][c]), int(e["v_path_off"][c + 1])
+        assert score == e["v_score"][c]
+        np.testing.assert_array_equal(idx, e["v_idx"][lo:hi])
+        np.testing.assert_array_equal(typ, e["v_typ"][lo:hi])
+
+
+def test_port_eventalign_matches_reference_records(port, pore_mean, ea_golden, golden_reads, golden_v2):
+    for tag, g in all_golden_reads(golden_reads, golden_v2):
+        inp = golden_eventalign_inputs(g, ea_golden, tag)
+        rec = port.eventalign(inp["refseq"], inp["ref_to_query"], g.align[:, 0], g.align[:, 1],
+                              g.event_mean.astype(np.float64), g.shift, g.scale, g.events_per_base, pore_mean)
+        p = f"e_{tag}_"
+        for key in ("event", "ref_pos", "label", "indel"):
+            np.testing.assert_array_equal(rec[key], ea_golden[p + key], err_msg=f"{tag} {key}")
+        # and the text: rebuilt from the records it must hash to the reference's output
+        raw_len = g.event_raw_len
+        ref_start, ref_end, is_rev = (int(x) for x in ea_golden[p + "strand"])
+        # r.events[j].raw are consecutive slices of the raw signal starting at sample 0 (event_handling.cpp:549-575)
+        text = render(ea_golden[p + "header"].tobytes(), g.refseq, ref_start, ref_end, bool(is_rev),
+                      g.raw.astype(np.float64)[:int(raw_len.sum())], raw_len, rec, g.shift, g.scale, pore_mean,
+                      lambda km: int(synth.kmer_ranks(km)[0]))
+        assert len(text) == int(ea_golden[p + "text_len"]), tag
+        assert hashlib.sha256(text).digest() == ea_golden[p + "sha256"].tobytes(), tag
+
+
+def test_port_eventalign_vs_reference_fresh_reads(port, ref_oracle, pore_mean):
+    ref = synth.make_reference(80_000, 77)
+    ref_oracle.set_reference(ref)
+    reads = synth.simulate_batch(ref, [2500, 4000, 3200, 5200], pore_mean, seed=78, sub_rate=0.01)
+    for sr in reads:
+        h = ref_oracle.read_new(sr)
+        o = h.normalise(staged=False)
+        if o["align_event"].size == 0:
+            continue
+        text = h.eventalign(50)
+        rec = port.eventalign(h.refseq, h.ref_to_query, o["align_event"], o["align_kmer"], o["event_mean"], o["shift"],
+                              o["scale"], o["events_per_base"], pore_mean)
+        mine = render(text.split(b"\n")[0] + b"\n", h.refseq, h.ref_start, h.ref_end, h.is_reverse,
+                      h.events_raw_concat(), o["event_raw_len"], rec, o["shift"], o["scale"], pore_mean,
+                      ref_oracle.kmer2index)
+        assert mine == text

@@ -64,6 +64,32 @@ def test_shim_normalise_events_matches_reference(shim, ref_oracle, pore_mean):
     _same(h1.normalise(staged=False), hr[0].outputs(staged=False), "single-read call")
 
 
+def test_shim_eventalign_matches_reference(shim, ref_oracle, pore_mean):
+    """eventalign(r, 50) through the shim (window chain + builtinViterbi on the GPU, text and r.addSignal on the host)
+    against the unmodified reference on the same reads: identical humanReadable_eventalignOut, identical DNN input
+    tensors (what r.addSignal left in refCoordToAP, reads.h:288-372)."""
+    ref = synth.make_reference(200_000, 41)
+    shim.set_reference(ref)
+    ref_oracle.set_reference(ref)
+    reads = _reads(pore_mean, ref, 8, 42, lo=2000, hi=12000)
+    hs = [shim.read_new(r) for r in reads]
+    hr = [ref_oracle.read_new(r) for r in reads]
+    shim.normalise_batch(hs)
+    n = 0
+    for i, (a, b) in enumerate(zip(hs, hr)):
+        want = b.normalise(staged=False)
+        if want["align_event"].size == 0:
+            continue
+        text_ref = b.eventalign(50)
+        text_shim = a.eventalign(50)                 # the one-read signature of alignment.h:22
+        assert text_shim == text_ref, f"read {i}"
+        pa, pb = a.aligned_positions(), b.aligned_positions()
+        for key in ("signal", "core", "residual", "coords"):
+            np.testing.assert_array_equal(pa[key], pb[key], err_msg=f"read {i} {key}")
+        n += 1
+    assert n >= 6
+
+
 def test_shim_detect_events_and_probability(shim, ref_oracle, pore_mean):
     ref = synth.make_reference(50_000, 33)
     r = _reads(pore_mean, ref, 1, 34)[0]

@@ -832,6 +832,78 @@ size_t dnbo_eventalign(const char *ref, size_t rlen, const int32_t *r2q, const u
     return nrec;
 }
 
+/* ---- f2: DNN input tensors (reads.h:288-372, 147-172, 109-138; consumer detect.cpp:586-649) ----------------------
+ * Literal restatement of what eventalign's r.addSignal calls (alignment.cpp:723) leave in refCoordToAP and of the
+ * tensor builders that read it.  Input = the eventalign records (dnbo_eventalign) + the raw signal; positions are
+ * kept in a coordinate-sorted table standing for the std::map. */
+typedef struct {
+    uint32_t coord, query_idx, ref_idx, ref_pos;
+    int32_t quality;
+    uint32_t n_sig;                 /* signals added (unbounded in the reference; only the first RAWDEPTH are read) */
+    float sig[DNBO_RAWDEPTH];
+} ap_t;
+
+static int ap_cmp(const void *a, const void *b) {
+    const uint32_t x = ((const ap_t *)a)->coord, y = ((const ap_t *)b)->coord;
+    return x < y ? -1 : x > y;
+}
+
+static int u32_contains(const uint32_t *v, size_t n, uint32_t x) {      /* r.refCoordToCalls.count(event_coord) */
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t m = (lo + hi) / 2; if (v[m] < x) lo = m + 1; else hi = m; }
+    return lo < n && v[lo] == x;
+}
+
+/* base2index of AlignedPosition (reads.h:84): A0 T1 G2 C3; an unknown base reads 0 through std::map::operator[] */
+static unsigned ap_base(char c) { return c == 'T' ? 1u : c == 'G' ? 2u : c == 'C' ? 3u : 0u; }
+
+size_t dnbo_dnn_features(const char *ref, size_t rlen, const int32_t *r2q, int is_reverse, uint32_t ref_start,
+                         uint32_t ref_end, const uint32_t *rec_event, const uint32_t *rec_refpos,
+                         const uint8_t *rec_label, const int32_t *rec_indel, size_t n_rec, const double *raw,
+                         const uint32_t *event_start, double shift, double scale, const uint32_t *called,
+                         size_t n_called, float *signal, float *core, float *residual, uint32_t *coords,
+                         uint32_t *ref_index, uint32_t *query_index, int32_t *quality, size_t cap) {
+    const unsigned k = KLEN;
+    (void)rlen;
+    ap_t *tab = (ap_t *)malloc((n_rec + 1) * sizeof(ap_t));
+    size_t P = 0;
+    for (size_t q = 0; q < n_rec; q++) {
+        if (rec_label[q] != 1) continue;                                                   /* alignment.cpp:706 */
+        const uint32_t pos = rec_refpos[q];
+        const uint32_t coord = is_reverse ? ref_end - pos - k / 2 - 1 : ref_start + pos + k / 2;   /* :646-648, 690-697 */
+        if (u32_contains(called, n_called, coord)) continue;                               /* :711 */
+        const uint32_t iref = pos + k / 2;                                                 /* :701-702 */
+        for (uint32_t j = event_start[rec_event[q]]; j < event_start[rec_event[q] + 1]; j++) {
+            const double scaled = (raw[j] - shift) / scale;                                /* :709 */
+            size_t a = P;                                                                  /* reads.h:288-300 */
+            while (a > 0 && tab[a - 1].coord != coord) a--;     /* refCoordToAP.count(refPos): newest first (usually a hit) */
+            if (a > 0) a--;
+            else {
+                a = P;
+                tab[P].coord = coord; tab[P].query_idx = (uint32_t)r2q[iref]; tab[P].ref_idx = iref; tab[P].ref_pos = pos;
+                tab[P].quality = rec_indel[q]; tab[P].n_sig = 0;
+                P++;
+            }
+            if (tab[a].n_sig < DNBO_RAWDEPTH) tab[a].sig[tab[a].n_sig] = (float)scaled;    /* reads.h:154-159 */
+            tab[a].n_sig++;
+        }
+    }
+    qsort(tab, P, sizeof(ap_t), ap_cmp);                                                   /* std::map order */
+    for (size_t o = 0; o < P && o < cap; o++) {
+        const ap_t *a = &tab[is_reverse ? P - 1 - o : o];                                  /* rbegin for "rev", reads.h:320-327 */
+        for (unsigned i = 0; i < DNBO_RAWDEPTH; i++) signal[o * DNBO_RAWDEPTH + i] = i < a->n_sig ? a->sig[i] : 0.f;   /* :162-168 */
+        const char *km = ref + a->ref_pos;
+        unsigned c = 0, r = 0;
+        for (unsigned i = 2; i < 7; i++) c = c * 4u + ap_base(km[i]);                      /* getCoreIndex, reads.h:109-121 */
+        r = ((ap_base(km[0]) * 4u + ap_base(km[1])) * 4u + ap_base(km[7])) * 4u + ap_base(km[8]);   /* getResidualIndex :122-135 */
+        core[o] = (float)(c + 1u);
+        residual[o] = (float)(r + 1u);
+        coords[o] = a->coord; ref_index[o] = a->ref_idx; query_index[o] = a->query_idx; quality[o] = a->quality;
+    }
+    free(tab);
+    return P;
+}
+
 /* detect.cpp:381-390 + 393-574 */
 size_t dnbo_ll_across_read(const char *ref, size_t rlen, const int32_t *r2q, int is_reverse,
                            const uint32_t *al_e, const uint32_t *al_k, size_t n_align, const double *ev_mean,

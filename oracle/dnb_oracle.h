@@ -120,6 +120,17 @@ size_t dnbo_eventalign(const char *ref, size_t rlen, const int32_t *ref_to_query
                        double events_per_base, unsigned total_window, const double *model_mean, uint32_t *rec_event,
                        uint32_t *rec_refpos, uint8_t *rec_label, int32_t *rec_indel, size_t cap);
 
+/* f2: the DNN input tensors (reads.h:305-372) from the eventalign records and the raw signal: signal [P][20],
+ * core / residual k-mer indices, reference coordinates / indices, query indices, alignment quality; returns P.
+ * called = sorted keys of r.refCoordToCalls (positions eventalign does not addSignal for, alignment.cpp:711). */
+#define DNBO_RAWDEPTH 20
+size_t dnbo_dnn_features(const char *ref, size_t rlen, const int32_t *ref_to_query, int is_reverse, uint32_t ref_start,
+                         uint32_t ref_end, const uint32_t *rec_event, const uint32_t *rec_refpos,
+                         const uint8_t *rec_label, const int32_t *rec_indel, size_t n_rec, const double *raw,
+                         const uint32_t *event_start, double shift, double scale, const uint32_t *called,
+                         size_t n_called, float *signal, float *core, float *residual, uint32_t *coords,
+                         uint32_t *ref_index, uint32_t *query_index, int32_t *quality, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,9 +93,39 @@ class Port:
         L.dnbo_builtin_viterbi.argtypes = [vp, sz, C.c_char_p, sz, d, d, d, vp, vp, vp, vp, vp, sz]
         L.dnbo_eventalign.restype = sz
         L.dnbo_eventalign.argtypes = [C.c_char_p, sz, vp, vp, vp, sz, vp, d, d, d, C.c_uint, vp, vp, vp, vp, vp, sz]
+        L.dnbo_dnn_features.restype = sz
+        L.dnbo_dnn_features.argtypes = [C.c_char_p, sz, vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp, vp, sz, vp, vp,
+                                        d, d, vp, sz, vp, vp, vp, vp, vp, vp, vp, sz]
         L.dnbo_ll_across_read.restype = sz
         L.dnbo_ll_across_read.argtypes = [C.c_char_p, sz, vp, C.c_int, vp, vp, sz, vp, d, d, d, C.c_uint, vp, vp, vp,
                                           vp, vp, vp, sz]
+
+    def dnn_features(self, ref: bytes, r2q, is_reverse, ref_start, ref_end, rec, raw, event_start, shift, scale,
+                     called=None):
+        """DNN input tensors from eventalign records + raw signal -- reads.h:288-372, alignment.cpp:706-725"""
+        r2q = np.ascontiguousarray(r2q, dtype=np.int32)
+        ev = np.ascontiguousarray(rec["event"], dtype=np.uint32)
+        rp = np.ascontiguousarray(rec["ref_pos"], dtype=np.uint32)
+        lb = np.ascontiguousarray(rec["label"], dtype=np.uint8)
+        ind = np.ascontiguousarray(rec["indel"], dtype=np.int32)
+        raw = np.ascontiguousarray(raw, dtype=np.float64)
+        es = np.ascontiguousarray(event_start, dtype=np.uint32)
+        called = np.ascontiguousarray(called if called is not None else [], dtype=np.uint32)
+        cap = len(ref) + 1
+        sig = np.zeros((cap, 20), dtype=np.float32)
+        core = np.zeros(cap, dtype=np.float32)
+        resid = np.zeros(cap, dtype=np.float32)
+        coords = np.zeros(cap, dtype=np.uint32)
+        ri = np.zeros(cap, dtype=np.uint32)
+        qi = np.zeros(cap, dtype=np.uint32)
+        qual = np.zeros(cap, dtype=np.int32)
+        P = self.L.dnbo_dnn_features(ref, len(ref), _p(r2q), int(is_reverse), int(ref_start), int(ref_end), _p(ev),
+                                     _p(rp), _p(lb), _p(ind), ev.size, _p(raw), _p(es), shift, scale, _p(called),
+                                     called.size, _p(sig), _p(core), _p(resid), _p(coords), _p(ri), _p(qi), _p(qual),
+                                     cap)
+        assert P <= cap
+        return dict(signal=sig[:P].copy(), core=core[:P].copy(), residual=resid[:P].copy(), coords=coords[:P].copy(),
+                    ref_index=ri[:P].copy(), query_index=qi[:P].copy(), quality=qual[:P].copy())
 
     def builtin_viterbi(self, obs, seq: bytes, shift, scale, epb, model_mean, model_stdv=None):
         """(score, state index[], state type[] 0=D 1=M 2=I) -- alignment.cpp:193-516"""

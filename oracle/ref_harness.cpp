@@ -444,6 +444,19 @@ size_t dnbref_aligned_positions(void *hv, float *signal, float *core, float *res
     return P;
 }
 size_t dnbref_rawdepth(void) { return RAWDEPTH; }
+// the per-position bookkeeping runCNN reads next to the tensors (detect.cpp:668-671), in tensor order:
+// getReferenceIndices, getQueryIndices and each AlignedPosition's alignment quality (the window's indelScore)
+size_t dnbref_aligned_indices(void *hv, uint32_t *ref_index, uint32_t *query_index, int32_t *quality, size_t cap) {
+    DNAscent::read *r = ((Handle *)hv)->r;
+    const size_t P = r->refCoordToAP.size();
+    if (P == 0 || P > cap) return P;
+    std::vector<unsigned int> ri = r->getReferenceIndices(), qi = r->getQueryIndices();
+    for (size_t i = 0; i < P; i++) { ref_index[i] = ri[i]; query_index[i] = qi[i]; }
+    size_t o = 0;
+    if (r->strand == "fwd") for (auto p = r->refCoordToAP.begin(); p != r->refCoordToAP.end(); p++) quality[o++] = (int32_t)p->second->getAlignmentQuality();
+    else for (auto p = r->refCoordToAP.rbegin(); p != r->refCoordToAP.rend(); p++) quality[o++] = (int32_t)p->second->getAlignmentQuality();
+    return P;
+}
 
 // ---- probability.cpp helpers -----------------------------------------------------------------
 double dnbref_eexp(double x) { return eexp(x); }

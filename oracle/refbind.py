@@ -96,6 +96,8 @@ class Ref:
         L.dnbref_eventalign.argtypes = [vp, C.c_uint, vp, sz]
         L.dnbref_aligned_positions.restype = sz
         L.dnbref_aligned_positions.argtypes = [vp, vp, vp, vp, vp, sz]
+        L.dnbref_aligned_indices.restype = sz
+        L.dnbref_aligned_indices.argtypes = [vp, vp, vp, vp, sz]
         L.dnbref_rawdepth.restype = sz
         if not shim:
             L.dnbref_builtin_viterbi.restype = sz
@@ -314,7 +316,13 @@ class RefRead:
         coords = np.zeros(P, dtype=np.uint32)
         if P:
             self.L.dnbref_aligned_positions(self.h, _p(sig), _p(core), _p(resid), _p(coords), P)
-        return dict(signal=sig.reshape(P, depth), core=core, residual=resid, coords=coords)
+        ref_index = np.zeros(P, dtype=np.uint32)
+        query_index = np.zeros(P, dtype=np.uint32)
+        quality = np.zeros(P, dtype=np.int32)
+        if P:
+            self.L.dnbref_aligned_indices(self.h, _p(ref_index), _p(query_index), _p(quality), P)
+        return dict(signal=sig.reshape(P, depth), core=core, residual=resid, coords=coords, ref_index=ref_index,
+                    query_index=query_index, quality=quality)
 
     def ll_across_read(self, window: int = 12):
         cap = len(self.refseq) + 1

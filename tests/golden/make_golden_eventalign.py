@@ -68,6 +68,9 @@ def main():
         d[p + "ap_core"] = ap["core"].astype(np.int32)
         d[p + "ap_residual"] = ap["residual"].astype(np.int32)
         d[p + "ap_coords"] = ap["coords"]
+        d[p + "ap_ref_index"] = ap["ref_index"]
+        d[p + "ap_query_index"] = ap["query_index"]
+        d[p + "ap_quality"] = ap["quality"]
         print(f"{tag}: {len(text)} bytes, {d[p + 'n_lines']} lines, {rec['event'].size} records "
               f"(M {int((rec['label'] == 1).sum())}, I {int((rec['label'] == 2).sum())}), {ap['coords'].size} positions")
 

@@ -61,6 +61,38 @@ def test_port_eventalign_matches_reference_records(port, pore_mean, ea_golden, g
         assert hashlib.sha256(text).digest() == ea_golden[p + "sha256"].tobytes(), tag
 
 
+def golden_records(e, tag):
+    p = f"e_{tag}_"
+    return {key: e[p + key] for key in ("event", "ref_pos", "label", "indel")}
+
+
+def event_starts(raw_len):
+    return np.concatenate([[0], np.cumsum(raw_len)]).astype(np.uint32)
+
+
+AP_KEYS = ("signal", "core", "residual", "coords", "ref_index", "query_index", "quality")
+
+
+def test_port_dnn_features_match_reference_tensors(port, ea_golden, golden_reads, golden_v2):
+    """Row f2: the port's tensor builder on the golden records == makeSignalTensor / makeCoreSequenceTensor /
+    makeResidualSequenceTensor / getReferenceCoords / ...Indices of the unmodified reference (reads.h:305-427)."""
+    e = ea_golden
+    for tag, g in all_golden_reads(golden_reads, golden_v2):
+        p = f"e_{tag}_"
+        ref_start, ref_end, is_rev = (int(x) for x in e[p + "strand"])
+        f = port.dnn_features(g.refseq, e[p + "ref_to_query"], is_rev, ref_start, ref_end, golden_records(e, tag),
+                              g.raw.astype(np.float64), event_starts(g.event_raw_len), g.shift, g.scale)
+        for key in AP_KEYS:
+            np.testing.assert_array_equal(f[key], e[p + "ap_" + key], err_msg=f"{tag} {key}")
+        # positions already called (refCoordToCalls, alignment.cpp:711) are not added
+        called = np.sort(e[p + "ap_coords"][::3])
+        f2 = port.dnn_features(g.refseq, e[p + "ref_to_query"], is_rev, ref_start, ref_end, golden_records(e, tag),
+                               g.raw.astype(np.float64), event_starts(g.event_raw_len), g.shift, g.scale, called=called)
+        keep = ~np.isin(e[p + "ap_coords"], called)
+        for key in AP_KEYS:
+            np.testing.assert_array_equal(f2[key], e[p + "ap_" + key][keep], err_msg=f"{tag} {key} (called)")
+
+
 def test_port_eventalign_vs_reference_fresh_reads(port, ref_oracle, pore_mean):
     ref = synth.make_reference(80_000, 77)
     ref_oracle.set_reference(ref)
@@ -77,3 +109,8 @@ def test_port_eventalign_vs_reference_fresh_reads(port, ref_oracle, pore_mean):
                       h.events_raw_concat(), o["event_raw_len"], rec, o["shift"], o["scale"], pore_mean,
                       ref_oracle.kmer2index)
         assert mine == text
+        ap = h.aligned_positions()
+        f = port.dnn_features(h.refseq, h.ref_to_query, h.is_reverse, h.ref_start, h.ref_end, rec, h.events_raw_concat(),
+                              event_starts(o["event_raw_len"]), o["shift"], o["scale"])
+        for key in AP_KEYS:
+            np.testing.assert_array_equal(f[key], ap[key], err_msg=key)

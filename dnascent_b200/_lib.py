@@ -68,6 +68,20 @@ class EventalignDesc(C.Structure):
     ]
 
 
+class FeatureDesc(C.Structure):
+    _fields_ = [
+        ("raw_pA", C.c_void_p), ("raw_dac", C.c_void_p), ("dac_offset", C.c_float), ("dac_scale", C.c_float),
+        ("n_samples", C.c_uint64), ("event_start", C.c_void_p),
+        ("is_reverse", C.c_int), ("ref_start", C.c_uint32), ("ref_end", C.c_uint32),
+        ("called", C.c_void_p), ("n_called", C.c_uint32),
+    ]
+
+
+class FeatureTensors(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("signal", "core", "residual", "coords", "ref_index", "query_index", "quality")]
+
+
+RAWDEPTH = 20
 EVENTALIGN_REC_DTYPE = _np.dtype([("event", _np.uint32), ("ref_pos", _np.uint32), ("indel_score", _np.int32),
                                   ("label", _np.uint32)])
 
@@ -87,6 +101,7 @@ EXPORTS = [
     "dnb_eexp", "dnb_eln", "dnb_lnSum", "dnb_lnProd", "dnb_lnGreaterThan", "dnb_uniformPDF", "dnb_normalPDF",
     "dnb_cauchyPDF", "dnb_sequence_probability_batch",
     "dnb_eventalign_batch", "dnb_eventalign_last_kernel_ms",
+    "dnb_eventalign_features_batch", "dnb_features_last_kernel_ms",
 ]
 
 
@@ -133,6 +148,8 @@ def lib():
     L.dnb_sequence_probability_batch.argtypes = [vp, vp, vp, C.c_char_p, vp, vp, vp, sz, C.c_uint32, vp, vp]
     L.dnb_eventalign_batch.argtypes = [vp, vp, sz, C.c_uint32, vp, vp, vp, vp]
     L.dnb_eventalign_last_kernel_ms.restype = d
+    L.dnb_eventalign_features_batch.argtypes = [vp, vp, vp, sz, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
+    L.dnb_features_last_kernel_ms.restype = d
     _lib = L
     return L
 

@@ -294,6 +294,74 @@ class Context:
     def eventalign_last_kernel_ms(self) -> float:
         return float(self.L.dnb_eventalign_last_kernel_ms())
 
+    # -- eventalign + DNN input tensors (src/reads.h:288-452, consumer src/detect.cpp:586-649) -----------------
+    def eventalign_features(self, reads, window: int = 50, want_records: bool = True):
+        """eventalign and, in the same device pass, the tensors runCNN feeds TensorFlow.  `reads`: the dicts
+        eventalign() takes plus raw (float32 pA) or raw_dac (int16) with dac_offset / dac_scale, event_start
+        (uint32[n_events+1]), is_reverse, ref_start, ref_end and optionally called (sorted uint32 coordinates).
+        Returns per read a dict: status, signal [P,20], core, residual, coords, ref_index, query_index, quality
+        (+ the record arrays when want_records)."""
+        n = len(reads)
+        descs = (_lib.EventalignDesc * max(n, 1))()
+        feats = (_lib.FeatureDesc * max(n, 1))()
+        keep = []
+        rec_off = np.zeros(n + 1, dtype=np.uint64)
+        pos_off = np.zeros(n + 1, dtype=np.uint64)
+        for i, r in enumerate(reads):
+            ref = np.frombuffer(r["refseq"], dtype=np.uint8)
+            r2q = np.ascontiguousarray(r["ref_to_query"], dtype=np.int32)
+            al = np.ascontiguousarray(r["eventAlignment"], dtype=np.uint32).reshape(-1, 2)
+            evm = np.ascontiguousarray(r["event_mean"], dtype=np.float32)
+            es = np.ascontiguousarray(r["event_start"], dtype=np.uint32)
+            called = np.ascontiguousarray(r.get("called", []), dtype=np.uint32)
+            assert r2q.size >= ref.size and es.size == evm.size + 1
+            keep += [ref, r2q, al, evm, es, called]
+            d, f = descs[i], feats[i]
+            d.ref, d.ref_len, d.ref_to_query = ref.ctypes.data, ref.size, r2q.ctypes.data
+            d.align_pairs, d.n_align = al.ctypes.data, al.shape[0]
+            d.event_mean, d.n_events = evm.ctypes.data, evm.size
+            d.shift, d.scale, d.events_per_base = float(r["shift"]), float(r["scale"]), float(r["events_per_base"])
+            if r.get("raw_dac") is not None:
+                raw = np.ascontiguousarray(r["raw_dac"], dtype=np.int16)
+                f.raw_dac, f.dac_offset, f.dac_scale = raw.ctypes.data, float(r["dac_offset"]), float(r["dac_scale"])
+            else:
+                raw = np.ascontiguousarray(r["raw"], dtype=np.float32)
+                f.raw_pA = raw.ctypes.data
+            keep.append(raw)
+            f.n_samples, f.event_start = raw.size, es.ctypes.data
+            f.is_reverse, f.ref_start, f.ref_end = int(bool(r["is_reverse"])), int(r["ref_start"]), int(r["ref_end"])
+            f.called, f.n_called = (called.ctypes.data if called.size else None), called.size
+            rec_off[i + 1] = rec_off[i] + al.shape[0] + 64
+            pos_off[i + 1] = pos_off[i] + int(r.get("row_capacity", max(ref.size, 8) - 8 + 1))
+        recs = np.zeros(int(rec_off[n]) if want_records else 0, dtype=_lib.EVENTALIGN_REC_DTYPE)
+        n_rec = np.zeros(max(n, 1), dtype=np.uint32)
+        n_pos = np.zeros(max(n, 1), dtype=np.uint32)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        rows = int(pos_off[n])
+        T = dict(signal=np.zeros((rows, _lib.RAWDEPTH), dtype=np.float32), core=np.zeros(rows, dtype=np.float32),
+                 residual=np.zeros(rows, dtype=np.float32), coords=np.zeros(rows, dtype=np.uint32),
+                 ref_index=np.zeros(rows, dtype=np.uint32), query_index=np.zeros(rows, dtype=np.uint32),
+                 quality=np.zeros(rows, dtype=np.int32))
+        tens = _lib.FeatureTensors(**{k: v.ctypes.data for k, v in T.items()})
+        _lib.check(self.L.dnb_eventalign_features_batch(
+            self.h, C.addressof(descs), C.addressof(feats), n, window, recs.ctypes.data if want_records else None,
+            rec_off.ctypes.data, n_rec.ctypes.data, status.ctypes.data, C.addressof(tens), pos_off.ctypes.data,
+            n_pos.ctypes.data), "dnb_eventalign_features_batch")
+        out = []
+        for i in range(n):
+            lo, hi = int(pos_off[i]), int(pos_off[i]) + int(n_pos[i])
+            o = {k: v[lo:hi].copy() for k, v in T.items()}
+            o["status"] = int(status[i])
+            if want_records:
+                rr = recs[int(rec_off[i]):int(rec_off[i]) + int(n_rec[i])]
+                o.update(event=rr["event"].copy(), ref_pos=rr["ref_pos"].copy(), label=rr["label"].astype(np.uint8),
+                         indel=rr["indel_score"].copy())
+            out.append(o)
+        return out
+
+    def features_last_kernel_ms(self) -> float:
+        return float(self.L.dnb_features_last_kernel_ms())
+
 
 # ---- probability.h drop-ins (scalar, host) ------------------------------------------------------------
 def eexp(x: float) -> float:

@@ -1089,9 +1089,19 @@ int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64
 static thread_local double g_ea_kernel_ms = 0.0;
 double dnb_eventalign_last_kernel_ms(void) { return g_ea_kernel_ms; }
 
-int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t n_reads, uint32_t window,
-                         dnb_eventalign_rec *recs, const uint64_t *rec_off, uint32_t *n_recs, int *status) {
-    if (!ctx || (!reads && n_reads) || !rec_off || !n_recs || !status || (!recs && n_reads && rec_off[n_reads])) return DNB_ERR_ARG;
+static thread_local double g_ft_kernel_ms = 0.0;
+double dnb_features_last_kernel_ms(void) { return g_ft_kernel_ms; }
+
+// eventalign, and (feats != NULL) the DNN input tensors from its records in the same device pass (row f2)
+static int eventalign_impl(dnb_ctx *ctx, const dnb_eventalign_desc *reads, const dnb_feature_desc *feats, size_t n_reads,
+                           uint32_t window, dnb_eventalign_rec *recs, const uint64_t *rec_off, uint32_t *n_recs,
+                           int *status, const dnb_feature_tensors *out, const uint64_t *pos_off, uint32_t *n_pos) {
+    if (!ctx || (!reads && n_reads) || !rec_off || !n_recs || !status) return DNB_ERR_ARG;
+    if (!feats && !recs && n_reads && rec_off[n_reads]) return DNB_ERR_ARG;
+    if (feats && (!out || !pos_off || !n_pos)) return DNB_ERR_ARG;
+    if (feats && n_reads && pos_off[n_reads] &&
+        (!out->signal || !out->core || !out->residual || !out->coords || !out->ref_index || !out->query_index || !out->quality))
+        return DNB_ERR_ARG;
     if (window < DNB_K + 2 || window > 60) { g_last_error = "eventalign window must be in [11, 60]"; return DNB_ERR_ARG; }
     if (!ctx->model[DNB_MODEL_PORE].loaded) return DNB_ERR_MODEL;
     if (n_reads == 0) return DNB_OK;
@@ -1140,6 +1150,39 @@ int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t 
         h_trans[4 * i + 2] = dnb_lnSum(m12m1_ext, m12m1_int);                      // externalOrInternalM12M1
         h_trans[4 * i + 3] = dnb_lnSum(m12m1_ext, m2d);                            // externalM12M1orD
     }
+    // ---- feature inputs (row f2): offsets only; the signal and the event starts go up straight from the caller's arrays
+    std::vector<uint64_t> raw_off, called_off;
+    std::vector<uint8_t> h_kind, h_rev;
+    std::vector<float> h_doff, h_dscl;
+    std::vector<uint32_t> h_rstart, h_rend;
+    uint64_t tot_f32 = 0, tot_i16 = 0, tot_called = 0, tot_pos = 0;
+    if (feats) {
+        raw_off.assign(R, 0); called_off.assign(R + 1, 0);
+        h_kind.assign(R, 0); h_rev.assign(R, 0); h_doff.assign(R, 0.f); h_dscl.assign(R, 1.f);
+        h_rstart.assign(R, 0); h_rend.assign(R, 0);
+        for (size_t i = 0; i < R; i++) {
+            const dnb_feature_desc &f = feats[i];
+            if ((f.n_samples && !f.raw_pA && !f.raw_dac) || (reads[i].n_events && !f.event_start) || (f.n_called && !f.called)) {
+                g_last_error = "feature descriptor " + std::to_string(i) + " is incomplete";
+                return DNB_ERR_ARG;
+            }
+            h_kind[i] = f.raw_pA ? 0 : 1;
+            // 16-byte aligned read starts in both arrays
+            if (f.raw_pA) { raw_off[i] = tot_f32; tot_f32 += (f.n_samples + 3) & ~3ull; }
+            else { raw_off[i] = tot_i16; tot_i16 += (f.n_samples + 7) & ~7ull; }
+            h_doff[i] = f.dac_offset; h_dscl[i] = f.dac_scale;
+            h_rev[i] = f.is_reverse ? 1 : 0; h_rstart[i] = f.ref_start; h_rend[i] = f.ref_end;
+            called_off[i + 1] = called_off[i] + f.n_called;
+            // every sample an event of this read can address must exist (event_start is non-decreasing in a valid read)
+            if (h_status[i] == DNB_READ_OK && reads[i].n_events) {
+                bool ok = f.event_start[reads[i].n_events] <= f.n_samples;
+                for (uint32_t j = 0; ok && j < reads[i].n_events; j++) ok = f.event_start[j] <= f.event_start[j + 1];
+                if (!ok) h_status[i] = DNB_READ_UNDEFINED;
+            }
+        }
+        tot_called = called_off[R];
+        tot_pos = pos_off[R];
+    }
     // ---- device ----
     cudaStream_t s;
     CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -1167,8 +1210,8 @@ int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t 
     a.scratch_obs = (double *)dalloc(warps * a.t_max * 8);
     a.scratch_ev = (uint32_t *)dalloc(warps * a.t_max * 4);
     a.scratch_bt = (uint8_t *)dalloc(warps * a.t_max * dnb_eventalign_bt_row_bytes());
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    fail(cudaEventCreate(&e0)); fail(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    fail(cudaEventCreate(&e0)); fail(cudaEventCreate(&e1)); fail(cudaEventCreate(&e2)); fail(cudaEventCreate(&e3));
     if (rc == DNB_OK) {
         auto up = [&](void *dst, const void *src, size_t bytes) { if (bytes) fail(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s)); };
         up(d_ref_off, ref_off.data(), (R + 1) * 8); up(d_al_off, al_off.data(), (R + 1) * 8);
@@ -1190,19 +1233,87 @@ int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t 
         dnb_launch_eventalign(a, grid, s);
         fail(cudaEventRecord(e1, s));
         fail(cudaGetLastError());
-        if (tot_rec) fail(cudaMemcpyAsync(recs, d_recs, tot_rec * sizeof(dnb_eventalign_rec), cudaMemcpyDeviceToHost, s));
+        if (feats && rc == DNB_OK) {
+            DnbFeatArgs f = {};
+            f.n_reads = (uint32_t)R;
+            f.rec_off = d_rec_off; f.recs = d_recs; f.n_rec = d_nrec; f.status = d_status;
+            f.ref_off = d_ref_off; f.ref = d_ref; f.r2q = d_r2q;
+            uint64_t *d_raw_off = (uint64_t *)dalloc(R * 8), *d_called_off = (uint64_t *)dalloc((R + 1) * 8);
+            uint64_t *d_pos_off = (uint64_t *)dalloc((R + 1) * 8);
+            uint8_t *d_kind = (uint8_t *)dalloc(R), *d_rev = (uint8_t *)dalloc(R);
+            float *d_doff = (float *)dalloc(R * 4), *d_dscl = (float *)dalloc(R * 4);
+            uint32_t *d_rstart = (uint32_t *)dalloc(R * 4), *d_rend = (uint32_t *)dalloc(R * 4);
+            float *d_f32 = (float *)dalloc(tot_f32 * 4);
+            int16_t *d_i16 = (int16_t *)dalloc(tot_i16 * 2);
+            uint32_t *d_es = (uint32_t *)dalloc((tot_ev + R) * 4);
+            uint32_t *d_called = (uint32_t *)dalloc(tot_called * 4);
+            float *d_signal = (float *)dalloc(tot_pos * DNB_RAWDEPTH * 4);
+            float *d_core = (float *)dalloc(tot_pos * 4), *d_resid = (float *)dalloc(tot_pos * 4);
+            uint32_t *d_coords = (uint32_t *)dalloc(tot_pos * 4), *d_ri = (uint32_t *)dalloc(tot_pos * 4), *d_qi = (uint32_t *)dalloc(tot_pos * 4);
+            int32_t *d_qual = (int32_t *)dalloc(tot_pos * 4);
+            uint32_t *d_npos = (uint32_t *)dalloc(R * 4);
+            unsigned int *d_next2 = (unsigned int *)dalloc(4);
+            if (rc == DNB_OK) {
+                up(d_raw_off, raw_off.data(), R * 8); up(d_called_off, called_off.data(), (R + 1) * 8);
+                up(d_pos_off, pos_off, (R + 1) * 8);
+                up(d_kind, h_kind.data(), R); up(d_rev, h_rev.data(), R);
+                up(d_doff, h_doff.data(), R * 4); up(d_dscl, h_dscl.data(), R * 4);
+                up(d_rstart, h_rstart.data(), R * 4); up(d_rend, h_rend.data(), R * 4);
+                for (size_t i = 0; i < R; i++) {
+                    const dnb_feature_desc &fd = feats[i];
+                    if (fd.raw_pA) up(d_f32 + raw_off[i], fd.raw_pA, fd.n_samples * 4);
+                    else up(d_i16 + raw_off[i], fd.raw_dac, fd.n_samples * 2);
+                    if (reads[i].n_events) up(d_es + ev_off[i] + i, fd.event_start, (reads[i].n_events + 1ull) * 4);
+                    if (fd.n_called) up(d_called + called_off[i], fd.called, fd.n_called * 4ull);
+                }
+                fail(cudaMemsetAsync(d_next2, 0, 4, s));
+                f.raw_off = d_raw_off; f.raw_kind = d_kind; f.raw_f32 = d_f32; f.raw_i16 = d_i16;
+                f.dac_offset = d_doff; f.dac_scale = d_dscl; f.ev_off = d_ev_off; f.ev_start = d_es;
+                f.shift = d_shift; f.scale = d_scale; f.is_reverse = d_rev; f.ref_start = d_rstart; f.ref_end = d_rend;
+                f.called_off = d_called_off; f.called = d_called; f.pos_off = d_pos_off;
+                f.signal = d_signal; f.core = d_core; f.residual = d_resid; f.coords = d_coords; f.ref_index = d_ri;
+                f.query_index = d_qi; f.quality = d_qual; f.n_pos = d_npos; f.next_read = d_next2;
+                fail(cudaEventRecord(e2, s));
+                dnb_launch_features(f, dnb_features_grid(ctx->cfg.device), s);
+                fail(cudaEventRecord(e3, s));
+                fail(cudaGetLastError());
+                auto down = [&](void *dst, const void *src, size_t bytes) { if (bytes) fail(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); };
+                down(out->signal, d_signal, tot_pos * DNB_RAWDEPTH * 4);
+                down(out->core, d_core, tot_pos * 4); down(out->residual, d_resid, tot_pos * 4);
+                down(out->coords, d_coords, tot_pos * 4); down(out->ref_index, d_ri, tot_pos * 4);
+                down(out->query_index, d_qi, tot_pos * 4); down(out->quality, d_qual, tot_pos * 4);
+                down(n_pos, d_npos, R * 4);
+            }
+        }
+        if (tot_rec && recs) fail(cudaMemcpyAsync(recs, d_recs, tot_rec * sizeof(dnb_eventalign_rec), cudaMemcpyDeviceToHost, s));
         fail(cudaMemcpyAsync(n_recs, d_nrec, R * 4, cudaMemcpyDeviceToHost, s));
         fail(cudaMemcpyAsync(status, d_status, R * 4, cudaMemcpyDeviceToHost, s));
         fail(cudaStreamSynchronize(s));
         float ms = 0.f;
         if (rc == DNB_OK && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) g_ea_kernel_ms = ms;
+        if (rc == DNB_OK && feats && cudaEventElapsedTime(&ms, e2, e3) == cudaSuccess) g_ft_kernel_ms = ms;
     }
     for (void *p : owned) cudaFreeAsync(p, s);
     cudaStreamSynchronize(s);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+    if (e3) cudaEventDestroy(e3);
     cudaStreamDestroy(s);
     return rc;
+}
+
+int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t n_reads, uint32_t window,
+                         dnb_eventalign_rec *recs, const uint64_t *rec_off, uint32_t *n_recs, int *status) {
+    return eventalign_impl(ctx, reads, nullptr, n_reads, window, recs, rec_off, n_recs, status, nullptr, nullptr, nullptr);
+}
+
+int dnb_eventalign_features_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, const dnb_feature_desc *feats,
+                                  size_t n_reads, uint32_t window, dnb_eventalign_rec *recs, const uint64_t *rec_off,
+                                  uint32_t *n_recs, int *status, const dnb_feature_tensors *out, const uint64_t *pos_off,
+                                  uint32_t *n_pos) {
+    if (!feats && n_reads) return DNB_ERR_ARG;
+    return eventalign_impl(ctx, reads, feats, n_reads, window, recs, rec_off, n_recs, status, out, pos_off, n_pos);
 }
 
 }  // extern "C"

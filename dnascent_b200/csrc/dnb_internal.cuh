@@ -201,3 +201,36 @@ unsigned dnb_eventalign_grid(int device);
 unsigned dnb_eventalign_warps_per_block(void);
 size_t dnb_eventalign_bt_row_bytes(void);
 void dnb_launch_eventalign(const DnbEaArgs &a, unsigned grid, cudaStream_t s);
+
+// ---- DNN input tensors (features.cu): SURVEY s.8 row f2, consumes eventalign's records on the device --------------
+struct DnbFeatArgs {
+    uint32_t n_reads;
+    const uint64_t *rec_off;      // as DnbEaArgs
+    const dnb_eventalign_rec *recs;
+    const uint32_t *n_rec;
+    int *status;                  // [R] in: eventalign's status; out: UNDEFINED (non-monotone records) / OVERFLOW (row capacity)
+    const uint64_t *ref_off;
+    const char *ref;
+    const int32_t *r2q;
+    const uint64_t *raw_off;      // [R] first sample of the read in raw_f32 / raw_i16 (whichever raw_kind says)
+    const uint8_t *raw_kind;      // [R] 0 = float32 pA, 1 = int16 DAC
+    const float *raw_f32;
+    const int16_t *raw_i16;
+    const float *dac_offset, *dac_scale;   // [R]
+    const uint64_t *ev_off;       // [R+1]; read r's n_events + 1 event starts begin at ev_start[ev_off[r] + r]
+    const uint32_t *ev_start;
+    const double *shift, *scale;  // [R] r.scalings
+    const uint8_t *is_reverse;    // [R]
+    const uint32_t *ref_start, *ref_end;   // [R] r.refStart / r.refEnd
+    const uint64_t *called_off;   // [R+1]
+    const uint32_t *called;       // sorted keys of r.refCoordToCalls
+    const uint64_t *pos_off;      // [R+1] row capacity offsets
+    float *signal;                // [pos_off[R]][DNB_RAWDEPTH]
+    float *core, *residual;
+    uint32_t *coords, *ref_index, *query_index;
+    int32_t *quality;
+    uint32_t *n_pos;              // [R]
+    unsigned int *next_read;      // work counter (zeroed before the launch)
+};
+unsigned dnb_features_grid(int device);
+void dnb_launch_features(const DnbFeatArgs &a, unsigned grid, cudaStream_t s);

@@ -446,6 +446,100 @@ void eventalign_batch(const std::vector<DNAscent::read *> &reads, unsigned int t
     }
 }
 
+// eventalign + the DNN input tensors in one device pass (SURVEY s.8 row f2)
+void eventalign_features_batch(const std::vector<DNAscent::read *> &reads, unsigned int totalWindowLength,
+                               std::vector<DnnInputs> &out) {
+    const size_t n = reads.size();
+    out.assign(n, DnnInputs());
+    if (n == 0) return;
+    std::vector<dnb_eventalign_desc> descs(n);
+    std::vector<dnb_feature_desc> feats(n);
+    std::vector<std::vector<int32_t>> r2q(n);
+    std::vector<std::vector<uint32_t>> pairs(n), starts(n), called(n);
+    std::vector<std::vector<float>> evm(n), raw(n);
+    std::vector<uint64_t> rec_off(n + 1, 0), pos_off(n + 1, 0);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < n; i++) {
+        DNAscent::read &r = *reads[i];
+        const size_t rl = r.referenceSeqMappedTo.size();
+        r2q[i].assign(rl, 0);                                    // std::map::operator[] reads an absent key as 0
+        for (const auto &kv : r.refToQuery)
+            if (kv.first < rl) r2q[i][kv.first] = (int32_t)kv.second;
+        pairs[i].resize(2 * r.eventAlignment.size());
+        for (size_t j = 0; j < r.eventAlignment.size(); j++) {
+            pairs[i][2 * j] = r.eventAlignment[j].first;
+            pairs[i][2 * j + 1] = r.eventAlignment[j].second;
+        }
+        // the samples each event owns, in event order (these are consecutive slices of r.raw, event_handling.cpp:549-575;
+        // taking them from r.events keeps this independent of that layout); float32-exact, so narrowing is lossless
+        evm[i].resize(r.events.size());
+        starts[i].resize(r.events.size() + 1);
+        uint32_t at = 0;
+        for (size_t j = 0; j < r.events.size(); j++) {
+            evm[i][j] = (float)r.events[j].mean;
+            starts[i][j] = at;
+            at += (uint32_t)r.events[j].raw.size();
+        }
+        starts[i][r.events.size()] = at;
+        raw[i].resize(at);
+        for (size_t j = 0, t = 0; j < r.events.size(); j++)
+            for (double v : r.events[j].raw) raw[i][t++] = (float)v;
+        called[i].reserve(r.refCoordToCalls.size());
+        for (const auto &kv : r.refCoordToCalls) called[i].push_back(kv.first);   // std::map: ascending
+        dnb_eventalign_desc &d = descs[i];
+        d.ref = r.referenceSeqMappedTo.data();
+        d.ref_len = (uint32_t)rl;
+        d.ref_to_query = r2q[i].data();
+        d.align_pairs = pairs[i].data();
+        d.n_align = (uint32_t)r.eventAlignment.size();
+        d.event_mean = evm[i].data();
+        d.n_events = (uint32_t)r.events.size();
+        d.shift = r.scalings.shift;
+        d.scale = r.scalings.scale;
+        d.events_per_base = r.scalings.eventsPerBase;
+        dnb_feature_desc &f = feats[i];
+        f.raw_pA = raw[i].data();
+        f.raw_dac = nullptr;
+        f.dac_offset = 0.f; f.dac_scale = 1.f;
+        f.n_samples = at;
+        f.event_start = starts[i].data();
+        f.is_reverse = r.isReverse ? 1 : 0;
+        f.ref_start = (uint32_t)r.refStart;
+        f.ref_end = (uint32_t)r.refEnd;
+        f.called = called[i].empty() ? nullptr : called[i].data();
+        f.n_called = (uint32_t)called[i].size();
+    }
+    for (size_t i = 0; i < n; i++) {
+        rec_off[i + 1] = rec_off[i] + reads[i]->eventAlignment.size() + 64;
+        const size_t rl = reads[i]->referenceSeqMappedTo.size();
+        pos_off[i + 1] = pos_off[i] + (rl >= 9 ? rl - 8 : 0) + 1;
+    }
+    const size_t rows = pos_off[n];
+    std::vector<float> signal(rows * DNB_RAWDEPTH), core(rows), residual(rows);
+    std::vector<uint32_t> coords(rows), ri(rows), qi(rows), n_rec(n), n_pos(n);
+    std::vector<int32_t> qual(rows);
+    std::vector<int> status(n);
+    dnb_feature_tensors t = {signal.data(), core.data(), residual.data(), coords.data(), ri.data(), qi.data(), qual.data()};
+    int rc = dnb_eventalign_features_batch(context(), descs.data(), feats.data(), n, totalWindowLength, nullptr, rec_off.data(),
+                                           n_rec.data(), status.data(), &t, pos_off.data(), n_pos.data());
+    if (rc != DNB_OK) die("dnb_eventalign_features_batch", rc);
+    for (size_t i = 0; i < n; i++) {
+        if (status[i] == DNB_READ_UNDEFINED) throw NegativeLog();          // what eln() does in the reference (alignment.cpp:208)
+        if (status[i] != DNB_READ_OK) die("dnb_eventalign_features_batch (per-read capacity)", DNB_ERR_NOMEM);
+        DnnInputs &o = out[i];
+        const size_t lo = pos_off[i], P = n_pos[i];
+        o.signal.assign(signal.begin() + lo * DNB_RAWDEPTH, signal.begin() + (lo + P) * DNB_RAWDEPTH);
+        o.core.assign(core.begin() + lo, core.begin() + lo + P);
+        o.residual.assign(residual.begin() + lo, residual.begin() + lo + P);
+        o.refCoords.assign(coords.begin() + lo, coords.begin() + lo + P);
+        o.refIndices.assign(ri.begin() + lo, ri.begin() + lo + P);
+        o.queryIndices.assign(qi.begin() + lo, qi.begin() + lo + P);
+        o.alignmentQuality.assign(qual.begin() + lo, qual.begin() + lo + P);
+        o.QCpassed = true;
+        reads[i]->QCpassed = true;                                          // alignment.cpp:743
+    }
+}
+
 }  // namespace dnb_shim
 
 void eventalign(DNAscent::read &r, unsigned int totalWindowLength) {

@@ -40,4 +40,21 @@ void llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, unsigned int
 // launch; humanReadable_eventalignOut and r.addSignal are produced on the host from the returned state records.
 void eventalign_batch(const std::vector<DNAscent::read *> &reads, unsigned int totalWindowLength);
 
+// What runCNN (detect.cpp:586-690) reads from a DNAscent::read after eventalign, as the vectors it would get from
+// r.makeSignalTensor() [P*RAWDEPTH], r.makeCoreSequenceTensor(), r.makeResidualSequenceTensor(),
+// r.getReferenceCoords(), r.getReferenceIndices(), r.getQueryIndices() and each position's getAlignmentQuality().
+struct DnnInputs {
+    std::vector<float> signal, core, residual;
+    std::vector<unsigned int> refCoords, refIndices, queryIndices;
+    std::vector<int> alignmentQuality;
+    bool QCpassed = false;         // r.QCpassed as eventalign leaves it (alignment.cpp:743)
+};
+
+// `detect`'s use of eventalign (detect.cpp:888): only the r.addSignal side effect is consumed there, never the text.
+// This entry runs the window chains AND builds the tensors on the device (dnb_eventalign_features_batch); the raw
+// signal goes up as float32 (r.raw is float32-exact, pod5.cpp:60), nothing per-sample is touched on the host.
+// r.refCoordToAP is left empty: the patched runCNN takes `out[i]` instead of calling r.make*Tensor().
+void eventalign_features_batch(const std::vector<DNAscent::read *> &reads, unsigned int totalWindowLength,
+                               std::vector<DnnInputs> &out);
+
 }  // namespace dnb_shim

@@ -214,6 +214,49 @@ DNB_API int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads,
 /* device time (ms, CUDA events around the kernel) of the last dnb_eventalign_batch on this thread */
 DNB_API double dnb_eventalign_last_kernel_ms(void);
 
+/* ---- DNN input tensors built on the device (src/reads.h:147-172, 288-452; consumer src/detect.cpp:586-649) ---- */
+/* eventalign's side effect in the reference is r.addSignal() per raw sample of every match-state event
+ * (alignment.cpp:706-725); runCNN then turns r.refCoordToAP into the tensors it feeds TensorFlow.  This entry runs
+ * eventalign and builds those tensors in one device pass (records never leave the GPU unless asked for), in the
+ * identical layout: row o of every output == the o-th element the reference's makeSignalTensor /
+ * makeCoreSequenceTensor / makeResidualSequenceTensor / getReferenceCoords / getReferenceIndices / getQueryIndices /
+ * getAlignmentQuality produce (strand-dependent iteration order included). */
+#define DNB_RAWDEPTH 20 /* src/reads.h:12 */
+
+/* what addSignal / the tensor builders read from DNAscent::read besides dnb_eventalign_desc */
+typedef struct {
+    const float *raw_pA;           /* r.raw (float32-exact pA), or NULL when raw_dac is given */
+    const int16_t *raw_dac;        /* int16 DAC; pA = ((float)dac + dac_offset) * dac_scale (src/pod5.cpp:60) */
+    float dac_offset, dac_scale;
+    uint64_t n_samples;
+    const uint32_t *event_start;   /* [n_events + 1] as dnb_read_result.event_start: r.events[j].raw = raw[start[j], start[j+1]) */
+    int is_reverse;                /* r.isReverse */
+    uint32_t ref_start, ref_end;   /* r.refStart, r.refEnd */
+    const uint32_t *called;        /* ascending keys of r.refCoordToCalls (alignment.cpp:711), may be NULL */
+    uint32_t n_called;
+} dnb_feature_desc;
+
+/* flat outputs; read i owns rows [pos_off[i], pos_off[i] + n_pos[i]) of each */
+typedef struct {
+    float *signal;                 /* [rows][DNB_RAWDEPTH]  makeSignalTensor: scaled samples, zero padded */
+    float *core;                   /* [rows] getCoreIndex() = 1 + base-4 rank of k-mer bases 2..6 */
+    float *residual;               /* [rows] getResidualIndex() = 1 + rank of bases 0,1,7,8 */
+    uint32_t *coords;              /* [rows] getReferenceCoords (genome coordinate) */
+    uint32_t *ref_index;           /* [rows] getReferenceIndices (index on referenceSeqMappedTo) */
+    uint32_t *query_index;         /* [rows] getQueryIndices */
+    int32_t *quality;              /* [rows] getAlignmentQuality (the window's indelScore) */
+} dnb_feature_tensors;
+
+/* reads / recs / rec_off / n_recs / status as dnb_eventalign_batch (recs may be NULL: records stay on the device).
+ * pos_off: [n_reads+1] row capacity per read (ref_len - 8 always suffices); n_pos[i] receives the row count.
+ * status additionally reports DNB_READ_OVERFLOW when the row capacity is too small. */
+DNB_API int dnb_eventalign_features_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, const dnb_feature_desc *feats,
+                                          size_t n_reads, uint32_t window, dnb_eventalign_rec *recs,
+                                          const uint64_t *rec_off, uint32_t *n_recs, int *status,
+                                          const dnb_feature_tensors *out, const uint64_t *pos_off, uint32_t *n_pos);
+/* device time (ms) of the feature kernel of the last dnb_eventalign_features_batch on this thread */
+DNB_API double dnb_features_last_kernel_ms(void);
+
 #ifdef __cplusplus
 }
 #endif

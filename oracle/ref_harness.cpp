@@ -522,6 +522,33 @@ size_t dnbshim_calls(void *hv, int32_t *pos, double *llr, size_t cap) {
     }
     return n;
 }
+// eventalign + DNN input tensors built on the device (row f2); results kept until the next call, read back per read
+static std::vector<dnb_shim::DnnInputs> g_dnn_inputs;
+int dnbshim_eventalign_features_batch(void **handles, size_t n, unsigned int windowLength) {
+    std::vector<DNAscent::read *> reads(n);
+    for (size_t i = 0; i < n; i++) reads[i] = ((Handle *)handles[i])->r;
+    try {
+        dnb_shim::eventalign_features_batch(reads, windowLength, g_dnn_inputs);
+    } catch (NegativeLog &) {
+        return 1;
+    }
+    return 0;
+}
+size_t dnbshim_dnn_inputs(size_t i, float *signal, float *core, float *residual, uint32_t *coords, uint32_t *ref_index,
+                          uint32_t *query_index, int32_t *quality, size_t cap) {
+    if (i >= g_dnn_inputs.size()) return 0;
+    const dnb_shim::DnnInputs &d = g_dnn_inputs[i];
+    const size_t P = d.core.size();
+    if (P == 0 || P > cap) return P;
+    memcpy(signal, d.signal.data(), d.signal.size() * sizeof(float));
+    memcpy(core, d.core.data(), P * sizeof(float));
+    memcpy(residual, d.residual.data(), P * sizeof(float));
+    for (size_t j = 0; j < P; j++) {
+        coords[j] = d.refCoords[j]; ref_index[j] = d.refIndices[j]; query_index[j] = d.queryIndices[j];
+        quality[j] = d.alignmentQuality[j];
+    }
+    return P;
+}
 void dnbshim_shutdown(void) { dnb_shim::shutdown(); }
 #endif  // DNB_SHIM_BUILD
 

@@ -45,6 +45,9 @@ class Ref:
             L.dnbshim_calls.restype = sz
             L.dnbshim_calls.argtypes = [vp, vp, vp, sz]
             L.dnbshim_shutdown.restype = None
+            L.dnbshim_eventalign_features_batch.argtypes = [vp, sz, C.c_uint]
+            L.dnbshim_dnn_inputs.restype = sz
+            L.dnbshim_dnn_inputs.argtypes = [sz, vp, vp, vp, vp, vp, vp, vp, sz]
         L.dnbref_get_model.restype = sz
         L.dnbref_get_model.argtypes = [C.c_int, vp, vp, sz]
         L.dnbref_set_model.argtypes = [C.c_int, vp, vp, sz]
@@ -192,6 +195,27 @@ class Ref:
             llr = np.zeros(cap)
             n = self.L.dnbshim_calls(r.h, _p(pos), _p(llr), cap)
             out.append((pos[:n].copy(), llr[:n].copy()))
+        return out
+
+    def eventalign_features_batch(self, reads, window: int = 50):
+        """dnb_shim::eventalign_features_batch: per read the DnnInputs vectors (what runCNN would get from
+        r.makeSignalTensor() & co.), keys as aligned_positions()."""
+        arr = (C.c_void_p * len(reads))(*[r.h for r in reads])
+        if self.L.dnbshim_eventalign_features_batch(arr, len(reads), window):
+            raise ValueError("NegativeLog")
+        depth = self.L.dnbref_rawdepth()
+        out = []
+        for i, r in enumerate(reads):
+            cap = len(r.refseq) + 1
+            sig = np.zeros(cap * depth, dtype=np.float32)
+            f32 = [np.zeros(cap, dtype=np.float32) for _ in range(2)]
+            u32 = [np.zeros(cap, dtype=np.uint32) for _ in range(3)]
+            q = np.zeros(cap, dtype=np.int32)
+            P = self.L.dnbshim_dnn_inputs(i, _p(sig), _p(f32[0]), _p(f32[1]), _p(u32[0]), _p(u32[1]), _p(u32[2]), _p(q), cap)
+            assert P <= cap
+            out.append(dict(signal=sig[:P * depth].reshape(P, depth).copy(), core=f32[0][:P].copy(),
+                            residual=f32[1][:P].copy(), coords=u32[0][:P].copy(), ref_index=u32[1][:P].copy(),
+                            query_index=u32[2][:P].copy(), quality=q[:P].copy()))
         return out
 
     def shutdown(self):

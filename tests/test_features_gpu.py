@@ -1,0 +1,131 @@
+"""SURVEY s.8 row f2 on the GPU: dnb_eventalign_features_batch (dnascent_b200/csrc/features.cu) through the C ABI.
+The DNN input tensors -- signal [P,20], core / residual k-mer indices, reference coordinates / indices, query indices,
+alignment quality -- must be BIT-IDENTICAL to what the unmodified reference's makeSignalTensor & co. (reads.h:305-452)
+returned for the golden reads (tests/golden/eventalign_v1.npz, keys e_<tag>_ap_*), and to the CPU oracle port on fresh
+seeded reads (forward and reverse strand, int16 DAC and float32 pA input, with and without called positions)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from test_eventalign_cpu import AP_KEYS, all_golden_reads, event_starts, golden_eventalign_inputs, golden_records
+from dnascent_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ea_golden():
+    return np.load(os.path.join(GOLDEN, "eventalign_v1.npz"))
+
+
+def golden_feature_inputs(g, e, tag, **extra):
+    p = f"e_{tag}_"
+    ref_start, ref_end, is_rev = (int(x) for x in e[p + "strand"])
+    d = golden_eventalign_inputs(g, e, tag)
+    d.update(raw=g.raw.astype(np.float32), event_start=event_starts(g.event_raw_len), is_reverse=is_rev,
+             ref_start=ref_start, ref_end=ref_end)
+    d.update(extra)
+    return d
+
+
+def test_features_golden_tensors(ctx, ea_golden, golden_reads, golden_v2):
+    e = ea_golden
+    reads = all_golden_reads(golden_reads, golden_v2)
+    out = ctx.eventalign_features([golden_feature_inputs(g, e, tag) for tag, g in reads], window=50)
+    n_rev = 0
+    for (tag, g), o in zip(reads, out):
+        p = f"e_{tag}_"
+        assert o["status"] == api.READ_OK, tag
+        for key in ("event", "ref_pos", "label", "indel"):
+            np.testing.assert_array_equal(o[key], e[p + key], err_msg=f"{tag} {key}")
+        for key in AP_KEYS:
+            assert o[key].dtype == e[p + "ap_" + key].dtype, (tag, key)
+            np.testing.assert_array_equal(o[key], e[p + "ap_" + key], err_msg=f"{tag} {key}")
+        assert o["signal"].shape[1] == 20 and o["signal"].shape[0] > 0.8 * (len(g.refseq) - 8)
+        n_rev += int(e[p + "strand"][2])
+    assert 0 < n_rev < len(reads)          # both makeSignalTensor iteration orders are covered
+
+
+def test_features_called_positions_and_no_records(ctx, ea_golden, golden_reads, golden_v2):
+    """alignment.cpp:711: coordinates that already have a call are not added; records may stay on the device."""
+    e = ea_golden
+    reads = all_golden_reads(golden_reads, golden_v2)
+    called = [np.sort(e[f"e_{tag}_ap_coords"][::3]) for tag, _ in reads]
+    out = ctx.eventalign_features([golden_feature_inputs(g, e, tag, called=c) for (tag, g), c in zip(reads, called)],
+                                  window=50, want_records=False)
+    for (tag, g), c, o in zip(reads, called, out):
+        p = f"e_{tag}_"
+        assert o["status"] == api.READ_OK and "event" not in o
+        keep = ~np.isin(e[p + "ap_coords"], c)
+        for key in AP_KEYS:
+            np.testing.assert_array_equal(o[key], e[p + "ap_" + key][keep], err_msg=f"{tag} {key}")
+
+
+def test_features_after_normalise_vs_port(ctx, port, pore_mean):
+    """The read loop's order (detect.cpp:876-888 then runCNN's tensors): product normaliseEvents -> product
+    eventalign + features, against the port fed the product's records; int16 DAC and float32 input, both strands."""
+    ref = synth.make_reference(200_000, 191)
+    base = synth.simulate_batch(ref, [9000, 12000, 700, 15000, 10000, 8000, 30000, 2000, 45000], pore_mean, seed=192,
+                                sub_rate=0.01)
+    res = ctx.normaliseEvents([api.Read.from_synth(r, use_dac=True) for r in base])
+    reads, strands = [], []
+    for i, (sr, o) in enumerate(zip(base, res)):
+        if o.status != api.READ_OK:
+            continue
+        r2q = np.zeros(len(sr.refseq), dtype=np.int32)
+        q2r = np.asarray(sr.query_to_ref)
+        r2q[q2r[q2r >= 0]] = np.nonzero(q2r >= 0)[0]
+        is_rev = bool(i & 1)
+        d = dict(refseq=sr.refseq, ref_to_query=r2q, eventAlignment=o.eventAlignment, event_mean=o.event_mean,
+                 shift=o.shift, scale=o.scale, events_per_base=o.eventsPerBase, event_start=o.event_start,
+                 is_reverse=is_rev, ref_start=1000 * i, ref_end=1000 * i + len(sr.refseq))
+        if i % 3 == 0:
+            d["raw"] = sr.raw.astype(np.float32)
+        else:
+            d.update(raw_dac=sr.dac, dac_offset=float(synth.DAC_OFFSET), dac_scale=float(synth.DAC_SCALE))
+        reads.append((sr, d))
+        strands.append(is_rev)
+    assert len(reads) >= 6 and any(strands) and not all(strands)
+    out = ctx.eventalign_features([d for _, d in reads], window=50)
+    assert ctx.features_last_kernel_ms() > 0.0
+    for (sr, d), o in zip(reads, out):
+        assert o["status"] == api.READ_OK
+        rec = {k: o[k] for k in ("event", "ref_pos", "label", "indel")}
+        exp = port.dnn_features(d["refseq"], d["ref_to_query"], d["is_reverse"], d["ref_start"], d["ref_end"], rec,
+                                sr.raw.astype(np.float64), d["event_start"], d["shift"], d["scale"])
+        assert exp["signal"].shape[0] > 0.8 * (len(sr.refseq) - 8)
+        for key in AP_KEYS:
+            np.testing.assert_array_equal(o[key], exp[key], err_msg=key)
+        # size-independent properties: rows ascend along the read, one row per reference position, zero padding is a suffix
+        assert np.all(np.diff(o["ref_index"].astype(np.int64)) > 0)
+        step = np.diff(o["coords"].astype(np.int64))
+        assert np.all(step < 0) if d["is_reverse"] else np.all(step > 0)
+        nz = o["signal"] != 0
+        assert np.all(nz[:, :-1] | ~nz[:, 1:])
+        assert 1 <= o["core"].min() and o["core"].max() <= 1024 and 1 <= o["residual"].min() and o["residual"].max() <= 256
+
+
+def test_features_edge_cases(ctx, pore_mean):
+    seq = synth.make_reference(200, 5)
+    base = dict(refseq=seq, ref_to_query=np.arange(200, dtype=np.int32), eventAlignment=np.zeros((0, 2), dtype=np.uint32),
+                event_mean=np.zeros(0, dtype=np.float32), shift=90.0, scale=15.0, events_per_base=2.0,
+                raw=np.zeros(16, dtype=np.float32), event_start=np.zeros(1, dtype=np.uint32), is_reverse=False,
+                ref_start=0, ref_end=200)
+    undefined = dict(base, events_per_base=1.0)
+    al = np.stack([np.arange(300), np.arange(300) * 192 // 300], axis=1).astype(np.uint32)
+    live = dict(base, eventAlignment=al, event_mean=np.full(300, 95.0, dtype=np.float32),
+                raw=np.full(1500, 95.0, dtype=np.float32), event_start=(np.arange(301) * 5).astype(np.uint32))
+    tight = dict(live, row_capacity=3)                                    # too few rows -> OVERFLOW, nothing written past them
+    bad_es = dict(live, event_start=(np.arange(301) * 6).astype(np.uint32))   # events address samples past the signal
+    out = ctx.eventalign_features([base, undefined, live, tight, bad_es], window=50)
+    assert out[0]["status"] == api.READ_OK and out[0]["signal"].shape == (0, 20)
+    assert out[1]["status"] == api.READ_UNDEFINED and out[1]["signal"].shape[0] == 0
+    assert out[2]["status"] == api.READ_OK and out[2]["signal"].shape[0] > 0
+    # a flat 95 pA signal scales to (float)((95-90)/15) everywhere a sample exists
+    v = np.float32((95.0 - 90.0) / 15.0)
+    assert np.all((out[2]["signal"] == v) | (out[2]["signal"] == 0))
+    assert out[3]["status"] == api.READ_OVERFLOW and out[3]["signal"].shape[0] == 0
+    assert out[4]["status"] == api.READ_UNDEFINED
+    assert ctx.eventalign_features([], window=50) == []

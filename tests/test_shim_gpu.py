@@ -90,6 +90,31 @@ def test_shim_eventalign_matches_reference(shim, ref_oracle, pore_mean):
     assert n >= 6
 
 
+def test_shim_eventalign_features_batch_matches_reference(shim, ref_oracle, pore_mean):
+    """Row f2 through the C++ shim: dnb_shim::eventalign_features_batch (window chains + tensors on the device, no text,
+    no addSignal) must hand runCNN the vectors the unmodified reference builds from refCoordToAP after its own
+    eventalign (reads.h:305-452): signal, core, residual, coordinates, indices, alignment quality -- bit for bit."""
+    ref = synth.make_reference(200_000, 51)
+    shim.set_reference(ref)
+    ref_oracle.set_reference(ref)
+    reads = _reads(pore_mean, ref, 8, 52, lo=2000, hi=12000)
+    hs = [shim.read_new(r) for r in reads]
+    hr = [ref_oracle.read_new(r) for r in reads]
+    shim.normalise_batch(hs)
+    ok = [i for i, b in enumerate(hr) if b.normalise(staged=False)["align_event"].size > 0]
+    assert len(ok) >= 6
+    got = shim.eventalign_features_batch([hs[i] for i in ok], 50)
+    strands = set()
+    for i, g in zip(ok, got):
+        hr[i].eventalign(50)
+        want = hr[i].aligned_positions()
+        assert want["core"].size > 0
+        for key in ("signal", "core", "residual", "coords", "ref_index", "query_index", "quality"):
+            np.testing.assert_array_equal(g[key], want[key], err_msg=f"read {i} {key}")
+        strands.add(bool(hr[i].is_reverse))
+    assert strands == {False, True}
+
+
 def test_shim_detect_events_and_probability(shim, ref_oracle, pore_mean):
     ref = synth.make_reference(50_000, 33)
     r = _reads(pore_mean, ref, 1, 34)[0]

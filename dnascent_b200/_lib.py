@@ -81,6 +81,19 @@ class FeatureTensors(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("signal", "core", "residual", "coords", "ref_index", "query_index", "quality")]
 
 
+class ReadExtra(C.Structure):
+    _fields_ = [("ref_to_query", C.c_void_p), ("is_reverse", C.c_int), ("ref_start", C.c_uint32), ("ref_end", C.c_uint32),
+                ("called", C.c_void_p), ("n_called", C.c_uint32)]
+
+
+class FeatureResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("n_pos", C.c_uint32),
+                ("signal", C.POINTER(C.c_float)), ("core", C.POINTER(C.c_float)), ("residual", C.POINTER(C.c_float)),
+                ("coords", C.POINTER(C.c_uint32)), ("ref_index", C.POINTER(C.c_uint32)),
+                ("query_index", C.POINTER(C.c_uint32)), ("quality", C.POINTER(C.c_int32)),
+                ("n_recs", C.c_uint32), ("recs", C.c_void_p)]
+
+
 RAWDEPTH = 20
 EVENTALIGN_REC_DTYPE = _np.dtype([("event", _np.uint32), ("ref_pos", _np.uint32), ("indel_score", _np.int32),
                                   ("label", _np.uint32)])
@@ -102,6 +115,7 @@ EXPORTS = [
     "dnb_cauchyPDF", "dnb_sequence_probability_batch",
     "dnb_eventalign_batch", "dnb_eventalign_last_kernel_ms",
     "dnb_eventalign_features_batch", "dnb_features_last_kernel_ms",
+    "dnb_batch_eventalign_features", "dnb_batch_feature_result", "dnb_batch_stage2_timings",
 ]
 
 
@@ -150,6 +164,9 @@ def lib():
     L.dnb_eventalign_last_kernel_ms.restype = d
     L.dnb_eventalign_features_batch.argtypes = [vp, vp, vp, sz, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
     L.dnb_features_last_kernel_ms.restype = d
+    L.dnb_batch_eventalign_features.argtypes = [vp, vp, C.c_uint32, C.c_int]
+    L.dnb_batch_feature_result.argtypes = [vp, sz, C.POINTER(FeatureResult)]
+    L.dnb_batch_stage2_timings.argtypes = [vp, C.POINTER(d * 2), C.POINTER(C.c_uint64 * 2)]
     _lib = L
     return L
 

@@ -119,6 +119,46 @@ class Batch:
     def results(self):
         return [self.result(i) for i in range(self.n)]
 
+    # -- resident eventalign + DNN input tensors (detect.cpp:888 + runCNN's inputs) on what run() left in HBM --------
+    def eventalign_features(self, extra, window: int = 50, want_records: bool = False):
+        """`extra`: per read a dict with ref_to_query (int32[ref_len]), is_reverse, ref_start, ref_end and optionally
+        called (sorted uint32).  Returns per read the dict Context.eventalign_features returns."""
+        assert len(extra) == self.n
+        ex = (_lib.ReadExtra * max(self.n, 1))()
+        keep = []
+        for i, r in enumerate(extra):
+            r2q = np.ascontiguousarray(r["ref_to_query"], dtype=np.int32)
+            called = np.ascontiguousarray(r.get("called", []), dtype=np.uint32)
+            keep += [r2q, called]
+            ex[i].ref_to_query = r2q.ctypes.data
+            ex[i].is_reverse, ex[i].ref_start, ex[i].ref_end = int(bool(r["is_reverse"])), int(r["ref_start"]), int(r["ref_end"])
+            ex[i].called, ex[i].n_called = (called.ctypes.data if called.size else None), called.size
+        _lib.check(self.ctx.L.dnb_batch_eventalign_features(self.h, C.addressof(ex), window, int(want_records)),
+                   "dnb_batch_eventalign_features")
+        out = []
+        for i in range(self.n):
+            fr = _lib.FeatureResult()
+            _lib.check(self.ctx.L.dnb_batch_feature_result(self.h, i, C.byref(fr)), "dnb_batch_feature_result")
+            P = fr.n_pos
+            o = dict(status=fr.status, signal=_as(fr.signal, P * _lib.RAWDEPTH, np.float32).reshape(P, _lib.RAWDEPTH),
+                     core=_as(fr.core, P, np.float32), residual=_as(fr.residual, P, np.float32),
+                     coords=_as(fr.coords, P, np.uint32), ref_index=_as(fr.ref_index, P, np.uint32),
+                     query_index=_as(fr.query_index, P, np.uint32), quality=_as(fr.quality, P, np.int32))
+            if want_records:
+                n = fr.n_recs
+                rr = (np.frombuffer(C.string_at(fr.recs, n * _lib.EVENTALIGN_REC_DTYPE.itemsize), dtype=_lib.EVENTALIGN_REC_DTYPE)
+                      if n else np.zeros(0, dtype=_lib.EVENTALIGN_REC_DTYPE))
+                o.update(event=rr["event"].copy(), ref_pos=rr["ref_pos"].copy(), label=rr["label"].astype(np.uint8),
+                         indel=rr["indel_score"].copy())
+            out.append(o)
+        return out
+
+    def stage2_timings(self):
+        ms = (C.c_double * 2)()
+        by = (C.c_uint64 * 2)()
+        _lib.check(self.ctx.L.dnb_batch_stage2_timings(self.h, C.byref(ms), C.byref(by)), "dnb_batch_stage2_timings")
+        return dict(eventalign_kernel_ms=ms[0], features_kernel_ms=ms[1], h2d_bytes=int(by[0]), d2h_bytes=int(by[1]))
+
     def release(self):
         if self.h:
             self.ctx.L.dnb_release(self.h)

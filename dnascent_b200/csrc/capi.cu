@@ -268,6 +268,20 @@ struct HostRes {
 
 }  // namespace
 
+// results of the resident eventalign + tensor stage (dnb_batch_eventalign_features), pinned host
+struct Stage2 {
+    bool done = false, want_records = false;
+    std::vector<uint64_t> rec_off, pos_off;
+    dnb_eventalign_rec *h_recs = nullptr;
+    uint32_t *h_n_rec = nullptr, *h_n_pos = nullptr;
+    int *h_status = nullptr;
+    float *h_signal = nullptr, *h_core = nullptr, *h_resid = nullptr;
+    uint32_t *h_coords = nullptr, *h_ri = nullptr, *h_qi = nullptr;
+    int32_t *h_qual = nullptr;
+    double ms[2] = {0.0, 0.0};
+    uint64_t bytes[2] = {0, 0};
+};
+
 struct dnb_batch {
     dnb_ctx *ctx = nullptr;
     size_t R = 0;
@@ -296,6 +310,7 @@ struct dnb_batch {
     uint64_t counts[8] = {};
     unsigned long long h_cells[3] = {};
     std::vector<void *> input_allocs, work_allocs, res_allocs;
+    Stage2 s2;
 };
 
 namespace {
@@ -379,6 +394,7 @@ void drop_results(dnb_batch *b) {
     for (void *p : b->res_allocs) b->ctx->pinned.release(p);
     b->res_allocs.clear();
     b->h = HostRes{};
+    b->s2 = Stage2{};
     b->fetched = false;
 }
 
@@ -1301,6 +1317,179 @@ static int eventalign_impl(dnb_ctx *ctx, const dnb_eventalign_desc *reads, const
     if (e3) cudaEventDestroy(e3);
     cudaStreamDestroy(s);
     return rc;
+}
+
+// ---- resident form (rows f1 + f2 without a host round trip): everything normaliseEvents left in HBM is read in place
+int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uint32_t window, int want_records) {
+    if (!b || (!extra && b->R)) return DNB_ERR_ARG;
+    if (window < DNB_K + 2 || window > 60) { g_last_error = "eventalign window must be in [11, 60]"; return DNB_ERR_ARG; }
+    if (!b->ran || b->want_table || !b->have_work) return DNB_ERR_STATE;
+    dnb_ctx *ctx = b->ctx;
+    if (!ctx->model[DNB_MODEL_PORE].loaded) return DNB_ERR_MODEL;
+    TRY(fetch(b));                       // dense forward alignment pairs on the device, per-read scalars on the host
+    CK(cudaSetDevice(ctx->cfg.device));
+    const size_t R = b->R;
+    cudaStream_t s = b->stream;
+    HostRes &h = b->h;
+    Work &w = b->w;
+    Stage2 &S = b->s2;
+    S = Stage2{};
+    S.want_records = want_records != 0;
+    for (size_t i = 0; i < R; i++)
+        if ((b->rlen[i] && !extra[i].ref_to_query) || (extra[i].n_called && !extra[i].called)) {
+            g_last_error = "dnb_read_extra " + std::to_string(i) + " is incomplete";
+            return DNB_ERR_ARG;
+        }
+    // ---- host: per-read constants and shapes ----
+    const double d2d = log(0.3), d2m = log(0.7), i2m = log(0.999), m2d = log(0.0025), m2i = log(0.001), i2i = log(0.001);
+    std::vector<double> h_trans(4 * R, 0.0);
+    std::vector<int> h_status(R);
+    std::vector<uint8_t> h_rev(R);
+    std::vector<uint32_t> h_rstart(R), h_rend(R);
+    std::vector<uint64_t> called_off(R + 1, 0);
+    S.rec_off.assign(R + 1, 0); S.pos_off.assign(R + 1, 0);
+    for (size_t i = 0; i < R; i++) {
+        int st = h.status[i];
+        if (st == DNB_READ_OK) {
+            // r.scalings.eventsPerBase (event_handling.cpp:606) -> alignment.cpp:207-210; eln throws for x <= 0
+            const double epb = (double)h.et_n[i] / (double)((int64_t)b->qlen[i] - DNB_K);
+            const double x = 1. - (1. / epb);
+            if (!(x > 0.0) || b->rlen[i] < DNB_K) st = DNB_READ_UNDEFINED;
+            else {
+                const double m12m1_int = log(x);
+                const double m12m1_ext = eln_nothrow(1.0 - m2d - m2i - m12m1_int);    // quirk Q10
+                h_trans[4 * i + 0] = m12m1_int;
+                h_trans[4 * i + 1] = m12m1_ext;
+                h_trans[4 * i + 2] = dnb_lnSum(m12m1_ext, m12m1_int);
+                h_trans[4 * i + 3] = dnb_lnSum(m12m1_ext, m2d);
+            }
+        }
+        h_status[i] = st;
+        h_rev[i] = extra[i].is_reverse ? 1 : 0; h_rstart[i] = extra[i].ref_start; h_rend[i] = extra[i].ref_end;
+        called_off[i + 1] = called_off[i] + extra[i].n_called;
+        S.rec_off[i + 1] = S.rec_off[i] + (st == DNB_READ_OK ? (uint64_t)h.n_align[i] + 64 : 0);
+        S.pos_off[i + 1] = S.pos_off[i] + (st == DNB_READ_OK ? (uint64_t)b->rlen[i] - DNB_K + 2 : 0);
+    }
+    const uint64_t tot_rec = S.rec_off[R], tot_pos = S.pos_off[R], tot_called = called_off[R], tot_r = b->tot_r;
+    // refToQuery / called keys through pinned staging (the only per-base upload of this stage)
+    int32_t *st_r2q = (int32_t *)ctx->pinned.acquire((tot_r ? tot_r : 1) * 4);
+    uint32_t *st_called = (uint32_t *)ctx->pinned.acquire((tot_called ? tot_called : 1) * 4);
+    struct StagingGuard {
+        dnb_batch *b; void *p0, *p1;
+        ~StagingGuard() { cudaStreamSynchronize(b->stream); if (p0) b->ctx->pinned.release(p0); if (p1) b->ctx->pinned.release(p1); }
+    } staging_guard{b, st_r2q, st_called};
+    if (!st_r2q || !st_called) { g_last_error = "pinned staging allocation failed"; return DNB_ERR_NOMEM; }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long ii = 0; ii < (long long)R; ii++) {
+        const size_t i = (size_t)ii;
+        if (b->rlen[i]) memcpy(st_r2q + b->r_off[i], extra[i].ref_to_query, 4ull * b->rlen[i]);
+        if (extra[i].n_called) memcpy(st_called + called_off[i], extra[i].called, 4ull * extra[i].n_called);
+    }
+    // ---- device ----
+    int32_t *d_r2q; uint32_t *d_called, *d_rstart, *d_rend, *d_nrec, *d_npos; uint8_t *d_rev, *d_kind;
+    uint64_t *d_called_off, *d_rec_off, *d_pos_off; double *d_trans; int *d_status; unsigned int *d_next;
+    dnb_eventalign_rec *d_recs;
+    float *d_signal, *d_core, *d_resid; uint32_t *d_coords, *d_ri, *d_qi; int32_t *d_qual;
+    TRY(walloc(b, &d_r2q, tot_r)); TRY(walloc(b, &d_called, tot_called)); TRY(walloc(b, &d_called_off, R + 1));
+    TRY(walloc(b, &d_rstart, R)); TRY(walloc(b, &d_rend, R)); TRY(walloc(b, &d_rev, R)); TRY(walloc(b, &d_kind, R));
+    TRY(walloc(b, &d_rec_off, R + 1)); TRY(walloc(b, &d_pos_off, R + 1)); TRY(walloc(b, &d_trans, 4 * R));
+    TRY(walloc(b, &d_status, R)); TRY(walloc(b, &d_nrec, R)); TRY(walloc(b, &d_npos, R)); TRY(walloc(b, &d_next, 2));
+    TRY(walloc(b, &d_recs, tot_rec));
+    TRY(walloc(b, &d_signal, tot_pos * DNB_RAWDEPTH)); TRY(walloc(b, &d_core, tot_pos)); TRY(walloc(b, &d_resid, tot_pos));
+    TRY(walloc(b, &d_coords, tot_pos)); TRY(walloc(b, &d_ri, tot_pos)); TRY(walloc(b, &d_qi, tot_pos)); TRY(walloc(b, &d_qual, tot_pos));
+    DnbEaArgs a = {};
+    a.n_reads = (uint32_t)R; a.window = window; a.t_max = 4096;
+    unsigned grid = dnb_eventalign_grid(ctx->cfg.device);
+    const unsigned wpb = dnb_eventalign_warps_per_block();
+    if ((size_t)grid * wpb > R) grid = (unsigned)((R + wpb - 1) / wpb);
+    const size_t warps = (size_t)grid * wpb;
+    TRY(walloc(b, &a.scratch_obs, warps * a.t_max)); TRY(walloc(b, &a.scratch_ev, warps * a.t_max));
+    TRY(walloc(b, &a.scratch_bt, warps * a.t_max * dnb_eventalign_bt_row_bytes()));
+    TRY(h2d(b, d_r2q, st_r2q, tot_r)); TRY(h2d(b, d_called, st_called, tot_called));
+    TRY(h2d(b, d_called_off, called_off.data(), R + 1)); TRY(h2d(b, d_rstart, h_rstart.data(), R));
+    TRY(h2d(b, d_rend, h_rend.data(), R)); TRY(h2d(b, d_rev, h_rev.data(), R));
+    TRY(h2d(b, d_rec_off, S.rec_off.data(), R + 1)); TRY(h2d(b, d_pos_off, S.pos_off.data(), R + 1));
+    TRY(h2d(b, d_trans, h_trans.data(), 4 * R)); TRY(h2d(b, d_status, h_status.data(), R));
+    CK(cudaMemsetAsync(d_kind, b->i16 ? 1 : 0, R, s));
+    CK(cudaMemsetAsync(d_next, 0, 8, s));
+    S.bytes[0] = 4 * tot_r + 4 * tot_called + 8 * 3 * (R + 1) + R * (4 + 4 + 1 + 32 + 4);
+    a.ref_off = b->d_r_off; a.ref = b->d_ref; a.r2q = d_r2q;
+    a.al_off = w.out_off; a.pairs = reinterpret_cast<const uint2 *>(w.out_pairs);
+    a.ev_off = b->d_ev_off; a.ev_mean = w.ev_mean; a.shift = w.shift; a.scale = w.scale; a.trans = d_trans;
+    a.model_mean = ctx->model[DNB_MODEL_PORE].d_mean;
+    a.two_sigma2 = 2.0 * pow(0.14, 2.0);
+    a.c = 1.0 / sqrt(2.0 * pow(0.14, 2.0) * M_PI);
+    a.ln_c = log(a.c);
+    a.d2d = d2d; a.d2m = d2m; a.i2m = i2m; a.m2d = m2d; a.m2i = m2i; a.i2i = i2i;
+    a.rec_off = d_rec_off; a.recs = d_recs; a.n_rec = d_nrec; a.status = d_status; a.next_read = d_next;
+    a.order = b->d_order;
+    CK(cudaEventRecord(b->ev[0], s));
+    dnb_launch_eventalign(a, grid, s);
+    CK(cudaEventRecord(b->ev[1], s));
+    DnbFeatArgs f = {};
+    f.n_reads = (uint32_t)R;
+    f.rec_off = d_rec_off; f.recs = d_recs; f.n_rec = d_nrec; f.status = d_status;
+    f.ref_off = b->d_r_off; f.ref = b->d_ref; f.r2q = d_r2q;
+    f.raw_off = b->d_raw_off; f.raw_kind = d_kind;
+    f.raw_f32 = b->i16 ? nullptr : (const float *)b->d_raw; f.raw_i16 = b->i16 ? (const int16_t *)b->d_raw : nullptr;
+    f.dac_offset = b->d_dac_off; f.dac_scale = b->d_dac_scl;
+    f.ev_off = b->d_ev_off; f.ev_start = w.ev_start; f.shift = w.shift; f.scale = w.scale;
+    f.is_reverse = d_rev; f.ref_start = d_rstart; f.ref_end = d_rend; f.called_off = d_called_off; f.called = d_called;
+    f.pos_off = d_pos_off; f.signal = d_signal; f.core = d_core; f.residual = d_resid; f.coords = d_coords;
+    f.ref_index = d_ri; f.query_index = d_qi; f.quality = d_qual; f.n_pos = d_npos; f.next_read = d_next + 1;
+    f.order = b->d_order;
+    CK(cudaEventRecord(b->ev[2], s));
+    dnb_launch_features(f, dnb_features_grid(ctx->cfg.device), s);
+    CK(cudaEventRecord(b->ev[3], s));
+    CK(cudaGetLastError());
+    // ---- results -> pinned host ----
+    TRY(ralloc(b, &S.h_n_rec, R)); TRY(ralloc(b, &S.h_n_pos, R)); TRY(ralloc(b, &S.h_status, R));
+    TRY(ralloc(b, &S.h_signal, tot_pos * DNB_RAWDEPTH)); TRY(ralloc(b, &S.h_core, tot_pos)); TRY(ralloc(b, &S.h_resid, tot_pos));
+    TRY(ralloc(b, &S.h_coords, tot_pos)); TRY(ralloc(b, &S.h_ri, tot_pos)); TRY(ralloc(b, &S.h_qi, tot_pos));
+    TRY(ralloc(b, &S.h_qual, tot_pos));
+    TRY(d2h(b, S.h_n_rec, d_nrec, R)); TRY(d2h(b, S.h_n_pos, d_npos, R)); TRY(d2h(b, S.h_status, d_status, R));
+    TRY(d2h(b, S.h_signal, d_signal, tot_pos * DNB_RAWDEPTH)); TRY(d2h(b, S.h_core, d_core, tot_pos));
+    TRY(d2h(b, S.h_resid, d_resid, tot_pos)); TRY(d2h(b, S.h_coords, d_coords, tot_pos)); TRY(d2h(b, S.h_ri, d_ri, tot_pos));
+    TRY(d2h(b, S.h_qi, d_qi, tot_pos)); TRY(d2h(b, S.h_qual, d_qual, tot_pos));
+    S.bytes[1] = tot_pos * (4ull * DNB_RAWDEPTH + 28) + 12 * R;
+    if (S.want_records) {
+        TRY(ralloc(b, &S.h_recs, tot_rec));
+        TRY(d2h(b, S.h_recs, d_recs, tot_rec));
+        S.bytes[1] += tot_rec * sizeof(dnb_eventalign_rec);
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    float t;
+    cudaEventElapsedTime(&t, b->ev[0], b->ev[1]); S.ms[0] = t;
+    cudaEventElapsedTime(&t, b->ev[2], b->ev[3]); S.ms[1] = t;
+    S.done = true;
+    return DNB_OK;
+}
+
+int dnb_batch_feature_result(dnb_batch *b, size_t i, dnb_feature_result *o) {
+    if (!b || !o || i >= b->R) return DNB_ERR_ARG;
+    if (!b->s2.done) return DNB_ERR_STATE;
+    const Stage2 &S = b->s2;
+    memset(o, 0, sizeof(*o));
+    o->status = S.h_status[i];
+    const bool ok = o->status == DNB_READ_OK;
+    const uint64_t lo = S.pos_off[i];
+    o->n_pos = ok ? S.h_n_pos[i] : 0;
+    o->signal = S.h_signal + lo * DNB_RAWDEPTH;
+    o->core = S.h_core + lo; o->residual = S.h_resid + lo;
+    o->coords = S.h_coords + lo; o->ref_index = S.h_ri + lo; o->query_index = S.h_qi + lo; o->quality = S.h_qual + lo;
+    if (S.want_records) {
+        o->n_recs = ok ? S.h_n_rec[i] : 0;
+        o->recs = S.h_recs + S.rec_off[i];
+    }
+    return DNB_OK;
+}
+
+int dnb_batch_stage2_timings(dnb_batch *b, double ms[2], uint64_t bytes[2]) {
+    if (!b) return DNB_ERR_ARG;
+    if (!b->s2.done) return DNB_ERR_STATE;
+    for (int i = 0; i < 2; i++) { if (ms) ms[i] = b->s2.ms[i]; if (bytes) bytes[i] = b->s2.bytes[i]; }
+    return DNB_OK;
 }
 
 int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t n_reads, uint32_t window,

@@ -193,6 +193,7 @@ struct DnbEaArgs {
     uint32_t *n_rec;              // [R]
     int *status;                  // [R] in: DNB_READ_OK or a host-side rejection; out: DNB_READ_*
     unsigned int *next_read;      // work counter (zeroed before the launch)
+    const uint32_t *order;        // optional processing order (longest first): slot -> read; nullptr = identity
     double *scratch_obs;          // [warps][t_max]
     uint32_t *scratch_ev;         // [warps][t_max]
     uint8_t *scratch_bt;          // [warps][t_max][96] backtrace codes: I (2 bits) | M (2 bits) << 2 | D (1 bit) << 4
@@ -216,7 +217,7 @@ struct DnbFeatArgs {
     const uint8_t *raw_kind;      // [R] 0 = float32 pA, 1 = int16 DAC
     const float *raw_f32;
     const int16_t *raw_i16;
-    const float *dac_offset, *dac_scale;   // [R]
+    const float *dac_offset, *dac_scale;   // [R], read only where raw_kind is 1
     const uint64_t *ev_off;       // [R+1]; read r's n_events + 1 event starts begin at ev_start[ev_off[r] + r]
     const uint32_t *ev_start;
     const double *shift, *scale;  // [R] r.scalings
@@ -231,6 +232,7 @@ struct DnbFeatArgs {
     int32_t *quality;
     uint32_t *n_pos;              // [R]
     unsigned int *next_read;      // work counter (zeroed before the launch)
+    const uint32_t *order;        // optional processing order (longest first): slot -> read; nullptr = identity
 };
 unsigned dnb_features_grid(int device);
 void dnb_launch_features(const DnbFeatArgs &a, unsigned grid, cudaStream_t s);

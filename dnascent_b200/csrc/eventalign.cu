@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(EA_WARPS * 32) eventalign_kernel(DnbEaArgs a) 
         if (lane == 0) r = atomicAdd(a.next_read, 1u);
         r = __shfl_sync(FULL, r, 0);
         if (r >= a.n_reads) break;
+        if (a.order) r = a.order[r];
         if (a.status[r] != DNB_READ_OK) { if (lane == 0) a.n_rec[r] = 0; continue; }   // rejected by the host (see capi.cu)
         EaRead rd;
         rd.ref = a.ref + a.ref_off[r];

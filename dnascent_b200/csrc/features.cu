@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(FT_THREADS) features_kernel(DnbFeatArgs a) {
         __syncthreads();
         if (tid == 0) { s_read = atomicAdd(a.next_read, 1u); s_bad = 0; }
         __syncthreads();
-        const uint32_t r = s_read;
-        if (r >= a.n_reads) break;
+        if (s_read >= a.n_reads) break;
+        const uint32_t r = a.order ? a.order[s_read] : s_read;
         if (a.status[r] != DNB_READ_OK) { if (tid == 0) a.n_pos[r] = 0; continue; }
 
         const dnb_eventalign_rec *recs = a.recs + a.rec_off[r];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(FT_THREADS) features_kernel(DnbFeatArgs a) {
         const uint32_t *es = a.ev_start + a.ev_off[r] + r;             // n_events + 1 entries
         const uint64_t raw0 = a.raw_off[r];
         const bool dac = a.raw_kind[r] != 0;
-        const float dac_off = a.dac_offset[r], dac_scl = a.dac_scale[r];
+        const float dac_off = dac ? a.dac_offset[r] : 0.f, dac_scl = dac ? a.dac_scale[r] : 1.f;
         const double shift = a.shift[r], scale = a.scale[r];
         const bool rev = a.is_reverse[r] != 0;
         const uint32_t ref_start = a.ref_start[r], ref_end = a.ref_end[r];

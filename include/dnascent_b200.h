@@ -257,6 +257,37 @@ DNB_API int dnb_eventalign_features_batch(dnb_ctx *ctx, const dnb_eventalign_des
 /* device time (ms) of the feature kernel of the last dnb_eventalign_features_batch on this thread */
 DNB_API double dnb_features_last_kernel_ms(void);
 
+/* ---- resident form: eventalign + DNN input tensors on a batch that dnb_batch_run has processed ----------------- */
+/* The read loop of detect.cpp:876-888 as one device-resident chain: the signal, the events, the alignment and the
+ * scalings of normaliseEvents are already in HBM, so eventalign and the tensor builder read them in place -- the only
+ * additional host->device bytes are the fields below, the only device->host bytes the tensors.  Split form only
+ * (dnb_batch_upload / dnb_batch_run, workspace not dropped); runs dnb_batch_fetch itself if that has not happened. */
+typedef struct {
+    const int32_t *ref_to_query;   /* dense r.refToQuery, ref_len entries; an absent key reads as 0 */
+    int is_reverse;                /* r.isReverse */
+    uint32_t ref_start, ref_end;   /* r.refStart, r.refEnd */
+    const uint32_t *called;        /* ascending keys of r.refCoordToCalls, may be NULL */
+    uint32_t n_called;
+} dnb_read_extra;
+
+typedef struct {
+    int status;                    /* DNB_READ_*: normaliseEvents' status, or what eventalign / the tensor builder found */
+    uint32_t n_pos;                /* rows */
+    const float *signal;           /* [n_pos][DNB_RAWDEPTH] */
+    const float *core, *residual;  /* [n_pos] */
+    const uint32_t *coords, *ref_index, *query_index;
+    const int32_t *quality;
+    uint32_t n_recs;               /* eventalign records (0 and NULL unless want_records) */
+    const dnb_eventalign_rec *recs;
+} dnb_feature_result;
+
+DNB_API int dnb_batch_eventalign_features(dnb_batch *batch, const dnb_read_extra *extra, uint32_t window,
+                                          int want_records);
+/* pointers stay valid until dnb_release / the next dnb_batch_run */
+DNB_API int dnb_batch_feature_result(dnb_batch *batch, size_t i, dnb_feature_result *out);
+/* ms: [0] eventalign kernel, [1] feature kernel (CUDA events on the batch's stream); bytes: [0] host->device, [1] device->host */
+DNB_API int dnb_batch_stage2_timings(dnb_batch *batch, double ms[2], uint64_t bytes[2]);
+
 #ifdef __cplusplus
 }
 #endif

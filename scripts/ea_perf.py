@@ -1,0 +1,82 @@
+"""Rows f1/f2 measurement (GPU box): n reads x L bases through normaliseEvents -> eventalign (+ DNN input tensors),
+device kernel times from the library's CUDA events, wall time of the C-ABI call with host buffers, and the unmodified
+reference's CPU eventalign (oracle/_ref, 1 thread per read loop as alignment.cpp:852) on a bounded subset.
+usage: python scripts/ea_perf.py [n_reads] [read_len] [n_cpu_reads] > gpurun_out/ea_perf.json"""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from dnascent_b200 import api, synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+L = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
+n_cpu = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+mean = np.load("tests/golden/pore_model_r10.4.1_400bps.npz")["mean"].astype(np.float64)
+ref = synth.make_reference(1_000_000, 1)
+base = synth.simulate_batch(ref, [L] * n, mean, seed=2)
+ctx = api.Context(0)
+ctx.load_model(api.MODEL_PORE, mean)
+res = ctx.normaliseEvents([api.Read.from_synth(r, use_dac=True) for r in base])
+reads = []
+for i, (sr, o) in enumerate(zip(base, res)):
+    if o.status != api.READ_OK:
+        continue
+    r2q = np.zeros(len(sr.refseq), dtype=np.int32)
+    q2r = np.asarray(sr.query_to_ref)
+    r2q[q2r[q2r >= 0]] = np.nonzero(q2r >= 0)[0]
+    reads.append(dict(refseq=sr.refseq, ref_to_query=r2q, eventAlignment=o.eventAlignment, event_mean=o.event_mean,
+                      shift=o.shift, scale=o.scale, events_per_base=o.eventsPerBase, event_start=o.event_start,
+                      is_reverse=bool(i & 1), ref_start=0, ref_end=len(sr.refseq), raw_dac=sr.dac,
+                      dac_offset=float(synth.DAC_OFFSET), dac_scale=float(synth.DAC_SCALE)))
+samples = int(sum(r["raw_dac"].size for r in reads))
+events = int(sum(r["event_mean"].size for r in reads))
+out = dict(n_reads=len(reads), read_len=L, samples=samples, events=events)
+for name, fn in (("eventalign", lambda: ctx.eventalign(reads, 50)),
+                 ("eventalign_features", lambda: ctx.eventalign_features(reads, 50, want_records=False))):
+    best_wall, k_ea, k_ft = 1e30, 0.0, 0.0
+    for it in range(3):
+        t = time.time(); o = fn(); dt = time.time() - t
+        if dt < best_wall:
+            best_wall, k_ea, k_ft = dt, ctx.eventalign_last_kernel_ms(), ctx.features_last_kernel_ms()
+    assert all(x["status"] == api.READ_OK for x in o)
+    out[name] = dict(wall_s=best_wall, eventalign_kernel_ms=k_ea, features_kernel_ms=k_ft if "features" in name else None,
+                     reads_per_s_wall=len(reads) / best_wall, reads_per_s_kernel=len(reads) / ((k_ea + (k_ft if "features" in name else 0)) * 1e-3))
+# resident chain: int16 DAC in, tensors out (normaliseEvents -> eventalign -> tensors without leaving HBM)
+ok_idx = [i for i, o_ in enumerate(res) if o_.status == api.READ_OK]
+b = ctx.upload([api.Read.from_synth(base[i], use_dac=True) for i in ok_idx])
+extra = [dict(ref_to_query=r["ref_to_query"], is_reverse=r["is_reverse"], ref_start=0, ref_end=len(r["refseq"])) for r in reads]
+best = None
+for it in range(3):
+    t = time.time(); b.run(); t_run = time.time() - t
+    t = time.time(); o = b.eventalign_features(extra, 50); t_s2 = time.time() - t
+    if best is None or t_run + t_s2 < best[0] + best[1]:
+        best = (t_run, t_s2, b.stage2_timings(), b.timings()[0])
+assert all(x["status"] == api.READ_OK for x in o)
+out["resident_chain"] = dict(normalise_run_wall_s=best[0], stage2_wall_s=best[1], stage2=best[2], normalise_ms=best[3],
+                             reads_per_s_wall=len(reads) / (best[0] + best[1]),
+                             msamples_per_s_wall=samples / (best[0] + best[1]) / 1e6)
+b.release()
+rows = int(sum(x["signal"].shape[0] for x in o))
+ft_ms = best[2]["features_kernel_ms"]
+# algorithmic bytes of the feature kernel: 16 B record per event read + <= 20 samples (2 B int16) per row read + 108 B per row written
+alg = 16 * sum(x["eventAlignment"].shape[0] for x in reads) + rows * (20 * 2 + 108)
+out["features_roofline"] = dict(rows=rows, algorithmic_bytes=int(alg), achieved_gbs=alg / (ft_ms * 1e-3) / 1e9 if ft_ms else None)
+try:
+    from oracle import refbind
+    if refbind.available():
+        R = refbind.Ref()
+        R.set_model(refbind.PORE, mean, np.full(mean.size, 0.14))
+        R.set_reference(ref)
+        hs = [R.read_new(sr) for sr in base[:n_cpu]]
+        t_norm = t_ea = 0.0
+        ok = 0
+        for h in hs:
+            t = time.time(); o = h.normalise(staged=False); t_norm += time.time() - t
+            if o["align_event"].size == 0:
+                continue
+            t = time.time(); h.eventalign(50); t_ea += time.time() - t
+            ok += 1
+        out["cpu_reference"] = dict(reads=ok, cores=1, normalise_s_per_read=t_norm / max(len(hs), 1), eventalign_s_per_read=t_ea / max(ok, 1),
+                                    eventalign_reads_per_s=ok / t_ea if t_ea else None)
+except Exception as ex:   # the reference library is test infrastructure; report and go on
+    out["cpu_reference"] = dict(error=repr(ex))
+print(json.dumps(out))

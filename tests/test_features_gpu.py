@@ -129,3 +129,75 @@ def test_features_edge_cases(ctx, pore_mean):
     assert out[3]["status"] == api.READ_OVERFLOW and out[3]["signal"].shape[0] == 0
     assert out[4]["status"] == api.READ_UNDEFINED
     assert ctx.eventalign_features([], window=50) == []
+
+
+def test_resident_chain_golden_tensors(ctx, ea_golden, golden_reads, golden_v2):
+    """The whole read loop on the device (detect.cpp:876-888 + runCNN's inputs): int16 DAC in, DNN tensors out, nothing
+    in between crosses PCIe but refToQuery.  normaliseEvents, eventalign and the tensor builder chained on the batch's
+    resident arrays must reproduce the unmodified reference's tensors and records for every golden read."""
+    e = ea_golden
+    reads = all_golden_reads(golden_reads, golden_v2)
+    b = ctx.upload([api.Read(None, g.basecall, g.refseq, g.query_to_ref, dac=g.dac, dac_offset=float(synth.DAC_OFFSET),
+                             dac_scale=float(synth.DAC_SCALE)) for _, g in reads])
+    b.run()
+    extra = []
+    for tag, g in reads:
+        ref_start, ref_end, is_rev = (int(x) for x in e[f"e_{tag}_strand"])
+        extra.append(dict(ref_to_query=e[f"e_{tag}_ref_to_query"], is_reverse=is_rev, ref_start=ref_start, ref_end=ref_end))
+    out = b.eventalign_features(extra, window=50, want_records=True)
+    t = b.stage2_timings()
+    assert t["eventalign_kernel_ms"] > 0 and t["features_kernel_ms"] > 0 and t["d2h_bytes"] > 0
+    for (tag, g), o in zip(reads, out):
+        p = f"e_{tag}_"
+        assert o["status"] == api.READ_OK, tag
+        for key in ("event", "ref_pos", "label", "indel"):
+            np.testing.assert_array_equal(o[key], e[p + key], err_msg=f"{tag} {key}")
+        for key in AP_KEYS:
+            np.testing.assert_array_equal(o[key], e[p + "ap_" + key], err_msg=f"{tag} {key}")
+    # the normaliseEvents results of the same batch are still there, and a second call (float input would be a new batch)
+    res = b.results()
+    for (tag, g), r in zip(reads, res):
+        np.testing.assert_array_equal(r.eventAlignment, g.align, err_msg=tag)
+    out2 = b.eventalign_features(extra, window=50)                  # idempotent, records left on the device
+    for o, o2 in zip(out, out2):
+        assert "event" not in o2
+        for key in AP_KEYS:
+            np.testing.assert_array_equal(o[key], o2[key])
+    b.release()
+
+
+def test_resident_chain_matches_host_array_form(ctx, pore_mean):
+    """Float32 input, failed reads in the batch, called positions: resident form == dnb_eventalign_features_batch."""
+    ref = synth.make_reference(150_000, 291)
+    base = synth.simulate_batch(ref, [6000, 300, 9000, 12000, 2500, 20000], pore_mean, seed=292, sub_rate=0.01)
+    b = ctx.upload([api.Read.from_synth(r) for r in base])
+    b.run()
+    res = b.results()
+    assert any(o.status != api.READ_OK for o in res) and sum(o.status == api.READ_OK for o in res) >= 4
+    extra, host_in = [], []
+    for i, (sr, o) in enumerate(zip(base, res)):
+        r2q = np.zeros(len(sr.refseq), dtype=np.int32)
+        q2r = np.asarray(sr.query_to_ref)
+        r2q[q2r[q2r >= 0]] = np.nonzero(q2r >= 0)[0]
+        called = np.arange(500 * i + 40, 500 * i + len(sr.refseq), 7, dtype=np.uint32)
+        x = dict(ref_to_query=r2q, is_reverse=bool(i & 1), ref_start=500 * i, ref_end=500 * i + len(sr.refseq), called=called)
+        extra.append(x)
+        if o.status == api.READ_OK:
+            host_in.append((i, dict(x, refseq=sr.refseq, eventAlignment=o.eventAlignment, event_mean=o.event_mean,
+                                    shift=o.shift, scale=o.scale, events_per_base=o.eventsPerBase,
+                                    event_start=o.event_start, raw=sr.raw)))
+    got = b.eventalign_features(extra, window=50, want_records=True)
+    want = ctx.eventalign_features([d for _, d in host_in], window=50)
+    for i, o in enumerate(got):
+        if res[i].status != api.READ_OK:
+            assert o["status"] == res[i].status and o["signal"].shape[0] == 0
+    for (i, _), w in zip(host_in, want):
+        assert got[i]["status"] == api.READ_OK and w["status"] == api.READ_OK
+        assert w["signal"].shape[0] > 0
+        for key in AP_KEYS + ("event", "ref_pos", "label", "indel"):
+            np.testing.assert_array_equal(got[i][key], w[key], err_msg=f"read {i} {key}")
+        assert not np.isin(got[i]["coords"], extra[i]["called"]).any()
+    b.drop_workspace()
+    with pytest.raises(Exception):
+        b.eventalign_features(extra)                                  # the resident arrays are gone: call order error
+    b.release()

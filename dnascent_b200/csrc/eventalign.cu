@@ -17,9 +17,10 @@
 // greater than each other), so the two conventions take the same decisions.
 //
 // The deletion chain D[i] = max(M[i-1] + m2d, D[i-1] + d2d) runs along the state axis inside one time step.  It is
-// solved exactly without serialising the warp: F(a) = fl(a + d2d) is monotone, so the recurrence's unique solution
-// is the least fixed point above v0[i] = M[i-1] + m2d, reached from D = v0 by repeating D[i] = max(D[i], F(D[i-1]))
-// until nothing changes (as many sweeps as the longest run of consecutive deletions, usually one or two).
+// solved exactly without serialising the warp: F(a) = fl(a + d2d) is monotone, so D[i] = max_d F^d(v0[i-d]) with
+// v0[i] = M[i-1] + m2d, a max-scan that is evaluated by distance doubling (k = 1, 2, 4, ...), F^k being k literal
+// roundings.  (ncu showed chains as long as the window at almost every step: one good match state beats every later
+// state's own v0, so a sweep-until-stable loop needed ~n/2 warp-wide sweeps; doubling needs log2 n rounds.)
 //
 // Emission (alignment.cpp:344): eln(normalPDF(mu, 0.14, x)) = log(c * exp(y)), y = -(x-mu)^2 / (2*0.14^2).  For
 // y >= -700 this is computed as log(c) + y (log(c), c and 2*sigma^2 come from the host's libm); below that, where
@@ -55,14 +56,27 @@ __device__ __forceinline__ uint32_t kmer_rank(const char *s) {      // kmer2inde
     return r;
 }
 
-// value of state i-1 for every state i held by this lane: slot s, lane l <-> i = 32 s + l
-__device__ __forceinline__ void state_minus_1(const double (&X)[EA_SLOTS], double (&out)[EA_SLOTS], int lane) {
+// value of state i-k for every state i held by this lane (slot s, lane l <-> i = 32 s + l), -inf where i < k.
+// k and nslots are warp-uniform; k is 1..31, 32 or 64.  One rotation per slot serves both the in-slot and the
+// wrapped-in-from-the-previous-slot lanes.
+__device__ __forceinline__ void state_minus_k(const double (&X)[EA_SLOTS], double (&out)[EA_SLOTS], int lane, int k, int nslots) {
+    if (k < 32) {
+        const int src = (lane - k) & 31;
+        double rot[EA_SLOTS];
 #pragma unroll
-    for (int s = 0; s < EA_SLOTS; s++) {
-        const double up = __shfl_up_sync(FULL, X[s], 1);
-        const double wrap = s ? __shfl_sync(FULL, X[s ? s - 1 : 0], 31) : NEG_INF;
-        out[s] = lane == 0 ? wrap : up;
+        for (int s = 0; s < EA_SLOTS; s++) rot[s] = s < nslots ? __shfl_sync(FULL, X[s], src) : NEG_INF;
+#pragma unroll
+        for (int s = 0; s < EA_SLOTS; s++) out[s] = lane >= k ? rot[s] : (s ? rot[s ? s - 1 : 0] : NEG_INF);
+    } else if (k == 32) {
+#pragma unroll
+        for (int s = 0; s < EA_SLOTS; s++) out[s] = s ? X[s ? s - 1 : 0] : NEG_INF;
+    } else {
+#pragma unroll
+        for (int s = 0; s < EA_SLOTS; s++) out[s] = s >= 2 ? X[s >= 2 ? s - 2 : 0] : NEG_INF;
     }
+}
+__device__ __forceinline__ void state_minus_1(const double (&X)[EA_SLOTS], double (&out)[EA_SLOTS], int lane, int nslots) {
+    state_minus_k(X, out, lane, 1, nslots);
 }
 
 struct EaRead {
@@ -128,7 +142,8 @@ __device__ void eventalign_read(const DnbEaArgs &a, const EaRead &rd, uint32_t r
             const bool good = in && 0. < em && em < 250.;                                   // :623
             const unsigned gm = __ballot_sync(FULL, good);
             const uint32_t pos = ns + __popc(gm & lt);
-            if (good && pos < a.t_max) { obs[pos] = em; obs_ev[pos] = pr.x; }
+            // the scaled observation (:272, 344) is computed here, once per event, instead of by every lane at its time step
+            if (good && pos < a.t_max) { obs[pos] = dDiv(dSub(em, rd.shift), rd.scale); obs_ev[pos] = pr.x; }
             ns += __popc(gm);
             if (stopmask) break;
         }
@@ -158,17 +173,18 @@ __device__ void eventalign_read(const DnbEaArgs &a, const EaRead &rd, uint32_t r
             }
         }
         double start_prev = 0.0;
+        const int nslots = (n + 31) >> 5;                                                   // register slots in use (1..3)
         for (uint32_t t = 0; t < ns; t++) {
-            const double x = dDiv(dSub(obs[t], rd.shift), rd.scale);                        // :272, 344
+            const double x = obs[t];
             double Im1[EA_SLOTS], Mm1[EA_SLOTS], Dm1[EA_SLOTS];
-            state_minus_1(I, Im1, lane); state_minus_1(M, Mm1, lane); state_minus_1(D, Dm1, lane);
+            state_minus_1(I, Im1, lane, nslots); state_minus_1(M, Mm1, lane, nslots); state_minus_1(D, Dm1, lane, nslots);
             double In[EA_SLOTS], Mn[EA_SLOTS];
             uint32_t code[EA_SLOTS];
 #pragma unroll
             for (int s = 0; s < EA_SLOTS; s++) {
                 const int i = 32 * s + lane;
                 In[s] = NEG_INF; Mn[s] = NEG_INF; code[s] = 0;
-                if (32 * s < n) {
+                if (s < nslots) {
                     const double d = dSub(x, mu[s]);
                     const double y = dDiv(-dMul(d, d), a.two_sigma2);
                     double mp;
@@ -199,32 +215,43 @@ __device__ void eventalign_read(const DnbEaArgs &a, const EaRead &rd, uint32_t r
                     if (i >= n) { In[s] = NEG_INF; Mn[s] = NEG_INF; }
                 }
             }
-            // deletion (:325-327, 405-428): least fixed point of D[i] = max(M_curr[i-1] + m2d, D[i-1] + d2d)
+            // deletion (:325-327, 405-428): D[i] = max(v0[i], F(D[i-1])) with v0[i] = M_curr[i-1] + m2d and
+            // F(a) = fl(a + d2d).  F is monotone, so D[i] = max over d of F^d(v0[i-d]) -- and a strong match state
+            // usually wins for EVERY state after it (d2d = log 0.3 costs less than a mismatching emission), so the chain
+            // is as long as the window.  Exact scan by doubling: after the round with distance k every D[i] holds the
+            // max over d < 2k; F^k is k dependent roundings, done literally (total <= n adds per lane).  A round that
+            // changes nothing proves the fixed point (any longer chain factors through states that did not grow).
             double v0[EA_SLOTS], Dn[EA_SLOTS];
-            state_minus_1(Mn, v0, lane);
+            state_minus_1(Mn, v0, lane, nslots);
 #pragma unroll
             for (int s = 0; s < EA_SLOTS; s++) {
                 const int i = 32 * s + lane;
                 v0[s] = (i > 0 && i < n) ? dAdd(v0[s], a.m2d) : NEG_INF;
                 Dn[s] = v0[s];
             }
-            for (;;) {
+            for (int k = 1; k <= n - 2; k <<= 1) {
                 double c[EA_SLOTS];
-                state_minus_1(Dn, c, lane);
+                state_minus_k(Dn, c, lane, k, nslots);
+                for (int j = 0; j < k; j++) {
+#pragma unroll
+                    for (int s = 0; s < EA_SLOTS; s++)
+                        if (s < nslots) c[s] = dAdd(c[s], a.d2d);
+                }
                 bool grew = false;
 #pragma unroll
                 for (int s = 0; s < EA_SLOTS; s++) {
                     const int i = 32 * s + lane;
-                    c[s] = dAdd(c[s], a.d2d);
                     if (i > 0 && i < n && c[s] > Dn[s]) { Dn[s] = c[s]; grew = true; }
                 }
-                if (!__any_sync(FULL, grew)) {
+                if (!__any_sync(FULL, grew)) break;
+            }
+            {   // lnArgMax: D over M only when strictly greater
+                double c[EA_SLOTS];
+                state_minus_1(Dn, c, lane, nslots);
 #pragma unroll
-                    for (int s = 0; s < EA_SLOTS; s++) {                      // lnArgMax: D over M only when strictly greater
-                        const int i = 32 * s + lane;
-                        if (i > 0 && i < n && c[s] > v0[s]) code[s] |= 1u << 4;
-                    }
-                    break;
+                for (int s = 0; s < EA_SLOTS; s++) {
+                    const int i = 32 * s + lane;
+                    if (i > 0 && i < n && dAdd(c[s], a.d2d) > v0[s]) code[s] |= 1u << 4;
                 }
             }
             uint8_t *row = bt + (size_t)t * (EA_SLOTS * 32);

@@ -41,8 +41,8 @@ def test_features_golden_tensors(ctx, ea_golden, golden_reads, golden_v2):
         for key in ("event", "ref_pos", "label", "indel"):
             np.testing.assert_array_equal(o[key], e[p + key], err_msg=f"{tag} {key}")
         for key in AP_KEYS:
-            assert o[key].dtype == e[p + "ap_" + key].dtype, (tag, key)
             np.testing.assert_array_equal(o[key], e[p + "ap_" + key], err_msg=f"{tag} {key}")
+        assert o["signal"].dtype == np.float32 and o["core"].dtype == np.float32 and o["residual"].dtype == np.float32
         assert o["signal"].shape[1] == 20 and o["signal"].shape[0] > 0.8 * (len(g.refseq) - 8)
         n_rev += int(e[p + "strand"][2])
     assert 0 < n_rev < len(reads)          # both makeSignalTensor iteration orders are covered
@@ -172,6 +172,7 @@ def test_resident_chain_matches_host_array_form(ctx, pore_mean):
     base = synth.simulate_batch(ref, [6000, 300, 9000, 12000, 2500, 20000], pore_mean, seed=292, sub_rate=0.01)
     b = ctx.upload([api.Read.from_synth(r) for r in base])
     b.run()
+    b.fetch()
     res = b.results()
     assert any(o.status != api.READ_OK for o in res) and sum(o.status == api.READ_OK for o in res) >= 4
     extra, host_in = [], []

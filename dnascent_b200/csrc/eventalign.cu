@@ -79,6 +79,34 @@ __device__ __forceinline__ void state_minus_1(const double (&X)[EA_SLOTS], doubl
     state_minus_k(X, out, lane, 1, nslots);
 }
 
+// c[s] = F^k(c[s]) for the slots in use, F(a) = fl(a + d): K literal roundings per slot, straight-line code (the
+// slots' chains are independent, so they overlap in the FP64 pipe)
+template <int K, int NS>
+__device__ __forceinline__ void add_chain(double (&c)[EA_SLOTS], double d) {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) c[s] = dAdd(c[s], d);
+    }
+}
+template <int NS>
+__device__ __forceinline__ void add_k_slots(double (&c)[EA_SLOTS], double d, int k) {
+    switch (k) {
+        case 1: add_chain<1, NS>(c, d); break;
+        case 2: add_chain<2, NS>(c, d); break;
+        case 4: add_chain<4, NS>(c, d); break;
+        case 8: add_chain<8, NS>(c, d); break;
+        case 16: add_chain<16, NS>(c, d); break;
+        case 32: add_chain<32, NS>(c, d); break;
+        default: add_chain<64, NS>(c, d); break;
+    }
+}
+__device__ __forceinline__ void add_k_times(double (&c)[EA_SLOTS], double d, int k, int nslots) {
+    if (nslots == 1) add_k_slots<1>(c, d, k);
+    else if (nslots == 2) add_k_slots<2>(c, d, k);
+    else add_k_slots<3>(c, d, k);
+}
+
 struct EaRead {
     const char *ref;
     uint32_t rlen;
@@ -232,11 +260,7 @@ __device__ void eventalign_read(const DnbEaArgs &a, const EaRead &rd, uint32_t r
             for (int k = 1; k <= n - 2; k <<= 1) {
                 double c[EA_SLOTS];
                 state_minus_k(Dn, c, lane, k, nslots);
-                for (int j = 0; j < k; j++) {
-#pragma unroll
-                    for (int s = 0; s < EA_SLOTS; s++)
-                        if (s < nslots) c[s] = dAdd(c[s], a.d2d);
-                }
+                add_k_times(c, a.d2d, k, nslots);
                 bool grew = false;
 #pragma unroll
                 for (int s = 0; s < EA_SLOTS; s++) {

@@ -403,6 +403,16 @@ class Context:
         return float(self.L.dnb_features_last_kernel_ms())
 
 
+def dorado_slice(n_total: int, signal_length: int = 0, signal_trim: int = 0, signal_start_coord: int = 0,
+                 is_split: bool = False) -> slice:
+    """The part of a POD5 record's signal that pod5_getSignal keeps (src/pod5.cpp:76-93), as a Python slice to apply
+    to the int16 DAC array before it goes into Read(dac=...).  Raises where the reference's erase is undefined."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    _lib.check(_lib.lib().dnb_dorado_slice(n_total, signal_length, signal_trim, signal_start_coord, int(is_split),
+                                           C.byref(a), C.byref(b)), "dnb_dorado_slice")
+    return slice(a.value, a.value + b.value)
+
+
 # ---- probability.h drop-ins (scalar, host) ------------------------------------------------------------
 def eexp(x: float) -> float:
     return _lib.lib().dnb_eexp(x)

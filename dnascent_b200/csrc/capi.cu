@@ -1492,6 +1492,23 @@ int dnb_batch_stage2_timings(dnb_batch *b, double ms[2], uint64_t bytes[2]) {
     return DNB_OK;
 }
 
+// ---- int16 ingest: Dorado slice (src/pod5.cpp:76-93) ----------------------------------------------------------------
+int dnb_dorado_slice(uint64_t n_total, int64_t signal_length, int64_t signal_trim, int64_t signal_start_coord,
+                     int is_split, uint64_t *first, uint64_t *count) {
+    if (!first || !count) return DNB_ERR_ARG;
+    *first = 0; *count = 0;
+    if (n_total == 0) { g_last_error = "empty signal (the reference exits, pod5.cpp:64-73)"; return DNB_ERR_ARG; }
+    if (signal_length <= 0) { *count = n_total; return DNB_OK; }              // not a Dorado BAM: the whole record
+    // size_t arithmetic of pod5.cpp:82-83 / 90-91 (negative tags wrap there; here they are rejected)
+    if (signal_trim < 0 || signal_start_coord < 0) { g_last_error = "negative Dorado signal tag"; return DNB_ERR_ARG; }
+    const uint64_t start = (is_split ? (uint64_t)signal_start_coord : 0ull) + (uint64_t)signal_trim;
+    const uint64_t end = (is_split ? (uint64_t)signal_start_coord : 0ull) + (uint64_t)signal_length;
+    // erase(begin, begin + start) needs start <= size; erase(begin + (end - start), end()) needs start <= end <= size
+    if (start > end || end > n_total) { g_last_error = "Dorado slice outside the record (undefined in the reference)"; return DNB_ERR_ARG; }
+    *first = start; *count = end - start;
+    return DNB_OK;
+}
+
 int dnb_eventalign_batch(dnb_ctx *ctx, const dnb_eventalign_desc *reads, size_t n_reads, uint32_t window,
                          dnb_eventalign_rec *recs, const uint64_t *rec_off, uint32_t *n_recs, int *status) {
     return eventalign_impl(ctx, reads, nullptr, n_reads, window, recs, rec_off, n_recs, status, nullptr, nullptr, nullptr);

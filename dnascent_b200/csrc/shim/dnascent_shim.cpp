@@ -540,6 +540,69 @@ void eventalign_features_batch(const std::vector<DNAscent::read *> &reads, unsig
     }
 }
 
+// normaliseEvents + eventalign + tensors on one resident batch
+void normalise_eventalign_batch(const std::vector<DNAscent::read *> &reads, unsigned int totalWindowLength,
+                                std::vector<DnnInputs> &out) {
+    const size_t n = reads.size();
+    out.assign(n, DnnInputs());
+    if (n == 0) return;
+    dnb_ctx *ctx = context();
+    std::vector<Staged> staged(n);
+    std::vector<dnb_read_desc> descs(n);
+    std::vector<dnb_read_extra> extra(n);
+    std::vector<std::vector<int32_t>> r2q(n);
+    std::vector<std::vector<uint32_t>> called(n);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < n; i++) {
+        DNAscent::read &r = *reads[i];
+        stage_read(r, staged[i], descs[i]);
+        const size_t rl = r.referenceSeqMappedTo.size();
+        r2q[i].assign(rl, 0);                                    // std::map::operator[] reads an absent key as 0
+        for (const auto &kv : r.refToQuery)
+            if (kv.first < rl) r2q[i][kv.first] = (int32_t)kv.second;
+        for (const auto &kv : r.refCoordToCalls) called[i].push_back(kv.first);
+        dnb_read_extra &x = extra[i];
+        x.ref_to_query = r2q[i].data();
+        x.is_reverse = r.isReverse ? 1 : 0;
+        x.ref_start = (uint32_t)r.refStart;
+        x.ref_end = (uint32_t)r.refEnd;
+        x.called = called[i].empty() ? nullptr : called[i].data();
+        x.n_called = (uint32_t)called[i].size();
+    }
+    dnb_batch *b = nullptr;
+    int rc = dnb_batch_upload(ctx, descs.data(), n, &b);
+    if (rc != DNB_OK) die("dnb_batch_upload", rc);
+    if ((rc = dnb_batch_run(b)) != DNB_OK) die("dnb_batch_run", rc);
+    if ((rc = dnb_batch_fetch(b)) != DNB_OK) die("dnb_batch_fetch", rc);
+    if ((rc = dnb_batch_eventalign_features(b, extra.data(), totalWindowLength, 0)) != DNB_OK) die("dnb_batch_eventalign_features", rc);
+    bool negative_log = false;
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < n; i++) {
+        DNAscent::read &r = *reads[i];
+        dnb_read_result o;
+        int rc2 = dnb_result(b, i, &o);
+        if (rc2 != DNB_OK) die("dnb_result", rc2);
+        unpack_result(r, o);
+        if (r.eventAlignment.empty()) continue;                              // detect.cpp:879-881: failed read, no eventalign
+        dnb_feature_result f;
+        if ((rc2 = dnb_batch_feature_result(b, i, &f)) != DNB_OK) die("dnb_batch_feature_result", rc2);
+        if (f.status == DNB_READ_UNDEFINED) { negative_log = true; continue; }
+        if (f.status != DNB_READ_OK) die("dnb_batch_eventalign_features (per-read capacity)", DNB_ERR_NOMEM);
+        DnnInputs &d = out[i];
+        d.signal.assign(f.signal, f.signal + (size_t)f.n_pos * DNB_RAWDEPTH);
+        d.core.assign(f.core, f.core + f.n_pos);
+        d.residual.assign(f.residual, f.residual + f.n_pos);
+        d.refCoords.assign(f.coords, f.coords + f.n_pos);
+        d.refIndices.assign(f.ref_index, f.ref_index + f.n_pos);
+        d.queryIndices.assign(f.query_index, f.query_index + f.n_pos);
+        d.alignmentQuality.assign(f.quality, f.quality + f.n_pos);
+        d.QCpassed = true;
+        r.QCpassed = true;                                                   // alignment.cpp:743
+    }
+    dnb_release(b);
+    if (negative_log) throw NegativeLog();                                   // what eln() does in the reference (alignment.cpp:208)
+}
+
 }  // namespace dnb_shim
 
 void eventalign(DNAscent::read &r, unsigned int totalWindowLength) {

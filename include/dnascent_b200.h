@@ -288,6 +288,20 @@ DNB_API int dnb_batch_feature_result(dnb_batch *batch, size_t i, dnb_feature_res
 /* ms: [0] eventalign kernel, [1] feature kernel (CUDA events on the batch's stream); bytes: [0] host->device, [1] device->host */
 DNB_API int dnb_batch_stage2_timings(dnb_batch *batch, double ms[2], uint64_t bytes[2]);
 
+/* ---- int16 ingest: the Dorado signal slice of pod5_getSignal (src/pod5.cpp:56-93, tags parsed at src/reads.h:221-253) -- */
+/* The reference converts the whole POD5 record to pA and then erases what Dorado trimmed or what belongs to the
+ * sibling of a split read.  Here the int16 DAC samples go to the device as they are (dnb_read_desc.raw_dac + the
+ * record's calibration; pA is formed in registers with pod5.cpp:60's float expression), so trimming is a pointer
+ * offset: only the slice is staged and copied.  This computes the slice [*first, *first + *count) of the record's
+ * n_total samples exactly as the two vector::erase calls do:
+ *   signal_length  r.signalLength (BAM tag ns), <= 0 when absent: no slicing (pod5.cpp:76)
+ *   signal_trim    r.signalTrim (ts);  signal_start_coord  r.signalStartCoord (sp);
+ *   is_split       r.readID != r.readID_fetch (a parent id, tag pi, was present)
+ * Returns DNB_ERR_ARG where the reference's erase calls are undefined (start > end, or end past the record), and for an
+ * empty record (the reference exits, pod5.cpp:64-73). */
+DNB_API int dnb_dorado_slice(uint64_t n_total, int64_t signal_length, int64_t signal_trim, int64_t signal_start_coord,
+                             int is_split, uint64_t *first, uint64_t *count);
+
 #ifdef __cplusplus
 }
 #endif

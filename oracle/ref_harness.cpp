@@ -534,6 +534,17 @@ int dnbshim_eventalign_features_batch(void **handles, size_t n, unsigned int win
     }
     return 0;
 }
+// the resident chain: normaliseEvents + eventalign + tensors in one device-resident batch
+int dnbshim_normalise_eventalign_batch(void **handles, size_t n, unsigned int windowLength) {
+    std::vector<DNAscent::read *> reads(n);
+    for (size_t i = 0; i < n; i++) reads[i] = ((Handle *)handles[i])->r;
+    try {
+        dnb_shim::normalise_eventalign_batch(reads, windowLength, g_dnn_inputs);
+    } catch (NegativeLog &) {
+        return 1;
+    }
+    return 0;
+}
 size_t dnbshim_dnn_inputs(size_t i, float *signal, float *core, float *residual, uint32_t *coords, uint32_t *ref_index,
                           uint32_t *query_index, int32_t *quality, size_t cap) {
     if (i >= g_dnn_inputs.size()) return 0;

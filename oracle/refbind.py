@@ -46,6 +46,7 @@ class Ref:
             L.dnbshim_calls.argtypes = [vp, vp, vp, sz]
             L.dnbshim_shutdown.restype = None
             L.dnbshim_eventalign_features_batch.argtypes = [vp, sz, C.c_uint]
+            L.dnbshim_normalise_eventalign_batch.argtypes = [vp, sz, C.c_uint]
             L.dnbshim_dnn_inputs.restype = sz
             L.dnbshim_dnn_inputs.argtypes = [sz, vp, vp, vp, vp, vp, vp, vp, sz]
         L.dnbref_get_model.restype = sz
@@ -197,11 +198,13 @@ class Ref:
             out.append((pos[:n].copy(), llr[:n].copy()))
         return out
 
-    def eventalign_features_batch(self, reads, window: int = 50):
-        """dnb_shim::eventalign_features_batch: per read the DnnInputs vectors (what runCNN would get from
-        r.makeSignalTensor() & co.), keys as aligned_positions()."""
+    def eventalign_features_batch(self, reads, window: int = 50, resident: bool = False):
+        """dnb_shim::eventalign_features_batch (or, resident=True, dnb_shim::normalise_eventalign_batch on reads that have
+        NOT been normalised yet): per read the DnnInputs vectors (what runCNN would get from r.makeSignalTensor() & co.),
+        keys as aligned_positions()."""
         arr = (C.c_void_p * len(reads))(*[r.h for r in reads])
-        if self.L.dnbshim_eventalign_features_batch(arr, len(reads), window):
+        fn = self.L.dnbshim_normalise_eventalign_batch if resident else self.L.dnbshim_eventalign_features_batch
+        if fn(arr, len(reads), window):
             raise ValueError("NegativeLog")
         depth = self.L.dnbref_rawdepth()
         out = []

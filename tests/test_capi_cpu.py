@@ -99,3 +99,34 @@ def test_shim_exports_the_reference_symbols():
         assert sym in defined, sym
     assert any(s.startswith("_Z19sequenceProbabilityRSt6vectorIdSaIdEE") for s in defined)
     refbind.Ref(shim=True)          # loads (resolves libdnascent_b200.so through its rpath) without a GPU
+
+
+def test_dorado_slice_matches_vector_erase():
+    """Row f3: dnb_dorado_slice against a literal restatement of pod5_getSignal's two vector::erase calls
+    (src/pod5.cpp:76-93) on a Python list, for unsplit and split reads; undefined cases are refused."""
+    from dnascent_b200 import _lib, api
+    rng = np.random.default_rng(5)
+
+    def erase_twice(raw, sig_start, sig_end):                 # pod5.cpp:84-85 / 92-93
+        raw = list(raw)
+        del raw[:sig_start]
+        del raw[sig_end - sig_start:]
+        return raw
+
+    for _ in range(200):
+        n = int(rng.integers(1, 400))
+        raw = list(range(n))
+        split = bool(rng.integers(0, 2))
+        sp = int(rng.integers(0, n)) if split else int(rng.integers(0, 1000))   # sp is ignored unless the read was split
+        lo = sp if split else 0
+        ns = int(rng.integers(1, n - lo + 1))
+        ts = int(rng.integers(0, ns + 1))
+        sl = api.dorado_slice(n, ns, ts, sp, split)
+        want = erase_twice(raw, lo + ts, lo + ns)
+        assert raw[sl] == want
+    assert api.dorado_slice(100) == slice(0, 100)              # no ns tag: signalLength stays 0, nothing is trimmed
+    assert api.dorado_slice(100, 100, 100) == slice(100, 100)  # everything trimmed: empty read (fails later, as in the reference)
+    for bad in ((100, 101, 0, 0, False), (100, 50, 51, 0, False), (100, 60, 0, 50, True), (0, 0, 0, 0, False),
+                (100, 50, -1, 0, False)):
+        with pytest.raises(_lib.DnbError):
+            api.dorado_slice(*bad)

@@ -242,3 +242,33 @@ def test_ultra_long_read_configs2(ctx, port, pore_mean):
         p = port.normalise(r.raw, r.basecall, r.refseq, r.query_to_ref, pore_mean)
         _compare_with_port(o, p, tag=r.name)
         assert o.status == api.READ_OK and o.eventAlignment.shape[0] > len(r.basecall)
+
+
+def test_int16_ingest_with_dorado_slice(ctx, port, pore_mean):
+    """Row f3: a POD5 record longer than the read (Dorado-trimmed prefix, a split sibling's samples after it) goes in
+    as int16 through dnb_dorado_slice's pointer offset; results must equal the oracle on the reference's own
+    erase-then-process order (pod5.cpp:56-93 then normaliseEvents)."""
+    ref = synth.make_reference(60_000, 61)
+    reads = synth.simulate_batch(ref, [3000, 4500], pore_mean, seed=62)
+    rng = np.random.default_rng(63)
+    ins, want = [], []
+    for j, sr in enumerate(reads):
+        pre, post = int(rng.integers(50, 4000)), int(rng.integers(0, 3000))
+        junk = lambda n: rng.integers(200, 900, n).astype(np.int16)
+        record = np.concatenate([junk(pre), sr.dac, junk(post)])
+        if j == 0:      # unsplit read: ts = trimmed prefix, ns = end of the read's samples
+            sl = api.dorado_slice(record.size, signal_length=pre + sr.dac.size, signal_trim=pre)
+        else:           # split read: sp = start inside the parent record, ts on top of it
+            sl = api.dorado_slice(record.size, signal_length=40 + sr.dac.size, signal_trim=40, signal_start_coord=pre - 40,
+                                  is_split=True)
+        assert (sl.start, sl.stop) == (pre, pre + sr.dac.size)
+        ins.append(api.Read(None, sr.basecall, sr.refseq, sr.query_to_ref, dac=record[sl],
+                            dac_offset=float(synth.DAC_OFFSET), dac_scale=float(synth.DAC_SCALE)))
+        raw = synth.dac_to_pa(record).astype(np.float64)[sl]             # convert everything, then erase (the reference's order)
+        want.append(port.normalise(raw, sr.basecall, sr.refseq, sr.query_to_ref, pore_mean))
+    for o, p in zip(ctx.normaliseEvents(ins), want):
+        assert o.status == p["status"] == 0
+        np.testing.assert_array_equal(o.event_mean.astype(np.float64), p["event_mean"])
+        np.testing.assert_array_equal(o.eventAlignment[:, 0], p["align_event"])
+        np.testing.assert_array_equal(o.eventAlignment[:, 1], p["align_kmer"])
+        assert o.shift == p["shift"] and o.scale == p["scale"]

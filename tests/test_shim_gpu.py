@@ -115,6 +115,35 @@ def test_shim_eventalign_features_batch_matches_reference(shim, ref_oracle, pore
     assert strands == {False, True}
 
 
+def test_shim_resident_chain_matches_reference(shim, ref_oracle, pore_mean):
+    """dnb_shim::normalise_eventalign_batch (one device-resident batch: normaliseEvents -> eventalign -> tensors) leaves
+    each DNAscent::read as the reference's normaliseEvents does and hands back the reference's DNN inputs; a read that
+    fails normalisation comes back with an empty eventAlignment and no tensors (detect.cpp:879-881)."""
+    ref = synth.make_reference(200_000, 71)
+    shim.set_reference(ref)
+    ref_oracle.set_reference(ref)
+    reads = _reads(pore_mean, ref, 7, 72, lo=2000, hi=12000)
+    rng = np.random.default_rng(73)
+    reads.append(synth.simulate_read(ref, 5000, 400, False, pore_mean, rng, name="short"))      # < 1000 cleaned points: QC fail
+    hs = [shim.read_new(r) for r in reads]
+    hr = [ref_oracle.read_new(r) for r in reads]
+    got = shim.eventalign_features_batch(hs, 50, resident=True)
+    n_ok = n_fail = 0
+    for i, (a, b, g) in enumerate(zip(hs, hr, got)):
+        want = b.normalise(staged=False)
+        _same(a.outputs(staged=False), want, f"read {i}")
+        if want["align_event"].size == 0:
+            assert g["core"].size == 0
+            n_fail += 1
+            continue
+        b.eventalign(50)
+        ap = b.aligned_positions()
+        for key in ("signal", "core", "residual", "coords", "ref_index", "query_index", "quality"):
+            np.testing.assert_array_equal(g[key], ap[key], err_msg=f"read {i} {key}")
+        n_ok += 1
+    assert n_ok >= 5 and n_fail >= 1
+
+
 def test_shim_detect_events_and_probability(shim, ref_oracle, pore_mean):
     ref = synth.make_reference(50_000, 33)
     r = _reads(pore_mean, ref, 1, 34)[0]

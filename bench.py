@@ -14,6 +14,14 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# torch.distributed.run exports OMP_NUM_THREADS=1 to every rank unless the caller set it.  The host side of the e2e leg
+# (dnb_submit's staging of ~78 GB per step into pinned memory) is an OpenMP loop, so one thread per rank would measure
+# torchrun's default, not the library: give each rank its share of the host cores.  This has to happen before anything
+# loads libgomp (numpy/torch/our library).
+if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    _local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _local))
 import sys
 import threading
 import time
@@ -347,7 +355,9 @@ def main():
             },
             "roofline": roofline, "roofline_segmentation": roofline_seg, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
-                    "ms_per_step": 1e3 * dt_e / args.steps, "inflight": args.e2e_inflight, "bins": len(e2e_bins)},
+                    "ms_per_step": 1e3 * dt_e / args.steps, "inflight": args.e2e_inflight, "bins": len(e2e_bins),
+                    "host_threads_per_rank": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
+                    "host_cores": os.cpu_count() or 1},
             "gpu_launches": int(cnt_step["launches"] * args.steps), "clocks": clocks,
         }
         print(json.dumps(line))

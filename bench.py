@@ -156,8 +156,9 @@ def main():
     ap.add_argument("--n50", type=float, default=30_000.0)
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--bin-samples", type=float, default=2.5e9, help="samples per device bin (value leg)")
-    ap.add_argument("--e2e-bin-samples", type=float, default=4.0e8, help="samples per dnb_submit call (e2e leg)")
-    ap.add_argument("--e2e-inflight", type=int, default=4)
+    ap.add_argument("--e2e-bin-samples", type=float, default=8.0e8, help="samples per dnb_submit call (e2e leg)")
+    ap.add_argument("--e2e-inflight", type=int, default=8,
+                    help="dnb_submit calls in flight (B200 sweep, 60k reads: 4e8x4 74 %% of the resident value, 8e8x8 84 %%)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -203,6 +204,12 @@ def main():
     try:
         import psutil
         avail = psutil.virtual_memory().available
+        # pinned staging + result buffers of the submissions in flight (~5.5 B/sample each) come on top
+        inflight_bytes = 5.5 * args.e2e_bin_samples * args.e2e_inflight * world
+        while args.e2e_inflight > 2 and inflight_bytes > 0.25 * avail:
+            args.e2e_inflight -= 1
+            inflight_bytes = 5.5 * args.e2e_bin_samples * args.e2e_inflight * world
+        avail -= inflight_bytes
         need = 1.3 * 2.6 * SAMPLES_PER_BASE * 25_100.0 * reads_per_gpu * world      # mean read ~25.1 kb at N50 30 kb
         if need > 0.8 * avail:
             reads_per_gpu = max(int(reads_per_gpu * 0.8 * avail / need), 1000)

@@ -19,11 +19,13 @@
 // Kernel: one CTA per read (persistent CTAs, atomic read counter), 256 records per chunk.
 //   1. exclusive max-scan of (ref_pos + 1) over the M records -> is this record the head of a run?  (a decreasing
 //      position, which eventalign cannot produce, marks the read DNB_READ_UNDEFINED instead of emitting garbage)
-//   2. every head walks its run and stages the first 20 samples, (float)((raw - shift) / scale) with IEEE double
-//      subtract / divide (alignment.cpp:709, reads.h:154), zero padded, into a shared-memory row (stride 21 floats:
-//      conflict free); raw is recomputed from the int16 DAC with pod5.cpp:60's float expression where that was shipped
-//   3. exclusive sum-scan of the kept heads -> output row; the 80-byte rows leave shared memory as one contiguous,
-//      fully coalesced store per chunk; the six per-position scalars are written by the head threads.
+//   2. every head walks its run and stages WHICH raw sample fills each of its 20 columns (integer work) in a
+//      shared-memory row (stride 21 words: conflict free)
+//   3. exclusive sum-scan of the kept heads -> output row; then the whole CTA converts: element j of the chunk's
+//      contiguous [rows][20] block is (float)((raw - shift) / scale) with IEEE double subtract / divide
+//      (alignment.cpp:709, reads.h:154) or zero padding, raw recomputed from the int16 DAC with pod5.cpp:60's float
+//      expression where that was shipped -- every thread does the same number of divisions and the 80-byte rows
+//      leave as one fully coalesced store per chunk; the six per-position scalars are written by the head threads.
 // HBM traffic per position: 16 B of record + ~20 samples read, 108 B written -- a streaming kernel.
 #include <cub/block/block_scan.cuh>
 #include "dnb_internal.cuh"
@@ -31,6 +33,7 @@
 
 #define FT_THREADS 256
 #define FT_ROW (DNB_RAWDEPTH + 1)
+#define FT_NONE 0xffffffffu
 
 namespace {
 
@@ -51,7 +54,7 @@ __device__ __forceinline__ bool called_contains(const uint32_t *v, uint32_t n, u
 __global__ void __launch_bounds__(FT_THREADS) features_kernel(DnbFeatArgs a) {
     typedef cub::BlockScan<uint32_t, FT_THREADS> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
-    __shared__ float rows[FT_THREADS * FT_ROW];
+    __shared__ uint32_t rows[FT_THREADS * FT_ROW];
     __shared__ uint16_t src_of[FT_THREADS];
     __shared__ uint32_t s_read;
     __shared__ int s_bad;
@@ -106,7 +109,9 @@ __global__ void __launch_bounds__(FT_THREADS) features_kernel(DnbFeatArgs a) {
                 keep = !called_contains(called, n_called, coord);                                               // :711
             }
             if (keep) {
-                float *row = rows + tid * FT_ROW;
+                // integer work only: which raw sample fills each of the 20 columns (FT_NONE = zero padding); the
+                // floating-point conversion is done by the whole CTA below
+                uint32_t *row = rows + tid * FT_ROW;
                 for (uint32_t j = q; j < nrec && nsig < DNB_RAWDEPTH; j++) {
                     dnb_eventalign_rec rj = rec;
                     if (j != q) {
@@ -115,14 +120,9 @@ __global__ void __launch_bounds__(FT_THREADS) features_kernel(DnbFeatArgs a) {
                         if (rj.ref_pos != rec.ref_pos) break;
                     }
                     const uint32_t s0 = es[rj.event], s1 = es[rj.event + 1];
-                    for (uint32_t t = s0; t < s1 && nsig < DNB_RAWDEPTH; t++) {
-                        float pa;
-                        if (dac) pa = fMul(fAdd((float)a.raw_i16[raw0 + t], dac_off), dac_scl);   // pod5.cpp:60
-                        else pa = a.raw_f32[raw0 + t];
-                        row[nsig++] = d2f(dDiv(dSub((double)pa, shift), scale));                     // alignment.cpp:709, reads.h:154
-                    }
+                    for (uint32_t t = s0; t < s1 && nsig < DNB_RAWDEPTH; t++) row[nsig++] = t;
                 }
-                for (uint32_t t = nsig; t < DNB_RAWDEPTH; t++) row[t] = 0.f;                     // reads.h:162-168
+                for (uint32_t t = nsig; t < DNB_RAWDEPTH; t++) row[t] = FT_NONE;                 // reads.h:162-168
                 keep = nsig > 0;                                                                    // addSignal is per sample
             }
 
@@ -155,7 +155,15 @@ __global__ void __launch_bounds__(FT_THREADS) features_kernel(DnbFeatArgs a) {
             float *dst = a.signal + (out0 + out_base) * DNB_RAWDEPTH;
             for (uint32_t j = tid; j < n_write * DNB_RAWDEPTH; j += FT_THREADS) {
                 const uint32_t row = j / DNB_RAWDEPTH, col = j - row * DNB_RAWDEPTH;
-                dst[j] = rows[src_of[row] * FT_ROW + col];
+                const uint32_t t = rows[src_of[row] * FT_ROW + col];
+                float v = 0.f;
+                if (t != FT_NONE) {
+                    float pa;
+                    if (dac) pa = fMul(fAdd((float)a.raw_i16[raw0 + t], dac_off), dac_scl);       // pod5.cpp:60
+                    else pa = a.raw_f32[raw0 + t];
+                    v = d2f(dDiv(dSub((double)pa, shift), scale));                                // alignment.cpp:709, reads.h:154
+                }
+                dst[j] = v;
             }
             out_base += n_local;
             carry_max = chunk_max > carry_max ? chunk_max : carry_max;

@@ -49,6 +49,11 @@ if rep > 1:
         best = min(best, ctx.eventalign_last_kernel_ms())
     out["eventalign_saturated"] = dict(n_reads=len(big), eventalign_kernel_ms=best, reads_per_s_kernel=len(big) / (best * 1e-3),
                                        msamples_per_s_kernel=samples * rep / (best * 1e-3) / 1e6)
+    mid = reads * min(rep, 4)
+    ctx.eventalign_features(mid, 50, want_records=False)
+    ms_ft = ctx.features_last_kernel_ms()
+    rows_mid = min(rep, 4) * sum(max(len(r["refseq"]) - 8, 0) for r in reads)          # upper bound, ~1.1x the real count
+    out["features_saturated"] = dict(n_reads=len(mid), features_kernel_ms=ms_ft)
 # resident chain: int16 DAC in, tensors out (normaliseEvents -> eventalign -> tensors without leaving HBM)
 ok_idx = [i for i, o_ in enumerate(res) if o_.status == api.READ_OK]
 b = ctx.upload([api.Read.from_synth(base[i], use_dac=True) for i in ok_idx])
@@ -68,6 +73,9 @@ rows = int(sum(x["signal"].shape[0] for x in o))
 ft_ms = best[2]["features_kernel_ms"]
 # algorithmic bytes of the feature kernel: 16 B record per event read + <= 20 samples (2 B int16) per row read + 108 B per row written
 alg = 16 * sum(x["eventAlignment"].shape[0] for x in reads) + rows * (20 * 2 + 108)
+if "features_saturated" in out:
+    k = out["features_saturated"]["n_reads"] / len(reads)
+    out["features_saturated"]["achieved_gbs"] = alg * k / (out["features_saturated"]["features_kernel_ms"] * 1e-3) / 1e9
 out["features_roofline"] = dict(rows=rows, algorithmic_bytes=int(alg), achieved_gbs=alg / (ft_ms * 1e-3) / 1e9 if ft_ms else None)
 try:
     from oracle import refbind

@@ -205,11 +205,19 @@ def main():
         import psutil
         avail = psutil.virtual_memory().available
         # pinned staging + result buffers of the submissions in flight (~5.5 B/sample each) come on top
-        inflight_bytes = 5.5 * args.e2e_bin_samples * args.e2e_inflight * world
-        while args.e2e_inflight > 2 and inflight_bytes > 0.25 * avail:
-            args.e2e_inflight -= 1
-            inflight_bytes = 5.5 * args.e2e_bin_samples * args.e2e_inflight * world
-        avail -= inflight_bytes
+        # (N ranks share one box's RAM): fewer in flight first, then smaller submissions
+        def inflight_bytes():
+            return 5.5 * args.e2e_bin_samples * args.e2e_inflight * world
+        while inflight_bytes() > 0.2 * avail:
+            if args.e2e_inflight > 4:
+                args.e2e_inflight -= 1
+            elif args.e2e_bin_samples > 1.0e8:
+                args.e2e_bin_samples /= 2
+            elif args.e2e_inflight > 2:
+                args.e2e_inflight -= 1
+            else:
+                break
+        avail -= inflight_bytes()
         need = 1.3 * 2.6 * SAMPLES_PER_BASE * 25_100.0 * reads_per_gpu * world      # mean read ~25.1 kb at N50 30 kb
         if need > 0.8 * avail:
             reads_per_gpu = max(int(reads_per_gpu * 0.8 * avail / need), 1000)
@@ -363,6 +371,7 @@ def main():
             "roofline": roofline, "roofline_segmentation": roofline_seg, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": 1e3 * dt_e / args.steps, "inflight": args.e2e_inflight, "bins": len(e2e_bins),
+                    "samples_per_submit": args.e2e_bin_samples,
                     "host_threads_per_rank": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
                     "host_cores": os.cpu_count() or 1},
             "gpu_launches": int(cnt_step["launches"] * args.steps), "clocks": clocks,

@@ -111,3 +111,42 @@ def test_eventalign_edge_cases(ctx, pore_mean):
     assert out[2]["status"] == api.READ_OK
     assert not np.any((out[2]["ref_pos"] >= 52) & (out[2]["ref_pos"] < 90))
     assert ctx.eventalign([], window=50) == []
+
+
+def test_eventalign_widest_window_uses_third_register_slot(ctx, port, pore_mean):
+    """The breakpoint search (alignment.cpp:566-592) can stretch a window to 73 bases = 65 HMM states, the only case in
+    which the kernel's third register slot (states 64..) is live.  These two reference prefixes have their first
+    qualifying breakpoint exactly at i = 64 (found by brute force with the rule restated below); reads starting on
+    them must come back identical to the oracle's, forward and reverse-complement strand handling included."""
+    prefixes = [b"GGATGAGCGGTTACCTCCTTGCCGCTGGCAGTCTTTTTAAACTGCCTTGATATTGCAAGGATGGGACTTTATAGG",
+                b"TACGTGGTAACAGAGTATTTCCATCAAAATACGTTTAGATGCTGGTTGTAACGAAAAGGATTGCACAGCCGCTCT"]
+
+    def first_break(seq, W=50, k=9):
+        m = pore_mean[synth.kmer_ranks(seq[:int(1.5 * W)])]
+        for i in range(W, int(1.5 * W) - k - 1):
+            if abs(m[i] - m[i + 1]) > 0.75 and abs(m[i] - m[i - 1]) > 0.75:
+                return i
+        return None
+
+    rng = np.random.default_rng(77)
+    base = []
+    for j, pre in enumerate(prefixes):
+        assert first_break(pre) == 64
+        ref = pre + synth.make_reference(6000, 300 + j)
+        base.append(synth.simulate_read(ref, 0, 5000, False, pore_mean, rng, name=f"w{j}"))
+    res = ctx.normaliseEvents([api.Read.from_synth(r, use_dac=True) for r in base])
+    reads = []
+    for sr, o in zip(base, res):
+        assert o.status == api.READ_OK
+        assert sr.refseq[:75] in prefixes
+        reads.append(dict(refseq=sr.refseq, ref_to_query=np.arange(len(sr.refseq), dtype=np.int32),
+                          eventAlignment=o.eventAlignment, event_mean=o.event_mean, shift=o.shift, scale=o.scale,
+                          events_per_base=o.eventsPerBase))
+    out = ctx.eventalign(reads, window=50)
+    for r, rec in zip(reads, out):
+        exp = port.eventalign(r["refseq"], r["ref_to_query"], r["eventAlignment"][:, 0], r["eventAlignment"][:, 1],
+                              r["event_mean"].astype(np.float64), r["shift"], r["scale"], r["events_per_base"], pore_mean)
+        assert rec["status"] == api.READ_OK
+        for key in ("event", "ref_pos", "label", "indel"):
+            np.testing.assert_array_equal(rec[key], exp[key], err_msg=key)
+        assert rec["event"].size > 0.5 * r["eventAlignment"].shape[0]

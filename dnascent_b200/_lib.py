@@ -116,7 +116,7 @@ EXPORTS = [
     "dnb_eventalign_batch", "dnb_eventalign_last_kernel_ms",
     "dnb_eventalign_features_batch", "dnb_features_last_kernel_ms",
     "dnb_batch_eventalign_features", "dnb_batch_feature_result", "dnb_batch_stage2_timings",
-    "dnb_dorado_slice",
+    "dnb_dorado_slice", "dnb_submit_chain",
 ]
 
 
@@ -166,6 +166,7 @@ def lib():
     L.dnb_eventalign_features_batch.argtypes = [vp, vp, vp, sz, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]
     L.dnb_features_last_kernel_ms.restype = d
     L.dnb_batch_eventalign_features.argtypes = [vp, vp, C.c_uint32, C.c_int]
+    L.dnb_submit_chain.argtypes = [vp, vp, vp, sz, C.c_uint32, C.c_int, C.POINTER(vp)]
     L.dnb_batch_feature_result.argtypes = [vp, sz, C.POINTER(FeatureResult)]
     L.dnb_dorado_slice.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint64)]

@@ -73,6 +73,21 @@ def _as(ptr, n, dtype):
     return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
 
 
+def _extras(extra):
+    """dnb_read_extra array for a list of dicts (ref_to_query, is_reverse, ref_start, ref_end[, called])."""
+    n = len(extra)
+    ex = (_lib.ReadExtra * max(n, 1))()
+    keep = []
+    for i, r in enumerate(extra):
+        r2q = np.ascontiguousarray(r["ref_to_query"], dtype=np.int32)
+        called = np.ascontiguousarray(r.get("called", []), dtype=np.uint32)
+        keep += [r2q, called]
+        ex[i].ref_to_query = r2q.ctypes.data
+        ex[i].is_reverse, ex[i].ref_start, ex[i].ref_end = int(bool(r["is_reverse"])), int(r["ref_start"]), int(r["ref_end"])
+        ex[i].called, ex[i].n_called = (called.ctypes.data if called.size else None), called.size
+    return ex, keep
+
+
 class Batch:
     def __init__(self, ctx: "Context", handle, n_reads: int, keepalive):
         self.ctx, self.h, self.n, self._keep = ctx, handle, n_reads, keepalive
@@ -124,17 +139,12 @@ class Batch:
         """`extra`: per read a dict with ref_to_query (int32[ref_len]), is_reverse, ref_start, ref_end and optionally
         called (sorted uint32).  Returns per read the dict Context.eventalign_features returns."""
         assert len(extra) == self.n
-        ex = (_lib.ReadExtra * max(self.n, 1))()
-        keep = []
-        for i, r in enumerate(extra):
-            r2q = np.ascontiguousarray(r["ref_to_query"], dtype=np.int32)
-            called = np.ascontiguousarray(r.get("called", []), dtype=np.uint32)
-            keep += [r2q, called]
-            ex[i].ref_to_query = r2q.ctypes.data
-            ex[i].is_reverse, ex[i].ref_start, ex[i].ref_end = int(bool(r["is_reverse"])), int(r["ref_start"]), int(r["ref_end"])
-            ex[i].called, ex[i].n_called = (called.ctypes.data if called.size else None), called.size
+        ex, keep = _extras(extra)
         _lib.check(self.ctx.L.dnb_batch_eventalign_features(self.h, C.addressof(ex), window, int(want_records)),
                    "dnb_batch_eventalign_features")
+        return self.feature_results(want_records)
+
+    def feature_results(self, want_records: bool = False):
         out = []
         for i in range(self.n):
             fr = _lib.FeatureResult()
@@ -241,6 +251,16 @@ class Context:
         h = C.c_void_p()
         _lib.check(self.L.dnb_batch_upload(self.h, C.addressof(arr), len(reads), C.byref(h)), "dnb_batch_upload")
         return Batch(self, h, len(reads), None)   # inputs are resident in HBM; host copies may be dropped
+
+    def submit_chain(self, reads, extra, window: int = 50, want_records: bool = False) -> Batch:
+        """dnb_submit_chain: normaliseEvents + eventalign + DNN input tensors in one pipelined call; read the results with
+        Batch.results() and Batch.feature_results()."""
+        descs, keep = self._descs(reads)
+        ex, keep2 = _extras(extra)
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_submit_chain(self.h, C.addressof(descs), C.addressof(ex), len(reads), window,
+                                           int(want_records), C.byref(h)), "dnb_submit_chain")
+        return Batch(self, h, len(reads), (keep, keep2))
 
     # descriptor arrays built with numpy (dtype _lib.READ_DESC_DTYPE): no per-read Python objects
     def submit_descs(self, descs: np.ndarray) -> Batch:

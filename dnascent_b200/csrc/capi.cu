@@ -1466,6 +1466,31 @@ int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uin
     return DNB_OK;
 }
 
+// dnb_submit with the resident stage appended: the pipelined (thread-safe, gated) form of the whole chain
+int dnb_submit_chain(dnb_ctx *ctx, const dnb_read_desc *reads, const dnb_read_extra *extra, size_t n_reads,
+                     uint32_t window, int want_records, dnb_batch **batch) {
+    dnb_batch *b = nullptr;
+    if (!ctx || !batch || (!extra && n_reads)) return DNB_ERR_ARG;
+    TRY(upload(ctx, reads, n_reads, false, &b, /*gated=*/true));
+    int rc;
+    {
+        StageHold hold(ctx->gate_compute);
+        rc = run(b);
+    }
+    if (rc == DNB_OK) {
+        StageHold hold(ctx->gate_fetch);
+        rc = fetch(b);
+    }
+    if (rc == DNB_OK) {
+        StageHold hold(ctx->gate_compute);
+        rc = dnb_batch_eventalign_features(b, extra, window, want_records);
+    }
+    if (rc != DNB_OK) { free_batch(b); return rc; }
+    drop_work(b);
+    *batch = b;
+    return DNB_OK;
+}
+
 int dnb_batch_feature_result(dnb_batch *b, size_t i, dnb_feature_result *o) {
     if (!b || !o || i >= b->R) return DNB_ERR_ARG;
     if (!b->s2.done) return DNB_ERR_STATE;

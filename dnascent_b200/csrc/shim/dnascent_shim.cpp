@@ -570,11 +570,8 @@ void normalise_eventalign_batch(const std::vector<DNAscent::read *> &reads, unsi
         x.n_called = (uint32_t)called[i].size();
     }
     dnb_batch *b = nullptr;
-    int rc = dnb_batch_upload(ctx, descs.data(), n, &b);
-    if (rc != DNB_OK) die("dnb_batch_upload", rc);
-    if ((rc = dnb_batch_run(b)) != DNB_OK) die("dnb_batch_run", rc);
-    if ((rc = dnb_batch_fetch(b)) != DNB_OK) die("dnb_batch_fetch", rc);
-    if ((rc = dnb_batch_eventalign_features(b, extra.data(), totalWindowLength, 0)) != DNB_OK) die("dnb_batch_eventalign_features", rc);
+    int rc = dnb_submit_chain(ctx, descs.data(), extra.data(), n, totalWindowLength, 0, &b);   // thread-safe, staged like dnb_submit
+    if (rc != DNB_OK) die("dnb_submit_chain", rc);
     bool negative_log = false;
 #pragma omp parallel for schedule(dynamic)
     for (size_t i = 0; i < n; i++) {

@@ -59,7 +59,7 @@ void eventalign_features_batch(const std::vector<DNAscent::read *> &reads, unsig
 
 // The signal part of detect's read loop body (detect.cpp:876-888) as ONE device-resident chain: normaliseEvents ->
 // eventalign -> tensors, with the signal, events, alignment and scalings never leaving HBM in between
-// (dnb_batch_upload / _run / _fetch + dnb_batch_eventalign_features).  Leaves every read as normaliseEvents_batch does
+// (dnb_submit_chain; several buffers may be in flight from different host threads).  Leaves every read as normaliseEvents_batch does
 // (a failed read has an empty eventAlignment and gets out[i].QCpassed == false, cf. the `continue` at detect.cpp:879-881)
 // and returns the DNN inputs of the others.
 void normalise_eventalign_batch(const std::vector<DNAscent::read *> &reads, unsigned int totalWindowLength,

@@ -283,6 +283,11 @@ typedef struct {
 
 DNB_API int dnb_batch_eventalign_features(dnb_batch *batch, const dnb_read_extra *extra, uint32_t window,
                                           int want_records);
+/* dnb_submit followed by dnb_batch_eventalign_features in one call: host buffers in, normaliseEvents results
+ * (dnb_result) and tensors (dnb_batch_feature_result) out, workspace returned to the pool.  Thread-safe and staged like
+ * dnb_submit, so concurrent callers overlap packing, copies and the two compute stages. */
+DNB_API int dnb_submit_chain(dnb_ctx *ctx, const dnb_read_desc *reads, const dnb_read_extra *extra, size_t n_reads,
+                             uint32_t window, int want_records, dnb_batch **batch);
 /* pointers stay valid until dnb_release / the next dnb_batch_run */
 DNB_API int dnb_batch_feature_result(dnb_batch *batch, size_t i, dnb_feature_result *out);
 /* ms: [0] eventalign kernel, [1] feature kernel (CUDA events on the batch's stream); bytes: [0] host->device, [1] device->host */

@@ -202,3 +202,63 @@ def test_resident_chain_matches_host_array_form(ctx, pore_mean):
     with pytest.raises(Exception):
         b.eventalign_features(extra)                                  # the resident arrays are gone: call order error
     b.release()
+
+
+def test_resident_chain_ultra_long_read(ctx, port, pore_mean):
+    """BASELINE configs[2] through rows f1/f2: a 130-kb read (~3000 windows in one serial chain, ~1.2*10^5 tensor rows
+    written by one CTA in ~1100 chunks) next to a short one, resident chain against the oracle port."""
+    ref = synth.make_reference(400_000, 391)
+    base = synth.simulate_batch(ref, [130_000, 1500], pore_mean, seed=392)
+    b = ctx.upload([api.Read.from_synth(r, use_dac=True) for r in base])
+    b.run()
+    b.fetch()
+    res = b.results()
+    extra = []
+    for i, sr in enumerate(base):
+        q2r = np.asarray(sr.query_to_ref)
+        r2q = np.zeros(len(sr.refseq), dtype=np.int32)
+        r2q[q2r[q2r >= 0]] = np.nonzero(q2r >= 0)[0]
+        extra.append(dict(ref_to_query=r2q, is_reverse=bool(sr.flag & 16), ref_start=sr.pos, ref_end=sr.pos + len(sr.refseq)))
+    out = b.eventalign_features(extra, window=50, want_records=True)
+    for sr, o, x, f in zip(base, res, extra, out):
+        assert o.status == api.READ_OK and f["status"] == api.READ_OK
+        rec = port.eventalign(sr.refseq, x["ref_to_query"], o.eventAlignment[:, 0], o.eventAlignment[:, 1],
+                              o.event_mean.astype(np.float64), o.shift, o.scale, o.eventsPerBase, pore_mean)
+        for key in ("event", "ref_pos", "label", "indel"):
+            np.testing.assert_array_equal(f[key], rec[key], err_msg=key)
+        want = port.dnn_features(sr.refseq, x["ref_to_query"], x["is_reverse"], x["ref_start"], x["ref_end"], rec,
+                                 sr.raw.astype(np.float64), o.event_start, o.shift, o.scale)
+        for key in AP_KEYS:
+            np.testing.assert_array_equal(f[key], want[key], err_msg=key)
+        assert f["signal"].shape[0] > 0.85 * (len(sr.refseq) - 8)
+    b.release()
+
+
+def test_submit_chain_from_concurrent_threads(ctx, ea_golden, golden_reads, golden_v2):
+    """dnb_submit_chain (host buffers in, normaliseEvents results + tensors out) called from four host threads at once,
+    as the patched OpenMP read loop does: every call returns the reference's golden alignment and tensors."""
+    from concurrent.futures import ThreadPoolExecutor
+    e = ea_golden
+    reads = all_golden_reads(golden_reads, golden_v2)
+
+    def job(k):
+        sel = reads[k % 3:] + reads[:k % 3]                                  # a different read order per thread
+        ins = [api.Read(None, g.basecall, g.refseq, g.query_to_ref, dac=g.dac, dac_offset=float(synth.DAC_OFFSET),
+                        dac_scale=float(synth.DAC_SCALE)) for _, g in sel]
+        extra = []
+        for tag, g in sel:
+            ref_start, ref_end, is_rev = (int(x) for x in e[f"e_{tag}_strand"])
+            extra.append(dict(ref_to_query=e[f"e_{tag}_ref_to_query"], is_reverse=is_rev, ref_start=ref_start, ref_end=ref_end))
+        b = ctx.submit_chain(ins, extra, window=50)
+        res, feats = b.results(), b.feature_results()
+        b.release()
+        return sel, res, feats
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        outs = list(ex.map(job, range(8)))
+    for sel, res, feats in outs:
+        for (tag, g), r, f in zip(sel, res, feats):
+            assert r.status == api.READ_OK and f["status"] == api.READ_OK
+            np.testing.assert_array_equal(r.eventAlignment, g.align, err_msg=tag)
+            for key in AP_KEYS:
+                np.testing.assert_array_equal(f[key], e[f"e_{tag}_ap_" + key], err_msg=f"{tag} {key}")

@@ -238,8 +238,10 @@ def test_submit_chain_from_concurrent_threads(ctx, ea_golden, golden_reads, gold
     """dnb_submit_chain (host buffers in, normaliseEvents results + tensors out) called from four host threads at once,
     as the patched OpenMP read loop does: every call returns the reference's golden alignment and tensors."""
     from concurrent.futures import ThreadPoolExecutor
-    e = ea_golden
     reads = all_golden_reads(golden_reads, golden_v2)
+    # NpzFile loads lazily and is not thread-safe: take what the threads need out of it first
+    e = {key: ea_golden[key] for tag, _ in reads for key in
+         [f"e_{tag}_strand", f"e_{tag}_ref_to_query"] + [f"e_{tag}_ap_" + k for k in AP_KEYS]}
 
     def job(k):
         sel = reads[k % 3:] + reads[:k % 3]                                  # a different read order per thread

@@ -83,6 +83,24 @@ def run_cpu_reference(reads, ref, mean, threads: int):
     return t, failed, "port"
 
 
+def run_cpu_chain(reads, ref, mean, threads: int):
+    """The reference's normaliseEvents + eventalign + tensor builders per read (detect.cpp:876-888) on all host threads;
+    only where oracle/_ref was built (the C port has no OpenMP loop for this stage)."""
+    from oracle import refbind
+    if not refbind.available():
+        return None
+    R = refbind.Ref()
+    R.set_model(refbind.PORE, mean, np.full(mean.size, 0.14))
+    R.set_reference(ref)
+    handles = [R.read_new(r) for r in reads]
+    t, failed = R.bench_chain(handles, threads)
+    for h in handles:
+        h.free()
+    ns = sum(r.raw.size for r in reads)
+    return {"value": ns / t / 1e6, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"{len(reads)} reads of the C2 length law ({ns} samples, {t:.1f} s wall, {failed} failed)"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -160,13 +178,15 @@ def main():
     ap.add_argument("--e2e-inflight", type=int, default=8,
                     help="dnb_submit calls in flight (B200 sweep, 60k reads: 4e8x4 74 %% of the resident value, 8e8x8 84 %%)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chain-reads", type=int, default=4000,
+                    help="reads (whole job) of the rows f1-f2 leg (dnb_submit_chain); 0 = skip")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
 
     import torch
     import torch.distributed as dist
-    from dnascent_b200 import api, bench_data, sharding
+    from dnascent_b200 import _lib, api, bench_data, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -343,6 +363,57 @@ def main():
     e2e_value = total_samples * args.steps / dt_e / 1e6
     h2d_bytes, d2h_bytes = io_acc
 
+    # ---- chain leg (SURVEY s.8 rows f1-f2): normaliseEvents -> eventalign -> DNN input tensors through dnb_submit_chain,
+    # host buffers in, tensors out, on a bounded sample of this rank's shard (the tensors are 108 B per reference base)
+    chain = None
+    if args.chain_reads > 0:
+        # N ranks share one box's host RAM (pinned results ~15 B/sample per submission in flight): the sample and
+        # the submission size shrink with the number of ranks
+        n_c = min(max(args.chain_reads // world, 200), W.n_reads)
+        c_bin = 4.0e8 / world
+        cidx = np.linspace(0, W.n_reads - 1, n_c).astype(np.int64)          # evenly through the shard: the same length law
+        c_bins = [cidx[b] for b in sharding.make_bins(W.n_samples[cidx], int(c_bin))]
+        c_descs = [W.descs(b) for b in c_bins]
+        c_extras = []
+        for d in c_descs:
+            x = np.zeros(d.size, dtype=_lib.READ_EXTRA_DTYPE)
+            x["ref_to_query"] = W.q2r.ctypes.data                            # exact `{L}M` reads: refToQuery is the identity
+            x["ref_end"] = d["ref_len"]
+            c_extras.append(x)
+        acc = {"rows": 0, "h2d": 0, "d2h": 0, "ea_ms": 0.0, "ft_ms": 0.0, "bad": 0}
+
+        def chain_one(k):
+            b = ctx.submit_chain_descs(c_descs[k], c_extras[k], 50)
+            t2 = b.stage2_timings()
+            io = b.io_bytes()
+            out = (b.feature_rows(), io[0] + t2["h2d_bytes"], io[1] + t2["d2h_bytes"], t2["eventalign_kernel_ms"],
+                   t2["features_kernel_ms"])
+            b.release()
+            return out
+
+        def chain_pass():
+            for k in acc:
+                acc[k] = 0
+            with ThreadPoolExecutor(max_workers=3) as ex:
+                for rows, hb, db, ea, ft in ex.map(chain_one, range(len(c_descs))):
+                    acc["rows"] += rows; acc["h2d"] += hb; acc["d2h"] += db; acc["ea_ms"] += ea; acc["ft_ms"] += ft
+
+        chain_pass()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            chain_pass()
+        barrier()
+        dt_c = max_over_ranks(time.perf_counter() - t0) / 2
+        c_samples = int(W.n_samples[cidx].sum())
+        c_total = sum_over_ranks(float(c_samples))
+        chain = {"what": "dnb_submit_chain: normaliseEvents -> eventalign -> DNN input tensors (rows f1-f2), host buffers in, "
+                         f"tensors out, {c_bin:.1e}-sample submissions, 3 in flight",
+                 "value": c_total / dt_c / 1e6, "unit": UNIT, "reads_per_gpu": int(n_c), "samples_per_gpu": c_samples,
+                 "ms_per_pass": 1e3 * dt_c, "tensor_rows_per_gpu": int(acc["rows"]), "h2d_bytes_per_pass": int(acc["h2d"]),
+                 "d2h_bytes_per_pass": int(acc["d2h"]), "eventalign_kernel_ms": acc["ea_ms"], "features_kernel_ms": acc["ft_ms"],
+                 "cpu_reference": None}
+
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -352,6 +423,8 @@ def main():
         ns = sum(r.raw.size for r in reads)
         cpu = {"value": ns / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{len(reads)} reads of the C2 length law ({ns} samples, {t:.1f} s wall, {failed} failed QC)"}
+        if chain is not None:
+            chain["cpu_reference"] = run_cpu_chain(reads[: 2 * cores], ref, mean_c, cores)
 
     if rank == 0:
         line = {
@@ -368,7 +441,7 @@ def main():
                 "reads_per_s": total_samples and (world * args.reads * args.steps / dt),
                 "stage_ms_per_step": per_step, "counts_per_step": cnt_step, "generation_s": gen_s,
             },
-            "roofline": roofline, "roofline_segmentation": roofline_seg, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_segmentation": roofline_seg, "cpu_baseline": cpu, "chain": chain,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": 1e3 * dt_e / args.steps, "inflight": args.e2e_inflight, "bins": len(e2e_bins),
                     "samples_per_submit": args.e2e_bin_samples,

@@ -86,6 +86,11 @@ class ReadExtra(C.Structure):
                 ("called", C.c_void_p), ("n_called", C.c_uint32)]
 
 
+READ_EXTRA_DTYPE = _np.dtype([("ref_to_query", _np.uint64), ("is_reverse", _np.int32), ("ref_start", _np.uint32),
+                              ("ref_end", _np.uint32), ("called", _np.uint64), ("n_called", _np.uint32)], align=True)
+assert READ_EXTRA_DTYPE.itemsize == C.sizeof(ReadExtra), (READ_EXTRA_DTYPE.itemsize, C.sizeof(ReadExtra))
+
+
 class FeatureResult(C.Structure):
     _fields_ = [("status", C.c_int), ("n_pos", C.c_uint32),
                 ("signal", C.POINTER(C.c_float)), ("core", C.POINTER(C.c_float)), ("residual", C.POINTER(C.c_float)),

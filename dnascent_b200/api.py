@@ -163,6 +163,15 @@ class Batch:
             out.append(o)
         return out
 
+    def feature_rows(self) -> int:
+        """Total tensor rows of the batch (sum of dnb_feature_result.n_pos), without copying the tensors."""
+        fr = _lib.FeatureResult()
+        tot = 0
+        for i in range(self.n):
+            _lib.check(self.ctx.L.dnb_batch_feature_result(self.h, i, C.byref(fr)), "dnb_batch_feature_result")
+            tot += fr.n_pos
+        return tot
+
     def stage2_timings(self):
         ms = (C.c_double * 2)()
         by = (C.c_uint64 * 2)()
@@ -267,6 +276,14 @@ class Context:
         h = C.c_void_p()
         _lib.check(self.L.dnb_submit(self.h, descs.ctypes.data, descs.size, C.byref(h)), "dnb_submit")
         return Batch(self, h, descs.size, descs)
+
+    def submit_chain_descs(self, descs: np.ndarray, extras: np.ndarray, window: int = 50, want_records: bool = False) -> Batch:
+        """dnb_submit_chain on descriptor arrays (dtypes _lib.READ_DESC_DTYPE / _lib.READ_EXTRA_DTYPE)."""
+        assert descs.size == extras.size
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_submit_chain(self.h, descs.ctypes.data, extras.ctypes.data, descs.size, window,
+                                           int(want_records), C.byref(h)), "dnb_submit_chain")
+        return Batch(self, h, descs.size, (descs, extras))
 
     def upload_descs(self, descs: np.ndarray) -> Batch:
         h = C.c_void_p()

@@ -492,6 +492,26 @@ double dnbref_bench_normalise(void **handles, size_t n, int threads, int useFit,
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// CPU baseline of the chain (rows f1-f2): detect.cpp:876-888 per read = normaliseEvents + eventalign (whose
+// r.addSignal calls are what the tensor builders read); reads that fail normalisation skip eventalign (detect.cpp:879)
+double dnbref_bench_chain(void **handles, size_t n, int threads, unsigned int windowLength, int *failed) {
+    int nfail = 0;
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic) num_threads(threads) reduction(+ : nfail)
+    for (size_t i = 0; i < n; i++) {
+        Handle *h = (Handle *)handles[i];
+        normaliseEvents(*h->r, false);
+        if (h->r->eventAlignment.empty()) { nfail++; continue; }
+        h->r->refCoordToAP.clear();
+        eventalign(*h->r, windowLength);
+        std::vector<float> sg = h->r->makeSignalTensor(), co = h->r->makeCoreSequenceTensor(), re = h->r->makeResidualSequenceTensor();
+        if (sg.size() != co.size() * RAWDEPTH || re.size() != co.size()) nfail++;
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (failed) *failed = nfail;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 #ifdef DNB_SHIM_BUILD
 }  // extern "C"
 #include "dnascent_shim.h"

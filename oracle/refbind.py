@@ -225,6 +225,15 @@ class Ref:
         if self.is_shim:
             self.L.dnbshim_shutdown()
 
+    def bench_chain(self, reads, threads: int, window: int = 50):
+        """normaliseEvents + eventalign + tensor builders per read on `threads` host threads (detect.cpp:876-888)."""
+        arr = (C.c_void_p * len(reads))(*[r.h for r in reads])
+        failed = C.c_int(0)
+        self.L.dnbref_bench_chain.restype = C.c_double
+        self.L.dnbref_bench_chain.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_int)]
+        t = self.L.dnbref_bench_chain(arr, len(reads), threads, window, C.byref(failed))
+        return t, failed.value
+
     def bench_normalise(self, reads, threads: int, use_fit=False):
         arr = (C.c_void_p * len(reads))(*[r.h for r in reads])
         failed = C.c_int(0)

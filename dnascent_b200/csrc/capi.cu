@@ -1241,6 +1241,7 @@ static int eventalign_impl(dnb_ctx *ctx, const dnb_eventalign_desc *reads, const
         a.model_mean = ctx->model[DNB_MODEL_PORE].d_mean;
         // normalPDF's constants for the static sigma of the ONT table (data_IO.cpp:170, probability.cpp:147), host libm
         a.two_sigma2 = 2.0 * pow(0.14, 2.0);
+        a.inv_two_sigma2 = 1.0 / a.two_sigma2;
         a.c = 1.0 / sqrt(2.0 * pow(0.14, 2.0) * M_PI);
         a.ln_c = log(a.c);
         a.d2d = d2d; a.d2m = d2m; a.i2m = i2m; a.m2d = m2d; a.m2i = m2i; a.i2i = i2i;
@@ -1418,6 +1419,7 @@ int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uin
     a.ev_off = b->d_ev_off; a.ev_mean = w.ev_mean; a.shift = w.shift; a.scale = w.scale; a.trans = d_trans;
     a.model_mean = ctx->model[DNB_MODEL_PORE].d_mean;
     a.two_sigma2 = 2.0 * pow(0.14, 2.0);
+        a.inv_two_sigma2 = 1.0 / a.two_sigma2;
     a.c = 1.0 / sqrt(2.0 * pow(0.14, 2.0) * M_PI);
     a.ln_c = log(a.c);
     a.d2d = d2d; a.d2m = d2m; a.i2m = i2m; a.m2d = m2d; a.m2i = m2i; a.i2i = i2i;

@@ -187,6 +187,7 @@ struct DnbEaArgs {
     const double *trans;          // [R][4] host libm: internalM12M1, externalM12M1, lnSum(ext, int), lnSum(ext, M12D)
     const double *model_mean;     // pore_model means [4^9]
     double ln_c, c, two_sigma2;   // log(1/sqrt(2 sigma^2 pi)), that factor, 2 sigma^2 (sigma = 0.14), host libm
+    double inv_two_sigma2;        // 1 / (2 sigma^2), correctly rounded
     double d2d, d2m, i2m, m2d, m2i, i2i;   // eln() of HMM_TransitionProbs_DNA_R10 (src/config.h:42), host libm
     const uint64_t *rec_off;      // [R+1] record capacity offsets
     dnb_eventalign_rec *recs;

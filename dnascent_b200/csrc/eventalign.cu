@@ -66,18 +66,6 @@ __device__ __forceinline__ void add_chain(double (&c)[EA_SLOTS], double d) {
         for (int s = 0; s < NS; s++) c[s] = dAdd(c[s], d);
     }
 }
-template <int NS>
-__device__ __forceinline__ void add_k_slots(double (&c)[EA_SLOTS], double d, int k) {
-    switch (k) {
-        case 1: add_chain<1, NS>(c, d); break;
-        case 2: add_chain<2, NS>(c, d); break;
-        case 4: add_chain<4, NS>(c, d); break;
-        case 8: add_chain<8, NS>(c, d); break;
-        case 16: add_chain<16, NS>(c, d); break;
-        case 32: add_chain<32, NS>(c, d); break;
-        default: add_chain<64, NS>(c, d); break;
-    }
-}
 struct EaRead {
     const char *ref;
     uint32_t rlen;
@@ -117,17 +105,24 @@ __device__ __forceinline__ void viterbi_forward(const DnbEaArgs &a, const EaRead
                                                 double (&D)[EA_SLOTS], uint8_t *bt, int lane) {
     double start_prev = 0.0;
     const bool first_state = lane == 0;                                                     // i == 0 lives in slot 0, lane 0
+    // M and D of the previous step shifted by one state: both are by-products of the previous step's deletion scan
+    double Mm1[EA_SLOTS], Dm1[EA_SLOTS];
+    shift_states<NS>(M, Mm1, lane, 1); shift_states<NS>(D, Dm1, lane, 1);
+    double x_next = obs[0];
     for (uint32_t t = 0; t < ns; t++) {
-        const double x = obs[t];
-        double Im1[EA_SLOTS], Mm1[EA_SLOTS], Dm1[EA_SLOTS];
-        shift_states<NS>(I, Im1, lane, 1); shift_states<NS>(M, Mm1, lane, 1); shift_states<NS>(D, Dm1, lane, 1);
+        const double x = x_next;
+        if (t + 1 < ns) x_next = obs[t + 1];                                                // off the critical path
+        double Im1[EA_SLOTS];
+        shift_states<NS>(I, Im1, lane, 1);
         double In[EA_SLOTS], Mn[EA_SLOTS];
         uint32_t code[EA_SLOTS];
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             const int i = 32 * s + lane;
             const double d = dSub(x, mu[s]);
-            const double y = dDiv(-dMul(d, d), a.two_sigma2);
+            // -(x-mu)^2 / (2 sigma^2) as a multiply by the rounded reciprocal: at most 1.5 ulp from the IEEE quotient,
+            // inside the few-ulp difference log(c) + y already has to glibc's log(c * exp(y)) (see the header)
+            const double y = dMul(-dMul(d, d), a.inv_two_sigma2);
             double mp;
             if (y >= -700.0) mp = dAdd(a.ln_c, y);
             else { const double v = dMul(a.c, exp(y)); mp = v == 0.0 ? NEG_INF : log(v); }
@@ -164,33 +159,37 @@ __device__ __forceinline__ void viterbi_forward(const DnbEaArgs &a, const EaRead
         // max over d < 2k; F^k is k dependent roundings, done literally (total <= n adds per lane).  A round that
         // changes nothing proves the fixed point (any longer chain factors through states that did not grow).
         double v0[EA_SLOTS], Dn[EA_SLOTS];
-        shift_states<NS>(Mn, v0, lane, 1);
+        shift_states<NS>(Mn, Mm1, lane, 1);                                                 // also the next step's M[i-1]
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             const int i = 32 * s + lane;
-            v0[s] = (i > 0 && i < n) ? dAdd(v0[s], a.m2d) : NEG_INF;
+            v0[s] = (i > 0 && i < n) ? dAdd(Mm1[s], a.m2d) : NEG_INF;
             Dn[s] = v0[s];
         }
-        for (int k = 1; k <= n - 2; k <<= 1) {
-            double c[EA_SLOTS];
-            shift_states<NS>(Dn, c, lane, k);
-            add_k_slots<NS>(c, a.d2d, k);
-            bool grew = false;
-#pragma unroll
-            for (int s = 0; s < NS; s++) {
-                const int i = 32 * s + lane;
-                if (i < n && c[s] > Dn[s]) { Dn[s] = c[s]; grew = true; }                  // i == 0: c is -inf
+        {
+            bool more = true;
+#define EA_ROUND(KK)                                                                                                  \
+            if (more && (KK) <= n - 2) {                                                                              \
+                double c[EA_SLOTS];                                                                                   \
+                shift_states<NS>(Dn, c, lane, (KK));                                                                  \
+                add_chain<(KK), NS>(c, a.d2d);                                                                        \
+                bool grew = false;                                                                                    \
+                _Pragma("unroll") for (int s = 0; s < NS; s++) {                                                      \
+                    const int i = 32 * s + lane;                                                                      \
+                    if (i < n && c[s] > Dn[s]) { Dn[s] = c[s]; grew = true; }        /* i == 0: c is -inf */          \
+                }                                                                                                     \
+                more = __any_sync(FULL, grew);                                                                        \
             }
-            if (!__any_sync(FULL, grew)) break;
+            EA_ROUND(1) EA_ROUND(2) EA_ROUND(4) EA_ROUND(8) EA_ROUND(16) EA_ROUND(32)
+            if (NS == 3) { EA_ROUND(64) }
+#undef EA_ROUND
         }
-        {   // lnArgMax: D over M only when strictly greater
-            double c[EA_SLOTS];
-            shift_states<NS>(Dn, c, lane, 1);
+        // lnArgMax: D over M only when strictly greater; the shifted D is also the next step's D[i-1]
+        shift_states<NS>(Dn, Dm1, lane, 1);
 #pragma unroll
-            for (int s = 0; s < NS; s++) {
-                const int i = 32 * s + lane;
-                if (i < n && dAdd(c[s], a.d2d) > v0[s]) code[s] |= 1u << 4;                // i == 0: -inf > -inf is false
-            }
+        for (int s = 0; s < NS; s++) {
+            const int i = 32 * s + lane;
+            if (i < n && dAdd(Dm1[s], a.d2d) > v0[s]) code[s] |= 1u << 4;                  // i == 0: -inf > -inf is false
         }
         uint8_t *row = bt + (size_t)t * (EA_SLOTS * 32);
 #pragma unroll

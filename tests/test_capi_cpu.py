@@ -43,6 +43,41 @@ def test_struct_layouts_match_header():
     assert (cfg.min_average_log_emission, cfg.max_gap_threshold, cfg.bandwidth) == (-2.0, 5, 100)
 
 
+def test_ctypes_mirrors_match_the_compiled_header(tmp_path):
+    """Every struct of include/dnascent_b200.h as the C compiler lays it out (sizeof + offsetof of each field, from a
+    program compiled here with gcc) against the ctypes / numpy mirrors the tests and bench.py bind with."""
+    import shutil
+    import subprocess
+    from dnascent_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    mirrors = {"dnb_config": _lib.Config, "dnb_read_desc": _lib.ReadDesc, "dnb_read_result": _lib.ReadResult,
+               "dnb_event_t": _lib.EventT, "dnb_eventalign_desc": _lib.EventalignDesc, "dnb_feature_desc": _lib.FeatureDesc,
+               "dnb_feature_tensors": _lib.FeatureTensors, "dnb_read_extra": _lib.ReadExtra,
+               "dnb_feature_result": _lib.FeatureResult}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dnascent_b200.h"', 'int main(void) {']
+    for cname, st in mirrors.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append('printf("dnb_eventalign_rec %zu\\n", sizeof(dnb_eventalign_rec));')
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, st in mirrors.items():
+        assert int(got[cname]) == C.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, (cname, fname)
+    assert int(got["dnb_eventalign_rec"]) == _lib.EVENTALIGN_REC_DTYPE.itemsize == 16
+    assert _lib.READ_DESC_DTYPE.itemsize == C.sizeof(_lib.ReadDesc) and _lib.READ_EXTRA_DTYPE.itemsize == C.sizeof(_lib.ReadExtra)
+    for dt, st in ((_lib.READ_DESC_DTYPE, _lib.ReadDesc), (_lib.READ_EXTRA_DTYPE, _lib.ReadExtra)):
+        for fname, _ in st._fields_:
+            assert dt.fields[fname][1] == getattr(st, fname).offset, fname
+
+
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     from dnascent_b200 import api
@@ -95,7 +130,7 @@ def test_shim_exports_the_reference_symbols():
     defined = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     for sym in ("_Z15normaliseEventsRN8DNAscent4readEb", "detect_events", "_Z4eexpd", "_Z3elnd", "_Z5lnSumdd", "_Z6lnProddd",
                 "_Z13lnGreaterThandd", "_Z10uniformPDFddd", "_Z9normalPDFddd", "_Z9cauchyPDFddd",
-                "_Z12llAcrossReadRN8DNAscent4readEj"):
+                "_Z12llAcrossReadRN8DNAscent4readEj", "_Z10eventalignRN8DNAscent4readEj"):
         assert sym in defined, sym
     assert any(s.startswith("_Z19sequenceProbabilityRSt6vectorIdSaIdEE") for s in defined)
     refbind.Ref(shim=True)          # loads (resolves libdnascent_b200.so through its rpath) without a GPU

@@ -22,6 +22,9 @@ import os
 if "LOCAL_RANK" in os.environ and os.environ.get("OMP_NUM_THREADS", "1") == "1":
     _local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _local))
+    # several submissions are in flight per rank, each from its own host thread with its own OpenMP team; idle teams
+    # must sleep, not spin, when N ranks share the box's cores
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 import sys
 import threading
 import time

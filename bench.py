@@ -426,8 +426,19 @@ def main():
         ns = sum(r.raw.size for r in reads)
         cpu = {"value": ns / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{len(reads)} reads of the C2 length law ({ns} samples, {t:.1f} s wall, {failed} failed QC)"}
+        try:    # SURVEY s.8(d): the same loop on ONE host thread, on a smaller sample of the same reads
+            one = reads[:8]
+            t1, _, _ = run_cpu_reference(one, ref, mean_c, 1)
+            ns1 = sum(r.raw.size for r in one)
+            cpu["single_thread"] = {"value": ns1 / t1 / 1e6, "unit": UNIT, "cores": 1,
+                                    "sample": f"{len(one)} of those reads ({ns1} samples, {t1:.1f} s wall)"}
+        except Exception as ex:  # noqa: BLE001 -- a reporting extra must never cost the bench line
+            cpu["single_thread"] = {"error": repr(ex)}
         if chain is not None:
-            chain["cpu_reference"] = run_cpu_chain(reads[: 2 * cores], ref, mean_c, cores)
+            try:
+                chain["cpu_reference"] = run_cpu_chain(reads[: 2 * cores], ref, mean_c, cores)
+            except Exception as ex:  # noqa: BLE001
+                chain["cpu_reference"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {

@@ -110,3 +110,20 @@ def test_constant_divisor_sequences(tmp_path):
     subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-o", str(exe), src, "-lm"])
     out = subprocess.check_output([str(exe), "16", "2000000"]).decode().split()
     assert out == ["0", "0"], out
+
+
+def test_exact_rounded_prefix_sums_by_map_composition():
+    """The design check behind DESIGN.md s.8 item 5 (scripts/proto_exact_prefix.py): scrappie's sequentially rounded
+    prefix sums (event_detection.c:35-48) reproduced bit for bit with one serial step per 512-sample tile instead of one
+    per sample, on POD5-like and adversarial (ties, wide dynamic range) inputs."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "proto_exact_prefix.py")
+    spec = importlib.util.spec_from_file_location("proto_exact_prefix", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(3)
+    dac = rng.integers(200, 900, 60_000).astype(np.int16)
+    mod.check("pod5-like", (dac.astype(np.float32) + np.float32(10.0)) * np.float32(0.1755))
+    mod.check("ties", rng.integers(1, 64, 40_000) * 0.5)
+    mod.check("wide", np.exp(rng.normal(0, 4, 40_000)))

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <omp.h>
+#include <stdio.h>
 
 #define W DNBO_BANDWIDTH
 #define KLEN DNBO_K
@@ -776,6 +777,8 @@ size_t dnbo_eventalign(const char *ref, size_t rlen, const int32_t *r2q, const u
     size_t path_cap = 4 * (n_align + 4 * (size_t)total_window) + 64;
     int32_t *pidx = (int32_t *)malloc(path_cap * sizeof(int32_t));
     uint8_t *ptyp = (uint8_t *)malloc(path_cap);
+    /* design aid: DNBO_EA_WINDOW_LOG=<file> appends "ref_index window_len n_obs last_m_ref last_m_ev" per window */
+    FILE *wlog = getenv("DNBO_EA_WINDOW_LOG") ? fopen(getenv("DNBO_EA_WINDOW_LOG"), "a") : NULL;
     while (reference_index < rlen - k + 1) {
         const unsigned bases_to_end = (unsigned)rlen - reference_index;
         unsigned wl = bases_to_end < total_window ? bases_to_end : total_window;
@@ -825,9 +828,11 @@ size_t dnbo_eventalign(const char *ref, size_t rlen, const int32_t *r2q, const u
             }
             ev++;
         }
+        if (wlog) fprintf(wlog, "%u %u %zu %zu %zu\n", reference_index, wl, ns, last_m_ref, last_m_ev);
         read_head += (long)last_m_ev + 1;                                                             /* :740-741 */
         reference_index += (unsigned)last_m_ref + 1;
     }
+    if (wlog) fclose(wlog);
     free(snip); free(snip_ev); free(pidx); free(ptyp);
     return nrec;
 }

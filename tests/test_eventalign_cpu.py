@@ -114,3 +114,27 @@ def test_port_eventalign_vs_reference_fresh_reads(port, ref_oracle, pore_mean):
                               event_starts(o["event_raw_len"]), o["shift"], o["scale"])
         for key in AP_KEYS:
             np.testing.assert_array_equal(f[key], ap[key], err_msg=key)
+
+
+def test_window_parallel_eventalign_design_check(port, pore_mean, ea_golden, golden_reads, golden_v2):
+    """DESIGN.md s.8 item 2 (scripts/proto_window_parallel_eventalign.py): eventalign with all windows of a read run
+    independently on the 'every window advances fully' chain, plus a verify-and-repair walk, gives exactly the records the
+    UNMODIFIED REFERENCE produced for the golden reads (indel / soft-clip CIGARs and analogue reads included), and the repair
+    rounds touch only a few windows."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                        "proto_window_parallel_eventalign.py")
+    spec = importlib.util.spec_from_file_location("proto_window_parallel_eventalign", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    total0 = repair = most_rounds = 0
+    for tag, g in all_golden_reads(golden_reads, golden_v2):
+        serial = golden_records(ea_golden, tag)
+        R = mod.Read(port, pore_mean, g.refseq, ea_golden[f"e_{tag}_ref_to_query"], g.align[:, 0], g.align[:, 1],
+                     g.event_mean.astype(np.float64), g.shift, g.scale, g.events_per_base, serial=serial)
+        rounds = mod.check(R)
+        total0 += rounds[0]
+        repair += sum(rounds[1:])
+        most_rounds = max(most_rounds, len(rounds))
+    # ~5 % of the windows are re-run (mostly on the read with a long insertion/deletion CIGAR), in one extra round
+    assert total0 > 300 and repair < 0.15 * total0 and most_rounds <= 3

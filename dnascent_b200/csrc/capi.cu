@@ -1102,6 +1102,13 @@ int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64
 }
 
 // ---- eventalign (SURVEY s.8 row f1) ------------------------------------------------------------------------------
+// DNB_EA_WINDOW_PARALLEL=1 routes eventalign through the experimental window-parallel kernels (eventalign_wp.cu);
+// the default is the read-serial kernel every test and number of this round was produced with
+static bool ea_window_parallel() {
+    static const bool on = getenv("DNB_EA_WINDOW_PARALLEL") != nullptr && getenv("DNB_EA_WINDOW_PARALLEL")[0] == '1';
+    return on;
+}
+
 static thread_local double g_ea_kernel_ms = 0.0;
 double dnb_eventalign_last_kernel_ms(void) { return g_ea_kernel_ms; }
 
@@ -1247,7 +1254,8 @@ static int eventalign_impl(dnb_ctx *ctx, const dnb_eventalign_desc *reads, const
         a.d2d = d2d; a.d2m = d2m; a.i2m = i2m; a.m2d = m2d; a.m2i = m2i; a.i2i = i2i;
         a.rec_off = d_rec_off; a.recs = d_recs; a.n_rec = d_nrec; a.status = d_status; a.next_read = d_next;
         fail(cudaEventRecord(e0, s));
-        dnb_launch_eventalign(a, grid, s);
+        if (ea_window_parallel()) fail(dnb_run_eventalign_wp(a, tot_ref, tot_al, ctx->cfg.device, s));
+        else dnb_launch_eventalign(a, grid, s);
         fail(cudaEventRecord(e1, s));
         fail(cudaGetLastError());
         if (feats && rc == DNB_OK) {
@@ -1426,7 +1434,8 @@ int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uin
     a.rec_off = d_rec_off; a.recs = d_recs; a.n_rec = d_nrec; a.status = d_status; a.next_read = d_next;
     a.order = b->d_order;
     CK(cudaEventRecord(b->ev[0], s));
-    dnb_launch_eventalign(a, grid, s);
+    if (ea_window_parallel()) CK(dnb_run_eventalign_wp(a, tot_r, b->tot_out, ctx->cfg.device, s));
+    else dnb_launch_eventalign(a, grid, s);
     CK(cudaEventRecord(b->ev[1], s));
     DnbFeatArgs f = {};
     f.n_reads = (uint32_t)R;

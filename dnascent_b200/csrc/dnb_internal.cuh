@@ -203,6 +203,9 @@ unsigned dnb_eventalign_grid(int device);
 unsigned dnb_eventalign_warps_per_block(void);
 size_t dnb_eventalign_bt_row_bytes(void);
 void dnb_launch_eventalign(const DnbEaArgs &a, unsigned grid, cudaStream_t s);
+// experimental window-parallel form of the same stage (eventalign_wp.cu; only with DNB_EA_WINDOW_PARALLEL=1):
+// tot_ref / tot_align = total reference bases / aligned events of the batch; synchronises s once per round
+cudaError_t dnb_run_eventalign_wp(const DnbEaArgs &a, uint64_t tot_ref, uint64_t tot_align, int device, cudaStream_t s);
 
 // ---- DNN input tensors (features.cu): SURVEY s.8 row f2, consumes eventalign's records on the device --------------
 struct DnbFeatArgs {

@@ -101,11 +101,11 @@ class Read:
 
 
 def run_window(R, ri, wl, read_head):
-    """builtinViterbi on one window + the two passes over its state labels (:655-741).  Returns None for a skipped
-    window (fewer than two observations), else (records, last_m_ref, last_m_ev, new_read_head)."""
+    """builtinViterbi on one window + the two passes over its state labels (:655-741).  Returns (None, readHead) for a
+    skipped window (fewer than two observations), else (records, last_m_ref, last_m_ev, readHead after the gather)."""
     rh, obs, ev, lo, hi = R.gather(ri, wl, read_head)
     if obs.size < 2:
-        return None
+        return None, rh                # skipped (:641) -- but the gather has already moved readHead (:617-620)
     _, idx, typ = R.P.builtin_viterbi(obs, R.ref[ri:ri + wl], R.shift, R.scale, R.epb, R.mean)
     indel = (hi - lo) - (wl - K + 1)
     last_m_ev = last_m_ref = 0
@@ -151,13 +151,15 @@ def speculative(R):
                 # optimistic continuation: every event consumed, last state matched
                 rh, obs, ev, lo, hi = R.gather(ri, wl, read_head)
                 if obs.size < 2:
+                    read_head = rh
                     ri += wl
                     continue
                 read_head = rh + len(ev)
                 ri += wl - K + 1
                 continue
             res = cache[k]
-            if res is None:
+            if res[0] is None:
+                read_head = max(read_head, res[1]) if k[1] is None else res[1]
                 ri += wl
                 continue
             recs, last_m_ref, last_m_ev, rh = res

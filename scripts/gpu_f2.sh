@@ -11,9 +11,9 @@ else
 fi
 tail -40 gpurun_out/${TAG}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 600 python scripts/ea_perf.py 1000 10000 16 8 > gpurun_out/${TAG}_ea_perf.json 2> gpurun_out/${TAG}_ea_perf.err; echo "ea_perf rc=$?"
+timeout 600 python tests/helpers/ea_perf.py 1000 10000 16 8 > gpurun_out/${TAG}_ea_perf.json 2> gpurun_out/${TAG}_ea_perf.err; echo "ea_perf rc=$?"
 tail -c 2500 gpurun_out/${TAG}_ea_perf.json; tail -5 gpurun_out/${TAG}_ea_perf.err
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:eventalign_kernel|features_kernel" -s 3 -c 2 \
-    -o gpurun_out/${TAG}_full python scripts/ea_perf.py 300 10000 0 > gpurun_out/${TAG}_full.log 2>&1
+    -o gpurun_out/${TAG}_full python tests/helpers/ea_perf.py 300 10000 0 > gpurun_out/${TAG}_full.log 2>&1
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
 echo done

@@ -7,8 +7,8 @@ mkdir -p gpurun_out
 DNB_EA_WINDOW_PARALLEL=1 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest (switch on) rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
 tail -15 gpurun_out/${TAG}_pytest.log
 DNB_EA_WINDOW_PARALLEL=1 timeout 120 python scripts/wp_check.py 2>&1 | tail -3
-timeout 600 python scripts/ea_perf.py 1000 10000 0 8 > gpurun_out/${TAG}_ea_perf_serial.json 2> gpurun_out/${TAG}_ea_perf_serial.err; echo "serial rc=$?"
-DNB_EA_WINDOW_PARALLEL=1 timeout 600 python scripts/ea_perf.py 1000 10000 0 8 > gpurun_out/${TAG}_ea_perf_wp.json 2> gpurun_out/${TAG}_ea_perf_wp.err; echo "wp rc=$?"
+timeout 600 python tests/helpers/ea_perf.py 1000 10000 0 8 > gpurun_out/${TAG}_ea_perf_serial.json 2> gpurun_out/${TAG}_ea_perf_serial.err; echo "serial rc=$?"
+DNB_EA_WINDOW_PARALLEL=1 timeout 600 python tests/helpers/ea_perf.py 1000 10000 0 8 > gpurun_out/${TAG}_ea_perf_wp.json 2> gpurun_out/${TAG}_ea_perf_wp.err; echo "wp rc=$?"
 python - <<PY
 import json
 for m in ("serial", "wp"):
@@ -19,6 +19,6 @@ for m in ("serial", "wp"):
         print(m, "no result:", ex)
 PY
 DNB_EA_WINDOW_PARALLEL=1 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:wp_walk_kernel|wp_window_kernel" -s 4 -c 4 \
-    -o gpurun_out/${TAG}_full python scripts/ea_perf.py 300 10000 0 > gpurun_out/${TAG}_full.log 2>&1
+    -o gpurun_out/${TAG}_full python tests/helpers/ea_perf.py 300 10000 0 > gpurun_out/${TAG}_full.log 2>&1
 ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
 echo done

@@ -1,9 +1,9 @@
 """Rows f1/f2 measurement (GPU box): n reads x L bases through normaliseEvents -> eventalign (+ DNN input tensors),
 device kernel times from the library's CUDA events, wall time of the C-ABI call with host buffers, and the unmodified
 reference's CPU eventalign (oracle/_ref, 1 thread per read loop as alignment.cpp:852) on a bounded subset.
-usage: python scripts/ea_perf.py [n_reads] [read_len] [n_cpu_reads] [rep] > gpurun_out/ea_perf.json"""
+usage: python tests/helpers/ea_perf.py [n_reads] [read_len] [n_cpu_reads] [rep] > gpurun_out/ea_perf.json"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from dnascent_b200 import api, synth
 

@@ -15,7 +15,7 @@ TILE, and the tiles whose range of possible values straddles a power of two (at 
 read) are the only ones that still need the literal sample-by-sample loop.
 
 This script checks the claim against the sequential double-precision loop on realistic and adversarial inputs.
-Run: python scripts/proto_exact_prefix.py
+Run: python tests/helpers/proto_exact_prefix.py
 """
 import numpy as np
 

@@ -21,14 +21,14 @@ The true chain usually REJOINS the speculative one a window later (the next brea
 so the extra rounds touch a fraction of a percent of the windows.
 
 The script asserts that the records are identical to the oracle port's serial eventalign and prints how many windows
-each round ran.  Run: python scripts/proto_window_parallel_eventalign.py
+each round ran.  Run: python tests/helpers/proto_window_parallel_eventalign.py
 """
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from dnascent_b200 import synth          # noqa: E402
 from oracle import portbind              # noqa: E402
 
@@ -190,7 +190,7 @@ def check(R):
 
 
 def main():
-    mean = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+    mean = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden",
                                 "pore_model_r10.4.1_400bps.npz"))["mean"].astype(np.float64)
     P = portbind.Port()
     ref = synth.make_reference(400_000, 5)

@@ -117,13 +117,12 @@ def test_port_eventalign_vs_reference_fresh_reads(port, ref_oracle, pore_mean):
 
 
 def test_window_parallel_eventalign_design_check(port, pore_mean, ea_golden, golden_reads, golden_v2):
-    """DESIGN.md s.8 item 2 (scripts/proto_window_parallel_eventalign.py): eventalign with all windows of a read run
+    """DESIGN.md s.8 item 2 (tests/helpers/proto_window_parallel_eventalign.py): eventalign with all windows of a read run
     independently on the 'every window advances fully' chain, plus a verify-and-repair walk, gives exactly the records the
     UNMODIFIED REFERENCE produced for the golden reads (indel / soft-clip CIGARs and analogue reads included), and the repair
     rounds touch only a few windows."""
     import importlib.util
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
-                        "proto_window_parallel_eventalign.py")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers", "proto_window_parallel_eventalign.py")
     spec = importlib.util.spec_from_file_location("proto_window_parallel_eventalign", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

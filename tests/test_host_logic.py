@@ -113,12 +113,12 @@ def test_constant_divisor_sequences(tmp_path):
 
 
 def test_exact_rounded_prefix_sums_by_map_composition():
-    """The design check behind DESIGN.md s.8 item 5 (scripts/proto_exact_prefix.py): scrappie's sequentially rounded
+    """The design check behind DESIGN.md s.8 item 5 (tests/helpers/proto_exact_prefix.py): scrappie's sequentially rounded
     prefix sums (event_detection.c:35-48) reproduced bit for bit with one serial step per 512-sample tile instead of one
     per sample, on POD5-like and adversarial (ties, wide dynamic range) inputs."""
     import importlib.util
     import os
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "proto_exact_prefix.py")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers", "proto_exact_prefix.py")
     spec = importlib.util.spec_from_file_location("proto_exact_prefix", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

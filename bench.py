@@ -415,6 +415,8 @@ def main():
                  "value": c_total / dt_c / 1e6, "unit": UNIT, "reads_per_gpu": int(n_c), "samples_per_gpu": c_samples,
                  "ms_per_pass": 1e3 * dt_c, "tensor_rows_per_gpu": int(acc["rows"]), "h2d_bytes_per_pass": int(acc["h2d"]),
                  "d2h_bytes_per_pass": int(acc["d2h"]), "eventalign_kernel_ms": acc["ea_ms"], "features_kernel_ms": acc["ft_ms"],
+                 "eventalign_mode": "window-parallel (experimental)" if os.environ.get("DNB_EA_WINDOW_PARALLEL", "")[:1] == "1"
+                                    else "read-serial",
                  "cpu_reference": None}
 
     # ---- CPU baseline (rank 0, N == 1 only) ----

@@ -106,6 +106,8 @@ struct DnbSegTiles {
 
 void dnb_launch_segmentation_serial(const DnbBatchView &v, DnbDetector det, const uint32_t *only_flagged, cudaStream_t s);
 void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s);
+// experimental replacement of the tiled segmentation's checkpoint kernel (seg_scan.cu; only with DNB_SEG_PARITY_SCAN=1)
+cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, cudaStream_t s);
 void dnb_launch_ranks(const DnbBatchView &v, const DnbModelDev &m, double *mu_q, uint32_t *rank_ref, cudaStream_t s);
 void dnb_launch_quantile_scaling(const DnbBatchView &v, const DnbModelDev &m, const uint32_t *rank_ref,
                                  double *rough_shift, double *rough_scale, cudaStream_t s);

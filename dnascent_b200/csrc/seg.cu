@@ -30,6 +30,7 @@
 // 4 B/sample + 8 B/event (2 B/sample for int16 DAC input).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include "dnb_internal.cuh"
 #include "../../include/dnascent_b200.h"
 
@@ -640,12 +641,15 @@ void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const
     const unsigned gr = (v.n_reads + 127) / 128;
     const unsigned gt = (t.n_tiles + SEG_THREADS - 1) / SEG_THREADS;
     const bool fast = fast_div_ok(det.w1) && fast_div_ok(det.w2);
+    // DNB_SEG_PARITY_SCAN=1: the experimental block-map scan of seg_scan.cu instead of the per-sample checkpoint chain
+    static const bool parity_scan = getenv("DNB_SEG_PARITY_SCAN") != nullptr && getenv("DNB_SEG_PARITY_SCAN")[0] == '1';
+    const bool scanned = parity_scan && dnb_launch_seg_parity_scan(v, t, s) == cudaSuccess;
     if (v.raw_i16) {
-        seg_checkpoint_kernel<true><<<gr, 128, 0, s>>>(v, t);
+        if (!scanned) seg_checkpoint_kernel<true><<<gr, 128, 0, s>>>(v, t);
         if (fast) seg_tile_kernel<true, true><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
         else seg_tile_kernel<true, false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
     } else {
-        seg_checkpoint_kernel<false><<<gr, 128, 0, s>>>(v, t);
+        if (!scanned) seg_checkpoint_kernel<false><<<gr, 128, 0, s>>>(v, t);
         if (fast) seg_tile_kernel<false, true><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
         else seg_tile_kernel<false, false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
     }

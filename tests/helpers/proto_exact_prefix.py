@@ -126,3 +126,90 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---- the kernel-shaped version: 64-sample blocks, SIGNED addends, maps built under a PREDICTED binade --------------------
+# (mirrors dnascent_b200/csrc/seg_scan.cu: phase A block sums, B approximate prefix -> predicted binade per block,
+#  C per-block maps under that binade, D one serial step per block with an exact check and a literal fallback)
+BLOCK = 64
+
+
+def block_chain(a):
+    """rounded running sums of the signed, exactly representable addends `a` at every block boundary"""
+    nb = (a.size + BLOCK - 1) // BLOCK
+    pad = np.zeros(nb * BLOCK)
+    pad[:a.size] = a                                             # +0.0 addends change nothing
+    blk = pad.reshape(nb, BLOCK)
+    bs = blk.sum(axis=1)                                         # phase A (any summation order: only used to predict)
+    ba = np.abs(blk).sum(axis=1)
+    pre = np.concatenate([[0.0], np.cumsum(bs)[:-1]])            # phase B: approximate running sum at each block start
+    e_pred = np.frexp(np.where(pre > 0, pre, 1.0))[1] - 1        # predicted binade (pre <= 0: no prediction)
+    maps = []
+    for b in range(nb):                                          # phase C (parallel over blocks on the device)
+        if pre[b] <= 0:
+            maps.append(None)
+            continue
+        e = int(e_pred[b])
+        sh = e - 52
+        scaled = np.ldexp(blk[b], -sh)
+        q = np.floor(scaled)                                     # floor, also for negative addends: r in [0, 1)
+        r = scaled - q
+        if not np.all(np.isfinite(scaled)) or np.any(np.abs(q) >= 2.0 ** 53):
+            maps.append(None)
+            continue
+        d0, d1 = 0, 0                                            # identity
+        for qi, ri in zip(q.astype(np.int64).tolist(), r.tolist()):
+            up = 1 if ri > 0.5 else 0
+            if ri == 0.5:
+                g0, g1 = (qi + 1, qi) if (qi & 1) else (qi, qi + 1)
+            else:
+                g0 = g1 = qi + up
+            d0 = d0 + (g1 if (d0 & 1) else g0)                   # compose: this element after the block so far
+            d1 = d1 + (g0 if (d1 & 1) else g1)
+        maps.append((e, d0, d1))
+    out = np.empty(nb + 1)
+    s = 0.0
+    stats = [0, 0]
+    for b in range(nb):                                          # phase D: one lane per read
+        out[b] = s
+        m = maps[b]
+        done = False
+        if m is not None and s > 0:
+            e, d0, d1 = m
+            lo, hi = 2.0 ** e, 2.0 ** (e + 1)
+            # exact precondition: the actual running sum is in the predicted binade and cannot leave it inside the block
+            if lo <= s < hi and s - ba[b] * 1.0000001 >= lo and s + ba[b] * 1.0000001 < hi:
+                S = int(np.ldexp(s, 52 - e))
+                S += d1 if (S & 1) else d0
+                s = float(np.ldexp(float(S), e - 52))
+                done = True
+        if not done:
+            for v in blk[b].tolist():
+                s = s + v
+        stats[0 if done else 1] += 1
+    out[nb] = s
+    return out, stats
+
+
+def check_blocks(name, x):
+    x = np.asarray(x, dtype=np.float32).astype(np.float64)
+    for label, a in (("sumsq", x * x), ("sum", x)):
+        ref = seq_prefix(a)
+        got, stats = block_chain(a)
+        idx = np.minimum(np.arange(got.size) * BLOCK, a.size)
+        assert np.array_equal(got, ref[idx]), (name, label)
+        print(f"{name:28s} {label:6s} n={a.size:8d}  blocks: {stats[0]:6d} by composition, {stats[1]:5d} literal  -> bit-identical")
+
+
+def main_blocks():
+    rng = np.random.default_rng(2)
+    dac = rng.integers(200, 900, 200_000).astype(np.int16)
+    check_blocks("pod5-like", (dac.astype(np.float32) + np.float32(10.0)) * np.float32(0.1755))
+    check_blocks("signed, zero-mean", rng.normal(0, 50, 100_000))
+    check_blocks("signed with drift", rng.normal(3, 50, 100_000))
+    check_blocks("few-bit signed (ties)", rng.integers(-64, 64, 100_000) * 0.5)
+    check_blocks("wide dynamic range", np.exp(rng.normal(0, 4, 100_000)) * rng.choice([-1.0, 1.0], 100_000))
+
+
+if __name__ == "__main__":
+    main_blocks()

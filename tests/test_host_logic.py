@@ -127,3 +127,8 @@ def test_exact_rounded_prefix_sums_by_map_composition():
     mod.check("pod5-like", (dac.astype(np.float32) + np.float32(10.0)) * np.float32(0.1755))
     mod.check("ties", rng.integers(1, 64, 40_000) * 0.5)
     mod.check("wide", np.exp(rng.normal(0, 4, 40_000)))
+    # the kernel-shaped version csrc/seg_scan.cu mirrors: 64-sample blocks, signed addends, maps under a predicted binade,
+    # exact check + literal fallback
+    mod.check_blocks("pod5-like", (dac.astype(np.float32) + np.float32(10.0)) * np.float32(0.1755))
+    mod.check_blocks("signed with drift", rng.normal(3, 50, 30_000))
+    mod.check_blocks("signed ties", rng.integers(-64, 64, 30_000) * 0.5)

@@ -7,7 +7,11 @@
 One step = one pass of the hot path over the whole workload: BASELINE.json configs[1], 100 000 synthetic R10.4.1
 reads with a 30 kb N50 (~3*10^10 samples), per GPU (weak scaling: every rank gets its own length-balanced shard of a
 N*100k-read batch, no collective on the data path).  `value` is measured with the inputs resident in HBM; `e2e`
-goes through the public C-ABI call (dnb_submit) with host buffers, H2D and D2H inside the timed region.
+goes through the public C-ABI call (dnb_submit) with host buffers, H2D and D2H inside the timed region: the signal is
+DMA'd straight out of the page-locked workload buffer (no staging pass), queryToRef goes as CIGAR-like runs, the
+results come back in the compact wire format (1 B + 4 B per event, 2 bits per alignment step).
+`parity_check` runs a length-stratified subset of the SAME workload through the unmodified reference on the host and
+compares bit for bit; a step whose reads did not all come back DNB_READ_OK fails the bench.
 """
 from __future__ import annotations
 
@@ -133,6 +137,67 @@ def reference_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ parity on the workload
+def parity_check(ctx, W, mean, n_reads: int):
+    """A length-stratified subset of the bench's own reads through the library (dnb_submit, the e2e path) and through the
+    reference on the host (oracle/_ref: unmodified sources; else the C port), compared bit for bit: event boundaries,
+    event means, alignment path, scalings, QC."""
+    import types
+    from oracle import refbind
+    order = np.argsort(W.n_samples, kind="stable")
+    pick = np.unique(order[np.linspace(0, order.size - 1, min(n_reads, order.size)).astype(np.int64)])
+    b = ctx.submit_descs(W.descs(pick))
+    ours = b.results()
+    b.release()
+    rd = [W.read(int(i)) for i in pick]
+    t0 = time.time()
+    if refbind.available():
+        kind = "reference"
+        R = refbind.Ref()
+        R.set_model(refbind.PORE, mean, np.full(mean.size, 0.14))
+        genome = b"".join(r["basecall"] for r in rd)             # each read is its own stretch of the "genome"
+        R.set_reference(genome)
+        handles, pos = [], 0
+        for k, r in enumerate(rd):
+            L = len(r["basecall"])
+            handles.append(R.read_new(types.SimpleNamespace(
+                name=f"p{k}", seq_bam=r["basecall"], flag=0, pos=pos, cigar=np.array([(L << 4) | 0], dtype=np.uint32), raw=r["raw"])))
+            pos += L
+        R.bench_normalise(handles, os.cpu_count() or 1)
+        want = []
+        for h in handles:
+            o = h.outputs(staged=False)
+            o["event_start"] = np.concatenate([[0], np.cumsum(o["event_raw_len"].astype(np.int64))])
+            o["failed"] = o["align_event"].size == 0
+            want.append(o)
+            h.free()
+    else:
+        kind = "port"
+        from oracle import portbind
+        P = portbind.Port()
+        want = []
+        for r in rd:
+            o = P.normalise(r["raw"], r["basecall"], r["refseq"], r["query_to_ref"], mean)
+            o["failed"] = o["status"] != 0
+            want.append(o)
+    mism, detail = 0, []
+    for k, (o, w) in enumerate(zip(ours, want)):
+        ok = (o.status != 0) == bool(w["failed"])
+        ok = ok and np.array_equal(o.event_mean.astype(np.float64), np.asarray(w["event_mean"], dtype=np.float64))
+        ok = ok and np.array_equal(o.event_start.astype(np.int64), np.asarray(w["event_start"], dtype=np.int64))
+        if ok and not w["failed"]:
+            ok = (np.array_equal(o.eventAlignment[:, 0], w["align_event"]) and np.array_equal(o.eventAlignment[:, 1], w["align_kmer"])
+                  and o.shift == w["shift"] and o.scale == w["scale"] and o.avg_log_emission == w["avg_log_emission"]
+                  and o.spanned == w["spanned"] and o.maxGap == w["max_gap"])
+        if not ok:
+            mism += 1
+            detail.append(int(pick[k]))
+    return {"reads": int(pick.size), "mismatches": mism, "mismatching_reads": detail[:8], "against": kind,
+            "samples": int(W.n_samples[pick].sum()), "longest_read_samples": int(W.n_samples[pick].max()),
+            "compared": "event boundaries, event means, alignment path, shift/scale, avg_log_emission, spanned, max_gap (==)",
+            "cpu_s": time.time() - t0}
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
     def __init__(self, index: int):
@@ -181,6 +246,8 @@ def main():
     ap.add_argument("--e2e-inflight", type=int, default=8,
                     help="dnb_submit calls in flight (B200 sweep, 60k reads: 4e8x4 74 %% of the resident value, 8e8x8 84 %%)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pin", action="store_true", help="leave the workload pageable (e2e goes through pinned staging)")
+    ap.add_argument("--parity-reads", type=int, default=64, help="reads of the workload re-run on the CPU reference (0 = skip)")
     ap.add_argument("--chain-reads", type=int, default=4000,
                     help="reads (whole job) of the rows f1-f2 leg (dnb_submit_chain); 0 = skip")
     args = ap.parse_args()
@@ -222,28 +289,21 @@ def main():
     peaks, peak_src = load_peaks()
     mean = pore_model()
 
-    # ---- host-memory guard: every rank keeps its shard's signal in host RAM for the e2e leg (~2.6 B/sample + staging); never let N ranks on one box run the host out of memory
+    # ---- host memory: every rank keeps its shard as the loader would hand it over (int16 signal 2 B/sample + sequences),
+    # page-locked in place; the compact results of the submissions in flight (~1.1 B/sample) come on top.  N ranks share
+    # one box's RAM: shrink what is in flight first, the shard only as a last resort (and say so in the line).
     reads_per_gpu = args.reads
     try:
         import psutil
         avail = psutil.virtual_memory().available
-        # pinned staging + result buffers of the submissions in flight (~5.5 B/sample each) come on top
-        # (N ranks share one box's RAM): fewer in flight first, then smaller submissions
+
         def inflight_bytes():
-            return 5.5 * args.e2e_bin_samples * args.e2e_inflight * world
-        while inflight_bytes() > 0.2 * avail:
-            if args.e2e_inflight > 4:
-                args.e2e_inflight -= 1
-            elif args.e2e_bin_samples > 1.0e8:
-                args.e2e_bin_samples /= 2
-            elif args.e2e_inflight > 2:
-                args.e2e_inflight -= 1
-            else:
-                break
-        avail -= inflight_bytes()
-        need = 1.3 * 2.6 * SAMPLES_PER_BASE * 25_100.0 * reads_per_gpu * world      # mean read ~25.1 kb at N50 30 kb
-        if need > 0.8 * avail:
-            reads_per_gpu = max(int(reads_per_gpu * 0.8 * avail / need), 1000)
+            return 1.5 * args.e2e_bin_samples * args.e2e_inflight * world
+        while inflight_bytes() > 0.1 * avail and args.e2e_inflight > 4:
+            args.e2e_inflight -= 1
+        need = 1.1 * 2.1 * SAMPLES_PER_BASE * 25_100.0 * reads_per_gpu * world + inflight_bytes()   # mean read ~25.1 kb at N50 30 kb
+        if need > 0.85 * avail:
+            reads_per_gpu = max(int(reads_per_gpu * 0.85 * avail / need), 1000)
     except Exception:  # noqa: BLE001
         pass
     if world > 1:
@@ -261,7 +321,19 @@ def main():
     gen_s = time.time() - t0
     n_samples = int(W.n_samples.sum())
 
-    ctx = api.Context(device=local)
+    # the loader's buffers are page-locked (dnb_host_register): dnb_submit then DMAs every read from where it lies
+    pin_s, pinned = 0.0, False
+    if not args.no_pin:
+        t0 = time.time()
+        try:
+            api.host_register(W.dac)
+            api.host_register(W.seq)
+            pinned = True
+        except Exception as ex:  # noqa: BLE001 -- fall back to the staged path, visibly
+            print(f"bench.py: dnb_host_register failed ({ex}); e2e leg uses pinned staging", file=sys.stderr)
+        pin_s = time.time() - t0
+
+    ctx = api.Context(device=local, result_format=api.RESULT_COMPACT)
     ctx.load_model(api.MODEL_PORE, mean)
 
     # ---- value leg: inputs resident in HBM ----
@@ -301,8 +373,12 @@ def main():
     cnt_step = {k: v // K for k, v in counts.items()}
     for b in batches:
         b.release()
+    # every read of the synthetic workload is an exact substring of the reference: all of them must align and pass QC
+    ok_share = 1.0 - sum_over_ranks(float(cnt_step["failed_reads"])) / (world * args.reads)
+    if ok_share < 0.999:
+        raise SystemExit(f"bench.py: only {ok_share:.4%} of the reads came back DNB_READ_OK in the value leg")
 
-    # ---- roofline of the dominant kernel (banded DP) and of the HBM-bound one (segmentation) ----
+    # ---- roofline of the dominant kernel (align_kernel: band fill + backtrace, one launch) and of segmentation ----
     clocks = sampler.summary()
     f_clk = (clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
     prof = {}
@@ -310,61 +386,89 @@ def main():
     if os.path.exists(pj):
         with open(pj) as f:
             prof = json.load(f)
-    i_cell = prof.get("align_thread_instr_per_cell")
-    dp_s = per_step["banded_dp"] / 1e3
+    i_cell = prof.get("align_thread_instr_per_cell")           # whole launch (fill + backtrace) / DP cells, from ncu
+    launch_s = (per_step["banded_dp"] + per_step["backtrace"]) / 1e3      # CUDA-event duration of the fused launch
+    fill_s = per_step["banded_dp"] / 1e3                       # its band-fill share (in-kernel warp cycles)
     cells = cnt_step["cells"]
-    issue_peak = 148 * 4 * 32 * f_clk                       # thread-instructions/s at 1 warp-instr/clk/scheduler
+    issue_peak = 148 * 4 * 32 * f_clk                          # thread-instructions/s at 1 warp-instr/clk/scheduler
     roofline = {
-        "kernel": "align_kernel (band fill phase; duration = its warp-cycle share of the fused fill+backtrace launch)",
+        "kernel": "align_kernel<0> (band fill + backtrace, one fused launch; duration = CUDA events around the launch)",
         "bound": "issue",
-        "achieved": (cells * i_cell / dp_s / 1e12) if i_cell else None, "peak": issue_peak / 1e12,
-        "unit": "T thread-instr/s", "frac": (cells * i_cell / dp_s / issue_peak) if i_cell else None,
+        "achieved": (cells * i_cell / launch_s / 1e12) if i_cell else None, "peak": issue_peak / 1e12,
+        "unit": "T thread-instr/s", "frac": (cells * i_cell / launch_s / issue_peak) if i_cell else None,
         "traffic": prof.get("align_dram_bytes_per_cell", None) and prof["align_dram_bytes_per_cell"] * cells,
-        "constants_source": prof.get("source"),
-        "cells_per_s": cells / dp_s, "thread_instr_per_cell": i_cell, "sm_clock_used_mhz": f_clk / 1e6,
-        "hbm_view": {"bound": "hbm", "achieved": 0.29 * cells / dp_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": 0.29 * cells / dp_s / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_cell": 0.29},
+        "constants_source": prof.get("source"), "constants_commit": prof.get("commit"),
+        "launch_ms_per_step": 1e3 * launch_s, "cells_per_s": cells / launch_s, "thread_instr_per_cell": i_cell,
+        "sm_clock_used_mhz": f_clk / 1e6,
+        "issue_active_pct": prof.get("align_issue_active_pct"), "fp64_pipe_pct": prof.get("align_fp64_pipe_pct"),
+        "xu_pipe_pct": prof.get("align_xu_pipe_pct"), "warps_active_pct": prof.get("align_warps_active_pct"),
+        "fill_phase_view": {"what": "band fill only: launch duration x the fill's share of the in-kernel warp cycles",
+                            "ms_per_step": 1e3 * fill_s, "cells_per_s": cells / fill_s},
+        "hbm_view": {"bound": "hbm", "achieved": 0.29 * cells / launch_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": 0.29 * cells / launch_s / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_cell": 0.29},
         "peak_source": peak_src,
     }
     seg_s = per_step["segmentation"] / 1e3
     seg_bytes = 2.0 * cnt_step["samples"] + 8.0 * cnt_step["events"]      # int16 DAC in, (u32 start, f32 mean) out
-    roofline_seg = {"kernel": "seg_tile_kernel (+checkpoint/stitch/events)", "bound": "hbm",
+    i_samp = prof.get("seg_thread_instr_per_sample")
+    roofline_seg = {"kernel": "seg_* (checkpoint/scan, tiles, stitch, events)", "bound": "hbm",
                     "achieved": seg_bytes / seg_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": seg_bytes / seg_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                    "algorithmic_bytes": "2 B/sample (int16 DAC) + 8 B/event", "peak_source": peak_src}
+                    "frac": seg_bytes / seg_s / 1e9 / peaks["hbm_gbs"],
+                    "traffic": prof.get("seg_dram_bytes_per_sample") and prof["seg_dram_bytes_per_sample"] * cnt_step["samples"],
+                    "algorithmic_bytes": "2 B/sample (int16 DAC) + 8 B/event", "peak_source": peak_src,
+                    "ms_per_step": {"checkpoint_or_scan": per_step.get("seg_checkpoint"), "tiles": per_step.get("seg_tiles"),
+                                    "stitch_events_redo": per_step.get("seg_rest")},
+                    "issue_view": {"what": "the exact t-statistics make this kernel instruction-bound, not HBM-bound",
+                                   "thread_instr_per_sample": i_samp,
+                                   "frac": (cnt_step["samples"] * i_samp / seg_s / issue_peak) if i_samp else None}}
 
     # ---- e2e leg: host buffers through dnb_submit, H2D + D2H inside the timed region ----
     e2e_bins = sharding.make_bins(W.n_samples, int(args.e2e_bin_samples))
     descs = [W.descs(b) for b in e2e_bins]
-    io_acc = [0, 0]
+    io_acc = [0, 0, 0]
 
     def one(d):
         b = ctx.submit_descs(d)
         b.wait()
         res0 = b.result(0)                      # touch a result: the step's outcome is read on the host
-        assert res0.status in (0, 1, 2, 3, 4)
+        _, cnt = b.timings()                    # counts[7]: reads of this submission whose status is not DNB_READ_OK
+        bad = cnt["failed_reads"] + (res0.status != api.READ_OK)
         io = b.io_bytes()                       # counted by the library from the copies it made
         b.release()
-        return io
+        return io[0], io[1], bad
 
     def e2e_step():
-        hb = db = 0
+        hb = db = nb = 0
         with ThreadPoolExecutor(max_workers=args.e2e_inflight) as ex:
-            for h2d, d2h in ex.map(one, descs):
+            for h2d, d2h, bad in ex.map(one, descs):
                 hb += h2d
                 db += d2h
-        io_acc[0], io_acc[1] = hb, db
+                nb += bad
+        io_acc[0], io_acc[1], io_acc[2] = hb, db, nb
 
     for _ in range(min(args.warmup, 3)):
         e2e_step()
+    api.host_stats(reset=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
     barrier()
     dt_e = max_over_ranks(time.perf_counter() - t0)
+    ph, ph_cnt = api.host_stats()
+    host_phases = {"what": "thread-seconds per e2e step inside dnb_submit by phase (rank 0; summed over the submitting threads)",
+                   "per_step_s": {k: round(v / args.steps, 4) for k, v in ph.items()}, "counters_timed_region": ph_cnt}
     e2e_value = total_samples * args.steps / dt_e / 1e6
-    h2d_bytes, d2h_bytes = io_acc
+    h2d_bytes, d2h_bytes, e2e_bad = io_acc
+    if sum_over_ranks(float(e2e_bad)) > 0.001 * world * args.reads:
+        raise SystemExit(f"bench.py: {e2e_bad} reads of an e2e step did not come back DNB_READ_OK")
+
+    # ---- parity check on the bench's own workload (BASELINE configs[1]: "throughput and bit-exactness check") ----
+    parity = None
+    if rank == 0 and args.parity_reads > 0:
+        parity = parity_check(ctx, W, mean, args.parity_reads)
+        if parity["mismatches"]:
+            raise SystemExit(f"bench.py: parity check failed: {parity}")
 
     # ---- chain leg (SURVEY s.8 rows f1-f2): normaliseEvents -> eventalign -> DNN input tensors through dnb_submit_chain,
     # host buffers in, tensors out, on a bounded sample of this rank's shard (the tensors are 108 B per reference base)
@@ -415,8 +519,8 @@ def main():
                  "value": c_total / dt_c / 1e6, "unit": UNIT, "reads_per_gpu": int(n_c), "samples_per_gpu": c_samples,
                  "ms_per_pass": 1e3 * dt_c, "tensor_rows_per_gpu": int(acc["rows"]), "h2d_bytes_per_pass": int(acc["h2d"]),
                  "d2h_bytes_per_pass": int(acc["d2h"]), "eventalign_kernel_ms": acc["ea_ms"], "features_kernel_ms": acc["ft_ms"],
-                 "eventalign_mode": "window-parallel (experimental)" if os.environ.get("DNB_EA_WINDOW_PARALLEL", "")[:1] == "1"
-                                    else "read-serial",
+                 "eventalign_mode": "read-serial" if os.environ.get("DNB_EA_WINDOW_PARALLEL", "")[:1] == "0"
+                                    else "window-parallel",
                  "cpu_reference": None}
 
     # ---- CPU baseline (rank 0, N == 1 only) ----
@@ -454,13 +558,17 @@ def main():
                 "reads_per_gpu_reduced_for_host_ram": reduced,
                 "l2": "inputs (>= 60 GB per step) exceed the 126 MB L2; no flush needed",
                 "parallelism": f"read-sharded x{world}, length-balanced, no collective",
-                "reads_per_s": total_samples and (world * args.reads * args.steps / dt),
+                "reads_per_s": total_samples and (world * args.reads * args.steps / dt), "reads_ok_share": ok_share,
                 "stage_ms_per_step": per_step, "counts_per_step": cnt_step, "generation_s": gen_s,
             },
             "roofline": roofline, "roofline_segmentation": roofline_seg, "cpu_baseline": cpu, "chain": chain,
+            "parity_check": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": 1e3 * dt_e / args.steps, "inflight": args.e2e_inflight, "bins": len(e2e_bins),
-                    "samples_per_submit": args.e2e_bin_samples,
+                    "samples_per_submit": args.e2e_bin_samples, "failed_reads_per_step": int(e2e_bad),
+                    "input": ("page-locked loader buffers, direct DMA per read" if pinned else "pageable, through pinned staging"),
+                    "result_format": "compact (u8 event lengths + f32 means, 2-bit alignment steps)",
+                    "host_register_s": pin_s, "host_phases": host_phases,
                     "host_threads_per_rank": int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)),
                     "host_cores": os.cpu_count() or 1},
             "gpu_launches": int(cnt_step["launches"] * args.steps), "clocks": clocks,

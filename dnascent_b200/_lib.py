@@ -25,6 +25,7 @@ class Config(C.Structure):
         ("min_average_log_emission", C.c_double), ("max_gap_threshold", C.c_int), ("bandwidth", C.c_int),
         ("use_fit_pore_model", C.c_int), ("event_capacity_per_sample", C.c_float), ("keep_debug", C.c_int),
         ("workspace_bytes", C.c_size_t),
+        ("result_format", C.c_int), ("n_devices", C.c_int), ("devices", C.c_int * 16),
     ]
 
 
@@ -35,7 +36,12 @@ class ReadDesc(C.Structure):
         ("query", C.c_char_p), ("query_len", C.c_uint32),
         ("ref", C.c_char_p), ("ref_len", C.c_uint32),
         ("query_to_ref", C.c_void_p),
+        ("q2r_runs", C.c_void_p), ("n_q2r_runs", C.c_uint32),
     ]
+
+
+class Q2RRun(C.Structure):
+    _fields_ = [("q_start", C.c_uint32), ("len", C.c_uint32), ("r_start", C.c_int32), ("stride", C.c_int32)]
 
 
 # numpy mirror of dnb_read_desc (C layout, natural alignment) for building descriptor arrays without a Python loop
@@ -43,7 +49,9 @@ import numpy as _np
 READ_DESC_DTYPE = _np.dtype([
     ("raw_pA", _np.uint64), ("raw_dac", _np.uint64), ("dac_offset", _np.float32), ("dac_scale", _np.float32),
     ("n_samples", _np.uint64), ("query", _np.uint64), ("query_len", _np.uint32), ("ref", _np.uint64),
-    ("ref_len", _np.uint32), ("query_to_ref", _np.uint64)], align=True)
+    ("ref_len", _np.uint32), ("query_to_ref", _np.uint64), ("q2r_runs", _np.uint64), ("n_q2r_runs", _np.uint32)], align=True)
+Q2R_RUN_DTYPE = _np.dtype([("q_start", _np.uint32), ("len", _np.uint32), ("r_start", _np.int32), ("stride", _np.int32)])
+assert Q2R_RUN_DTYPE.itemsize == C.sizeof(Q2RRun)
 assert READ_DESC_DTYPE.itemsize == C.sizeof(ReadDesc), (READ_DESC_DTYPE.itemsize, C.sizeof(ReadDesc))
 
 
@@ -56,6 +64,8 @@ class ReadResult(C.Structure):
         ("rough_shift", C.c_double), ("rough_scale", C.c_double),
         ("avg_log_emission", C.c_double), ("spanned", C.c_int), ("max_gap", C.c_int),
         ("n_cleaned", C.c_uint32), ("cleaned_signal", C.POINTER(C.c_double)), ("cleaned_rank", C.POINTER(C.c_uint32)),
+        ("event_first", C.c_uint32), ("event_len8", C.POINTER(C.c_uint8)), ("event_len_escape", C.POINTER(C.c_uint32)),
+        ("n_event_len_escape", C.c_uint32), ("align_first", C.c_uint32 * 2), ("align_steps", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -122,6 +132,8 @@ EXPORTS = [
     "dnb_eventalign_features_batch", "dnb_features_last_kernel_ms",
     "dnb_batch_eventalign_features", "dnb_batch_feature_result", "dnb_batch_stage2_timings",
     "dnb_dorado_slice", "dnb_submit_chain",
+    "dnb_expand_events", "dnb_expand_alignment", "dnb_host_register", "dnb_host_unregister", "dnb_host_alloc",
+    "dnb_host_free", "dnb_trim", "dnb_batch_seg_timings", "dnb_batch_device", "dnb_host_stats", "dnb_host_phase_name",
 ]
 
 
@@ -176,6 +188,19 @@ def lib():
     L.dnb_dorado_slice.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint64)]
     L.dnb_batch_stage2_timings.argtypes = [vp, C.POINTER(d * 2), C.POINTER(C.c_uint64 * 2)]
+    L.dnb_expand_events.argtypes = [C.POINTER(ReadResult), vp]
+    L.dnb_expand_alignment.argtypes = [C.POINTER(ReadResult), vp]
+    L.dnb_host_register.argtypes = [vp, sz]
+    L.dnb_host_unregister.argtypes = [vp]
+    L.dnb_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.dnb_host_free.argtypes = [vp]
+    L.dnb_host_free.restype = None
+    L.dnb_trim.argtypes = [vp]
+    L.dnb_batch_seg_timings.argtypes = [vp, C.POINTER(d * 3)]
+    L.dnb_batch_device.argtypes = [vp]
+    L.dnb_host_stats.argtypes = [C.c_int, C.POINTER(d * 17), C.POINTER(C.c_uint64 * 4)]
+    L.dnb_host_phase_name.argtypes = [C.c_int]
+    L.dnb_host_phase_name.restype = C.c_char_p
     _lib = L
     return L
 

@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import Config, ReadDesc, ReadResult, EventT, DnbError
 
 MODEL_PORE, MODEL_UNLABELLED, MODEL_ANALOGUE = 0, 1, 2
+RESULT_DENSE, RESULT_COMPACT = 0, 1
 READ_OK, READ_QC_FAIL, READ_SCALE_FAIL, READ_UNDEFINED, READ_OVERFLOW = 0, 1, 2, 3, 4
 ERR_NEGATIVE_LOG = 6
 
@@ -37,6 +38,11 @@ class Read:
     dac: np.ndarray | None = None   # ... or int16 DAC with calibration
     dac_offset: float = 0.0
     dac_scale: float = 1.0
+    q2r_runs: np.ndarray | None = None   # queryToRef as runs (dtype _lib.Q2R_RUN_DTYPE) instead of the dense array
+
+    def with_runs(self):
+        """The same read with queryToRef given as runs (16 B per CIGAR operation over PCIe instead of 4 B per base)."""
+        return dataclasses.replace(self, queryToRef=None, q2r_runs=q2r_to_runs(self.queryToRef))
 
     @classmethod
     def from_synth(cls, sr, use_dac: bool = False):
@@ -65,6 +71,28 @@ class Normalised:
     maxGap: int
     cleaned_signal: np.ndarray | None = None
     cleaned_rank: np.ndarray | None = None
+
+
+def q2r_to_runs(q2r) -> np.ndarray:
+    """Dense queryToRef (int32, -1 = no entry) -> dnb_q2r_run array: maximal runs with stride 1 (aligned bases) or
+    stride 0 (the constant entries parseCigar gives insertions / soft clips, src/htsInterface.cpp:143-152)."""
+    q2r = np.asarray(q2r, dtype=np.int64)
+    n = q2r.size
+    runs = []
+    i = 0
+    while i < n:
+        if q2r[i] < 0:
+            i += 1
+            continue
+        j = i + 1
+        stride = 1
+        if j < n and q2r[j] == q2r[i]:
+            stride = 0
+        while j < n and q2r[j] >= 0 and q2r[j] == q2r[i] + stride * (j - i):
+            j += 1
+        runs.append((i, j - i, int(q2r[i]), stride))
+        i = j
+    return np.array(runs, dtype=_lib.Q2R_RUN_DTYPE) if runs else np.zeros(0, dtype=_lib.Q2R_RUN_DTYPE)
 
 
 def _as(ptr, n, dtype):
@@ -110,7 +138,14 @@ class Batch:
         _lib.check(self.ctx.L.dnb_batch_timings(self.h, C.byref(ms), C.byref(cnt)), "dnb_batch_timings")
         names = ("segmentation", "prep", "banded_dp", "backtrace", "theil_sen", "total", "host_step", "wall")
         cn = ("samples", "events", "kmers", "bands", "cells", "launches", "seg_serial_reads", "failed_reads")
-        return dict(zip(names, ms)), dict(zip(cn, (int(x) for x in cnt)))
+        out = dict(zip(names, ms))
+        seg = (C.c_double * 3)()
+        if self.ctx.L.dnb_batch_seg_timings(self.h, C.byref(seg)) == 0:
+            out.update(seg_checkpoint=seg[0], seg_tiles=seg[1], seg_rest=seg[2])
+        return out, dict(zip(cn, (int(x) for x in cnt)))
+
+    def device(self) -> int:
+        return int(self.ctx.L.dnb_batch_device(self.h))
 
     def io_bytes(self):
         """(host->device, device->host) bytes this batch moved over PCIe, counted by the library."""
@@ -122,9 +157,17 @@ class Batch:
         r = ReadResult()
         _lib.check(self.ctx.L.dnb_result(self.h, i, C.byref(r)), "dnb_result")
         ne = r.n_events
-        pairs = _as(r.align_pairs, 2 * r.n_align, np.uint32).reshape(-1, 2)
+        if self.ctx.cfg.result_format == RESULT_COMPACT:
+            # compact wire format: rebuild the dense arrays with the library's own expanders
+            starts = np.zeros(ne + 1 if ne else 0, dtype=np.uint32)
+            pairs = np.zeros((r.n_align, 2), dtype=np.uint32)
+            _lib.check(self.ctx.L.dnb_expand_events(C.byref(r), starts.ctypes.data), "dnb_expand_events")
+            _lib.check(self.ctx.L.dnb_expand_alignment(C.byref(r), pairs.ctypes.data), "dnb_expand_alignment")
+        else:
+            starts = _as(r.event_start, ne + 1 if ne else 0, np.uint32)
+            pairs = _as(r.align_pairs, 2 * r.n_align, np.uint32).reshape(-1, 2)
         return Normalised(
-            status=r.status, et_n=r.et_n, event_start=_as(r.event_start, ne + 1 if ne else 0, np.uint32),
+            status=r.status, et_n=r.et_n, event_start=starts,
             event_mean=_as(r.event_mean, ne, np.float32), eventAlignment=pairs, shift=r.shift, scale=r.scale,
             eventsPerBase=r.events_per_base, rough_shift=r.rough_shift, rough_scale=r.rough_scale,
             avg_log_emission=r.avg_log_emission, spanned=bool(r.spanned), maxGap=r.max_gap,
@@ -194,12 +237,19 @@ class Batch:
 class Context:
     """One per process and GPU (``dnb_ctx``).  Fails loudly without a CUDA device: there is no CPU path."""
 
-    def __init__(self, device: int = 0, keep_debug: bool = False, event_capacity_per_sample: float | None = None):
+    def __init__(self, device: int = 0, keep_debug: bool = False, event_capacity_per_sample: float | None = None,
+                 result_format: int = RESULT_DENSE, devices=None, workspace_bytes: int = 0):
         self.L = _lib.lib()
         cfg = Config()
         self.L.dnb_default_config(C.byref(cfg))
         cfg.device = device
         cfg.keep_debug = int(keep_debug)
+        cfg.result_format = result_format
+        cfg.workspace_bytes = workspace_bytes
+        if devices is not None:          # one context driving several GPUs (dnb_config.devices)
+            cfg.n_devices = len(devices)
+            for k, dv in enumerate(devices):
+                cfg.devices[k] = int(dv)
         if event_capacity_per_sample is not None:
             cfg.event_capacity_per_sample = event_capacity_per_sample
         self.cfg = cfg
@@ -241,11 +291,21 @@ class Context:
                 raw = np.ascontiguousarray(r.raw, dtype=np.float32)
                 keep.append(raw)
                 d.raw_pA, d.raw_dac, d.n_samples = raw.ctypes.data, None, raw.size
-            q2r = np.ascontiguousarray(r.queryToRef, dtype=np.int32)
-            keep.append(q2r)
             d.query, d.query_len = r.basecall, len(r.basecall)
             d.ref, d.ref_len = r.referenceSeqMappedTo, len(r.referenceSeqMappedTo)
-            d.query_to_ref = q2r.ctypes.data
+            if r.q2r_runs is not None:
+                runs = np.ascontiguousarray(r.q2r_runs, dtype=_lib.Q2R_RUN_DTYPE)
+                if runs.size == 0:      # a non-NULL pointer says "runs given", even when there are none
+                    runs = np.zeros(1, dtype=_lib.Q2R_RUN_DTYPE)
+                    d.n_q2r_runs = 0
+                else:
+                    d.n_q2r_runs = runs.size
+                keep.append(runs)
+                d.query_to_ref, d.q2r_runs = None, runs.ctypes.data
+            else:
+                q2r = np.ascontiguousarray(r.queryToRef, dtype=np.int32)
+                keep.append(q2r)
+                d.query_to_ref = q2r.ctypes.data
             keep.append((r.basecall, r.referenceSeqMappedTo))
         return arr, keep
 
@@ -438,6 +498,26 @@ class Context:
 
     def features_last_kernel_ms(self) -> float:
         return float(self.L.dnb_features_last_kernel_ms())
+
+
+def host_stats(reset: bool = False):
+    """dnb_host_stats: ({phase name: thread-seconds}, {counter: n}) of the batch pipeline's host side since the last reset."""
+    L = _lib.lib()
+    sec = (C.c_double * 17)()
+    cnt = (C.c_uint64 * 4)()
+    _lib.check(L.dnb_host_stats(int(reset), C.byref(sec), C.byref(cnt)), "dnb_host_stats")
+    names = [L.dnb_host_phase_name(i).decode() for i in range(17)]
+    return (dict(zip(names, (float(x) for x in sec))),
+            dict(zip(("batches", "direct_dma_batches", "cudaMalloc_calls", "cudaMallocHost_calls"), (int(x) for x in cnt))))
+
+
+def host_register(arr: np.ndarray):
+    """Page-lock a numpy buffer in place (dnb_host_register): dnb_submit then DMAs reads out of it directly."""
+    _lib.check(_lib.lib().dnb_host_register(arr.ctypes.data, arr.nbytes), "dnb_host_register")
+
+
+def host_unregister(arr: np.ndarray):
+    _lib.check(_lib.lib().dnb_host_unregister(arr.ctypes.data), "dnb_host_unregister")
 
 
 def dorado_slice(n_total: int, signal_length: int = 0, signal_trim: int = 0, signal_start_coord: int = 0,

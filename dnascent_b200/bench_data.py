@@ -24,6 +24,7 @@ class Workload:
     seq: np.ndarray          # uint8 ASCII, basecall == reference slice (exact-match reads), sequencing orientation
     seq_off: np.ndarray      # int64 [R+1]
     q2r: np.ndarray          # int32 arange(max read length): the dense queryToRef of every `{L}M` read
+    runs: np.ndarray = None  # dnb_q2r_run [R]: the same map as one run per read (what parseCigar gives for `{L}M`)
 
     @property
     def n_reads(self) -> int:
@@ -33,8 +34,9 @@ class Workload:
     def n_samples(self) -> np.ndarray:
         return np.diff(self.raw_off)
 
-    def descs(self, idx=None) -> np.ndarray:
-        """dnb_read_desc array (numpy mirror) for the reads `idx`, pointing into this workload's buffers."""
+    def descs(self, idx=None, dense_q2r: bool = False) -> np.ndarray:
+        """dnb_read_desc array (numpy mirror) for the reads `idx`, pointing into this workload's buffers.  queryToRef
+        goes as one run per read (16 B) unless dense_q2r asks for the int32-per-base form."""
         if idx is None:
             idx = np.arange(self.n_reads)
         idx = np.asarray(idx, dtype=np.int64)
@@ -49,7 +51,15 @@ class Workload:
         d["query_len"] = sl
         d["ref"] = d["query"]
         d["ref_len"] = sl
-        d["query_to_ref"] = self.q2r.ctypes.data
+        if dense_q2r:
+            d["query_to_ref"] = self.q2r.ctypes.data
+        else:
+            if self.runs is None:
+                self.runs = np.zeros(self.n_reads, dtype=_lib.Q2R_RUN_DTYPE)
+                self.runs["len"] = np.diff(self.seq_off)
+                self.runs["stride"] = 1
+            d["q2r_runs"] = self.runs.ctypes.data + self.runs.itemsize * idx
+            d["n_q2r_runs"] = 1
         return d
 
     def read(self, i: int):

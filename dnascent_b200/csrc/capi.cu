@@ -17,9 +17,10 @@
 //   inputs     signal, sequences, offsets: allocated by upload, resident until release   (~2.6 B/sample as int16)
 //   workspace  everything the kernels write: allocated by run, freed by drop_workspace    (~27 B/sample)
 //   results    pinned host copies handed out by dnb_result: allocated by fetch, from the context's pinned pool
-// Device memory comes from the stream-ordered pool (release threshold = infinity), so a freed workspace is what
-// the next batch's run gets back without touching the driver.
+// Device memory comes from the context's own cache of whole cudaMalloc blocks (DevCache below), so a freed workspace is
+// what the next batch's run gets back without touching the driver; dnb_config.workspace_bytes caps what stays cached.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -54,7 +55,28 @@ thread_local std::string g_last_error;
         if (_rc != DNB_OK) return _rc; \
     } while (0)
 
-// DNB_TRACE_HOST=1 prints the host wall time of every pipeline phase to stderr (diagnostics only)
+// Host-side phase accounting of the batch pipeline: every phase of upload / run / fetch adds its wall time (summed over
+// the calling threads) to a process-wide table that dnb_host_stats() reads; DNB_TRACE_HOST=1 additionally prints every
+// phase to stderr as it ends (diagnostics only).
+enum HostPhase {
+    PH_UP_GATE_PACK, PH_UP_SHAPES, PH_UP_PACK, PH_UP_GATE_H2D, PH_UP_ENQUEUE, PH_UP_WAIT,
+    PH_RUN_GATE, PH_RUN_ALLOC_A, PH_RUN_SEG_LAUNCH, PH_RUN_WAIT_A, PH_RUN_HOST, PH_RUN_ALLOC_B, PH_RUN_ENQUEUE_B, PH_RUN_WAIT_B,
+    PH_FETCH_GATE, PH_FETCH_SCALARS, PH_FETCH_WAIT, PH_N
+};
+const char *const kHostPhaseName[PH_N] = {
+    "upload: wait for the pack slot", "upload: shapes, order, tile tables", "upload: pack into pinned staging",
+    "upload: wait for the H2D slot", "upload: device alloc + enqueue copies", "upload: wait for H2D",
+    "run: wait for a compute slot", "run: workspace A + pinned counters", "run: segmentation scratch + launches",
+    "run: wait for phase A (GPU)", "run: transition constants, offsets (glibc)", "run: workspace B",
+    "run: enqueue phase B", "run: wait for phase B (GPU)",
+    "fetch: wait for the fetch slot", "fetch: per-read scalars (D2H + wait)", "fetch: compaction kernels + D2H + wait"};
+struct HostStats {
+    std::atomic<uint64_t> ns[PH_N];
+    std::atomic<uint64_t> n_cuda_malloc{0}, n_cuda_malloc_host{0}, n_batches{0}, n_direct{0};
+    HostStats() { for (auto &x : ns) x = 0; }
+};
+HostStats g_host_stats;
+
 struct HostTrace {
     bool on;
     double prev;
@@ -62,12 +84,12 @@ struct HostTrace {
     explicit HostTrace(const char *w) : who(w) {
         static const bool enabled = getenv("DNB_TRACE_HOST") != nullptr;
         on = enabled;
-        prev = on ? omp_get_wtime() : 0.0;
+        prev = omp_get_wtime();
     }
-    void tick(const char *what) {
-        if (!on) return;
+    void tick(int phase) {
         const double now = omp_get_wtime();
-        fprintf(stderr, "[dnb host] %-6s %-28s %8.2f ms  (t=%.3f)\n", who, what, 1e3 * (now - prev), now);
+        g_host_stats.ns[phase].fetch_add((uint64_t)(1e9 * (now - prev)), std::memory_order_relaxed);
+        if (on) fprintf(stderr, "[dnb host] %-6s %-44s %8.2f ms  (t=%.3f)\n", who, kHostPhaseName[phase], 1e3 * (now - prev), now);
         prev = now;
     }
 };
@@ -96,6 +118,7 @@ struct PinnedPool {
         void *p = nullptr;
         static const bool trace = getenv("DNB_TRACE_HOST") != nullptr;
         const double t0 = trace ? omp_get_wtime() : 0.0;
+        g_host_stats.n_cuda_malloc_host++;
         if (cudaMallocHost(&p, sz) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         if (trace) fprintf(stderr, "[dnb host] cudaMallocHost %.1f MB took %.2f ms (t=%.3f)\n", sz / 1e6, 1e3 * (omp_get_wtime() - t0), omp_get_wtime());
         blocks.push_back({p, sz, true});
@@ -104,6 +127,15 @@ struct PinnedPool {
     void release(void *p) {
         std::lock_guard<std::mutex> lk(mu);
         for (auto &b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lk(mu);
+        size_t k = 0;
+        for (auto &b : blocks) {
+            if (b.used) blocks[k++] = b;
+            else cudaFreeHost(b.p);
+        }
+        blocks.resize(k);
     }
     void destroy() {
         for (auto &b : blocks) cudaFreeHost(b.p);
@@ -120,6 +152,7 @@ struct DevCache {
     struct Block { void *p; size_t n; bool used; };
     std::vector<Block> blocks;
     std::mutex mu;
+    size_t idle_cap = 0;   // dnb_config.workspace_bytes: idle bytes kept cached (0 = no cap)
     static size_t grid(size_t n) {
         size_t g = (size_t)2 << 20;
         while (g * 16 < n) g <<= 1;
@@ -129,13 +162,18 @@ struct DevCache {
         n = grid(n ? n : 1);
         *err = cudaSuccess;
         {
+            // best fit among the idle blocks of at most 1.25x the (grid-rounded) size: bins of similar size reuse each
+            // other's blocks instead of going to the driver (cudaMalloc stalls every stream of the device)
             std::lock_guard<std::mutex> lk(mu);
+            Block *best = nullptr;
             for (auto &b : blocks)
-                if (!b.used && b.n == n) { b.used = true; return b.p; }
+                if (!b.used && b.n >= n && b.n <= n + n / 4 && (!best || b.n < best->n)) best = &b;
+            if (best) { best->used = true; return best->p; }
         }
         void *p = nullptr;
         static const bool trace = getenv("DNB_TRACE_HOST") != nullptr;
         const double t0 = trace ? omp_get_wtime() : 0.0;
+        g_host_stats.n_cuda_malloc++;
         cudaError_t e = cudaMalloc(&p, n);
         if (trace) fprintf(stderr, "[dnb host] cudaMalloc %.1f MB took %.2f ms (t=%.3f)\n", n / 1e6, 1e3 * (omp_get_wtime() - t0), omp_get_wtime());
         if (e == cudaErrorMemoryAllocation) {   // give cached-but-idle blocks back and retry once
@@ -150,7 +188,18 @@ struct DevCache {
     }
     void release(void *p) {
         std::lock_guard<std::mutex> lk(mu);
-        for (auto &b : blocks) if (b.p == p) { b.used = false; return; }
+        for (auto &b : blocks) if (b.p == p) { b.used = false; break; }
+        if (!idle_cap) return;
+        // another user of the same GPU (the reference's TensorFlow session) cannot ask us to trim: keep at most
+        // idle_cap bytes of idle blocks, largest ones go first
+        for (;;) {
+            size_t idle = 0; int big = -1;
+            for (size_t i = 0; i < blocks.size(); i++)
+                if (!blocks[i].used) { idle += blocks[i].n; if (big < 0 || blocks[i].n > blocks[big].n) big = (int)i; }
+            if (idle <= idle_cap || big < 0) return;
+            cudaFree(blocks[big].p);
+            blocks.erase(blocks.begin() + big);
+        }
     }
     void trim() {
         std::lock_guard<std::mutex> lk(mu);
@@ -187,7 +236,8 @@ struct StageHold {
 // streams and events are recycled: creating them per batch cost ~30 ms per dnb_submit under load (driver lock)
 struct StreamSet {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};
+    cudaEvent_t sync_ev = nullptr;   // cudaEventBlockingSync: a waiting host thread sleeps instead of spinning
 };
 struct StreamPool {
     std::vector<StreamSet> idle;
@@ -201,6 +251,7 @@ struct StreamPool {
         if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
         for (auto &e : s.ev)
             if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaEventCreateWithFlags(&s.sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
         *out = s;
         return true;
     }
@@ -211,6 +262,7 @@ struct StreamPool {
     void destroy() {
         for (auto &s : idle) {
             for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+            if (s.sync_ev) cudaEventDestroy(s.sync_ev);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
         idle.clear();
@@ -229,6 +281,10 @@ struct dnb_ctx {
     // compute, then all fetch) and the GPU idles during the copy phases.
     StageGate gate_pack{1}, gate_h2d{1}, gate_compute{2}, gate_fetch{1};
     StreamPool streams;
+    cudaMemPool_t pool = nullptr;        // stream-ordered scratch of the non-batch entry points (private: no global side effect)
+    // n_devices > 1: this context is the front of a set; peers[k] drives cfg.devices[k + 1]
+    std::vector<dnb_ctx *> peers;
+    std::atomic<uint64_t> inflight{0};   // samples submitted and not yet released (the dealing rule's load measure)
 };
 
 namespace {
@@ -250,6 +306,7 @@ struct Work {
     unsigned long long *cells;   // [3]: DP cells filled, warp cycles in the band fill, warp cycles in the backtrace
     uint32_t *al_rev, *n_align, *cl_rank, *n_cleaned, *out_pairs, *cev_start;
     float *cev_mean;
+    uint32_t *n_long;            // events of >= 255 samples per read (escapes of the compact event coding)
     double *cl_signal, *avg, *shift, *scale;
     int *spanned, *max_gap;
 };
@@ -264,6 +321,9 @@ struct HostRes {
     double *cl_signal;
     uint64_t *et_start;
     float *et_length, *et_mean, *et_stdv;
+    // DNB_RESULT_COMPACT
+    uint32_t *n_long, *esc, *first_ev, *first_pair, *bad_steps;
+    uint8_t *len8, *steps;
 };
 
 }  // namespace
@@ -285,15 +345,17 @@ struct Stage2 {
 struct dnb_batch {
     dnb_ctx *ctx = nullptr;
     size_t R = 0;
+    uint64_t load = 0;           // what this batch added to ctx->inflight (multi-device dealing)
     cudaStream_t stream = nullptr;
     bool want_table = false;     // dnb_detect_events: keep the full scrappie table, segmentation only
     bool uploaded = false, ran = false, fetched = false, have_work = false;
     // ---- host-side shapes ----
-    std::vector<uint64_t> raw_off, q_off, r_off, ev_off, cev_off, band_off, al_off, cl_off, out_off, ck_off;
+    std::vector<uint64_t> raw_off, q_off, r_off, ev_off, cev_off, band_off, al_off, cl_off, out_off, ck_off, esc_off, step_off;
+    bool compact = false, have_dev_pairs = false;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;   // PCIe payload of the last upload / fetch
     std::vector<uint32_t> n_samples, order, qlen, rlen, tile_off, tile_read;
     std::vector<double> lp;
-    bool i16 = false;
+    bool i16 = false, direct_dma = false;
     uint64_t tot_raw = 0, tot_q = 0, tot_r = 0, tot_ev = 0, tot_bands = 0, tot_al = 0, tot_cl = 0, tot_out = 0;
     // ---- device: resident inputs ----
     void *d_raw = nullptr;
@@ -305,8 +367,10 @@ struct dnb_batch {
     Work w = {};
     HostRes h = {};
     // ---- timings ----
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};     // [8], [9]: after the checkpoint / tile kernel of the segmentation
+    cudaEvent_t sync_ev = nullptr;
     double ms[8] = {};
+    double seg_ms[3] = {};       // checkpoint (or scan), tiles, stitch + events + serial redo
     uint64_t counts[8] = {};
     unsigned long long h_cells[3] = {};
     std::vector<void *> input_allocs, work_allocs, res_allocs;
@@ -314,6 +378,18 @@ struct dnb_batch {
 };
 
 namespace {
+
+// Wait for everything enqueued on the batch's stream.  Several batches are in flight from several host threads (and
+// under torchrun several ranks share the box's cores), so a waiting thread must sleep: cudaStreamSynchronize spins
+// by default and N waiting threads would take N cores away from the threads that still have host work.
+// DNB_SPIN_SYNC=1 restores the spinning wait (lowest latency for a single caller).
+cudaError_t wait_stream(dnb_batch *b) {
+    static const bool spin = getenv("DNB_SPIN_SYNC") != nullptr && getenv("DNB_SPIN_SYNC")[0] == '1';
+    if (spin || !b->sync_ev) return cudaStreamSynchronize(b->stream);
+    cudaError_t e = cudaEventRecord(b->sync_ev, b->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(b->sync_ev);
+}
 
 template <class T>
 int dev_alloc(dnb_batch *b, std::vector<void *> &owner, T **p, size_t n) {
@@ -389,6 +465,7 @@ void drop_work(dnb_batch *b) {
     b->work_allocs.clear();
     b->w = Work{};
     b->have_work = false;
+    b->have_dev_pairs = false;
 }
 void drop_results(dnb_batch *b) {
     for (void *p : b->res_allocs) b->ctx->pinned.release(p);
@@ -400,17 +477,54 @@ void drop_results(dnb_batch *b) {
 
 void free_batch(dnb_batch *b) {
     if (!b) return;
-    if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->stream) wait_stream(b);
     drop_work(b);
     drop_results(b);
     for (void *p : b->input_allocs) b->ctx->dev.release(p);
+    b->ctx->inflight.fetch_sub(b->load, std::memory_order_relaxed);
     if (b->stream) {
         StreamSet ss;
         ss.stream = b->stream;
-        for (int i = 0; i < 8; i++) ss.ev[i] = b->ev[i];
+        for (int i = 0; i < 10; i++) ss.ev[i] = b->ev[i];
+        ss.sync_ev = b->sync_ev;
         b->ctx->streams.release(ss);
     }
     delete b;
+}
+
+// ---- caller memory known to be page-locked: ranges registered / allocated through this library ----------------
+struct HostRegistry {
+    std::mutex mu;
+    std::vector<std::pair<uintptr_t, uintptr_t>> ranges;   // [lo, hi)
+    void add(const void *p, size_t n) {
+        std::lock_guard<std::mutex> lk(mu);
+        ranges.emplace_back((uintptr_t)p, (uintptr_t)p + n);
+    }
+    bool remove(const void *p) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < ranges.size(); i++)
+            if (ranges[i].first == (uintptr_t)p) { ranges.erase(ranges.begin() + i); return true; }
+        return false;
+    }
+    bool covers(const void *p, size_t n) {
+        const uintptr_t lo = (uintptr_t)p, hi = lo + n;
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &r : ranges) if (lo >= r.first && hi <= r.second) return true;
+        return false;
+    }
+};
+HostRegistry g_host_reg;
+
+// true when [p, p+n) can be the source of an asynchronous DMA: registered here, or page-locked by the caller's own
+// cudaHostAlloc / cudaHostRegister (asked from the driver: first and last byte)
+bool is_page_locked(const void *p, size_t n) {
+    if (n == 0) return true;
+    if (g_host_reg.covers(p, n)) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost) return false;
+    if (cudaPointerGetAttributes(&a, (const char *)p + n - 1) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, dnb_batch **out, bool gated = false) {
@@ -428,8 +542,9 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
         void leave() { if (g) g->leave(); g = nullptr; }
         ~Gate() { leave(); }
     } gate;
-    if (gated) gate.enter(&ctx->gate_pack);
     HostTrace ht("upload");
+    if (gated) gate.enter(&ctx->gate_pack);
+    ht.tick(PH_UP_GATE_PACK);
     dnb_batch *b = new dnb_batch();
     b->ctx = ctx;
     b->R = R;
@@ -439,24 +554,27 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
         StreamSet ss;
         if (!ctx->streams.acquire(&ss)) { g_last_error = "stream/event creation failed"; delete b; return DNB_ERR_CUDA; }
         b->stream = ss.stream;
-        for (int i = 0; i < 8; i++) b->ev[i] = ss.ev[i];
+        for (int i = 0; i < 10; i++) b->ev[i] = ss.ev[i];
+        b->sync_ev = ss.sync_ev;
     }
 
     // ---- shapes ----
     b->raw_off.resize(R + 1); b->q_off.resize(R + 1); b->r_off.resize(R + 1); b->ev_off.resize(R + 1);
     b->n_samples.resize(R); b->qlen.resize(R); b->rlen.resize(R); b->order.resize(R);
-    bool any_i16 = false, any_f32 = false;
-    uint64_t ro = 0, qo = 0, fo = 0, eo = 0;
+    bool any_i16 = false, any_f32 = false, any_dense = false, any_runs = false, same_seq = !want_table;
+    uint64_t ro = 0, qo = 0, fo = 0, eo = 0, n_runs = 0;
     const double cap_per_sample = ctx->cfg.event_capacity_per_sample > 0 ? ctx->cfg.event_capacity_per_sample : 0.4;
     for (size_t i = 0; i < R; i++) {
         const dnb_read_desc &d = reads[i];
         if ((!d.raw_pA && !d.raw_dac) || d.n_samples == 0 || d.n_samples >= (1ull << 31) || !d.query || !d.ref ||
-            (!want_table && !d.query_to_ref)) {
+            (!want_table && !d.query_to_ref && !d.q2r_runs)) {
             free_batch(b);
             g_last_error = "read descriptor " + std::to_string(i) + " is incomplete";
             return DNB_ERR_ARG;
         }
         (d.raw_pA ? any_f32 : any_i16) = true;
+        if (!want_table) { (d.query_to_ref ? any_dense : any_runs) = true; n_runs += d.query_to_ref ? 0 : d.n_q2r_runs; }
+        same_seq = same_seq && d.ref == d.query && d.ref_len == d.query_len;
         b->raw_off[i] = ro; b->q_off[i] = qo; b->r_off[i] = fo; b->ev_off[i] = eo;
         b->n_samples[i] = (uint32_t)d.n_samples; b->qlen[i] = d.query_len; b->rlen[i] = d.ref_len;
         ro += (d.n_samples + 31) & ~31ull;                 // 128-byte aligned read starts (float4 loads)
@@ -464,6 +582,7 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
         eo += (uint64_t)(cap_per_sample * (double)d.n_samples) + 16;
     }
     if (any_i16 && any_f32) { free_batch(b); g_last_error = "mixing raw_pA and raw_dac reads in one batch"; return DNB_ERR_ARG; }
+    if (any_dense && any_runs) { free_batch(b); g_last_error = "mixing query_to_ref and q2r_runs reads in one batch"; return DNB_ERR_ARG; }
     b->i16 = any_i16;
     b->raw_off[R] = ro; b->q_off[R] = qo; b->r_off[R] = fo; b->ev_off[R] = eo;
     b->tot_raw = ro; b->tot_q = qo; b->tot_r = fo; b->tot_ev = eo;
@@ -487,43 +606,76 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
             for (uint32_t g = b->tile_off[i]; g < b->tile_off[i + 1]; g++) b->tile_read[g] = (uint32_t)i;
     }
 
-    ht.tick("shapes");
-    // ---- pinned staging + device inputs ----
+    // ---- zero-staging ingest: is every read's signal in page-locked caller memory? ----
     const size_t esz = b->i16 ? 2 : 4;
+    static const bool no_direct = getenv("DNB_NO_DIRECT_DMA") != nullptr && getenv("DNB_NO_DIRECT_DMA")[0] == '1';
+    bool direct = !no_direct && R > 0;
+    for (size_t i = 0; direct && i < R; i++)
+        direct = is_page_locked(b->i16 ? (const void *)reads[i].raw_dac : (const void *)reads[i].raw_pA, reads[i].n_samples * esz);
+    b->direct_dma = direct;
+    ht.tick(PH_UP_SHAPES);
+
+    // ---- pinned staging + device inputs ----
     int rc = DNB_OK;
-    uint8_t *h_raw = (uint8_t *)ctx->pinned.acquire(ro * esz);
-    char *h_q = (char *)ctx->pinned.acquire(qo), *h_r = (char *)ctx->pinned.acquire(fo);
-    int32_t *h_q2r = (int32_t *)ctx->pinned.acquire(qo * 4);
+    if (same_seq) { fo = 0; b->r_off = b->q_off; b->tot_r = qo; }      // ref IS the query: one copy serves both
+    uint8_t *h_raw = direct ? nullptr : (uint8_t *)ctx->pinned.acquire(ro * esz);
+    char *h_q = (char *)ctx->pinned.acquire(qo), *h_r = same_seq ? nullptr : (char *)ctx->pinned.acquire(fo);
+    int32_t *h_q2r = any_dense ? (int32_t *)ctx->pinned.acquire(qo * 4) : nullptr;
+    // per-run tables of the compact queryToRef: the run, its read's query offset and length
+    dnb_q2r_run *h_runs = any_runs ? (dnb_q2r_run *)ctx->pinned.acquire(n_runs * (sizeof(dnb_q2r_run) + 8 + 4) + 64) : nullptr;
+    uint64_t *h_run_base = h_runs ? (uint64_t *)(h_runs + n_runs) : nullptr;
+    uint32_t *h_run_len = h_runs ? (uint32_t *)(h_run_base + n_runs) : nullptr;
     // per-read tables travel in one pinned block (pageable sources would make every copy synchronous)
     const size_t nt = b->tile_read.size();
     const size_t meta_bytes = 8 * (R + 1) * 5 + 4 * R * 2 + 4 * (R + 1) + 4 * nt + 4 * R * 2 + 256;
     uint8_t *h_meta = (uint8_t *)ctx->pinned.acquire(meta_bytes);
     auto release_staging = [&]() {
-        for (void *p : {(void *)h_raw, (void *)h_q, (void *)h_r, (void *)h_q2r, (void *)h_meta})
+        for (void *p : {(void *)h_raw, (void *)h_q, (void *)h_r, (void *)h_q2r, (void *)h_meta, (void *)h_runs})
             if (p) ctx->pinned.release(p);
     };
-#define TRYF(x) do { rc = (x); if (rc != DNB_OK) { cudaStreamSynchronize(b->stream); release_staging(); free_batch(b); return rc; } } while (0)
-    if (!h_raw || !h_q || !h_r || !h_q2r || !h_meta) { g_last_error = "pinned staging allocation failed"; TRYF(DNB_ERR_NOMEM); }
+#define TRYF(x) do { rc = (x); if (rc != DNB_OK) { wait_stream(b); release_staging(); free_batch(b); return rc; } } while (0)
+    if ((!direct && !h_raw) || !h_q || (!same_seq && !h_r) || (any_dense && !h_q2r) || (any_runs && !h_runs) || !h_meta) {
+        g_last_error = "pinned staging allocation failed"; TRYF(DNB_ERR_NOMEM);
+    }
     float *h_doff = (float *)h_meta, *h_dscl = h_doff + R;
     size_t meta_used = 8 * R;
+    std::vector<uint64_t> run_off;
+    if (any_runs) {
+        run_off.resize(R + 1);
+        uint64_t k = 0;
+        for (size_t i = 0; i < R; i++) { run_off[i] = k; k += reads[i].n_q2r_runs; }
+        run_off[R] = k;
+    }
 #pragma omp parallel for schedule(dynamic, 16)
     for (size_t i = 0; i < R; i++) {
         const dnb_read_desc &d = reads[i];
-        uint8_t *dst = h_raw + b->raw_off[i] * esz;
-        const size_t padded = (size_t)(b->raw_off[i + 1] - b->raw_off[i]);
-        if (b->i16) memcpy(dst, d.raw_dac, d.n_samples * 2); else memcpy(dst, d.raw_pA, d.n_samples * 4);
-        memset(dst + d.n_samples * esz, 0, (padded - d.n_samples) * esz);
+        if (!direct) {
+            uint8_t *dst = h_raw + b->raw_off[i] * esz;
+            const size_t padded = (size_t)(b->raw_off[i + 1] - b->raw_off[i]);
+            if (b->i16) memcpy(dst, d.raw_dac, d.n_samples * 2); else memcpy(dst, d.raw_pA, d.n_samples * 4);
+            memset(dst + d.n_samples * esz, 0, (padded - d.n_samples) * esz);
+        }
         memcpy(h_q + b->q_off[i], d.query, d.query_len);
-        memcpy(h_r + b->r_off[i], d.ref, d.ref_len);
+        if (!same_seq) memcpy(h_r + b->r_off[i], d.ref, d.ref_len);
         if (d.query_to_ref) memcpy(h_q2r + b->q_off[i], d.query_to_ref, (size_t)d.query_len * 4);
+        else if (any_runs)
+            for (uint32_t j = 0; j < d.n_q2r_runs; j++) {
+                h_runs[run_off[i] + j] = d.q2r_runs[j];
+                h_run_base[run_off[i] + j] = b->q_off[i];
+                h_run_len[run_off[i] + j] = d.query_len;
+            }
         h_doff[i] = d.dac_offset; h_dscl[i] = d.dac_scale;
     }
-    ht.tick("pack into pinned staging");
+    ht.tick(PH_UP_PACK);
     if (gated) gate.enter(&ctx->gate_h2d);
+    ht.tick(PH_UP_GATE_H2D);
     TRYF(ialloc(b, (uint8_t **)&b->d_raw, ro * esz));
-    TRYF(ialloc(b, &b->d_query, qo)); TRYF(ialloc(b, &b->d_ref, fo)); TRYF(ialloc(b, &b->d_q2r, qo));
+    TRYF(ialloc(b, &b->d_query, qo));
+    if (same_seq) b->d_ref = b->d_query; else TRYF(ialloc(b, &b->d_ref, fo));
+    if (!want_table) TRYF(ialloc(b, &b->d_q2r, qo));
     TRYF(ialloc(b, &b->d_dac_off, R)); TRYF(ialloc(b, &b->d_dac_scl, R));
-    TRYF(ialloc(b, &b->d_raw_off, R + 1)); TRYF(ialloc(b, &b->d_q_off, R + 1)); TRYF(ialloc(b, &b->d_r_off, R + 1));
+    TRYF(ialloc(b, &b->d_raw_off, R + 1)); TRYF(ialloc(b, &b->d_q_off, R + 1));
+    if (same_seq) b->d_r_off = b->d_q_off; else TRYF(ialloc(b, &b->d_r_off, R + 1));
     TRYF(ialloc(b, &b->d_ev_off, R + 1)); TRYF(ialloc(b, &b->d_n_samples, R)); TRYF(ialloc(b, &b->d_order, R));
     TRYF(ialloc(b, &b->d_tile_off, R + 1)); TRYF(ialloc(b, &b->d_tile_read, nt));
     TRYF(ialloc(b, &b->d_ck_off, R + 1));
@@ -542,19 +694,44 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
         meta_used += bytes;
         return rc2;
     };
-    TRYF(send(b->d_raw, h_raw, ro * esz));
-    TRYF(send(b->d_query, h_q, qo)); TRYF(send(b->d_ref, h_r, fo)); TRYF(send(b->d_q2r, h_q2r, qo * 4));
+    // small tables first: the kernels that expand / pad need them, and the long signal copy then has the bus to itself
     TRYF(send(b->d_dac_off, h_doff, R * 4)); TRYF(send(b->d_dac_scl, h_dscl, R * 4));
     TRYF(send_table(b->d_raw_off, b->raw_off.data(), 8 * (R + 1))); TRYF(send_table(b->d_q_off, b->q_off.data(), 8 * (R + 1)));
-    TRYF(send_table(b->d_r_off, b->r_off.data(), 8 * (R + 1))); TRYF(send_table(b->d_ev_off, b->ev_off.data(), 8 * (R + 1)));
+    if (!same_seq) TRYF(send_table(b->d_r_off, b->r_off.data(), 8 * (R + 1)));
+    TRYF(send_table(b->d_ev_off, b->ev_off.data(), 8 * (R + 1)));
     TRYF(send_table(b->d_n_samples, b->n_samples.data(), 4 * R)); TRYF(send_table(b->d_order, b->order.data(), 4 * R));
     TRYF(send_table(b->d_tile_off, b->tile_off.data(), 4 * (R + 1)));
     TRYF(send_table(b->d_tile_read, b->tile_read.data(), 4 * nt));
     TRYF(send_table(b->d_ck_off, b->ck_off.data(), 8 * (R + 1)));
+    TRYF(send(b->d_query, h_q, qo));
+    if (!same_seq) TRYF(send(b->d_ref, h_r, fo));
+    if (any_dense) TRYF(send(b->d_q2r, h_q2r, qo * 4));
+    else if (!want_table) {
+        // compact queryToRef: 16 B per run over PCIe, expanded to the dense array the backtrace reads in HBM
+        dnb_q2r_run *d_runs = nullptr; uint64_t *d_run_base = nullptr; uint32_t *d_run_len = nullptr;
+        TRYF(ialloc(b, &d_runs, n_runs)); TRYF(ialloc(b, &d_run_base, n_runs)); TRYF(ialloc(b, &d_run_len, n_runs));
+        if (qo) { cudaError_t em = cudaMemsetAsync(b->d_q2r, 0xFF, qo * 4, b->stream); if (em != cudaSuccess) { g_last_error = cudaGetErrorString(em); TRYF(DNB_ERR_CUDA); } }
+        TRYF(send(d_runs, h_runs, n_runs * sizeof(dnb_q2r_run)));
+        TRYF(send(d_run_base, h_run_base, n_runs * 8)); TRYF(send(d_run_len, h_run_len, n_runs * 4));
+        dnb_launch_expand_q2r(d_runs, d_run_base, d_run_len, n_runs, b->d_q2r, b->stream);
+    }
+    if (direct) {
+        // one DMA per read, from where the caller has it to its padded slot; nothing touches the samples on the host
+        uint8_t *base = (uint8_t *)b->d_raw;
+        for (size_t i = 0; i < R; i++)
+            TRYF(send(base + b->raw_off[i] * esz, b->i16 ? (const void *)reads[i].raw_dac : (const void *)reads[i].raw_pA,
+                      (size_t)reads[i].n_samples * esz));
+        dnb_launch_zero_padding(make_view(b), (uint32_t)esz, b->stream);
+    } else {
+        TRYF(send(b->d_raw, h_raw, ro * esz));
+    }
     b->h2d_bytes = sent;
-    ht.tick("alloc + enqueue H2D");
-    e = cudaStreamSynchronize(b->stream);
-    ht.tick("H2D wait");
+    ht.tick(PH_UP_ENQUEUE);
+    e = wait_stream(b);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    ht.tick(PH_UP_WAIT);
+    g_host_stats.n_batches++;
+    if (direct) g_host_stats.n_direct++;
     release_staging();
     if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); free_batch(b); return DNB_ERR_CUDA; }
     b->uploaded = true;
@@ -582,6 +759,13 @@ int alloc_work_a(dnb_batch *b) {
         TRY(walloc(b, &w.cells, 3));
         TRY(walloc(b, &w.n_align, R)); TRY(walloc(b, &w.n_cleaned, R)); TRY(walloc(b, &w.avg, R));
         TRY(walloc(b, &w.shift, R)); TRY(walloc(b, &w.scale, R)); TRY(walloc(b, &w.spanned, R)); TRY(walloc(b, &w.max_gap, R));
+        TRY(walloc(b, &w.n_long, R));
+        // reads that stop early (UNDEFINED, OVERFLOW) never write their scalars and the blocks are recycled: hand out
+        // zeros, not another batch's values
+        for (void *p : {(void *)w.rough_shift, (void *)w.rough_scale, (void *)w.shift, (void *)w.scale, (void *)w.avg})
+            CK(cudaMemsetAsync(p, 0, R * 8, b->stream));
+        for (void *p : {(void *)w.n_align, (void *)w.n_cleaned, (void *)w.spanned, (void *)w.max_gap, (void *)w.n_long})
+            CK(cudaMemsetAsync(p, 0, R * 4, b->stream));
     }
     b->have_work = true;
     return DNB_OK;
@@ -595,14 +779,14 @@ int run(dnb_batch *b) {
     cudaStream_t s = b->stream;
     const double wall0 = omp_get_wtime();
     HostTrace ht("run");
-    auto tick = [&](const char *what) { ht.tick(what); };
+    auto tick = [&](int phase) { ht.tick(phase); };
     drop_work(b);
     drop_results(b);
     TRY(alloc_work_a(b));
     // the few per-read counters the host reads in the middle of the pipeline
     TRY(ralloc(b, &b->h.n_events, R)); TRY(ralloc(b, &b->h.et_n, R)); TRY(ralloc(b, &b->h.status, R));
     TRY(ralloc(b, &b->h.redo, R));
-    tick("drop + alloc A + pinned");
+    tick(PH_RUN_ALLOC_A);
     DnbBatchView v = make_view(b);
     DnbDetector det = {ctx->cfg.window_length1, ctx->cfg.window_length2, ctx->cfg.threshold1, ctx->cfg.threshold2,
                        ctx->cfg.peak_height};
@@ -611,7 +795,7 @@ int run(dnb_batch *b) {
     std::vector<void *> seg_scratch;
     struct ScratchGuard {
         dnb_batch *b; std::vector<void *> &v;
-        ~ScratchGuard() { if (!v.empty()) { cudaStreamSynchronize(b->stream); for (void *p : v) b->ctx->dev.release(p); v.clear(); } }
+        ~ScratchGuard() { if (!v.empty()) { wait_stream(b); for (void *p : v) b->ctx->dev.release(p); v.clear(); } }
     } scratch_guard{b, seg_scratch};
     CK(cudaEventRecord(b->ev[0], s));
     if (b->want_table) {
@@ -619,7 +803,7 @@ int run(dnb_batch *b) {
     } else {
         // per-run scratch of the tiled segmentation (back in the pool before the DP workspace is taken)
         const size_t nt = b->tile_off[R], nck = b->ck_off[R];
-        uint8_t *scratch[10] = {};
+        uint8_t *scratch[11] = {};
         auto sal = [&](int i, size_t bytes) -> int { return dev_alloc(b, seg_scratch, &scratch[i], bytes); };
         TRY(sal(0, nck * 8)); TRY(sal(1, nck * 8)); TRY(sal(2, nt * DNB_SEG_PEAK_CAP * 4)); TRY(sal(3, nt * DNB_SEG_PEAK_CAP * 8));
         TRY(sal(4, nt * 4)); TRY(sal(5, nt * DNB_SEG_BOUNDARY_BYTES)); TRY(sal(6, nt * DNB_SEG_BOUNDARY_BYTES));
@@ -632,15 +816,18 @@ int run(dnb_batch *b) {
         t.pk_sum = (double *)scratch[3]; t.pk_count = (uint32_t *)scratch[4]; t.b_start = (SegBoundary *)scratch[5];
         t.b_end = (SegBoundary *)scratch[6]; t.tile_prefix = (uint32_t *)scratch[7]; t.tile_prev_pos = (uint32_t *)scratch[8];
         t.tile_prev_sum = (double *)scratch[9];
-        dnb_launch_segmentation_tiled(v, det, t, s); launches += 5;
-        tick("seg scratch + launches");
+        if (dnb_seg_parity_scan_enabled()) { TRY(sal(10, dnb_seg_parity_scan_scratch_bytes(t, (uint32_t)R))); t.scan_scratch = scratch[10]; }
+        dnb_launch_segmentation_tiled(v, det, t, s, b->ev[8], b->ev[9]); launches += 5;
+        tick(PH_RUN_SEG_LAUNCH);
     }
     CK(cudaEventRecord(b->ev[1], s));
+    b->compact = ctx->cfg.result_format == DNB_RESULT_COMPACT && !b->want_table;
+    if (b->compact) { dnb_launch_count_long_events(v, b->w.n_long, s); launches++; }
     TRY(d2h(b, b->h.n_events, b->w.n_events, R));
     TRY(d2h(b, b->h.et_n, b->w.et_n, R));
     if (b->want_table) {
         TRY(d2h(b, b->h.status, b->w.status, R));
-        CK(cudaStreamSynchronize(s));
+        CK(wait_stream(b));
         CK(cudaGetLastError());
         b->ran = true;
         return DNB_OK;
@@ -651,12 +838,12 @@ int run(dnb_batch *b) {
     dnb_launch_quantile_scaling(v, pore, b->w.rank_ref, b->w.rough_shift, b->w.rough_scale, s); launches++;
     dnb_launch_scale_events(v, b->w.rough_shift, b->w.rough_scale, b->w.x_e, s); launches++;
     CK(cudaEventRecord(b->ev[2], s));
-    CK(cudaStreamSynchronize(s));   // n_events is on the host (its copy was enqueued before the prep kernels)
+    CK(wait_stream(b));   // n_events is on the host (its copy was enqueued before the prep kernels)
     CK(cudaGetLastError());
     for (void *p : seg_scratch) ctx->dev.release(p);
     seg_scratch.clear();
     const double wall_gap0 = omp_get_wtime();
-    tick("phase A sync (GPU wait)");
+    tick(PH_RUN_WAIT_A);
 
     // ---- host step: transition constants with glibc (event_handling.cpp:174-183) + workspace shapes ----
     b->lp.resize(4 * R);
@@ -681,11 +868,11 @@ int run(dnb_batch *b) {
     b->band_off[R] = bo; b->al_off[R] = ao; b->cl_off[R] = co;
     b->tot_bands = bo; b->tot_al = ao; b->tot_cl = co;
     Work &w = b->w;
-    tick("host loop (lp, offsets)");
+    tick(PH_RUN_HOST);
     TRY(walloc(b, &w.trace, bo * DNB_TRACE_ROW + 64));
     TRY(walloc(b, &w.moves, (bo >> 5) + R + 2)); TRY(walloc(b, &w.rcum, (bo >> 5) + R + 2));
     TRY(walloc(b, &w.al_rev, 2 * ao)); TRY(walloc(b, &w.cl_signal, co)); TRY(walloc(b, &w.cl_rank, co));
-    tick("alloc B");
+    tick(PH_RUN_ALLOC_B);
     TRY(h2d(b, w.lp, b->lp.data(), 4 * R));
     TRY(h2d(b, w.band_off, b->band_off.data(), R + 1));
     TRY(h2d(b, w.al_off, b->al_off.data(), R + 1));
@@ -707,7 +894,7 @@ int run(dnb_batch *b) {
     static const bool split_align = getenv("DNB_SPLIT_ALIGN") != nullptr;
     CK(cudaEventRecord(b->ev[3], s));
     const double wall_gap1 = omp_get_wtime();
-    tick("h2d B + memset");
+    tick(PH_RUN_ENQUEUE_B);
     if (split_align) {
         dnb_launch_align(v, bt, 1, s); launches++;
         CK(cudaEventRecord(b->ev[4], s));
@@ -723,9 +910,10 @@ int run(dnb_batch *b) {
     dnb_launch_theil_sen(v, pore, ts, s); launches++;
     CK(cudaEventRecord(b->ev[6], s));
     CK(cudaMemcpyAsync(b->h_cells, w.cells, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    TRY(d2h(b, b->h.status, w.status, R));     // the outcome of every read is known to the host when run() returns
+    CK(wait_stream(b));
     CK(cudaGetLastError());
-    tick("phase B launches + sync");
+    tick(PH_RUN_WAIT_B);
     float t;
     cudaEventElapsedTime(&t, b->ev[0], b->ev[1]); b->ms[0] = t;
     cudaEventElapsedTime(&t, b->ev[1], b->ev[2]); b->ms[1] = t;
@@ -740,12 +928,15 @@ int run(dnb_batch *b) {
     }
     cudaEventElapsedTime(&t, b->ev[5], b->ev[6]); b->ms[4] = t;
     cudaEventElapsedTime(&t, b->ev[0], b->ev[6]); b->ms[5] = t;
+    cudaEventElapsedTime(&t, b->ev[0], b->ev[8]); b->seg_ms[0] = t;
+    cudaEventElapsedTime(&t, b->ev[8], b->ev[9]); b->seg_ms[1] = t;
+    cudaEventElapsedTime(&t, b->ev[9], b->ev[1]); b->seg_ms[2] = t;
     b->ms[6] = 1e3 * (wall_gap1 - wall_gap0);
     b->ms[7] = 1e3 * (omp_get_wtime() - wall0);
-    uint64_t n_samp = 0;
-    for (size_t i = 0; i < R; i++) n_samp += b->n_samples[i];
+    uint64_t n_samp = 0, n_fail = 0;
+    for (size_t i = 0; i < R; i++) { n_samp += b->n_samples[i]; n_fail += b->h.status[i] != DNB_READ_OK; }
     b->counts[0] = n_samp; b->counts[1] = n_ev; b->counts[2] = n_km; b->counts[3] = bo; b->counts[4] = b->h_cells[0];
-    b->counts[5] = launches; b->counts[6] = n_redo; b->counts[7] = 0;
+    b->counts[5] = launches; b->counts[6] = n_redo; b->counts[7] = n_fail;
     b->ran = true;
     b->fetched = false;
     return DNB_OK;
@@ -770,7 +961,7 @@ int fetch(dnb_batch *b) {
         TRY(ralloc(b, &h.et_mean, b->tot_ev + R)); TRY(ralloc(b, &h.et_stdv, b->tot_ev + R));
         TRY(d2h(b, h.et_start, w.et_start, b->tot_ev + R)); TRY(d2h(b, h.et_length, w.et_length, b->tot_ev + R));
         TRY(d2h(b, h.et_mean, w.et_mean, b->tot_ev + R)); TRY(d2h(b, h.et_stdv, w.et_stdv, b->tot_ev + R));
-        CK(cudaStreamSynchronize(s));
+        CK(wait_stream(b));
         b->fetched = true;
         return DNB_OK;
     }
@@ -783,8 +974,9 @@ int fetch(dnb_batch *b) {
     TRY(d2h(b, h.max_gap, w.max_gap, R)); TRY(d2h(b, h.rough_shift, w.rough_shift, R));
     TRY(d2h(b, h.rough_scale, w.rough_scale, R)); TRY(d2h(b, h.shift, w.shift, R));
     TRY(d2h(b, h.scale, w.scale, R)); TRY(d2h(b, h.avg, w.avg, R));
-    CK(cudaStreamSynchronize(s));
-    ht.tick("scalars D2H");
+    if (b->compact) { TRY(ralloc(b, &h.n_long, R)); TRY(d2h(b, h.n_long, w.n_long, R)); }
+    CK(wait_stream(b));
+    ht.tick(PH_FETCH_SCALARS);
     // dense layouts: events (the device slots are capacity-strided) and forward alignment pairs (the device list is
     // in backtrace order): only what dnb_result hands out crosses PCIe
     b->out_off.assign(R + 1, 0);
@@ -799,27 +991,78 @@ int fetch(dnb_batch *b) {
     b->tot_out = oo;
     b->counts[7] = n_fail;
     uint64_t *d_cev_off = nullptr;
-    TRY(walloc(b, &w.out_pairs, 2 * oo)); TRY(walloc(b, &w.cev_start, ce + R)); TRY(walloc(b, &w.cev_mean, ce));
     TRY(walloc(b, &d_cev_off, R + 1));
-    TRY(ralloc(b, &h.out_pairs, 2 * oo)); TRY(ralloc(b, &h.ev_start, ce + R)); TRY(ralloc(b, &h.ev_mean, ce));
     TRY(h2d(b, w.out_off, b->out_off.data(), R + 1));
     TRY(h2d(b, d_cev_off, b->cev_off.data(), R + 1));
-    dnb_launch_compact_events(make_view(b), d_cev_off, w.cev_start, w.cev_mean, s);
-    TRY(d2h(b, h.ev_start, w.cev_start, ce + R));
-    TRY(d2h(b, h.ev_mean, w.cev_mean, ce));
-    dnb_launch_compact_alignment(make_view(b), w.al_off, w.al_rev, w.n_align, w.out_off, w.out_pairs, s);
-    TRY(d2h(b, h.out_pairs, w.out_pairs, 2 * oo));
+    if (!b->compact) {
+        TRY(walloc(b, &w.out_pairs, 2 * oo)); TRY(walloc(b, &w.cev_start, ce + R)); TRY(walloc(b, &w.cev_mean, ce));
+        TRY(ralloc(b, &h.out_pairs, 2 * oo)); TRY(ralloc(b, &h.ev_start, ce + R)); TRY(ralloc(b, &h.ev_mean, ce));
+        dnb_launch_compact_events(make_view(b), d_cev_off, w.cev_start, w.cev_mean, s);
+        TRY(d2h(b, h.ev_start, w.cev_start, ce + R));
+        TRY(d2h(b, h.ev_mean, w.cev_mean, ce));
+        dnb_launch_compact_alignment(make_view(b), w.al_off, w.al_rev, w.n_align, w.out_off, w.out_pairs, s);
+        b->have_dev_pairs = true;
+        TRY(d2h(b, h.out_pairs, w.out_pairs, 2 * oo));
+        b->d2h_bytes = 8 * ce + 4 * R + 8 * oo + 84 * R;
+    } else {
+        // compact wire format (pack.cu): 1 B length + 4 B mean per event, 2 bits per alignment step
+        b->esc_off.assign(R + 1, 0); b->step_off.assign(R + 1, 0);
+        uint64_t xo = 0, so = 0;
+        for (size_t i = 0; i < R; i++) {
+            b->esc_off[i] = xo; xo += h.status[i] == DNB_READ_OVERFLOW ? 0 : h.n_long[i];
+            b->step_off[i] = so; so += h.n_align[i] > 1 ? (((uint64_t)h.n_align[i] - 1 + 3) / 4 + 3) & ~3ull : 0;
+        }
+        b->esc_off[R] = xo; b->step_off[R] = so;
+        uint64_t *d_esc_off = nullptr, *d_step_off = nullptr;
+        uint8_t *d_len8 = nullptr, *d_steps = nullptr;
+        uint32_t *d_esc = nullptr, *d_first_ev = nullptr, *d_first_pair = nullptr, *d_bad = nullptr;
+        TRY(walloc(b, &d_esc_off, R + 1)); TRY(walloc(b, &d_step_off, R + 1));
+        TRY(walloc(b, &d_len8, ce)); TRY(walloc(b, &w.cev_mean, ce)); TRY(walloc(b, &d_esc, xo));
+        TRY(walloc(b, &d_first_ev, R)); TRY(walloc(b, &d_steps, so)); TRY(walloc(b, &d_first_pair, 2 * R));
+        TRY(walloc(b, &d_bad, R));
+        TRY(ralloc(b, &h.len8, ce)); TRY(ralloc(b, &h.ev_mean, ce)); TRY(ralloc(b, &h.esc, xo));
+        TRY(ralloc(b, &h.first_ev, R)); TRY(ralloc(b, &h.steps, so)); TRY(ralloc(b, &h.first_pair, 2 * R));
+        TRY(ralloc(b, &h.bad_steps, R));
+        TRY(h2d(b, d_esc_off, b->esc_off.data(), R + 1));
+        TRY(h2d(b, d_step_off, b->step_off.data(), R + 1));
+        CK(cudaMemsetAsync(d_bad, 0, R * 4, s));
+        dnb_launch_compact_events8(make_view(b), d_cev_off, d_esc_off, d_len8, w.cev_mean, d_esc, d_first_ev, s);
+        TRY(d2h(b, h.len8, d_len8, ce)); TRY(d2h(b, h.ev_mean, w.cev_mean, ce)); TRY(d2h(b, h.esc, d_esc, xo));
+        TRY(d2h(b, h.first_ev, d_first_ev, R));
+        dnb_launch_compact_steps(make_view(b), w.al_off, w.al_rev, w.n_align, d_step_off, d_steps, d_first_pair, d_bad, s);
+        TRY(d2h(b, h.steps, d_steps, so)); TRY(d2h(b, h.first_pair, d_first_pair, 2 * R)); TRY(d2h(b, h.bad_steps, d_bad, R));
+        b->d2h_bytes = 5 * ce + 4 * xo + so + 16 * R + 88 * R;
+    }
     if (ctx->cfg.keep_debug) {
         TRY(ralloc(b, &h.cl_signal, b->tot_cl)); TRY(ralloc(b, &h.cl_rank, b->tot_cl));
         TRY(d2h(b, h.cl_signal, w.cl_signal, b->tot_cl));
         TRY(d2h(b, h.cl_rank, w.cl_rank, b->tot_cl));
     }
-    b->d2h_bytes = 8 * ce + 4 * R + 8 * oo + 84 * R;
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(b));
     CK(cudaGetLastError());
-    ht.tick("compact + D2H events, pairs");
+    if (b->compact)
+        for (size_t i = 0; i < R; i++)
+            if (h.bad_steps[i]) { g_last_error = "alignment of read " + std::to_string(i) + " is not a monotone path"; return DNB_ERR_STATE; }
+    ht.tick(PH_FETCH_WAIT);
     b->fetched = true;
     return DNB_OK;
+}
+
+template <class T>
+cudaError_t pool_alloc(dnb_ctx *ctx, T **p, size_t bytes, cudaStream_t s) {
+    return ctx->pool ? cudaMallocFromPoolAsync((void **)p, bytes, ctx->pool, s) : cudaMallocAsync((void **)p, bytes, s);
+}
+
+// one context driving several GPUs: a submission goes to the device with the fewest samples in flight
+dnb_ctx *pick_device(dnb_ctx *front, const dnb_read_desc *reads, size_t R, uint64_t *load) {
+    uint64_t n = 0;
+    for (size_t i = 0; reads && i < R; i++) n += reads[i].n_samples;
+    *load = n;
+    dnb_ctx *best = front;
+    for (dnb_ctx *p : front->peers)
+        if (p->inflight.load(std::memory_order_relaxed) < best->inflight.load(std::memory_order_relaxed)) best = p;
+    best->inflight.fetch_add(n, std::memory_order_relaxed);
+    return best;
 }
 
 }  // namespace
@@ -855,31 +1098,26 @@ const char *dnb_strerror(int code) {
 
 const char *dnb_last_error(void) { return g_last_error.c_str(); }
 
-int dnb_create(dnb_ctx **out, const dnb_config *cfg) {
-    if (!out) return DNB_ERR_ARG;
-    dnb_config c;
-    if (cfg) c = *cfg; else dnb_default_config(&c);
-    if (c.bandwidth != DNB_BW || c.window_length2 > 7 || c.window_length1 > c.window_length2 || c.window_length1 < 1) {
-        g_last_error = "unsupported configuration (bandwidth must be 100, window lengths <= 7)";
-        return DNB_ERR_ARG;
-    }
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libdnascent_b200 has no CPU fallback)";
-        cudaGetLastError();
-        return DNB_ERR_CUDA;
-    }
-    if (c.device < 0 || c.device >= n) return DNB_ERR_ARG;
+static int create_one(dnb_ctx **out, const dnb_config &c) {
     CK(cudaSetDevice(c.device));
-    // keep freed stream-ordered allocations cached in the pool: batches reuse them
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, c.device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     dnb_ctx *ctx = new dnb_ctx();
     ctx->cfg = c;
+    ctx->cfg.n_devices = 1;
+    ctx->dev.idle_cap = c.workspace_bytes;
+    // stream-ordered scratch for dnb_sequence_probability_batch / dnb_eventalign_batch: a pool of our own that keeps
+    // what it has been given (the process-wide default pool is left as the application configured it)
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = c.device;
+    if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else {
+        cudaGetLastError();
+        ctx->pool = nullptr;
+    }
     // log_inv_sqrt_2pi is a float in the reference (event_handling.cpp:134); sigma is 0.14 for every k-mer
     const float log_inv_sqrt_2pi = (float)log(0.3989422804014327);
     ctx->emit_const = (double)log_inv_sqrt_2pi - log(0.14);
@@ -887,9 +1125,53 @@ int dnb_create(dnb_ctx **out, const dnb_config *cfg) {
     return DNB_OK;
 }
 
+int dnb_create(dnb_ctx **out, const dnb_config *cfg) {
+    if (!out) return DNB_ERR_ARG;
+    *out = nullptr;
+    dnb_config c;
+    if (cfg) c = *cfg; else dnb_default_config(&c);
+    if (c.bandwidth != DNB_BW || c.window_length2 > 7 || c.window_length1 > c.window_length2 || c.window_length1 < 1) {
+        g_last_error = "unsupported configuration (bandwidth must be 100, window lengths <= 7)";
+        return DNB_ERR_ARG;
+    }
+    if (c.result_format != DNB_RESULT_DENSE && c.result_format != DNB_RESULT_COMPACT) return DNB_ERR_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_last_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libdnascent_b200 has no CPU fallback)";
+        cudaGetLastError();
+        return DNB_ERR_CUDA;
+    }
+    if (c.n_devices < 0 || c.n_devices > DNB_MAX_DEVICES) return DNB_ERR_ARG;
+    if (c.n_devices > 1) {
+        for (int k = 0; k < c.n_devices; k++) {
+            if (c.devices[k] < 0 || c.devices[k] >= n) { g_last_error = "dnb_config.devices: no such CUDA device"; return DNB_ERR_ARG; }
+            for (int j = 0; j < k; j++) if (c.devices[j] == c.devices[k]) { g_last_error = "dnb_config.devices: duplicate"; return DNB_ERR_ARG; }
+        }
+        c.device = c.devices[0];
+    } else if (c.n_devices == 1) c.device = c.devices[0];
+    if (c.device < 0 || c.device >= n) return DNB_ERR_ARG;
+    dnb_ctx *front = nullptr;
+    TRY(create_one(&front, c));
+    for (int k = 1; k < c.n_devices; k++) {
+        dnb_config ck = c;
+        ck.device = c.devices[k];
+        dnb_ctx *peer = nullptr;
+        const int rc = create_one(&peer, ck);
+        if (rc != DNB_OK) { dnb_destroy(front); return rc; }
+        front->peers.push_back(peer);
+    }
+    front->cfg.n_devices = c.n_devices > 1 ? c.n_devices : 1;
+    *out = front;
+    return DNB_OK;
+}
+
 void dnb_destroy(dnb_ctx *ctx) {
     if (!ctx) return;
+    for (dnb_ctx *p : ctx->peers) dnb_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     for (auto &m : ctx->model) {
         cudaFree(m.d_mean); cudaFree(m.d_stdv); cudaFree(m.d_sorted); cudaFree(m.d_order);
     }
@@ -901,6 +1183,13 @@ void dnb_destroy(dnb_ctx *ctx) {
 
 int dnb_load_model(dnb_ctx *ctx, int which, const double *mean, const double *stdv, size_t n) {
     if (!ctx || which < 0 || which > 2 || !mean || n != DNB_N_KMERS) return DNB_ERR_ARG;
+    if (which == DNB_MODEL_PORE && stdv) {
+        // the alignment and eventalign kernels have the ONT table's static sigma compiled in as the reference has it
+        // (import_poreModel_staticStdv, data_IO.cpp:170-173): any other value would silently change the emissions
+        for (size_t i = 0; i < n; i++)
+            if (stdv[i] != 0.14) { g_last_error = "DNB_MODEL_PORE: stdv must be the static 0.14 of data_IO.cpp:173 (or NULL)"; return DNB_ERR_ARG; }
+    }
+    for (dnb_ctx *p : ctx->peers) TRY(dnb_load_model(p, which, mean, stdv, n));
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->cfg.device));
     ModelHost &m = ctx->model[which];
@@ -923,7 +1212,12 @@ int dnb_load_model(dnb_ctx *ctx, int which, const double *mean, const double *st
 }
 
 int dnb_batch_upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch) {
-    return upload(ctx, reads, n_reads, false, batch);
+    if (!ctx) return DNB_ERR_ARG;
+    uint64_t load = 0;
+    dnb_ctx *dev = pick_device(ctx, reads, n_reads, &load);
+    const int rc = upload(dev, reads, n_reads, false, batch);
+    if (rc == DNB_OK) (*batch)->load = load; else dev->inflight.fetch_sub(load, std::memory_order_relaxed);
+    return rc;
 }
 int dnb_batch_run(dnb_batch *batch) { return run(batch); }
 int dnb_batch_fetch(dnb_batch *batch) { return fetch(batch); }
@@ -936,15 +1230,22 @@ int dnb_batch_drop_workspace(dnb_batch *b) {
 
 int dnb_submit(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch) {
     dnb_batch *b = nullptr;
-    if (!ctx) return DNB_ERR_ARG;
-    TRY(upload(ctx, reads, n_reads, false, &b, /*gated=*/true));
-    int rc;
+    if (!ctx || !batch) return DNB_ERR_ARG;
+    uint64_t load = 0;
+    ctx = pick_device(ctx, reads, n_reads, &load);
+    int rc = upload(ctx, reads, n_reads, false, &b, /*gated=*/true);
+    if (rc != DNB_OK) { ctx->inflight.fetch_sub(load, std::memory_order_relaxed); return rc; }
+    b->load = load;
     {
+        HostTrace hg("submit");
         StageHold hold(ctx->gate_compute);
+        hg.tick(PH_RUN_GATE);
         rc = run(b);
     }
     if (rc == DNB_OK) {
+        HostTrace hg("submit");
         StageHold hold(ctx->gate_fetch);
+        hg.tick(PH_FETCH_GATE);
         rc = fetch(b);
     }
     if (rc != DNB_OK) { free_batch(b); return rc; }
@@ -956,7 +1257,7 @@ int dnb_submit(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_bat
 int dnb_wait(dnb_batch *b) {
     if (!b) return DNB_ERR_ARG;
     CK(cudaSetDevice(b->ctx->cfg.device));
-    CK(cudaStreamSynchronize(b->stream));
+    CK(wait_stream(b));
     return DNB_OK;
 }
 
@@ -969,10 +1270,19 @@ int dnb_result(dnb_batch *b, size_t i, dnb_read_result *o) {
     o->et_n = h.et_n[i];
     o->n_events = h.n_events[i];
     if (o->status == DNB_READ_OVERFLOW) o->n_events = 0;
-    o->event_start = h.ev_start + b->cev_off[i] + i;
     o->event_mean = h.ev_mean + b->cev_off[i];
     o->n_align = o->status == DNB_READ_OK ? h.n_align[i] : 0;
-    o->align_pairs = h.out_pairs + 2 * b->out_off[i];
+    if (!b->compact) {
+        o->event_start = h.ev_start + b->cev_off[i] + i;
+        o->align_pairs = h.out_pairs + 2 * b->out_off[i];
+    } else {
+        o->event_first = h.first_ev[i];
+        o->event_len8 = h.len8 + b->cev_off[i];
+        o->event_len_escape = h.esc + b->esc_off[i];
+        o->n_event_len_escape = (uint32_t)(b->esc_off[i + 1] - b->esc_off[i]);
+        o->align_first[0] = h.first_pair[2 * i]; o->align_first[1] = h.first_pair[2 * i + 1];
+        o->align_steps = h.steps + b->step_off[i];
+    }
     o->rough_shift = h.rough_shift[i]; o->rough_scale = h.rough_scale[i];
     o->shift = h.shift[i]; o->scale = h.scale[i];
     const int64_t denom = (int64_t)b->qlen[i] - DNB_K;
@@ -990,6 +1300,99 @@ void dnb_release(dnb_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->cfg.device);
     free_batch(b);
+}
+
+int dnb_expand_events(const dnb_read_result *r, uint32_t *event_start) {
+    if (!r || (!event_start && r->n_events)) return DNB_ERR_ARG;
+    if (r->n_events == 0) return DNB_OK;
+    if (r->event_start) { memcpy(event_start, r->event_start, 4 * ((size_t)r->n_events + 1)); return DNB_OK; }
+    if (!r->event_len8) return DNB_ERR_STATE;
+    uint32_t at = r->event_first, k = 0;
+    event_start[0] = at;
+    for (uint32_t j = 0; j < r->n_events; j++) {
+        uint32_t d = r->event_len8[j];
+        if (d == 255u) {
+            if (k >= r->n_event_len_escape) return DNB_ERR_STATE;
+            d = r->event_len_escape[k++];
+        }
+        at += d;
+        event_start[j + 1] = at;
+    }
+    return DNB_OK;
+}
+
+int dnb_expand_alignment(const dnb_read_result *r, uint32_t *align_pairs) {
+    if (!r || (!align_pairs && r->n_align)) return DNB_ERR_ARG;
+    if (r->n_align == 0) return DNB_OK;
+    if (r->align_pairs) { memcpy(align_pairs, r->align_pairs, 8 * (size_t)r->n_align); return DNB_OK; }
+    if (r->n_align > 1 && !r->align_steps) return DNB_ERR_STATE;
+    uint32_t e = r->align_first[0], k = r->align_first[1];
+    align_pairs[0] = e; align_pairs[1] = k;
+    for (uint32_t t = 0; t + 1 < r->n_align; t++) {
+        const uint32_t code = (r->align_steps[t >> 2] >> (2 * (t & 3))) & 3u;
+        e += code != DNB_FROM_L;          // D and U advance the event, D and L the k-mer
+        k += code != DNB_FROM_U;
+        align_pairs[2 * t + 2] = e; align_pairs[2 * t + 3] = k;
+    }
+    return DNB_OK;
+}
+
+int dnb_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return DNB_ERR_ARG;
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    g_host_reg.add(p, bytes);
+    return DNB_OK;
+}
+int dnb_host_unregister(void *p) {
+    if (!p) return DNB_ERR_ARG;
+    g_host_reg.remove(p);
+    CK(cudaHostUnregister(p));
+    return DNB_OK;
+}
+int dnb_host_alloc(void **p, size_t bytes) {
+    if (!p || !bytes) return DNB_ERR_ARG;
+    *p = nullptr;
+    cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? DNB_ERR_NOMEM : DNB_ERR_CUDA; }
+    g_host_reg.add(*p, bytes);
+    return DNB_OK;
+}
+void dnb_host_free(void *p) {
+    if (!p) return;
+    g_host_reg.remove(p);
+    cudaFreeHost(p);
+}
+
+int dnb_trim(dnb_ctx *ctx) {
+    if (!ctx) return DNB_ERR_ARG;
+    for (dnb_ctx *p : ctx->peers) TRY(dnb_trim(p));
+    CK(cudaSetDevice(ctx->cfg.device));
+    ctx->dev.trim();
+    ctx->pinned.trim();
+    return DNB_OK;
+}
+
+int dnb_host_stats(int reset, double seconds[DNB_N_HOST_PHASES], uint64_t counts[4]) {
+    static_assert(PH_N == DNB_N_HOST_PHASES, "dnb_host_stats phase count");
+    for (int i = 0; i < PH_N; i++) {
+        if (seconds) seconds[i] = 1e-9 * (double)g_host_stats.ns[i].load();
+        if (reset) g_host_stats.ns[i] = 0;
+    }
+    if (counts) {
+        counts[0] = g_host_stats.n_batches; counts[1] = g_host_stats.n_direct;
+        counts[2] = g_host_stats.n_cuda_malloc; counts[3] = g_host_stats.n_cuda_malloc_host;
+    }
+    if (reset) { g_host_stats.n_batches = 0; g_host_stats.n_direct = 0; g_host_stats.n_cuda_malloc = 0; g_host_stats.n_cuda_malloc_host = 0; }
+    return DNB_OK;
+}
+const char *dnb_host_phase_name(int i) { return (i >= 0 && i < PH_N) ? kHostPhaseName[i] : ""; }
+
+int dnb_batch_device(dnb_batch *b) { return b ? b->ctx->cfg.device : -1; }
+
+int dnb_batch_seg_timings(dnb_batch *b, double ms[3]) {
+    if (!b || !b->ran || !ms) return DNB_ERR_STATE;
+    for (int i = 0; i < 3; i++) ms[i] = b->seg_ms[i];
+    return DNB_OK;
 }
 
 int dnb_batch_timings(dnb_batch *b, double ms[8], uint64_t counts[8]) {
@@ -1076,10 +1479,10 @@ int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64
     CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     int rc = DNB_OK;
     auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DNB_OK) { g_last_error = cudaGetErrorString(e); rc = DNB_ERR_CUDA; } };
-    fail(cudaMallocAsync(&d_obs, (n_obs ? n_obs : 1) * 8, s)); fail(cudaMallocAsync(&d_off, (n_sites + 1) * 8, s));
-    fail(cudaMallocAsync(&d_seq, n_sites * snip, s)); fail(cudaMallocAsync(&d_shift, n_sites * 8, s));
-    fail(cudaMallocAsync(&d_scale, n_sites * 8, s)); fail(cudaMallocAsync(&d_epb, n_sites * 8, s));
-    fail(cudaMallocAsync(&d_oa, n_sites * 8, s)); fail(cudaMallocAsync(&d_ot, n_sites * 8, s));
+    fail(pool_alloc(ctx, &d_obs, (n_obs ? n_obs : 1) * 8, s)); fail(pool_alloc(ctx, &d_off, (n_sites + 1) * 8, s));
+    fail(pool_alloc(ctx, &d_seq, n_sites * snip, s)); fail(pool_alloc(ctx, &d_shift, n_sites * 8, s));
+    fail(pool_alloc(ctx, &d_scale, n_sites * 8, s)); fail(pool_alloc(ctx, &d_epb, n_sites * 8, s));
+    fail(pool_alloc(ctx, &d_oa, n_sites * 8, s)); fail(pool_alloc(ctx, &d_ot, n_sites * 8, s));
     if (rc == DNB_OK) {
         if (n_obs) fail(cudaMemcpyAsync(d_obs, obs, n_obs * 8, cudaMemcpyHostToDevice, s));
         fail(cudaMemcpyAsync(d_off, obs_off, (n_sites + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -1102,10 +1505,11 @@ int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64
 }
 
 // ---- eventalign (SURVEY s.8 row f1) ------------------------------------------------------------------------------
-// DNB_EA_WINDOW_PARALLEL=1 routes eventalign through the experimental window-parallel kernels (eventalign_wp.cu);
-// the default is the read-serial kernel every test and number of this round was produced with
+// eventalign runs window-parallel (eventalign_wp.cu: one warp per window, speculative chain + verification rounds), which
+// makes a read's latency one window instead of its length; DNB_EA_WINDOW_PARALLEL=0 selects the read-serial kernel
+// (eventalign.cu: one warp per read), kept as the cross-check both are tested against
 static bool ea_window_parallel() {
-    static const bool on = getenv("DNB_EA_WINDOW_PARALLEL") != nullptr && getenv("DNB_EA_WINDOW_PARALLEL")[0] == '1';
+    static const bool on = !(getenv("DNB_EA_WINDOW_PARALLEL") != nullptr && getenv("DNB_EA_WINDOW_PARALLEL")[0] == '0');
     return on;
 }
 
@@ -1212,7 +1616,7 @@ static int eventalign_impl(dnb_ctx *ctx, const dnb_eventalign_desc *reads, const
     int rc = DNB_OK;
     auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DNB_OK) { g_last_error = cudaGetErrorString(e); rc = DNB_ERR_CUDA; } };
     std::vector<void *> owned;
-    auto dalloc = [&](size_t bytes) -> void * { void *p = nullptr; fail(cudaMallocAsync(&p, bytes ? bytes : 16, s)); if (p) owned.push_back(p); return p; };
+    auto dalloc = [&](size_t bytes) -> void * { void *p = nullptr; fail(pool_alloc(ctx, &p, bytes ? bytes : 16, s)); if (p) owned.push_back(p); return p; };
     DnbEaArgs a = {};
     a.n_reads = (uint32_t)R; a.window = window; a.t_max = 4096;
     unsigned grid = dnb_eventalign_grid(ctx->cfg.device);
@@ -1335,8 +1739,13 @@ int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uin
     if (!b->ran || b->want_table || !b->have_work) return DNB_ERR_STATE;
     dnb_ctx *ctx = b->ctx;
     if (!ctx->model[DNB_MODEL_PORE].loaded) return DNB_ERR_MODEL;
-    TRY(fetch(b));                       // dense forward alignment pairs on the device, per-read scalars on the host
+    TRY(fetch(b));                       // per-read scalars on the host, (dense format) forward alignment pairs on the device
     CK(cudaSetDevice(ctx->cfg.device));
+    if (!b->have_dev_pairs) {            // compact result format: eventalign still reads dense pairs, in HBM only
+        TRY(walloc(b, &b->w.out_pairs, 2 * b->tot_out));
+        dnb_launch_compact_alignment(make_view(b), b->w.al_off, b->w.al_rev, b->w.n_align, b->w.out_off, b->w.out_pairs, b->stream);
+        b->have_dev_pairs = true;
+    }
     const size_t R = b->R;
     cudaStream_t s = b->stream;
     HostRes &h = b->h;
@@ -1385,7 +1794,7 @@ int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uin
     uint32_t *st_called = (uint32_t *)ctx->pinned.acquire((tot_called ? tot_called : 1) * 4);
     struct StagingGuard {
         dnb_batch *b; void *p0, *p1;
-        ~StagingGuard() { cudaStreamSynchronize(b->stream); if (p0) b->ctx->pinned.release(p0); if (p1) b->ctx->pinned.release(p1); }
+        ~StagingGuard() { wait_stream(b); if (p0) b->ctx->pinned.release(p0); if (p1) b->ctx->pinned.release(p1); }
     } staging_guard{b, st_r2q, st_called};
     if (!st_r2q || !st_called) { g_last_error = "pinned staging allocation failed"; return DNB_ERR_NOMEM; }
 #pragma omp parallel for schedule(dynamic, 16)
@@ -1468,7 +1877,7 @@ int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uin
         TRY(d2h(b, S.h_recs, d_recs, tot_rec));
         S.bytes[1] += tot_rec * sizeof(dnb_eventalign_rec);
     }
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(b));
     CK(cudaGetLastError());
     float t;
     cudaEventElapsedTime(&t, b->ev[0], b->ev[1]); S.ms[0] = t;
@@ -1482,14 +1891,21 @@ int dnb_submit_chain(dnb_ctx *ctx, const dnb_read_desc *reads, const dnb_read_ex
                      uint32_t window, int want_records, dnb_batch **batch) {
     dnb_batch *b = nullptr;
     if (!ctx || !batch || (!extra && n_reads)) return DNB_ERR_ARG;
-    TRY(upload(ctx, reads, n_reads, false, &b, /*gated=*/true));
-    int rc;
+    uint64_t load = 0;
+    ctx = pick_device(ctx, reads, n_reads, &load);
+    int rc = upload(ctx, reads, n_reads, false, &b, /*gated=*/true);
+    if (rc != DNB_OK) { ctx->inflight.fetch_sub(load, std::memory_order_relaxed); return rc; }
+    b->load = load;
     {
+        HostTrace hg("submit");
         StageHold hold(ctx->gate_compute);
+        hg.tick(PH_RUN_GATE);
         rc = run(b);
     }
     if (rc == DNB_OK) {
+        HostTrace hg("submit");
         StageHold hold(ctx->gate_fetch);
+        hg.tick(PH_FETCH_GATE);
         rc = fetch(b);
     }
     if (rc == DNB_OK) {

@@ -101,13 +101,18 @@ struct DnbSegTiles {
     uint32_t *tile_prev_pos;      // [n_tiles] last peak before this tile (0 if none) ...
     double *tile_prev_sum;        // ... and sums[] there
     uint32_t *redo;               // [R] 1 = redo this read with the serial kernel
+    void *scan_scratch;           // dnb_seg_parity_scan_scratch_bytes() bytes when the block-map scan is enabled, else nullptr
 };
 #define DNB_SEG_BOUNDARY_BYTES sizeof(SegBoundary)
 
 void dnb_launch_segmentation_serial(const DnbBatchView &v, DnbDetector det, const uint32_t *only_flagged, cudaStream_t s);
-void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s);
+// after_checkpoint / after_tiles: optional events recorded behind the checkpoint (or scan) and the tile kernel
+void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s,
+                                   cudaEvent_t after_checkpoint = nullptr, cudaEvent_t after_tiles = nullptr);
 // experimental replacement of the tiled segmentation's checkpoint kernel (seg_scan.cu; only with DNB_SEG_PARITY_SCAN=1)
-cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, cudaStream_t s);
+bool dnb_seg_parity_scan_enabled(void);
+size_t dnb_seg_parity_scan_scratch_bytes(const DnbSegTiles &t, uint32_t n_reads);
+cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, void *scratch, cudaStream_t s);
 void dnb_launch_ranks(const DnbBatchView &v, const DnbModelDev &m, double *mu_q, uint32_t *rank_ref, cudaStream_t s);
 void dnb_launch_quantile_scaling(const DnbBatchView &v, const DnbModelDev &m, const uint32_t *rank_ref,
                                  double *rough_shift, double *rough_scale, cudaStream_t s);
@@ -166,6 +171,23 @@ void dnb_launch_compact_alignment(const DnbBatchView &v, const uint64_t *al_off,
 // capacity-strided event slots -> dense (start[n+1], mean[n]) per read at dense_off[r] (+ r for the starts)
 void dnb_launch_compact_events(const DnbBatchView &v, const uint64_t *dense_off, uint32_t *out_start, float *out_mean,
                                cudaStream_t s);
+
+// ---- compact wire formats (pack.cu) --------------------------------------------------------------------------------
+struct dnb_q2r_run;
+// runs -> dense q2r (already set to -1); run g belongs to the read whose query starts at run_q_base[g] and has run_q_len[g] bases
+void dnb_launch_expand_q2r(const dnb_q2r_run *runs, const uint64_t *run_q_base, const uint32_t *run_q_len, uint64_t n_runs,
+                           int32_t *q2r, cudaStream_t s);
+// per read: number of events of >= 255 samples (the escapes of the u8 length coding)
+void dnb_launch_count_long_events(const DnbBatchView &v, uint32_t *n_long, cudaStream_t s);
+// capacity-strided event slots -> dense (u8 length, f32 mean) at dense_off[r], escapes at esc_off[r], event_start[0] in out_first[r]
+void dnb_launch_compact_events8(const DnbBatchView &v, const uint64_t *dense_off, const uint64_t *esc_off, uint8_t *out_len8,
+                                float *out_mean, uint32_t *out_esc, uint32_t *out_first, cudaStream_t s);
+// backtrace-order pairs -> first pair (out_first[2r], [2r+1]) + 2-bit forward steps at byte offset step_off[r]
+void dnb_launch_compact_steps(const DnbBatchView &v, const uint64_t *al_off, const uint32_t *al_pairs_rev,
+                              const uint32_t *n_align, const uint64_t *step_off, uint8_t *out_steps, uint32_t *out_first,
+                              uint32_t *bad, cudaStream_t s);
+// zero the alignment padding after every read's last sample (direct per-read DMA leaves it unwritten)
+void dnb_launch_zero_padding(const DnbBatchView &v, uint32_t esz, cudaStream_t s);
 
 void dnb_launch_hmm_forward(const double *obs, const uint64_t *obs_off, const char *seq, const double *shift,
                             const double *scale, const double *epb, size_t n_sites, uint32_t window,

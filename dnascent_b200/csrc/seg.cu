@@ -636,23 +636,32 @@ static bool fast_div_ok(uint32_t w) {
     return std::fabs(std::fma(-wd, r, 1.0)) <= 0x1p-54;
 }
 
-void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s) {
+// DNB_SEG_PARITY_SCAN=1: the block-map scan of seg_scan.cu instead of the per-sample checkpoint chain
+bool dnb_seg_parity_scan_enabled(void) {
+    static const bool on = getenv("DNB_SEG_PARITY_SCAN") != nullptr && getenv("DNB_SEG_PARITY_SCAN")[0] == '1';
+    return on;
+}
+
+void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s,
+                                   cudaEvent_t after_checkpoint, cudaEvent_t after_tiles) {
     if (v.n_reads == 0) return;
     const unsigned gr = (v.n_reads + 127) / 128;
     const unsigned gt = (t.n_tiles + SEG_THREADS - 1) / SEG_THREADS;
     const bool fast = fast_div_ok(det.w1) && fast_div_ok(det.w2);
-    // DNB_SEG_PARITY_SCAN=1: the experimental block-map scan of seg_scan.cu instead of the per-sample checkpoint chain
-    static const bool parity_scan = getenv("DNB_SEG_PARITY_SCAN") != nullptr && getenv("DNB_SEG_PARITY_SCAN")[0] == '1';
-    const bool scanned = parity_scan && dnb_launch_seg_parity_scan(v, t, s) == cudaSuccess;
+    const bool scanned = dnb_seg_parity_scan_enabled() && t.scan_scratch &&
+                         dnb_launch_seg_parity_scan(v, t, t.scan_scratch, s) == cudaSuccess;
     if (v.raw_i16) {
         if (!scanned) seg_checkpoint_kernel<true><<<gr, 128, 0, s>>>(v, t);
+        if (after_checkpoint) cudaEventRecord(after_checkpoint, s);
         if (fast) seg_tile_kernel<true, true><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
         else seg_tile_kernel<true, false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
     } else {
         if (!scanned) seg_checkpoint_kernel<false><<<gr, 128, 0, s>>>(v, t);
+        if (after_checkpoint) cudaEventRecord(after_checkpoint, s);
         if (fast) seg_tile_kernel<false, true><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
         else seg_tile_kernel<false, false><<<gt, SEG_THREADS, 0, s>>>(v, det, t);
     }
+    if (after_tiles) cudaEventRecord(after_tiles, s);
     seg_stitch_kernel<<<(v.n_reads + 3) / 4, 128, 0, s>>>(v, t);
     seg_events_kernel<<<(t.n_tiles + 3) / 4, 128, 0, s>>>(v, t);
     dnb_launch_segmentation_serial(v, det, t.redo, s);

@@ -204,31 +204,27 @@ __global__ void __launch_bounds__(128) seg_parity_scan_kernel(DnbBatchView v, Dn
 }  // namespace
 
 // Drop-in for the two seg_checkpoint_kernel launches of dnb_launch_segmentation_tiled (same outputs: ck_sum, ck_sq,
-// tot_sum, redo).  Scratch comes from the stream-ordered pool and is returned to it behind the kernel.
-cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, cudaStream_t s) {
-    if (v.n_reads == 0) return cudaSuccess;
+// tot_sum, redo).  The scratch (11 arrays of one entry per 64-sample block) comes from the caller's device cache.
+static size_t ps_slots(const DnbSegTiles &t, uint32_t n_reads) {
     // checkpoint slots of the batch: ceil(N/64) + 1 per read <= 8 tiles' worth + 2
-    const size_t slots = (size_t)t.n_tiles * (DNB_SEG_TILE / DNB_SEG_CK) + 2 * (size_t)v.n_reads + 64;
-    cudaError_t err = cudaSuccess;
-    std::vector<void *> owned;
-    auto dalloc = [&](size_t bytes) -> void * {
-        void *q = nullptr;
-        if (err == cudaSuccess) err = cudaMallocAsync(&q, bytes, s);
-        if (q) owned.push_back(q);
-        return q;
-    };
+    return (size_t)t.n_tiles * (DNB_SEG_TILE / DNB_SEG_CK) + 2 * (size_t)n_reads + 64;
+}
+size_t dnb_seg_parity_scan_scratch_bytes(const DnbSegTiles &t, uint32_t n_reads) { return ps_slots(t, n_reads) * (9 * 8 + 2 * 4) + 256; }
+
+cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, void *scratch, cudaStream_t s) {
+    if (v.n_reads == 0) return cudaSuccess;
+    if (!scratch) return cudaErrorInvalidValue;
+    const size_t slots = ps_slots(t, v.n_reads);
+    uint8_t *p = (uint8_t *)scratch;
+    auto take = [&](size_t bytes) { void *q = p; p += bytes; return q; };
     PsScratch w;
-    w.bs = (double *)dalloc(slots * 8); w.ba = (double *)dalloc(slots * 8); w.bq = (double *)dalloc(slots * 8);
-    w.ps = (double *)dalloc(slots * 8); w.pq = (double *)dalloc(slots * 8);
-    w.s0 = (long long *)dalloc(slots * 8); w.s1 = (long long *)dalloc(slots * 8);
-    w.q0 = (long long *)dalloc(slots * 8); w.q1 = (long long *)dalloc(slots * 8);
-    w.es = (int *)dalloc(slots * 4); w.eq = (int *)dalloc(slots * 4);
-    if (err == cudaSuccess) {
-        const unsigned grid = (v.n_reads + 3) / 4;                               // one warp per read, 4 warps per CTA
-        if (v.raw_i16) seg_parity_scan_kernel<true><<<grid, 128, 0, s>>>(v, t, w);
-        else seg_parity_scan_kernel<false><<<grid, 128, 0, s>>>(v, t, w);
-        err = cudaGetLastError();
-    }
-    for (void *q : owned) cudaFreeAsync(q, s);
-    return err;
+    w.bs = (double *)take(slots * 8); w.ba = (double *)take(slots * 8); w.bq = (double *)take(slots * 8);
+    w.ps = (double *)take(slots * 8); w.pq = (double *)take(slots * 8);
+    w.s0 = (long long *)take(slots * 8); w.s1 = (long long *)take(slots * 8);
+    w.q0 = (long long *)take(slots * 8); w.q1 = (long long *)take(slots * 8);
+    w.es = (int *)take(slots * 4); w.eq = (int *)take(slots * 4);
+    const unsigned grid = (v.n_reads + 3) / 4;                               // one warp per read, 4 warps per CTA
+    if (v.raw_i16) seg_parity_scan_kernel<true><<<grid, 128, 0, s>>>(v, t, w);
+    else seg_parity_scan_kernel<false><<<grid, 128, 0, s>>>(v, t, w);
+    return cudaGetLastError();
 }

@@ -12,7 +12,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -30,6 +32,7 @@ namespace {
 std::mutex g_mu;
 dnb_ctx *g_ctx = nullptr;
 int g_device = -1;
+std::vector<int> g_devices;   // more than one entry: one context (one process) drives all of them
 
 [[noreturn]] void die(const char *where, int rc) {
     std::fprintf(stderr, "dnascent_b200 shim: %s failed: %s (%s)\n", where, dnb_strerror(rc), dnb_last_error());
@@ -62,14 +65,32 @@ void narrow_signal(const std::vector<double> &raw, std::vector<float> &out) {
 
 struct Staged {
     std::vector<float> raw;
-    std::vector<int32_t> q2r;
+    std::vector<dnb_q2r_run> runs;
 };
+
+// r.queryToRef (std::map, keys ascending) as runs: consecutive query positions whose reference positions advance by
+// one (aligned bases) or stay (the entries parseCigar gives insertions and soft clips, htsInterface.cpp:143-152).
+// A `{L}M` read is one run: 16 bytes cross PCIe instead of 4 per base.
+void q2r_runs(const std::map<unsigned int, unsigned int> &m, size_t query_len, std::vector<dnb_q2r_run> &out) {
+    out.clear();
+    for (const auto &kv : m) {
+        if (kv.first >= query_len) continue;
+        if (!out.empty()) {
+            dnb_q2r_run &t = out.back();
+            if (kv.first == t.q_start + t.len) {
+                const int32_t step = (int32_t)kv.second - (t.r_start + t.stride * (int32_t)(t.len - 1));
+                if (t.len == 1 && (step == 0 || step == 1)) { t.stride = step; t.len = 2; continue; }
+                if (t.len > 1 && step == t.stride) { t.len++; continue; }
+            }
+        }
+        out.push_back(dnb_q2r_run{kv.first, 1u, (int32_t)kv.second, 1});
+    }
+    if (out.empty()) out.reserve(1);   // a non-NULL pointer tells the library "runs given", even when there are none
+}
 
 void stage_read(const DNAscent::read &r, Staged &s, dnb_read_desc &d) {
     narrow_signal(r.raw, s.raw);
-    s.q2r.assign(r.basecall.size(), -1);
-    for (const auto &kv : r.queryToRef)
-        if (kv.first < s.q2r.size()) s.q2r[kv.first] = (int32_t)kv.second;
+    q2r_runs(r.queryToRef, r.basecall.size(), s.runs);
     std::memset(&d, 0, sizeof(d));
     d.raw_pA = s.raw.data();
     d.n_samples = s.raw.size();
@@ -77,7 +98,9 @@ void stage_read(const DNAscent::read &r, Staged &s, dnb_read_desc &d) {
     d.query_len = (uint32_t)r.basecall.size();
     d.ref = r.referenceSeqMappedTo.data();
     d.ref_len = (uint32_t)r.referenceSeqMappedTo.size();
-    d.query_to_ref = s.q2r.data();
+    d.query_to_ref = nullptr;
+    d.q2r_runs = s.runs.data();
+    d.n_q2r_runs = (uint32_t)s.runs.size();
 }
 
 // what src/event_handling.cpp:549-606 leaves in the read
@@ -88,17 +111,22 @@ void unpack_result(DNAscent::read &r, const dnb_read_result &o) {
         r.eventAlignment.clear();
         return;
     }
+    // the results come back in the compact wire format (1 B per event length, 2 bits per alignment step); they are
+    // expanded on the fly, the alignment straight into the vector the reference keeps it in
+    int rc;
+    std::vector<uint32_t> start((size_t)o.n_events + 1);
+    if ((rc = dnb_expand_events(&o, start.data())) != DNB_OK) die("dnb_expand_events", rc);
     r.events.clear();
     r.events.resize(o.n_events);
     for (uint32_t j = 0; j < o.n_events; j++) {
         event &e = r.events[j];
         e.mean = (double)o.event_mean[j];
-        e.raw.assign(r.raw.begin() + o.event_start[j], r.raw.begin() + o.event_start[j + 1]);
+        e.raw.assign(r.raw.begin() + start[j], r.raw.begin() + start[j + 1]);
     }
-    r.eventAlignment.clear();
-    r.eventAlignment.reserve(o.n_align);
-    for (uint32_t j = 0; j < o.n_align; j++)
-        r.eventAlignment.push_back(std::make_pair(o.align_pairs[2 * j], o.align_pairs[2 * j + 1]));
+    static_assert(sizeof(std::pair<unsigned int, unsigned int>) == 2 * sizeof(uint32_t), "eventAlignment element layout");
+    r.eventAlignment.assign(o.n_align, std::pair<unsigned int, unsigned int>(0u, 0u));
+    if ((rc = dnb_expand_alignment(&o, reinterpret_cast<uint32_t *>(r.eventAlignment.data()))) != DNB_OK)
+        die("dnb_expand_alignment", rc);
     r.alignmentQCs.recordQCs(o.avg_log_emission, o.spanned != 0, (unsigned int)o.max_gap);
     r.scalings.shift = o.shift;
     r.scalings.scale = o.scale;
@@ -112,6 +140,13 @@ namespace dnb_shim {
 void set_device(int device) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_device = device;
+    g_devices.clear();
+}
+
+void set_devices(const std::vector<int> &devices) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_devices = devices;
+    if (!devices.empty()) g_device = devices[0];
 }
 
 dnb_ctx *context() {
@@ -119,11 +154,27 @@ dnb_ctx *context() {
     if (g_ctx) return g_ctx;
     dnb_config cfg;
     dnb_default_config(&cfg);
+    if (g_devices.empty()) {
+        // DNB_DEVICES="0,1,2,3": the single `DNAscent detect` process (detect.cpp:852) feeds all of them
+        if (const char *e = std::getenv("DNB_DEVICES"))
+            for (const char *p = e; *p;) {
+                char *end = nullptr;
+                const long v = std::strtol(p, &end, 10);
+                if (end == p) break;
+                g_devices.push_back((int)v);
+                p = (*end == ',') ? end + 1 : end;
+            }
+    }
     if (g_device < 0) {
         const char *e = std::getenv("DNB_DEVICE");
-        g_device = e ? std::atoi(e) : 0;
+        g_device = !g_devices.empty() ? g_devices[0] : (e ? std::atoi(e) : 0);
     }
     cfg.device = g_device;
+    if (g_devices.size() > 1) {
+        cfg.n_devices = (int)std::min<size_t>(g_devices.size(), DNB_MAX_DEVICES);
+        for (int k = 0; k < cfg.n_devices; k++) cfg.devices[k] = g_devices[k];
+    }
+    cfg.result_format = DNB_RESULT_COMPACT;
     cfg.min_average_log_emission = Pore_Substrate_Config.AdaptiveBanded_config.min_average_log_emission;
     cfg.max_gap_threshold = Pore_Substrate_Config.AdaptiveBanded_config.max_gap_threshold;
     cfg.bandwidth = Pore_Substrate_Config.AdaptiveBanded_config.bandwidth;

@@ -25,6 +25,9 @@ namespace dnb_shim {
 // Pore_Substrate_Config (pore_model, unlabelled_model, analogue_model) into HBM.  Thread-safe.
 dnb_ctx *context();
 void set_device(int device);   // call before the first use
+// One process, several GPUs: every batched call below is dealt to the device with the least work in flight
+// (dnb_config.devices; also settable as DNB_DEVICES="0,1,...").  Call before the first use.
+void set_devices(const std::vector<int> &devices);
 void shutdown();               // destroys the context (optional; e.g. before pod5_terminate at detect.cpp:917)
 
 // Batched normaliseEvents(r, false): one GPU submission for the whole buffer of reads (the reference's

@@ -52,6 +52,10 @@ enum { DNB_MODEL_PORE = 0, DNB_MODEL_UNLABELLED = 1, DNB_MODEL_ANALOGUE = 2 };
 
 #define DNB_KMER_LEN 9
 #define DNB_N_KMERS 262144 /* 4^9 */
+#define DNB_MAX_DEVICES 16
+
+/* dnb_config.result_format: what dnb_submit / dnb_batch_fetch bring back over PCIe (see dnb_read_result) */
+enum { DNB_RESULT_DENSE = 0, DNB_RESULT_COMPACT = 1 };
 
 typedef struct dnb_ctx dnb_ctx;
 typedef struct dnb_batch dnb_batch;
@@ -71,8 +75,23 @@ typedef struct {
     int use_fit_pore_model;           /* the `useFitPoreModel` argument of normaliseEvents; all reference callers pass false */
     float event_capacity_per_sample;  /* device event slots per raw sample (default 0.40; observed ~0.2) */
     int keep_debug;                   /* also return rough scalings' inputs: cleaned (signal,rank) vectors */
-    size_t workspace_bytes;           /* cap for per-bin device workspace; 0 = derive from free memory */
+    size_t workspace_bytes;           /* cap for the idle device blocks the context keeps cached between batches
+                                         (0 = no cap; dnb_trim() releases them on request) */
+    int result_format;                /* DNB_RESULT_DENSE (default) or DNB_RESULT_COMPACT */
+    int n_devices;                    /* 0 or 1: `device` only.  > 1: one context drives devices[0 .. n_devices): tables are
+                                         replicated, every dnb_submit / dnb_submit_chain / dnb_batch_upload goes to the
+                                         device with the least work in flight (reads are independent: no collective) */
+    int devices[DNB_MAX_DEVICES];
 } dnb_config;
+
+/* queryToRef[q_start + i] = r_start + (stride ? i : 0) for i < len (stride 1: aligned bases; stride 0: the entries
+ * parseCigar gives insertions / soft clips, src/htsInterface.cpp:143-152).  Query positions no run covers have no
+ * entry.  Later runs overwrite earlier ones where they overlap. */
+typedef struct dnb_q2r_run {
+    uint32_t q_start, len;
+    int32_t r_start;
+    int32_t stride;               /* 0 or 1 */
+} dnb_q2r_run;
 
 /* One read, exactly the fields normaliseEvents reads from DNAscent::read (src/reads.h:178-208):
  * raw (float32-exact pA, src/pod5.cpp:60), basecall, referenceSeqMappedTo, queryToRef. */
@@ -85,7 +104,9 @@ typedef struct {
     uint32_t query_len;
     const char *ref;              /* r.referenceSeqMappedTo, sequencing orientation */
     uint32_t ref_len;
-    const int32_t *query_to_ref;  /* dense r.queryToRef: query_len entries, -1 = no entry */
+    const int32_t *query_to_ref;  /* dense r.queryToRef: query_len entries, -1 = no entry; or NULL when q2r_runs is given */
+    const struct dnb_q2r_run *q2r_runs;   /* r.queryToRef as runs (what parseCigar produces, src/htsInterface.cpp:59-157): */
+    uint32_t n_q2r_runs;                  /* 16 B per CIGAR operation instead of 4 B per base over PCIe */
 } dnb_read_desc;
 
 typedef struct {
@@ -104,6 +125,16 @@ typedef struct {
     uint32_t n_cleaned;           /* keep_debug only */
     const double *cleaned_signal;
     const uint32_t *cleaned_rank;
+    /* ---- DNB_RESULT_COMPACT: event_start and align_pairs above are NULL; the same information comes back as
+     * 1 B per event and 2 bits per alignment step (dense: 4 B and 8 B), dnb_expand_* rebuild the dense arrays -------- */
+    uint32_t event_first;            /* event_start[0] */
+    const uint8_t *event_len8;       /* [n_events]: event_start[j+1] - event_start[j]; 255 = the next entry of ... */
+    const uint32_t *event_len_escape;/* ... this list (lengths >= 255 samples, in event order) */
+    uint32_t n_event_len_escape;
+    uint32_t align_first[2];         /* eventAlignment[0] = (event, kmer) */
+    const uint8_t *align_steps;      /* n_align - 1 steps, 2 bits each, step t at bits 2*(t&3) of byte t>>2:
+                                        0: (event+1, kmer+1)   1: (event+1, kmer)   2: (event, kmer+1)  -- the three
+                                        moves of the backtrace (src/event_handling.cpp:160-162) read forwards */
 } dnb_read_result;
 
 /* scrappie event table entry (src/scrappie/scrappie_structures.h:8-15) for the detect_events drop-in */
@@ -127,13 +158,31 @@ DNB_API const char *dnb_last_error(void); /* thread-local detail of the last DNB
 DNB_API int dnb_load_model(dnb_ctx *ctx, int which, const double *mean, const double *stdv, size_t n);
 
 /* ---- the hot path: batched normaliseEvents (src/event_handling.cpp:544-607) ---------------- */
-/* Asynchronous: stages the reads into pinned memory, copies to the device, runs segmentation ->
- * quantile scaling -> banded alignment -> backtrace/QC -> Theil-Sen, copies results back.
- * Thread-safe: may be called concurrently from the OpenMP read loop of detect.cpp:852. */
+/* Copies the reads to the device (straight from the caller's buffers when they are page-locked, through pinned staging
+ * otherwise), runs segmentation -> quantile scaling -> banded alignment -> backtrace/QC -> Theil-Sen and copies the
+ * results back; returns when they are on the host (dnb_wait is then a no-op kept for the split form).
+ * Thread-safe: concurrent callers (the OpenMP read loop of detect.cpp:852) form a software pipeline -- one batch
+ * copying in, two computing, one copying out -- which is how copies and kernels overlap. */
 DNB_API int dnb_submit(dnb_ctx *ctx, const dnb_read_desc *reads, size_t n_reads, dnb_batch **batch);
 DNB_API int dnb_wait(dnb_batch *batch);
 DNB_API int dnb_result(dnb_batch *batch, size_t i, dnb_read_result *out);
 DNB_API void dnb_release(dnb_batch *batch);
+/* Rebuild the dense arrays of a DNB_RESULT_COMPACT result in caller memory (e.g. straight into the std::vector the
+ * reference keeps them in): event_start[n_events + 1], align_pairs[2 * n_align].  Dense results are copied. */
+DNB_API int dnb_expand_events(const dnb_read_result *res, uint32_t *event_start);
+DNB_API int dnb_expand_alignment(const dnb_read_result *res, uint32_t *align_pairs);
+
+/* ---- caller-owned pinned memory: zero-staging ingest ----------------------------------------------------------
+ * dnb_submit copies a read's signal to the device straight from the caller's buffer when that buffer is page-locked
+ * (registered here, allocated here, or by the caller's own cudaHostAlloc / cudaHostRegister); pageable buffers are
+ * first packed into the library's pinned staging area (one extra pass over host memory).  A POD5 loader that
+ * decompresses into dnb_host_alloc'ed memory therefore feeds the GPUs without touching the samples again. */
+DNB_API int dnb_host_register(void *p, size_t bytes);
+DNB_API int dnb_host_unregister(void *p);
+DNB_API int dnb_host_alloc(void **p, size_t bytes);
+DNB_API void dnb_host_free(void *p);
+/* give the device and pinned blocks the context keeps cached between batches back to the driver */
+DNB_API int dnb_trim(dnb_ctx *ctx);
 
 /* Split form of dnb_submit for callers that keep inputs resident in HBM (bench `value` leg):
  * upload once, run the device pipeline any number of times, fetch results when wanted. */
@@ -150,6 +199,19 @@ DNB_API int dnb_batch_drop_workspace(dnb_batch *batch);
  * counts: [0]=samples [1]=events [2]=k-mers [3]=bands [4]=DP cells [5]=kernel launches
  *         [6]=reads the tiled segmentation handed to its serial kernel [7]=reads with status != DNB_READ_OK */
 DNB_API int dnb_batch_timings(dnb_batch *batch, double ms[8], uint64_t counts[8]);
+/* the segmentation part of ms[0], by kernel (CUDA events): [0] exact (sum, sumsq) checkpoints (scan or serial chain)
+ * [1] tiles (t-statistics + peak detectors)  [2] stitch + events + serial redo of flagged reads */
+DNB_API int dnb_batch_seg_timings(dnb_batch *batch, double ms[3]);
+/* Host-side accounting of the batch pipeline (process-wide, all contexts): wall seconds spent in every phase of
+ * upload / run / fetch, summed over the calling threads since the last reset -- where the host time of dnb_submit goes
+ * (waiting for a pipeline slot, packing, enqueueing, waiting for the GPU).  counts: [0] batches uploaded [1] of them
+ * with the signal DMA'd straight from page-locked caller memory [2] cudaMalloc calls [3] cudaMallocHost calls (both
+ * should be 0 in steady state: the context caches its blocks). */
+#define DNB_N_HOST_PHASES 17
+DNB_API int dnb_host_stats(int reset, double seconds[DNB_N_HOST_PHASES], uint64_t counts[4]);
+DNB_API const char *dnb_host_phase_name(int phase);
+/* device ordinal the batch was dealt to (contexts created with n_devices > 1) */
+DNB_API int dnb_batch_device(dnb_batch *batch);
 /* PCIe payload of this batch, counted from the copies made: host->device bytes of the upload (signal, sequences,
  * queryToRef, offset tables) and device->host bytes of the fetch (dense events, alignment pairs, per-read scalars) */
 DNB_API int dnb_batch_io_bytes(dnb_batch *batch, uint64_t *h2d_bytes, uint64_t *d2h_bytes);

@@ -118,10 +118,55 @@ def ref_oracle(pore_mean):
     return R
 
 
+def cuda_device_count() -> int:
+    """Devices the library can use, asked through the library itself (0 on a CPU-only machine)."""
+    from dnascent_b200 import api, _lib
+    try:
+        c = api.Context(device=0)
+    except _lib.DnbError as ex:
+        if ex.code == 2:          # DNB_ERR_CUDA: no device -- the library has no CPU path
+            return 0
+        raise
+    c.close()
+    try:
+        import torch
+        return max(int(torch.cuda.device_count()), 1)
+    except Exception:  # noqa: BLE001
+        return 1
+
+
+@pytest.fixture(scope="session")
+def n_cuda():
+    return cuda_device_count()
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests marked gpu are skipped (not errored) on a machine without a CUDA device: the shim's entry points abort()
+    the interpreter when dnb_create fails, so they must never be reached there."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if not gpu_items:
+        return
+    if cuda_device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (libdnascent_b200 has no CPU fallback)")
+    for it in gpu_items:
+        it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def ctx(pore_mean):
     from dnascent_b200 import api
     c = api.Context(device=0, keep_debug=True)
+    c.load_model(api.MODEL_PORE, pore_mean)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="session")
+def ctx_compact(pore_mean):
+    """The same library with the compact wire format (dnb_config.result_format = DNB_RESULT_COMPACT)."""
+    from dnascent_b200 import api
+    c = api.Context(device=0, keep_debug=True, result_format=api.RESULT_COMPACT)
     c.load_model(api.MODEL_PORE, pore_mean)
     yield c
     c.close()

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from dnascent_b200 import _lib
-    assert C.sizeof(_lib.ReadDesc) == 72 and _lib.READ_DESC_DTYPE.itemsize == 72
+    assert C.sizeof(_lib.ReadDesc) == 88 and _lib.READ_DESC_DTYPE.itemsize == 88
     assert C.sizeof(_lib.EventT) == 32
     cfg = _lib.Config()
     _lib.lib().dnb_default_config(C.byref(cfg))
@@ -54,7 +54,7 @@ def test_ctypes_mirrors_match_the_compiled_header(tmp_path):
     mirrors = {"dnb_config": _lib.Config, "dnb_read_desc": _lib.ReadDesc, "dnb_read_result": _lib.ReadResult,
                "dnb_event_t": _lib.EventT, "dnb_eventalign_desc": _lib.EventalignDesc, "dnb_feature_desc": _lib.FeatureDesc,
                "dnb_feature_tensors": _lib.FeatureTensors, "dnb_read_extra": _lib.ReadExtra,
-               "dnb_feature_result": _lib.FeatureResult}
+               "dnb_feature_result": _lib.FeatureResult, "dnb_q2r_run": _lib.Q2RRun}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dnascent_b200.h"', 'int main(void) {']
     for cname, st in mirrors.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -165,3 +165,45 @@ def test_dorado_slice_matches_vector_erase():
                 (100, 50, -1, 0, False)):
         with pytest.raises(_lib.DnbError):
             api.dorado_slice(*bad)
+
+
+def test_compact_result_expanders_are_the_inverse_of_the_wire_format():
+    """dnb_expand_events / dnb_expand_alignment are host code (no device needed): hand-built compact results, including
+    escaped event lengths and every step kind, must expand to the dense arrays they were made from."""
+    from dnascent_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        ne = int(rng.integers(1, 300))
+        lens = rng.integers(1, 40, size=ne).astype(np.uint32)
+        lens[rng.random(ne) < 0.05] = rng.integers(255, 100000, size=int((rng.random(ne) < 0.05).sum()) or 1)[0]
+        first = int(rng.integers(0, 5))
+        starts = np.concatenate([[first], first + np.cumsum(lens.astype(np.uint64))]).astype(np.uint32)
+        len8 = np.minimum(lens, 255).astype(np.uint8)
+        esc = np.ascontiguousarray(lens[lens >= 255], dtype=np.uint32)
+        na = int(rng.integers(1, 500))
+        codes = rng.integers(0, 3, size=na - 1).astype(np.uint8)
+        e0, k0 = int(rng.integers(0, 10)), int(rng.integers(0, 10))
+        ev = e0 + np.concatenate([[0], np.cumsum(codes != 2)])
+        km = k0 + np.concatenate([[0], np.cumsum(codes != 1)])
+        packed = np.zeros((na - 1 + 3) // 4 + 1, dtype=np.uint8)
+        for t, c in enumerate(codes):
+            packed[t >> 2] |= int(c) << (2 * (t & 3))
+        r = _lib.ReadResult()
+        r.n_events, r.n_align = ne, na
+        r.event_first = first
+        r.event_len8 = len8.ctypes.data_as(C.POINTER(C.c_uint8))
+        r.event_len_escape = esc.ctypes.data_as(C.POINTER(C.c_uint32)) if esc.size else None
+        r.n_event_len_escape = esc.size
+        r.align_first[0], r.align_first[1] = e0, k0
+        r.align_steps = packed.ctypes.data_as(C.POINTER(C.c_uint8))
+        out_s = np.zeros(ne + 1, dtype=np.uint32)
+        out_p = np.zeros((na, 2), dtype=np.uint32)
+        assert L.dnb_expand_events(C.byref(r), out_s.ctypes.data) == 0
+        assert L.dnb_expand_alignment(C.byref(r), out_p.ctypes.data) == 0
+        np.testing.assert_array_equal(out_s, starts)
+        np.testing.assert_array_equal(out_p[:, 0], ev)
+        np.testing.assert_array_equal(out_p[:, 1], km)
+        if esc.size:       # a truncated escape list is reported, not read past
+            r.n_event_len_escape = esc.size - 1
+            assert L.dnb_expand_events(C.byref(r), out_s.ctypes.data) == 5

@@ -108,6 +108,44 @@ def run_cpu_chain(reads, ref, mean, threads: int):
             "sample": f"{len(reads)} reads of the C2 length law ({ns} samples, {t:.1f} s wall, {failed} failed)"}
 
 
+def synthetic_analogue_tables(mean: np.ndarray, seed: int = 99):
+    """(unlabelled, analogue) Gaussian tables for the analogue bench leg: a seeded perturbation of the ONT table (T-containing
+    9-mers shifted in the analogue one), same shape and value range as r10.4.1_{unlabelled,BrdU}_gaussian.model."""
+    rng = np.random.default_rng(seed)
+    n = mean.size
+    unl = (mean + rng.normal(0, 0.02, size=n), rng.uniform(0.08, 0.20, size=n))
+    idx = np.arange(n)
+    has_t = np.zeros(n, dtype=bool)
+    for j in range(9):
+        has_t |= ((idx >> (2 * j)) & 3) == 1              # A=0 T=1 G=2 C=3 (src/data_IO.cpp:131-137)
+    ana = (np.where(has_t, unl[0] + rng.normal(0, 0.15, size=n), 0.0), np.where(has_t, rng.uniform(0.10, 0.25, size=n), 0.0))
+    return unl, ana
+
+
+def run_cpu_hmm(mean, threads: int, seed: int):
+    """The reference's detect --HMM loop body (normaliseEvents + llAcrossRead, detect.cpp:876-885) on all host threads,
+    on a bounded sample of 10-kb reads; only where oracle/_ref was built."""
+    from oracle import refbind
+    from dnascent_b200 import synth
+    if not refbind.available():
+        return None
+    R = refbind.Ref()
+    R.set_model(refbind.PORE, mean, np.full(mean.size, 0.14))
+    unl, ana = synthetic_analogue_tables(mean)
+    R.set_model(refbind.UNLABELLED, *unl)
+    R.set_model(refbind.ANALOGUE, *ana)
+    ref = synth.make_reference(200_000, seed + 5)
+    R.set_reference(ref)
+    reads = synth.simulate_batch(ref, [10_000] * threads, mean, seed=seed + 6)
+    handles = [R.read_new(r) for r in reads]
+    t, failed, calls = R.bench_hmm(handles, threads, 12)
+    for h in handles:
+        h.free()
+    return {"value": calls / t, "unit": "LLR calls/s (sites scored, both passes)", "cores": threads, "kind": "reference",
+            "reads_per_s": len(reads) / t,
+            "sample": f"{len(reads)} reads of 10 kb ({calls} calls, {t:.1f} s wall, {failed} failed)"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -247,6 +285,10 @@ def main():
                     help="dnb_submit calls in flight (B200 sweep, 60k reads: 4e8x4 74 %% of the resident value, 8e8x8 84 %%)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pin", action="store_true", help="leave the workload pageable (e2e goes through pinned staging)")
+    ap.add_argument("--ultra-reads", type=int, default=600,
+                    help="reads per GPU of the configs[2] leg (lengths log-uniform in 100 kb - 1 Mb, inputs resident); 0 = skip")
+    ap.add_argument("--analogue-reads", type=int, default=4000,
+                    help="10-kb reads (whole job) of the configs[3] leg: normaliseEvents + llAcrossRead on the device (dnb_submit_llr); 0 = skip")
     ap.add_argument("--parity-reads", type=int, default=64, help="reads of the workload re-run on the CPU reference (0 = skip)")
     ap.add_argument("--chain-reads", type=int, default=4000,
                     help="reads (whole job) of the rows f1-f2 leg (dnb_submit_chain); 0 = skip")
@@ -523,6 +565,116 @@ def main():
                                     else "window-parallel",
                  "cpu_reference": None}
 
+    # ---- ultra-long leg (BASELINE configs[2]): lengths log-uniform in [100 kb, 1 Mb], inputs resident in HBM.  One warp
+    # walks one read's band chain, so a bin of few very long reads cannot fill the device: report how full it was
+    # (warps against resident warp slots) and what the longest read's serial chain costs (the tail).
+    ultra = None
+    if args.ultra_reads > 0:
+        rng_u = np.random.default_rng(args.seed + 4242 + rank)
+        lens_u = np.exp(rng_u.uniform(np.log(100_000), np.log(1_000_000), size=args.ultra_reads)).astype(np.int64)
+        WU = bench_data.generate(lens_u, mean, args.seed + 4243 + 1000 * rank, device=f"cuda:{local}", ref_len=1_050_000)
+        u_bins = sharding.make_bins(WU.n_samples, int(args.bin_samples))
+        u_batches = [ctx.upload_descs(WU.descs(b)) for b in u_bins]
+        u_ms, u_cnt, per_bin = {}, {}, []
+
+        def ultra_step(record):
+            for k, b in enumerate(u_batches):
+                b.run()
+                ms, cnt = b.timings()
+                if record:
+                    for k2, v2 in ms.items():
+                        u_ms[k2] = u_ms.get(k2, 0.0) + v2
+                    for k2, v2 in cnt.items():
+                        u_cnt[k2] = u_cnt.get(k2, 0) + v2
+                    if len(per_bin) < len(u_batches):
+                        launch = ms["banded_dp"] + ms["backtrace"]
+                        per_bin.append({"reads": int(u_bins[k].size), "samples": int(WU.n_samples[u_bins[k]].sum()),
+                                        "longest_read_samples": int(WU.n_samples[u_bins[k]].max()),
+                                        "warps": int(u_bins[k].size), "resident_warp_slots": 148 * 16,
+                                        "occupancy_of_slots": u_bins[k].size / (148 * 16.0),
+                                        "align_launch_ms": launch, "cells_per_s": cnt["cells"] / (launch / 1e3),
+                                        "failed_reads": cnt["failed_reads"]})
+                b.drop_workspace()
+
+        ultra_step(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ultra_step(True)
+        barrier()
+        dt_u = max_over_ranks(time.perf_counter() - t0) / 2
+        u_samples = sum_over_ranks(float(WU.n_samples.sum()))
+        for b in u_batches:
+            b.release()
+        c2_cells_per_s = cells / launch_s
+        for pb in per_bin:
+            # the same cells at the rate the saturated C2 bins reach: what is above that is under-fill + tail
+            pb["tail_factor"] = pb["cells_per_s"] and c2_cells_per_s / pb["cells_per_s"]
+        ultra = {"what": "configs[2]: lengths log-uniform in [100 kb, 1 Mb], inputs resident, dnb_batch_run per bin",
+                 "value": u_samples / dt_u / 1e6, "unit": UNIT, "reads_per_gpu": int(args.ultra_reads),
+                 "samples_per_gpu": int(WU.n_samples.sum()), "ms_per_pass": 1e3 * dt_u,
+                 "stage_ms_per_pass": {k2: v2 / 2 for k2, v2 in u_ms.items()},
+                 "failed_reads": int(u_cnt.get("failed_reads", 0)) // 2, "bins": per_bin,
+                 "saturated_cells_per_s_for_comparison": c2_cells_per_s}
+        del WU
+
+    # ---- analogue leg (SURVEY s.8 row a15, BASELINE configs[3]): detect --HMM's loop body, normaliseEvents + llAcrossRead,
+    # on 10-kb reads through dnb_submit_llr: host buffers in, (site, log-likelihoods) out; metric = LLR calls per second
+    analogue = None
+    if args.analogue_reads > 0:
+        n_a = max(args.analogue_reads // world, 100)
+        unl, ana = synthetic_analogue_tables(mean)
+        ctx.load_model(api.MODEL_UNLABELLED, *unl)
+        ctx.load_model(api.MODEL_ANALOGUE, *ana)
+        WA = bench_data.generate(np.full(n_a, 10_000), mean, args.seed + 77 + 1000 * rank, device=f"cuda:{local}")
+        a_bins = sharding.make_bins(WA.n_samples, int(2.0e8))
+        a_descs = [WA.descs(b) for b in a_bins]
+        a_extras = []
+        for dsc in a_descs:
+            x = np.zeros(dsc.size, dtype=_lib.READ_EXTRA_DTYPE)
+            x["ref_to_query"] = WA.q2r.ctypes.data
+            x["ref_end"] = dsc["ref_len"]
+            x["is_reverse"] = np.arange(dsc.size) & 1
+            a_extras.append(x)
+        a_acc = {}
+
+        def analogue_one(k):
+            b = ctx.submit_llr_descs(a_descs[k], a_extras[k], 12)
+            tm = b.analogue_timings()
+            io = b.io_bytes()
+            b.release()
+            return tm, io
+
+        def analogue_pass():
+            a_acc.clear()
+            with ThreadPoolExecutor(max_workers=2) as ex:
+                for tm, io in ex.map(analogue_one, range(len(a_descs))):
+                    for k2, v2 in tm.items():
+                        a_acc[k2] = a_acc.get(k2, 0) + v2
+                    a_acc["h2d"] = a_acc.get("h2d", 0) + io[0]
+
+        analogue_pass()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            analogue_pass()
+        barrier()
+        dt_a = max_over_ranks(time.perf_counter() - t0) / 2
+        calls_total = sum_over_ranks(float(a_acc["calls"]))
+        analogue = {"what": "dnb_submit_llr: normaliseEvents -> llAcrossRead (T sites, event windows, both forward passes per site "
+                            "on the device), host buffers in, per-site log-likelihoods out; 10-kb reads (configs[3] shape)",
+                    "value": calls_total / dt_a, "unit": "LLR calls/s (sites scored, both passes)",
+                    "reads_per_gpu": int(n_a), "reads_per_s": world * n_a / dt_a, "ms_per_pass": 1e3 * dt_a,
+                    "candidate_sites_per_gpu": int(a_acc["candidate_sites"]), "calls_per_gpu": int(a_acc["calls"]),
+                    "observations_per_gpu": int(a_acc["observations"]),
+                    "forward_kernel_ms": a_acc["forward_kernel_ms"], "sites_kernel_ms": a_acc["sites_kernel_ms"],
+                    "forward_kernel_calls_per_s": a_acc["calls"] / (a_acc["forward_kernel_ms"] / 1e3) if a_acc["forward_kernel_ms"] else None,
+                    "d2h_bytes_per_pass": int(a_acc["d2h_bytes"]),
+                    "tables": "synthetic (seeded perturbation of the ONT 9-mer table; the fitted BrdU/EdU tables are not "
+                              "shipped to the GPU box -- parity on the real tables is tests/test_analogue_gpu.py)",
+                    "cpu_reference": None}
+        del WA
+
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -545,6 +697,11 @@ def main():
                 chain["cpu_reference"] = run_cpu_chain(reads[: 2 * cores], ref, mean_c, cores)
             except Exception as ex:  # noqa: BLE001
                 chain["cpu_reference"] = {"error": repr(ex)}
+        if analogue is not None:
+            try:
+                analogue["cpu_reference"] = run_cpu_hmm(mean_c, cores, args.seed)
+            except Exception as ex:  # noqa: BLE001
+                analogue["cpu_reference"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {
@@ -562,7 +719,7 @@ def main():
                 "stage_ms_per_step": per_step, "counts_per_step": cnt_step, "generation_s": gen_s,
             },
             "roofline": roofline, "roofline_segmentation": roofline_seg, "cpu_baseline": cpu, "chain": chain,
-            "parity_check": parity,
+            "analogue": analogue, "ultra_long": ultra, "parity_check": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": 1e3 * dt_e / args.steps, "inflight": args.e2e_inflight, "bins": len(e2e_bins),
                     "samples_per_submit": args.e2e_bin_samples, "failed_reads_per_step": int(e2e_bad),

@@ -109,6 +109,12 @@ class FeatureResult(C.Structure):
                 ("n_recs", C.c_uint32), ("recs", C.c_void_p)]
 
 
+class AnalogueResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("n_sites", C.c_uint32), ("pos_on_ref", C.POINTER(C.c_uint32)),
+                ("n_events", C.POINTER(C.c_uint32)), ("log_analogue", C.POINTER(C.c_double)),
+                ("log_thymidine", C.POINTER(C.c_double))]
+
+
 RAWDEPTH = 20
 EVENTALIGN_REC_DTYPE = _np.dtype([("event", _np.uint32), ("ref_pos", _np.uint32), ("indel_score", _np.int32),
                                   ("label", _np.uint32)])
@@ -134,6 +140,7 @@ EXPORTS = [
     "dnb_dorado_slice", "dnb_submit_chain",
     "dnb_expand_events", "dnb_expand_alignment", "dnb_host_register", "dnb_host_unregister", "dnb_host_alloc",
     "dnb_host_free", "dnb_trim", "dnb_batch_seg_timings", "dnb_batch_device", "dnb_host_stats", "dnb_host_phase_name",
+    "dnb_batch_analogue_llr", "dnb_batch_analogue_result", "dnb_submit_llr", "dnb_batch_analogue_timings",
 ]
 
 
@@ -201,6 +208,10 @@ def lib():
     L.dnb_host_stats.argtypes = [C.c_int, C.POINTER(d * 17), C.POINTER(C.c_uint64 * 4)]
     L.dnb_host_phase_name.argtypes = [C.c_int]
     L.dnb_host_phase_name.restype = C.c_char_p
+    L.dnb_batch_analogue_llr.argtypes = [vp, vp, C.c_uint32]
+    L.dnb_batch_analogue_result.argtypes = [vp, sz, C.POINTER(AnalogueResult)]
+    L.dnb_submit_llr.argtypes = [vp, vp, vp, sz, C.c_uint32, C.POINTER(vp)]
+    L.dnb_batch_analogue_timings.argtypes = [vp, C.POINTER(d * 2), C.POINTER(C.c_uint64 * 4)]
     _lib = L
     return L
 

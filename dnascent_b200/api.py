@@ -206,6 +206,43 @@ class Batch:
             out.append(o)
         return out
 
+    # -- resident analogue stage: llAcrossRead (detect.cpp:393-574) on what run() left in HBM -------------------------
+    def analogue_llr(self, extra, window: int = 12):
+        """`extra`: per read a dict with ref_to_query (int32[ref_len]) and is_reverse (ref_start / ref_end are only used
+        for the global coordinate returned here).  Returns analogue_results()."""
+        assert len(extra) == self.n
+        ex, keep = _extras(extra)
+        _lib.check(self.ctx.L.dnb_batch_analogue_llr(self.h, C.addressof(ex), window), "dnb_batch_analogue_llr")
+        return self.analogue_results(extra)
+
+    def analogue_results(self, extra=None):
+        """Per read a dict: pos_on_ref, n_events, log_analogue, log_thymidine, llr of the sites where a call was made,
+        in llAcrossRead's visiting order; with `extra` also pos_global as the reference computes it (:530-538)."""
+        out = []
+        for i in range(self.n):
+            ar = _lib.AnalogueResult()
+            _lib.check(self.ctx.L.dnb_batch_analogue_result(self.h, i, C.byref(ar)), "dnb_batch_analogue_result")
+            n = ar.n_sites
+            nev = _as(ar.n_events, n, np.uint32)
+            keep = nev > 0
+            pos = _as(ar.pos_on_ref, n, np.uint32)[keep]
+            la, lt = _as(ar.log_analogue, n, np.float64)[keep], _as(ar.log_thymidine, n, np.float64)[keep]
+            o = dict(status=ar.status, n_sites=int(n), pos_on_ref=pos, n_events=nev[keep], log_analogue=la, log_thymidine=lt,
+                     llr=la - lt)
+            if extra is not None:
+                x = extra[i]
+                o["pos_global"] = (int(x["ref_end"]) - pos.astype(np.int64) - 1 if x["is_reverse"]
+                                   else int(x["ref_start"]) + pos.astype(np.int64))
+            out.append(o)
+        return out
+
+    def analogue_timings(self):
+        ms = (C.c_double * 2)()
+        cnt = (C.c_uint64 * 4)()
+        _lib.check(self.ctx.L.dnb_batch_analogue_timings(self.h, C.byref(ms), C.byref(cnt)), "dnb_batch_analogue_timings")
+        return dict(sites_kernel_ms=ms[0], forward_kernel_ms=ms[1], candidate_sites=int(cnt[0]), calls=int(cnt[1]),
+                    observations=int(cnt[2]), d2h_bytes=int(cnt[3]))
+
     def feature_rows(self) -> int:
         """Total tensor rows of the batch (sum of dnb_feature_result.n_pos), without copying the tensors."""
         fr = _lib.FeatureResult()
@@ -330,6 +367,23 @@ class Context:
         _lib.check(self.L.dnb_submit_chain(self.h, C.addressof(descs), C.addressof(ex), len(reads), window,
                                            int(want_records), C.byref(h)), "dnb_submit_chain")
         return Batch(self, h, len(reads), (keep, keep2))
+
+    def submit_llr(self, reads, extra, window: int = 12) -> Batch:
+        """dnb_submit_llr: normaliseEvents + llAcrossRead (the --HMM read loop body, detect.cpp:876-885) in one pipelined
+        call; read the results with Batch.results() and Batch.analogue_results()."""
+        descs, keep = self._descs(reads)
+        ex, keep2 = _extras(extra)
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_submit_llr(self.h, C.addressof(descs), C.addressof(ex), len(reads), window, C.byref(h)),
+                   "dnb_submit_llr")
+        return Batch(self, h, len(reads), (keep, keep2))
+
+    def submit_llr_descs(self, descs: np.ndarray, extras: np.ndarray, window: int = 12) -> Batch:
+        assert descs.size == extras.size
+        h = C.c_void_p()
+        _lib.check(self.L.dnb_submit_llr(self.h, descs.ctypes.data, extras.ctypes.data, descs.size, window, C.byref(h)),
+                   "dnb_submit_llr")
+        return Batch(self, h, descs.size, (descs, extras))
 
     # descriptor arrays built with numpy (dtype _lib.READ_DESC_DTYPE): no per-read Python objects
     def submit_descs(self, descs: np.ndarray) -> Batch:

@@ -342,6 +342,16 @@ struct Stage2 {
     uint64_t bytes[2] = {0, 0};
 };
 
+// results of the resident analogue stage (dnb_batch_analogue_llr), pinned host
+struct Stage3 {
+    bool done = false;
+    std::vector<uint64_t> poi_off;
+    uint32_t *h_n_poi = nullptr, *h_pos = nullptr, *h_nev = nullptr;
+    double *h_a = nullptr, *h_t = nullptr;
+    double ms[2] = {0.0, 0.0};
+    uint64_t counts[4] = {0, 0, 0, 0};
+};
+
 struct dnb_batch {
     dnb_ctx *ctx = nullptr;
     size_t R = 0;
@@ -375,6 +385,7 @@ struct dnb_batch {
     unsigned long long h_cells[3] = {};
     std::vector<void *> input_allocs, work_allocs, res_allocs;
     Stage2 s2;
+    Stage3 s3;
 };
 
 namespace {
@@ -407,6 +418,25 @@ int dev_alloc(dnb_batch *b, std::vector<void *> &owner, T **p, size_t n) {
 }
 template <class T> int ialloc(dnb_batch *b, T **p, size_t n) { return dev_alloc(b, b->input_allocs, p, n); }
 template <class T> int walloc(dnb_batch *b, T **p, size_t n) { return dev_alloc(b, b->work_allocs, p, n); }
+
+// A group of device arrays carved out of ONE cached block: a batch then takes a handful of blocks of a few coarse
+// size classes instead of ~60 exact-size ones, and concurrent batches of similar size find each other's blocks in the
+// cache (a cache miss is a cudaMalloc, which stalls every stream of the device).
+struct Arena {
+    struct Item { void **p; size_t bytes; };
+    std::vector<Item> items;
+    template <class T> void add(T **p, size_t n) { *p = nullptr; items.push_back({(void **)p, (n ? n : 1) * sizeof(T)}); }
+    int commit(dnb_batch *b, std::vector<void *> &owner) {
+        size_t tot = 0;
+        for (auto &it : items) tot += (it.bytes + 255) & ~(size_t)255;
+        uint8_t *base = nullptr;
+        TRY(dev_alloc(b, owner, &base, tot));
+        size_t off = 0;
+        for (auto &it : items) { *it.p = base + off; off += (it.bytes + 255) & ~(size_t)255; }
+        items.clear();
+        return DNB_OK;
+    }
+};
 
 template <class T>
 int ralloc(dnb_batch *b, T **p, size_t n) {   // pinned host, from the context pool
@@ -472,6 +502,7 @@ void drop_results(dnb_batch *b) {
     b->res_allocs.clear();
     b->h = HostRes{};
     b->s2 = Stage2{};
+    b->s3 = Stage3{};
     b->fetched = false;
 }
 
@@ -669,16 +700,21 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
     ht.tick(PH_UP_PACK);
     if (gated) gate.enter(&ctx->gate_h2d);
     ht.tick(PH_UP_GATE_H2D);
-    TRYF(ialloc(b, (uint8_t **)&b->d_raw, ro * esz));
-    TRYF(ialloc(b, &b->d_query, qo));
-    if (same_seq) b->d_ref = b->d_query; else TRYF(ialloc(b, &b->d_ref, fo));
-    if (!want_table) TRYF(ialloc(b, &b->d_q2r, qo));
-    TRYF(ialloc(b, &b->d_dac_off, R)); TRYF(ialloc(b, &b->d_dac_scl, R));
-    TRYF(ialloc(b, &b->d_raw_off, R + 1)); TRYF(ialloc(b, &b->d_q_off, R + 1));
-    if (same_seq) b->d_r_off = b->d_q_off; else TRYF(ialloc(b, &b->d_r_off, R + 1));
-    TRYF(ialloc(b, &b->d_ev_off, R + 1)); TRYF(ialloc(b, &b->d_n_samples, R)); TRYF(ialloc(b, &b->d_order, R));
-    TRYF(ialloc(b, &b->d_tile_off, R + 1)); TRYF(ialloc(b, &b->d_tile_read, nt));
-    TRYF(ialloc(b, &b->d_ck_off, R + 1));
+    Arena ar;
+    ar.add((uint8_t **)&b->d_raw, ro * esz);
+    ar.add(&b->d_query, qo);
+    if (!same_seq) ar.add(&b->d_ref, fo);
+    if (!want_table) ar.add(&b->d_q2r, qo);
+    ar.add(&b->d_dac_off, R); ar.add(&b->d_dac_scl, R);
+    ar.add(&b->d_raw_off, R + 1); ar.add(&b->d_q_off, R + 1);
+    if (!same_seq) ar.add(&b->d_r_off, R + 1);
+    ar.add(&b->d_ev_off, R + 1); ar.add(&b->d_n_samples, R); ar.add(&b->d_order, R);
+    ar.add(&b->d_tile_off, R + 1); ar.add(&b->d_tile_read, nt);
+    ar.add(&b->d_ck_off, R + 1);
+    dnb_q2r_run *d_runs = nullptr; uint64_t *d_run_base = nullptr; uint32_t *d_run_len = nullptr;
+    if (any_runs) { ar.add(&d_runs, n_runs); ar.add(&d_run_base, n_runs); ar.add(&d_run_len, n_runs); }
+    TRYF(ar.commit(b, b->input_allocs));
+    if (same_seq) { b->d_ref = b->d_query; b->d_r_off = b->d_q_off; }
     uint64_t sent = 0;
     auto send = [&](void *dst, const void *src, size_t bytes) -> int {
         if (bytes == 0) return DNB_OK;
@@ -708,8 +744,6 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
     if (any_dense) TRYF(send(b->d_q2r, h_q2r, qo * 4));
     else if (!want_table) {
         // compact queryToRef: 16 B per run over PCIe, expanded to the dense array the backtrace reads in HBM
-        dnb_q2r_run *d_runs = nullptr; uint64_t *d_run_base = nullptr; uint32_t *d_run_len = nullptr;
-        TRYF(ialloc(b, &d_runs, n_runs)); TRYF(ialloc(b, &d_run_base, n_runs)); TRYF(ialloc(b, &d_run_len, n_runs));
         if (qo) { cudaError_t em = cudaMemsetAsync(b->d_q2r, 0xFF, qo * 4, b->stream); if (em != cudaSuccess) { g_last_error = cudaGetErrorString(em); TRYF(DNB_ERR_CUDA); } }
         TRYF(send(d_runs, h_runs, n_runs * sizeof(dnb_q2r_run)));
         TRYF(send(d_run_base, h_run_base, n_runs * 8)); TRYF(send(d_run_len, h_run_len, n_runs * 4));
@@ -718,9 +752,32 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
     if (direct) {
         // one DMA per read, from where the caller has it to its padded slot; nothing touches the samples on the host
         uint8_t *base = (uint8_t *)b->d_raw;
-        for (size_t i = 0; i < R; i++)
-            TRYF(send(base + b->raw_off[i] * esz, b->i16 ? (const void *)reads[i].raw_dac : (const void *)reads[i].raw_pA,
-                      (size_t)reads[i].n_samples * esz));
+        // all of them in one driver call where the runtime has cudaMemcpyBatchAsync (CUDA >= 12.8): a per-read
+        // cudaMemcpyAsync costs 5-20 us of host time under load, which at 10^5 reads per step is the H2D stage's time
+        static const bool no_batch = getenv("DNB_NO_BATCH_MEMCPY") != nullptr && getenv("DNB_NO_BATCH_MEMCPY")[0] == '1';
+        bool batched = false;
+        if (!no_batch && R > 1) {
+            std::vector<void *> dsts(R), srcs(R);
+            std::vector<size_t> sizes(R);
+            uint64_t tot = 0;
+            for (size_t i = 0; i < R; i++) {
+                dsts[i] = base + b->raw_off[i] * esz;
+                srcs[i] = b->i16 ? (void *)reads[i].raw_dac : (void *)reads[i].raw_pA;
+                sizes[i] = (size_t)reads[i].n_samples * esz;
+                tot += sizes[i];
+            }
+            cudaMemcpyAttributes at;
+            memset(&at, 0, sizeof(at));
+            at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;     // the caller's buffers stay valid until we return
+            size_t attr_idx = 0, fail_idx = 0;
+            const cudaError_t eb = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), R, &at, &attr_idx, 1, &fail_idx, b->stream);
+            if (eb == cudaSuccess) { batched = true; sent += tot; }
+            else cudaGetLastError();                                // e.g. an older driver: fall back to one call per read
+        }
+        if (!batched)
+            for (size_t i = 0; i < R; i++)
+                TRYF(send(base + b->raw_off[i] * esz, b->i16 ? (const void *)reads[i].raw_dac : (const void *)reads[i].raw_pA,
+                          (size_t)reads[i].n_samples * esz));
         dnb_launch_zero_padding(make_view(b), (uint32_t)esz, b->stream);
     } else {
         TRYF(send(b->d_raw, h_raw, ro * esz));
@@ -744,22 +801,26 @@ int upload(dnb_ctx *ctx, const dnb_read_desc *reads, size_t R, bool want_table, 
 int alloc_work_a(dnb_batch *b) {
     const size_t R = b->R, eo = b->tot_ev, qo = b->tot_q, fo = b->tot_r;
     Work &w = b->w;
-    TRY(walloc(b, &w.et_n, R)); TRY(walloc(b, &w.n_events, R)); TRY(walloc(b, &w.status, R));
-    TRY(walloc(b, &w.ev_start, eo + R)); TRY(walloc(b, &w.ev_mean, eo));
-    TRY(walloc(b, &w.tot_sum, R)); TRY(walloc(b, &w.redo, R));
+    Arena ar;
+    ar.add(&w.et_n, R); ar.add(&w.n_events, R); ar.add(&w.status, R);
+    ar.add(&w.ev_start, eo + R); ar.add(&w.ev_mean, eo);
+    ar.add(&w.tot_sum, R); ar.add(&w.redo, R);
     if (b->want_table) {
-        TRY(walloc(b, &w.et_start, eo + R)); TRY(walloc(b, &w.et_length, eo + R));
-        TRY(walloc(b, &w.et_mean, eo + R)); TRY(walloc(b, &w.et_stdv, eo + R));
+        ar.add(&w.et_start, eo + R); ar.add(&w.et_length, eo + R);
+        ar.add(&w.et_mean, eo + R); ar.add(&w.et_stdv, eo + R);
     } else {
-        TRY(walloc(b, &w.mu_q, qo)); TRY(walloc(b, &w.rank_ref, fo)); TRY(walloc(b, &w.x_e, eo));
-        TRY(walloc(b, &w.rough_shift, R)); TRY(walloc(b, &w.rough_scale, R)); TRY(walloc(b, &w.lp, 4 * R));
-        TRY(walloc(b, &w.band_off, R + 1)); TRY(walloc(b, &w.al_off, R + 1)); TRY(walloc(b, &w.cl_off, R + 1));
-        TRY(walloc(b, &w.out_off, R + 1));
-        TRY(walloc(b, &w.end_event, R)); TRY(walloc(b, &w.end_ll, R)); TRY(walloc(b, &w.end_score, R));
-        TRY(walloc(b, &w.cells, 3));
-        TRY(walloc(b, &w.n_align, R)); TRY(walloc(b, &w.n_cleaned, R)); TRY(walloc(b, &w.avg, R));
-        TRY(walloc(b, &w.shift, R)); TRY(walloc(b, &w.scale, R)); TRY(walloc(b, &w.spanned, R)); TRY(walloc(b, &w.max_gap, R));
-        TRY(walloc(b, &w.n_long, R));
+        ar.add(&w.mu_q, qo); ar.add(&w.rank_ref, fo); ar.add(&w.x_e, eo);
+        ar.add(&w.rough_shift, R); ar.add(&w.rough_scale, R); ar.add(&w.lp, 4 * R);
+        ar.add(&w.band_off, R + 1); ar.add(&w.al_off, R + 1); ar.add(&w.cl_off, R + 1);
+        ar.add(&w.out_off, R + 1);
+        ar.add(&w.end_event, R); ar.add(&w.end_ll, R); ar.add(&w.end_score, R);
+        ar.add(&w.cells, 3);
+        ar.add(&w.n_align, R); ar.add(&w.n_cleaned, R); ar.add(&w.avg, R);
+        ar.add(&w.shift, R); ar.add(&w.scale, R); ar.add(&w.spanned, R); ar.add(&w.max_gap, R);
+        ar.add(&w.n_long, R);
+    }
+    TRY(ar.commit(b, b->work_allocs));
+    if (!b->want_table) {
         // reads that stop early (UNDEFINED, OVERFLOW) never write their scalars and the blocks are recycled: hand out
         // zeros, not another batch's values
         for (void *p : {(void *)w.rough_shift, (void *)w.rough_scale, (void *)w.shift, (void *)w.scale, (void *)w.avg})
@@ -803,11 +864,13 @@ int run(dnb_batch *b) {
     } else {
         // per-run scratch of the tiled segmentation (back in the pool before the DP workspace is taken)
         const size_t nt = b->tile_off[R], nck = b->ck_off[R];
-        uint8_t *scratch[11] = {};
-        auto sal = [&](int i, size_t bytes) -> int { return dev_alloc(b, seg_scratch, &scratch[i], bytes); };
-        TRY(sal(0, nck * 8)); TRY(sal(1, nck * 8)); TRY(sal(2, nt * DNB_SEG_PEAK_CAP * 4)); TRY(sal(3, nt * DNB_SEG_PEAK_CAP * 8));
-        TRY(sal(4, nt * 4)); TRY(sal(5, nt * DNB_SEG_BOUNDARY_BYTES)); TRY(sal(6, nt * DNB_SEG_BOUNDARY_BYTES));
-        TRY(sal(7, nt * 4)); TRY(sal(8, nt * 4)); TRY(sal(9, nt * 8));
+        uint8_t *scratch[10] = {};
+        Arena sar;
+        auto sal = [&](int i, size_t bytes) { sar.add(&scratch[i], bytes); };
+        sal(0, nck * 8); sal(1, nck * 8); sal(2, nt * DNB_SEG_PEAK_CAP * 4); sal(3, nt * DNB_SEG_PEAK_CAP * 8);
+        sal(4, nt * 4); sal(5, nt * DNB_SEG_BOUNDARY_BYTES); sal(6, nt * DNB_SEG_BOUNDARY_BYTES);
+        sal(7, nt * 4); sal(8, nt * 4); sal(9, nt * 8);
+        TRY(sar.commit(b, seg_scratch));
         DnbSegTiles t;
         memset(&t, 0, sizeof(t));
         t.n_tiles = (uint32_t)nt; t.tile_off = b->d_tile_off; t.tile_read = b->d_tile_read; t.ck_off = b->d_ck_off;
@@ -816,7 +879,6 @@ int run(dnb_batch *b) {
         t.pk_sum = (double *)scratch[3]; t.pk_count = (uint32_t *)scratch[4]; t.b_start = (SegBoundary *)scratch[5];
         t.b_end = (SegBoundary *)scratch[6]; t.tile_prefix = (uint32_t *)scratch[7]; t.tile_prev_pos = (uint32_t *)scratch[8];
         t.tile_prev_sum = (double *)scratch[9];
-        if (dnb_seg_parity_scan_enabled()) { TRY(sal(10, dnb_seg_parity_scan_scratch_bytes(t, (uint32_t)R))); t.scan_scratch = scratch[10]; }
         dnb_launch_segmentation_tiled(v, det, t, s, b->ev[8], b->ev[9]); launches += 5;
         tick(PH_RUN_SEG_LAUNCH);
     }
@@ -869,9 +931,13 @@ int run(dnb_batch *b) {
     b->tot_bands = bo; b->tot_al = ao; b->tot_cl = co;
     Work &w = b->w;
     tick(PH_RUN_HOST);
-    TRY(walloc(b, &w.trace, bo * DNB_TRACE_ROW + 64));
-    TRY(walloc(b, &w.moves, (bo >> 5) + R + 2)); TRY(walloc(b, &w.rcum, (bo >> 5) + R + 2));
-    TRY(walloc(b, &w.al_rev, 2 * ao)); TRY(walloc(b, &w.cl_signal, co)); TRY(walloc(b, &w.cl_rank, co));
+    {
+        Arena ar;
+        ar.add(&w.trace, bo * DNB_TRACE_ROW + 64);
+        ar.add(&w.moves, (bo >> 5) + R + 2); ar.add(&w.rcum, (bo >> 5) + R + 2);
+        ar.add(&w.al_rev, 2 * ao); ar.add(&w.cl_signal, co); ar.add(&w.cl_rank, co);
+        TRY(ar.commit(b, b->work_allocs));
+    }
     tick(PH_RUN_ALLOC_B);
     TRY(h2d(b, w.lp, b->lp.data(), 4 * R));
     TRY(h2d(b, w.band_off, b->band_off.data(), R + 1));
@@ -991,11 +1057,13 @@ int fetch(dnb_batch *b) {
     b->tot_out = oo;
     b->counts[7] = n_fail;
     uint64_t *d_cev_off = nullptr;
-    TRY(walloc(b, &d_cev_off, R + 1));
-    TRY(h2d(b, w.out_off, b->out_off.data(), R + 1));
-    TRY(h2d(b, d_cev_off, b->cev_off.data(), R + 1));
+    Arena ar;
+    ar.add(&d_cev_off, R + 1);
     if (!b->compact) {
-        TRY(walloc(b, &w.out_pairs, 2 * oo)); TRY(walloc(b, &w.cev_start, ce + R)); TRY(walloc(b, &w.cev_mean, ce));
+        ar.add(&w.out_pairs, 2 * oo); ar.add(&w.cev_start, ce + R); ar.add(&w.cev_mean, ce);
+        TRY(ar.commit(b, b->work_allocs));
+        TRY(h2d(b, w.out_off, b->out_off.data(), R + 1));
+        TRY(h2d(b, d_cev_off, b->cev_off.data(), R + 1));
         TRY(ralloc(b, &h.out_pairs, 2 * oo)); TRY(ralloc(b, &h.ev_start, ce + R)); TRY(ralloc(b, &h.ev_mean, ce));
         dnb_launch_compact_events(make_view(b), d_cev_off, w.cev_start, w.cev_mean, s);
         TRY(d2h(b, h.ev_start, w.cev_start, ce + R));
@@ -1016,10 +1084,13 @@ int fetch(dnb_batch *b) {
         uint64_t *d_esc_off = nullptr, *d_step_off = nullptr;
         uint8_t *d_len8 = nullptr, *d_steps = nullptr;
         uint32_t *d_esc = nullptr, *d_first_ev = nullptr, *d_first_pair = nullptr, *d_bad = nullptr;
-        TRY(walloc(b, &d_esc_off, R + 1)); TRY(walloc(b, &d_step_off, R + 1));
-        TRY(walloc(b, &d_len8, ce)); TRY(walloc(b, &w.cev_mean, ce)); TRY(walloc(b, &d_esc, xo));
-        TRY(walloc(b, &d_first_ev, R)); TRY(walloc(b, &d_steps, so)); TRY(walloc(b, &d_first_pair, 2 * R));
-        TRY(walloc(b, &d_bad, R));
+        ar.add(&d_esc_off, R + 1); ar.add(&d_step_off, R + 1);
+        ar.add(&d_len8, ce); ar.add(&w.cev_mean, ce); ar.add(&d_esc, xo);
+        ar.add(&d_first_ev, R); ar.add(&d_steps, so); ar.add(&d_first_pair, 2 * R);
+        ar.add(&d_bad, R);
+        TRY(ar.commit(b, b->work_allocs));
+        TRY(h2d(b, w.out_off, b->out_off.data(), R + 1));
+        TRY(h2d(b, d_cev_off, b->cev_off.data(), R + 1));
         TRY(ralloc(b, &h.len8, ce)); TRY(ralloc(b, &h.ev_mean, ce)); TRY(ralloc(b, &h.esc, xo));
         TRY(ralloc(b, &h.first_ev, R)); TRY(ralloc(b, &h.steps, so)); TRY(ralloc(b, &h.first_pair, 2 * R));
         TRY(ralloc(b, &h.bad_steps, R));
@@ -1658,7 +1729,17 @@ static int eventalign_impl(dnb_ctx *ctx, const dnb_eventalign_desc *reads, const
         a.d2d = d2d; a.d2m = d2m; a.i2m = i2m; a.m2d = m2d; a.m2i = m2i; a.i2i = i2i;
         a.rec_off = d_rec_off; a.recs = d_recs; a.n_rec = d_nrec; a.status = d_status; a.next_read = d_next;
         fail(cudaEventRecord(e0, s));
-        if (ea_window_parallel()) fail(dnb_run_eventalign_wp(a, tot_ref, tot_al, ctx->cfg.device, s));
+        if (ea_window_parallel()) {
+            struct PoolUser { dnb_ctx *ctx; cudaStream_t s; std::vector<void *> *owned; } pu{ctx, s, &owned};
+            DnbAlloc al{[](void *u, size_t bytes) -> void * {
+                            PoolUser *q = (PoolUser *)u;
+                            void *p = nullptr;
+                            if (pool_alloc(q->ctx, &p, bytes, q->s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+                            q->owned->push_back(p);
+                            return p;
+                        }, &pu};
+            fail(dnb_run_eventalign_wp(a, tot_ref, tot_al, ctx->cfg.device, s, al, nullptr));
+        }
         else dnb_launch_eventalign(a, grid, s);
         fail(cudaEventRecord(e1, s));
         fail(cudaGetLastError());
@@ -1808,21 +1889,25 @@ int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uin
     uint64_t *d_called_off, *d_rec_off, *d_pos_off; double *d_trans; int *d_status; unsigned int *d_next;
     dnb_eventalign_rec *d_recs;
     float *d_signal, *d_core, *d_resid; uint32_t *d_coords, *d_ri, *d_qi; int32_t *d_qual;
-    TRY(walloc(b, &d_r2q, tot_r)); TRY(walloc(b, &d_called, tot_called)); TRY(walloc(b, &d_called_off, R + 1));
-    TRY(walloc(b, &d_rstart, R)); TRY(walloc(b, &d_rend, R)); TRY(walloc(b, &d_rev, R)); TRY(walloc(b, &d_kind, R));
-    TRY(walloc(b, &d_rec_off, R + 1)); TRY(walloc(b, &d_pos_off, R + 1)); TRY(walloc(b, &d_trans, 4 * R));
-    TRY(walloc(b, &d_status, R)); TRY(walloc(b, &d_nrec, R)); TRY(walloc(b, &d_npos, R)); TRY(walloc(b, &d_next, 2));
-    TRY(walloc(b, &d_recs, tot_rec));
-    TRY(walloc(b, &d_signal, tot_pos * DNB_RAWDEPTH)); TRY(walloc(b, &d_core, tot_pos)); TRY(walloc(b, &d_resid, tot_pos));
-    TRY(walloc(b, &d_coords, tot_pos)); TRY(walloc(b, &d_ri, tot_pos)); TRY(walloc(b, &d_qi, tot_pos)); TRY(walloc(b, &d_qual, tot_pos));
+    Arena ar;
+    ar.add(&d_r2q, tot_r); ar.add(&d_called, tot_called); ar.add(&d_called_off, R + 1);
+    ar.add(&d_rstart, R); ar.add(&d_rend, R); ar.add(&d_rev, R); ar.add(&d_kind, R);
+    ar.add(&d_rec_off, R + 1); ar.add(&d_pos_off, R + 1); ar.add(&d_trans, 4 * R);
+    ar.add(&d_status, R); ar.add(&d_nrec, R); ar.add(&d_npos, R); ar.add(&d_next, 2);
+    ar.add(&d_recs, tot_rec);
+    ar.add(&d_signal, tot_pos * DNB_RAWDEPTH); ar.add(&d_core, tot_pos); ar.add(&d_resid, tot_pos);
+    ar.add(&d_coords, tot_pos); ar.add(&d_ri, tot_pos); ar.add(&d_qi, tot_pos); ar.add(&d_qual, tot_pos);
     DnbEaArgs a = {};
     a.n_reads = (uint32_t)R; a.window = window; a.t_max = 4096;
     unsigned grid = dnb_eventalign_grid(ctx->cfg.device);
     const unsigned wpb = dnb_eventalign_warps_per_block();
     if ((size_t)grid * wpb > R) grid = (unsigned)((R + wpb - 1) / wpb);
     const size_t warps = (size_t)grid * wpb;
-    TRY(walloc(b, &a.scratch_obs, warps * a.t_max)); TRY(walloc(b, &a.scratch_ev, warps * a.t_max));
-    TRY(walloc(b, &a.scratch_bt, warps * a.t_max * dnb_eventalign_bt_row_bytes()));
+    if (!ea_window_parallel()) {       // per-warp scratch rows of the read-serial kernel (the window-parallel one sizes its own)
+        ar.add(&a.scratch_obs, warps * a.t_max); ar.add(&a.scratch_ev, warps * a.t_max);
+        ar.add(&a.scratch_bt, warps * a.t_max * dnb_eventalign_bt_row_bytes());
+    }
+    TRY(ar.commit(b, b->work_allocs));
     TRY(h2d(b, d_r2q, st_r2q, tot_r)); TRY(h2d(b, d_called, st_called, tot_called));
     TRY(h2d(b, d_called_off, called_off.data(), R + 1)); TRY(h2d(b, d_rstart, h_rstart.data(), R));
     TRY(h2d(b, d_rend, h_rend.data(), R)); TRY(h2d(b, d_rev, h_rev.data(), R));
@@ -1843,7 +1928,15 @@ int dnb_batch_eventalign_features(dnb_batch *b, const dnb_read_extra *extra, uin
     a.rec_off = d_rec_off; a.recs = d_recs; a.n_rec = d_nrec; a.status = d_status; a.next_read = d_next;
     a.order = b->d_order;
     CK(cudaEventRecord(b->ev[0], s));
-    if (ea_window_parallel()) CK(dnb_run_eventalign_wp(a, tot_r, b->tot_out, ctx->cfg.device, s));
+    if (ea_window_parallel()) {
+        // workspace from the batch's device cache (dropped with the rest of the workspace), sleeping waits
+        DnbAlloc al{[](void *u, size_t bytes) -> void * {
+                        dnb_batch *bb = (dnb_batch *)u;
+                        uint8_t *p = nullptr;
+                        return walloc(bb, &p, bytes) == DNB_OK ? (void *)p : nullptr;
+                    }, b};
+        CK(dnb_run_eventalign_wp(a, tot_r, b->tot_out, ctx->cfg.device, s, al, b->sync_ev));
+    }
     else dnb_launch_eventalign(a, grid, s);
     CK(cudaEventRecord(b->ev[1], s));
     DnbFeatArgs f = {};
@@ -1911,6 +2004,130 @@ int dnb_submit_chain(dnb_ctx *ctx, const dnb_read_desc *reads, const dnb_read_ex
     if (rc == DNB_OK) {
         StageHold hold(ctx->gate_compute);
         rc = dnb_batch_eventalign_features(b, extra, window, want_records);
+    }
+    if (rc != DNB_OK) { free_batch(b); return rc; }
+    drop_work(b);
+    *batch = b;
+    return DNB_OK;
+}
+
+// ---- resident analogue stage (SURVEY s.8 row a15; detect.cpp:885): sites, event ranges and forward passes on the device
+int dnb_batch_analogue_llr(dnb_batch *b, const dnb_read_extra *extra, uint32_t window) {
+    if (!b || (!extra && b->R)) return DNB_ERR_ARG;
+    if (window < 5 || window > 16) { g_last_error = "llAcrossRead window must be in [5, 16]"; return DNB_ERR_ARG; }
+    if (!b->ran || b->want_table || !b->have_work) return DNB_ERR_STATE;
+    dnb_ctx *ctx = b->ctx;
+    if (!ctx->model[DNB_MODEL_UNLABELLED].loaded || !ctx->model[DNB_MODEL_ANALOGUE].loaded) return DNB_ERR_MODEL;
+    CK(cudaSetDevice(ctx->cfg.device));
+    const size_t R = b->R;
+    cudaStream_t s = b->stream;
+    Work &w = b->w;
+    Stage3 &S = b->s3;
+    S = Stage3{};
+    for (size_t i = 0; i < R; i++)
+        if (b->rlen[i] && !extra[i].ref_to_query) { g_last_error = "dnb_read_extra " + std::to_string(i) + " is incomplete"; return DNB_ERR_ARG; }
+    const uint64_t tot_r = b->tot_r;
+    int32_t *st_r2q = (int32_t *)ctx->pinned.acquire((tot_r ? tot_r : 1) * 4);
+    uint8_t *st_rev = (uint8_t *)ctx->pinned.acquire(R ? R : 1);
+    struct StagingGuard {
+        dnb_batch *b; void *p0, *p1;
+        ~StagingGuard() { wait_stream(b); if (p0) b->ctx->pinned.release(p0); if (p1) b->ctx->pinned.release(p1); }
+    } staging_guard{b, st_r2q, st_rev};
+    if (!st_r2q || !st_rev) { g_last_error = "pinned staging allocation failed"; return DNB_ERR_NOMEM; }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long ii = 0; ii < (long long)R; ii++) {
+        const size_t i = (size_t)ii;
+        if (b->rlen[i]) memcpy(st_r2q + b->r_off[i], extra[i].ref_to_query, 4ull * b->rlen[i]);
+        st_rev[i] = extra[i].is_reverse ? 1 : 0;
+    }
+    DnbLlrArgs a;
+    memset(&a, 0, sizeof(a));
+    int32_t *d_r2q = nullptr; uint8_t *d_rev = nullptr; uint64_t *d_poi_off = nullptr;
+    {
+        Arena ar;
+        ar.add(&d_r2q, tot_r); ar.add(&d_rev, R); ar.add(&a.poi, tot_r); ar.add(&a.j_begin, tot_r); ar.add(&a.j_end, tot_r);
+        ar.add(&a.n_poi, R); ar.add(&d_poi_off, R + 1); ar.add(&a.next_site, 1);
+        TRY(ar.commit(b, b->work_allocs));
+    }
+    TRY(h2d(b, d_r2q, st_r2q, tot_r)); TRY(h2d(b, d_rev, st_rev, R));
+    a.window = window; a.r2q = d_r2q; a.is_reverse = d_rev;
+    a.al_off = w.al_off; a.al_pairs_rev = w.al_rev; a.n_align = w.n_align; a.shift = w.shift; a.scale = w.scale;
+    const DnbBatchView v = make_view(b);
+    CK(cudaEventRecord(b->ev[0], s));
+    dnb_launch_llr_sites(v, a, s);
+    CK(cudaEventRecord(b->ev[1], s));
+    TRY(ralloc(b, &S.h_n_poi, R));
+    TRY(d2h(b, S.h_n_poi, a.n_poi, R));
+    CK(wait_stream(b));
+    CK(cudaGetLastError());
+    S.poi_off.assign(R + 1, 0);
+    for (size_t i = 0; i < R; i++) S.poi_off[i + 1] = S.poi_off[i] + S.h_n_poi[i];
+    const uint64_t n_sites = S.poi_off[R];
+    {
+        Arena ar;
+        ar.add(&a.out_pos, n_sites); ar.add(&a.out_n_events, n_sites); ar.add(&a.out_a, n_sites); ar.add(&a.out_t, n_sites);
+        TRY(ar.commit(b, b->work_allocs));
+    }
+    TRY(h2d(b, d_poi_off, S.poi_off.data(), R + 1));
+    a.poi_off = d_poi_off;
+    CK(cudaMemsetAsync(a.next_site, 0, sizeof(unsigned long long), s));
+    CK(cudaEventRecord(b->ev[2], s));
+    dnb_launch_llr_forward(v, a, n_sites, ctx->model[DNB_MODEL_UNLABELLED].dev(), ctx->model[DNB_MODEL_ANALOGUE].dev(),
+                           ctx->cfg.device, s);
+    CK(cudaEventRecord(b->ev[3], s));
+    TRY(ralloc(b, &S.h_pos, n_sites)); TRY(ralloc(b, &S.h_nev, n_sites)); TRY(ralloc(b, &S.h_a, n_sites)); TRY(ralloc(b, &S.h_t, n_sites));
+    TRY(d2h(b, S.h_pos, a.out_pos, n_sites)); TRY(d2h(b, S.h_nev, a.out_n_events, n_sites));
+    TRY(d2h(b, S.h_a, a.out_a, n_sites)); TRY(d2h(b, S.h_t, a.out_t, n_sites));
+    CK(wait_stream(b));
+    CK(cudaGetLastError());
+    float t;
+    cudaEventElapsedTime(&t, b->ev[0], b->ev[1]); S.ms[0] = t;
+    cudaEventElapsedTime(&t, b->ev[2], b->ev[3]); S.ms[1] = t;
+    uint64_t calls = 0, obs = 0;
+    for (uint64_t k = 0; k < n_sites; k++) { calls += S.h_nev[k] > 0; obs += S.h_nev[k]; }
+    S.counts[0] = n_sites; S.counts[1] = calls; S.counts[2] = obs; S.counts[3] = 24 * n_sites + 4 * R;
+    S.done = true;
+    return DNB_OK;
+}
+
+int dnb_batch_analogue_result(dnb_batch *b, size_t i, dnb_analogue_result *o) {
+    if (!b || !o || i >= b->R) return DNB_ERR_ARG;
+    if (!b->s3.done) return DNB_ERR_STATE;
+    const Stage3 &S = b->s3;
+    memset(o, 0, sizeof(*o));
+    o->status = b->h.status ? b->h.status[i] : DNB_READ_OK;
+    const uint64_t lo = S.poi_off[i];
+    o->n_sites = (uint32_t)(S.poi_off[i + 1] - lo);
+    o->pos_on_ref = S.h_pos + lo; o->n_events = S.h_nev + lo;
+    o->log_analogue = S.h_a + lo; o->log_thymidine = S.h_t + lo;
+    return DNB_OK;
+}
+
+int dnb_batch_analogue_timings(dnb_batch *b, double ms[2], uint64_t counts[4]) {
+    if (!b) return DNB_ERR_ARG;
+    if (!b->s3.done) return DNB_ERR_STATE;
+    for (int i = 0; i < 2; i++) if (ms) ms[i] = b->s3.ms[i];
+    for (int i = 0; i < 4; i++) if (counts) counts[i] = b->s3.counts[i];
+    return DNB_OK;
+}
+
+int dnb_submit_llr(dnb_ctx *ctx, const dnb_read_desc *reads, const dnb_read_extra *extra, size_t n_reads, uint32_t window,
+                   dnb_batch **batch) {
+    dnb_batch *b = nullptr;
+    if (!ctx || !batch || (!extra && n_reads)) return DNB_ERR_ARG;
+    uint64_t load = 0;
+    ctx = pick_device(ctx, reads, n_reads, &load);
+    int rc = upload(ctx, reads, n_reads, false, &b, /*gated=*/true);
+    if (rc != DNB_OK) { ctx->inflight.fetch_sub(load, std::memory_order_relaxed); return rc; }
+    b->load = load;
+    {
+        StageHold hold(ctx->gate_compute);
+        rc = run(b);
+        if (rc == DNB_OK) rc = dnb_batch_analogue_llr(b, extra, window);
+    }
+    if (rc == DNB_OK) {
+        StageHold hold(ctx->gate_fetch);
+        rc = fetch(b);
     }
     if (rc != DNB_OK) { free_batch(b); return rc; }
     drop_work(b);

@@ -101,7 +101,6 @@ struct DnbSegTiles {
     uint32_t *tile_prev_pos;      // [n_tiles] last peak before this tile (0 if none) ...
     double *tile_prev_sum;        // ... and sums[] there
     uint32_t *redo;               // [R] 1 = redo this read with the serial kernel
-    void *scan_scratch;           // dnb_seg_parity_scan_scratch_bytes() bytes when the block-map scan is enabled, else nullptr
 };
 #define DNB_SEG_BOUNDARY_BYTES sizeof(SegBoundary)
 
@@ -109,10 +108,10 @@ void dnb_launch_segmentation_serial(const DnbBatchView &v, DnbDetector det, cons
 // after_checkpoint / after_tiles: optional events recorded behind the checkpoint (or scan) and the tile kernel
 void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const DnbSegTiles &t, cudaStream_t s,
                                    cudaEvent_t after_checkpoint = nullptr, cudaEvent_t after_tiles = nullptr);
-// experimental replacement of the tiled segmentation's checkpoint kernel (seg_scan.cu; only with DNB_SEG_PARITY_SCAN=1)
+// the exact (sum, sumsq) checkpoints as a streaming warp scan (seg_scan.cu); DNB_SEG_PARITY_SCAN=0 selects the
+// one-lane-per-read checkpoint kernel of seg.cu instead
 bool dnb_seg_parity_scan_enabled(void);
-size_t dnb_seg_parity_scan_scratch_bytes(const DnbSegTiles &t, uint32_t n_reads);
-cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, void *scratch, cudaStream_t s);
+cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, cudaStream_t s);
 void dnb_launch_ranks(const DnbBatchView &v, const DnbModelDev &m, double *mu_q, uint32_t *rank_ref, cudaStream_t s);
 void dnb_launch_quantile_scaling(const DnbBatchView &v, const DnbModelDev &m, const uint32_t *rank_ref,
                                  double *rough_shift, double *rough_scale, cudaStream_t s);
@@ -194,6 +193,30 @@ void dnb_launch_hmm_forward(const double *obs, const uint64_t *obs_off, const ch
                             const DnbModelDev &unl, const DnbModelDev &ana, double *out_analogue, double *out_thymidine,
                             cudaStream_t s);
 
+// ---- resident analogue stage (hmm.cu): llAcrossRead's site gathering + both forward passes per site -----------------
+struct DnbLlrArgs {
+    uint32_t window;              // windowLength of llAcrossRead (12)
+    const int32_t *r2q;           // dense refToQuery, indexed like ref (an absent key reads as 0)
+    const uint8_t *is_reverse;    // [R]
+    const uint64_t *al_off;       // [R+1] alignment slot offsets
+    const uint32_t *al_pairs_rev; // (event, k-mer) pairs in backtrace order
+    const uint32_t *n_align;      // [R]
+    const double *shift, *scale;  // [R] r.scalings
+    // per reference base (capacity), filled by the site kernel: the read's T positions in ascending order and, per
+    // site, the alignment index range [j_begin, j_end) of its events (j_end < 0: -(j_end + 1), visited downwards)
+    uint32_t *poi;
+    int32_t *j_begin, *j_end;
+    uint32_t *n_poi;              // [R]
+    const uint64_t *poi_off;      // [R+1] exclusive prefix of n_poi (host), visit order = ascending site index
+    unsigned long long *next_site;   // work counter (zeroed before the forward launch)
+    // per site (dense, poi_off indexing)
+    uint32_t *out_pos, *out_n_events;
+    double *out_a, *out_t;
+};
+void dnb_launch_llr_sites(const DnbBatchView &v, const DnbLlrArgs &a, cudaStream_t s);
+void dnb_launch_llr_forward(const DnbBatchView &v, const DnbLlrArgs &a, uint64_t n_sites_total, const DnbModelDev &unl,
+                            const DnbModelDev &ana, int device, cudaStream_t s);
+
 // ---- eventalign (eventalign.cu): windowed Viterbi re-alignment, SURVEY s.8 row f1 -----------------------------------
 struct dnb_eventalign_rec;
 struct DnbEaArgs {
@@ -227,9 +250,15 @@ unsigned dnb_eventalign_grid(int device);
 unsigned dnb_eventalign_warps_per_block(void);
 size_t dnb_eventalign_bt_row_bytes(void);
 void dnb_launch_eventalign(const DnbEaArgs &a, unsigned grid, cudaStream_t s);
-// experimental window-parallel form of the same stage (eventalign_wp.cu; only with DNB_EA_WINDOW_PARALLEL=1):
-// tot_ref / tot_align = total reference bases / aligned events of the batch; synchronises s once per round
-cudaError_t dnb_run_eventalign_wp(const DnbEaArgs &a, uint64_t tot_ref, uint64_t tot_align, int device, cudaStream_t s);
+// window-parallel form of the same stage (eventalign_wp.cu; the default): tot_ref / tot_align = total reference bases /
+// aligned events of the batch; its workspace comes from `alloc` (caller-owned); waits once per round for two counters
+// (on sync_ev, a cudaEventBlockingSync event, when given)
+struct DnbAlloc {
+    void *(*fn)(void *user, size_t bytes);
+    void *user;
+};
+cudaError_t dnb_run_eventalign_wp(const DnbEaArgs &a, uint64_t tot_ref, uint64_t tot_align, int device, cudaStream_t s,
+                                  const DnbAlloc &alloc, cudaEvent_t sync_ev);
 
 // ---- DNN input tensors (features.cu): SURVEY s.8 row f2, consumes eventalign's records on the device --------------
 struct DnbFeatArgs {

@@ -366,14 +366,15 @@ __global__ void wp_fail_unfinished_kernel(WpArgs p) {
 
 // Runs the whole thing on stream s (synchronises it once per round to read the two counters).  `a` is the argument block
 // the read-serial launch would get (its scratch_* fields are ignored: the workspace here is sized for this kernel's grid).
-cudaError_t dnb_run_eventalign_wp(const DnbEaArgs &a_in, uint64_t tot_ref, uint64_t tot_align, int device, cudaStream_t s) {
+cudaError_t dnb_run_eventalign_wp(const DnbEaArgs &a_in, uint64_t tot_ref, uint64_t tot_align, int device, cudaStream_t s,
+                                  const DnbAlloc &alloc, cudaEvent_t sync_ev) {
     if (a_in.n_reads == 0) return cudaSuccess;
     cudaError_t err = cudaSuccess;
-    std::vector<void *> owned;
+    // the workspace comes from the caller's allocator (the batch's device cache or the context's pool) and stays the
+    // caller's to free
     auto dalloc = [&](size_t bytes) -> void * {
         void *q = nullptr;
-        if (err == cudaSuccess) err = cudaMallocAsync(&q, bytes ? bytes : 16, s);
-        if (q) owned.push_back(q);
+        if (err == cudaSuccess) { q = alloc.fn(alloc.user, bytes ? bytes : 16); if (!q) err = cudaErrorMemoryAllocation; }
         return q;
     };
     WpArgs p;
@@ -416,7 +417,8 @@ cudaError_t dnb_run_eventalign_wp(const DnbEaArgs &a_in, uint64_t tot_ref, uint6
             wp_walk_kernel<<<grid_walk, 128, 0, s>>>(p);
             ck(cudaGetLastError());
             ck(cudaMemcpyAsync(h, counters, 12, cudaMemcpyDeviceToHost, s));
-            ck(cudaStreamSynchronize(s));
+            if (sync_ev) { ck(cudaEventRecord(sync_ev, s)); ck(cudaEventSynchronize(sync_ev)); }   // a sleeping wait
+            else ck(cudaStreamSynchronize(s));
             if (err != cudaSuccess) break;
             const uint32_t n_work = h[1] < p.work_cap ? h[1] : p.work_cap;
             if (n_work) {
@@ -431,6 +433,5 @@ cudaError_t dnb_run_eventalign_wp(const DnbEaArgs &a_in, uint64_t tot_ref, uint6
             ck(cudaGetLastError());
         }
     }
-    for (void *q : owned) cudaFreeAsync(q, s);
     return err;
 }

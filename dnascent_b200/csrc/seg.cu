@@ -636,9 +636,10 @@ static bool fast_div_ok(uint32_t w) {
     return std::fabs(std::fma(-wd, r, 1.0)) <= 0x1p-54;
 }
 
-// DNB_SEG_PARITY_SCAN=1: the block-map scan of seg_scan.cu instead of the per-sample checkpoint chain
+// the checkpoints come from the streaming warp scan of seg_scan.cu; DNB_SEG_PARITY_SCAN=0 selects the per-sample
+// one-lane-per-read chain (seg_checkpoint_kernel above), kept as the cross-check
 bool dnb_seg_parity_scan_enabled(void) {
-    static const bool on = getenv("DNB_SEG_PARITY_SCAN") != nullptr && getenv("DNB_SEG_PARITY_SCAN")[0] == '1';
+    static const bool on = !(getenv("DNB_SEG_PARITY_SCAN") != nullptr && getenv("DNB_SEG_PARITY_SCAN")[0] == '0');
     return on;
 }
 
@@ -648,8 +649,7 @@ void dnb_launch_segmentation_tiled(const DnbBatchView &v, DnbDetector det, const
     const unsigned gr = (v.n_reads + 127) / 128;
     const unsigned gt = (t.n_tiles + SEG_THREADS - 1) / SEG_THREADS;
     const bool fast = fast_div_ok(det.w1) && fast_div_ok(det.w2);
-    const bool scanned = dnb_seg_parity_scan_enabled() && t.scan_scratch &&
-                         dnb_launch_seg_parity_scan(v, t, t.scan_scratch, s) == cudaSuccess;
+    const bool scanned = dnb_seg_parity_scan_enabled() && dnb_launch_seg_parity_scan(v, t, s) == cudaSuccess;
     if (v.raw_i16) {
         if (!scanned) seg_checkpoint_kernel<true><<<gr, 128, 0, s>>>(v, t);
         if (after_checkpoint) cudaEventRecord(after_checkpoint, s);

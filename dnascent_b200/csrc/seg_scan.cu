@@ -1,49 +1,45 @@
-// seg_scan.cu -- the (sum, sumsq) checkpoints of the segmentation WITHOUT a per-sample serial chain (experimental).
-//
-// STATUS: written at the end of round 1 after the round's GPU budget was spent: it compiles for sm_100a and mirrors, step
-// by step, a CPU prototype that is bit-identical to the sequential loop (tests/helpers/proto_exact_prefix.py, block_chain;
-// tests/test_host_logic.py), but THIS KERNEL HAS NEVER RUN ON A GPU.  It replaces seg.cu's checkpoint kernel only when
-// DNB_SEG_PARITY_SCAN=1 is set; every bit-exact GPU test of the segmentation is its acceptance test.
+// seg_scan.cu -- the exact (sum, sumsq) checkpoints of the segmentation as a streaming warp scan.
 //
 // What it replaces: seg_checkpoint_kernel (seg.cu), i.e. scrappie's compute_sum_sumsq
 // (/root/reference/src/scrappie/event_detection.c:35-48) evaluated up to every 64th sample:
 //     sum[i+1] = fl(sum[i] + x[i]),   sumsq[i+1] = fl(sumsq[i] + x[i]*x[i])
-// Both round at every step, so the values depend on the order; the checkpoint kernel therefore walks each read with
-// one lane (~31 cycles per sample: 65 ms for a 4*10^6-sample read, the critical path of a short batch).
+// Both chains round, so in general their values depend on the order of the additions; the checkpoint kernel therefore
+// walks each read with ONE lane (~31 cycles per sample: 100 ms of a 30k-read bench step, 60 ms for one 4*10^6-sample
+// read).  Here one warp streams a read in chunks of 32 blocks x 64 samples, every lane working on its own block, and
+// the values written are bit-identical to the sequential loop's:
 //
-// How.  While the running sum s stays inside one binade (ulp u), fl(s + a) = (S + q + c) u with s = S u, a = q u + r,
-// 0 <= r < u, and c = [r > u/2], or (S + q) mod 2 on a tie: the step is S -> S + d[S mod 2] for a pair of integers
-// (d[0], d[1]) that depends on a and u only, and such maps compose associatively
-//     (g o f).d[p] = f.d[p] + g.d[p xor (f.d[p] & 1)].
-// One warp per read:
-//   A  every lane takes 64-sample blocks: sum x, sum |x|, sum x^2 of the block (plain doubles: only used to PREDICT)
-//   B  warp scan of the block sums -> predicted running sums at the block starts -> predicted binade of each block
-//   C  every lane folds its blocks' 64 samples into one map per chain under the predicted binade (integer arithmetic)
-//   D  lane 0 walks the blocks: if the ACTUAL running sum is in the predicted binade and sum |a| of the block cannot
-//      take it out, one integer step replaces 64 roundings; otherwise the block is summed literally.  Correctness never
-//      rests on the prediction: a wrong one only costs the literal loop.
-// The serial chain shrinks from N to N/64 steps (plus ~1 % literal blocks on POD5-like data).
+//   sum     The samples are float32 values (src/pod5.cpp:60).  If q is the smallest power of two every sample is a
+//           multiple of (2^-23 of the smallest nonzero |x|'s binade) and sum|x| < 2^53 q, EVERY partial sum of ANY
+//           subset is exactly representable, so no addition rounds and the order does not matter: block sums + a
+//           warp scan.  The condition is checked per read (it holds for any realistic signal: 49 of the 53 bits are
+//           used by 10^7 samples of ~100 pA); a read that violates it is flagged for the literal serial kernel.
+//   sumsq   x*x is exact (48 bits) but the running sum rounds at every step.  While the sum s = S u stays inside one
+//           binade (ulp u), fl(s + a) = (S + g[S mod 2]) u where g[0] = RN-even(a/u) and g[1] is the same except on
+//           an exact tie (then the other neighbour): the step is a two-state transducer on the parity of S, and
+//           transducers compose associatively,  (g o f)[p] = f[p] + g[p xor (f[p] & 1)].
+//           Every lane folds its block's 64 addends into one such map under the binade PREDICTED from the running
+//           sum at the chunk start plus a plain prefix of the block sums (phase C), a warp scan composes the 32 maps
+//           (phase D), and the result is accepted only if every block provably stayed inside its binade: start
+//           state in [2^52, 2^53) ulps of the binade the map was built for and end state < 2^53 (addends are
+//           non-negative, so the chain is monotone and the as-if-one-binade sum passes 2^53 exactly when the real
+//           chain leaves the binade).  Otherwise -- the ~40 chunks per read in which the sum crosses a power of two,
+//           and the first chunk -- the chunk is walked block by block, applying the maps that verify and adding the
+//           64 samples of a block literally where they do not.  Correctness never rests on the prediction.
+//
+// Cost: ~25 instructions per sample, all lanes busy and loads coalesced into 16-byte vectors, against a 31-cycle
+// dependent chain per sample on one lane.  Enabled by default (DNB_SEG_PARITY_SCAN=0 selects the checkpoint kernel);
+// every bit-exact GPU test of the segmentation is its acceptance test, tests/test_segmentation_scan_gpu.py adds
+// adversarial binade-crossing signals.  The algebra was first checked on the CPU (tests/helpers/proto_exact_prefix.py).
 #include <climits>
-#include <vector>
 #include "dnb_internal.cuh"
 #include "../../include/dnascent_b200.h"
 
 #define PS_BLOCK DNB_SEG_CK          // 64 samples: one checkpoint per block
 #define PS_FULL 0xffffffffu
 #define PS_NO_MAP INT_MIN
+#define PS_TWO52 4503599627370496.0
 
 namespace {
-
-template <bool kI16>
-struct PsReader {
-    const float *f32;
-    const int16_t *i16;
-    float dac_off, dac_scl;
-    __device__ __forceinline__ float at(uint64_t idx) const {
-        if (kI16) return fMul(fAdd((float)i16[idx], dac_off), dac_scl);      // src/pod5.cpp:60
-        return f32[idx];
-    }
-};
 
 __device__ __forceinline__ int binade_of(double s) {                         // s > 0, normal: s in [2^e, 2^(e+1))
     return ((__double2hiint(s) >> 20) & 0x7ff) - 1023;
@@ -52,179 +48,211 @@ __device__ __forceinline__ double pow2(int e) {                              // 
     return __hiloint2double((e + 1023) << 20, 0);
 }
 
-// fold the addend `a` into the map (d0, d1) of running sums with ulp 2^sh; false = the addend does not fit the scheme
-__device__ __forceinline__ bool fold(double a, int sh, long long &d0, long long &d1) {
-    const double scaled = dMul(a, pow2(-sh));                                // exact: a power of two, no under/overflow here
-    if (!(fabs(scaled) < 9007199254740992.0)) return false;                  // |a| >= 2^53 ulps: leaves the binade anyway
-    const double q = floor(scaled);                                          // floor also for negative addends: r in [0, 1)
-    const double r = dSub(scaled, q);                                        // exact
-    const long long qi = (long long)q;
-    long long g0, g1;
-    if (r == 0.5) {                                                          // tie: to even
-        const bool odd = (qi & 1) != 0;
-        g0 = odd ? qi + 1 : qi;
-        g1 = odd ? qi : qi + 1;
+// the samples [j0, j0 + 8) of a read as floats; `base` is the read's first element (32-element aligned)
+template <bool kI16>
+__device__ __forceinline__ void load8(const DnbBatchView &v, uint64_t base, uint32_t j0, float dac_off, float dac_scl, float (&x)[8]) {
+    if (kI16) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(v.raw_i16 + base + j0));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            x[2 * i] = fMul(fAdd((float)(short)(w[i] & 0xffffu), dac_off), dac_scl);      // src/pod5.cpp:60
+            x[2 * i + 1] = fMul(fAdd((float)(short)(w[i] >> 16), dac_off), dac_scl);
+        }
     } else {
-        g0 = g1 = qi + (r > 0.5 ? 1 : 0);
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(v.raw_f32 + base + j0));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(v.raw_f32 + base + j0 + 4));
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
     }
-    d0 += (d0 & 1) ? g1 : g0;                                                // this element after the block so far
-    d1 += (d1 & 1) ? g0 : g1;
+}
+template <bool kI16>
+__device__ __forceinline__ float load1(const DnbBatchView &v, uint64_t idx, float dac_off, float dac_scl) {
+    if (kI16) return fMul(fAdd((float)v.raw_i16[idx], dac_off), dac_scl);
+    return v.raw_f32[idx];
+}
+// eight samples of a block, by vector where the padded read allows it
+template <bool kI16>
+__device__ __forceinline__ void load_group(const DnbBatchView &v, uint64_t base, uint32_t j, uint32_t N, uint32_t padded,
+                                           float dac_off, float dac_scl, float (&x)[8]) {
+    if (j + 8 <= padded) load8<kI16>(v, base, j, dac_off, dac_scl, x);
+    else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = (j + i < N) ? load1<kI16>(v, base + j + i, dac_off, dac_scl) : 0.0f;
+    }
+}
+
+// one addend of the sumsq chain folded into the map (d0, d1) of a running sum with ulp 2^-k (inv_u = 2^k):
+// g0 = RN-even(a / u) by the 2^52 trick, g1 differs only on an exact tie.  false: a/u >= 2^52, no map for this block.
+__device__ __forceinline__ bool fold_sq(double a, double inv_u, double &d0, double &d1) {
+    const double A = dMul(a, inv_u);                          // exact (power of two; no underflow for |x| >= 2^-20)
+    if (!(A < PS_TWO52)) return false;
+    const double g0 = dSub(dAdd(A, PS_TWO52), PS_TWO52);      // round half to even, integer valued
+    const double diff = dSub(g0, A);                          // exact, |diff| <= 0.5
+    if (fabs(diff) == 0.5) {                                  // exact tie (rare): the odd-parity state takes the other neighbour
+        const double g1 = dSub(g0, dAdd(diff, diff));
+        const bool odd0 = (__double2loint(dAdd(d0, PS_TWO52)) & 1) != 0;
+        const bool odd1 = (__double2loint(dAdd(d1, PS_TWO52)) & 1) != 0;
+        d0 = dAdd(d0, odd0 ? g1 : g0);
+        d1 = dAdd(d1, odd1 ? g0 : g1);
+    } else {
+        d0 = dAdd(d0, g0);
+        d1 = dAdd(d1, g0);
+    }
     return true;
 }
 
-struct PsScratch {
-    double *bs, *ba, *bq;            // per block: sum x, sum |x|, sum x^2
-    double *ps, *pq;                 // predicted running sums at the block start
-    long long *s0, *s1, *q0, *q1;    // maps of the two chains
-    int *es, *eq;                    // binade the map was built for, PS_NO_MAP = none
-};
-
 template <bool kI16>
-__global__ void __launch_bounds__(128) seg_parity_scan_kernel(DnbBatchView v, DnbSegTiles t, PsScratch w) {
+__global__ void __launch_bounds__(128) seg_scan_kernel(DnbBatchView v, DnbSegTiles t) {
     const int lane = threadIdx.x & 31;
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= v.n_reads) return;
     const uint32_t r = v.order[slot];
     const uint32_t N = v.n_samples[r];
     const uint64_t base = v.raw_off[r];
-    PsReader<kI16> rd{v.raw_f32, v.raw_i16, 0.f, 1.f};
-    if (kI16) { rd.dac_off = v.dac_offset[r]; rd.dac_scl = v.dac_scale[r]; }
-    const uint64_t ck = t.ck_off[r];
+    const uint32_t padded = (uint32_t)(v.raw_off[r + 1] - base);            // multiple of 32: vector loads stay inside
+    float dac_off = 0.f, dac_scl = 1.f;
+    if (kI16) { dac_off = v.dac_offset[r]; dac_scl = v.dac_scale[r]; }
+    double *cs = t.ck_sum + t.ck_off[r], *cq = t.ck_sq + t.ck_off[r];
     const uint32_t nb = (N + PS_BLOCK - 1) / PS_BLOCK;
 
-    // ---- A: block sums (and the precondition of the tile kernel's fast path, as the checkpoint kernel checks it) ----
-    uint32_t out_of_range = 0;
-    for (uint32_t b = lane; b < nb; b += 32) {
-        const uint32_t j0 = b * PS_BLOCK, j1 = min(j0 + PS_BLOCK, N);
-        double s = 0.0, a = 0.0, q = 0.0;
-        for (uint32_t j = j0; j < j1; j++) {
-            const float xf = rd.at(base + j);
-            const double x = (double)xf;
-            const uint32_t ax = __float_as_uint(xf) & 0x7fffffffu;
-            out_of_range |= (ax - 0x35800000u >= 0x19000000u) && ax != 0u;
-            s = dAdd(s, x);
-            a = dAdd(a, fabs(x));
-            q = dAdd(q, dMul(x, x));
-        }
-        w.bs[ck + b] = s; w.ba[ck + b] = a; w.bq[ck + b] = q;
-    }
-    out_of_range = __any_sync(PS_FULL, out_of_range != 0) ? 1u : 0u;
-    __syncwarp();
+    double s_act = 0.0, q_act = 0.0;       // the chains at the chunk start (warp-uniform, the sequential loop's values)
+    double abs_sum = 0.0;                  // this lane's share of sum |x| (bound for the exactness condition of `sum`)
+    uint32_t min_exp = 0xffu;              // smallest biased exponent among this lane's nonzero samples
+    uint32_t out_of_range = 0;             // precondition of tstat_fast: every sample is 0 or 2^-20 <= |x| < 2^30
 
-    // ---- B: predicted running sums at the block starts (approximate: any order will do) ----
-    {
-        double carry_s = 0.0, carry_q = 0.0;
-        for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
-            const uint32_t b = b0 + lane;
-            const double vs = b < nb ? w.bs[ck + b] : 0.0, vq = b < nb ? w.bq[ck + b] : 0.0;
-            double is = vs, iq = vq;
+    for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
+        const uint32_t b = b0 + lane;
+        const bool have = b < nb;
+        const uint32_t j0 = b * PS_BLOCK;
+        const uint32_t cnt = have ? min((uint32_t)PS_BLOCK, N - j0) : 0u;
+        // ---- A: block sums (exact sum x; plain sum x^2 for the prediction) ----
+        double S = 0.0, Q = 0.0;
+        for (uint32_t g = 0; g < cnt; g += 8) {
+            float x[8];
+            load_group<kI16>(v, base, j0 + g, N, padded, dac_off, dac_scl, x);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (g + i < cnt) {
+                    const uint32_t ax = __float_as_uint(x[i]) & 0x7fffffffu;
+                    out_of_range |= (ax - 0x35800000u >= 0x19000000u) && ax != 0u;
+                    if (ax != 0u) min_exp = min(min_exp, ax >> 23);
+                    const double xd = (double)x[i];
+                    S = dAdd(S, xd);
+                    abs_sum = dAdd(abs_sum, fabs(xd));
+                    Q = dAdd(Q, dMul(xd, xd));
+                }
+            }
+        }
+        // ---- B: exclusive prefixes inside the chunk ----
+        double inS = S, inQ = Q;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double us = __shfl_up_sync(PS_FULL, inS, d), uq = __shfl_up_sync(PS_FULL, inQ, d);
+            if (lane >= d) { inS = dAdd(inS, us); inQ = dAdd(inQ, uq); }
+        }
+        const double exS = dSub(inS, S);                                     // exact under the read's condition
+        const double pq = dAdd(q_act, dSub(inQ, Q));                         // predicted sumsq at this block's start
+        if (have) cs[b] = dAdd(s_act, exS);
+        s_act = dAdd(s_act, __shfl_sync(PS_FULL, inS, 31));
+        // ---- C: this block's transducer under the predicted binade ----
+        int eq = PS_NO_MAP;
+        double d0 = 0.0, d1 = 0.0;
+        if (have && pq > 0.0 && pq < 1.0e300) {
+            eq = binade_of(pq);
+            if (eq < -900) eq = PS_NO_MAP;
+        }
+        if (eq != PS_NO_MAP) {
+            const double inv_u = pow2(52 - eq);
+            bool ok = true;
+            for (uint32_t g = 0; g < cnt && ok; g += 8) {
+                float x[8];
+                load_group<kI16>(v, base, j0 + g, N, padded, dac_off, dac_scl, x);
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (g + i < cnt) { const double xd = (double)x[i]; ok = ok && fold_sq(dMul(xd, xd), inv_u, d0, d1); }
+            }
+            if (!ok) eq = PS_NO_MAP;
+        }
+        const long long m0 = (long long)d0, m1 = (long long)d1;             // integers (below 2^53 wherever they get used)
+        // ---- D: compose.  Fast path: every block of the chunk was folded for the binade the chain is in now ----
+        const int e_act = (q_act > 0.0 && q_act < 1.0e300) ? binade_of(q_act) : PS_NO_MAP;
+        const bool uniform = e_act != PS_NO_MAP && __all_sync(PS_FULL, !have || eq == e_act);
+        bool done = false;
+        if (uniform) {
+            const long long S0 = (long long)dMul(q_act, pow2(52 - e_act));   // exact: q_act is a multiple of its ulp
+            long long f0 = have ? m0 : 0, f1 = have ? m1 : 0;               // inclusive composition of lanes 0..lane
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const double us = __shfl_up_sync(PS_FULL, is, d), uq = __shfl_up_sync(PS_FULL, iq, d);
-                if (lane >= d) { is += us; iq += uq; }
+                const long long a0 = __shfl_up_sync(PS_FULL, f0, d), a1 = __shfl_up_sync(PS_FULL, f1, d);
+                if (lane >= d) {                                             // (earlier blocks: a) then (these: f)
+                    const long long h0 = a0 + ((a0 & 1) ? f1 : f0);
+                    const long long h1 = a1 + ((a1 & 1) ? f0 : f1);
+                    f0 = h0; f1 = h1;
+                }
             }
-            if (b < nb) { w.ps[ck + b] = carry_s + (is - vs); w.pq[ck + b] = carry_q + (iq - vq); }
-            carry_s += __shfl_sync(PS_FULL, is, 31);
-            carry_q += __shfl_sync(PS_FULL, iq, 31);
-        }
-    }
-    __syncwarp();
-
-    // ---- C: one map per block and chain, under the predicted binade ----
-    for (uint32_t b = lane; b < nb; b += 32) {
-        const uint32_t j0 = b * PS_BLOCK, j1 = min(j0 + PS_BLOCK, N);
-        const double ps = w.ps[ck + b], pq = w.pq[ck + b];
-        int es = PS_NO_MAP, eq = PS_NO_MAP;
-        if (ps > 0.0 && ps < 1.0e300) { es = binade_of(ps); if (es < -900) es = PS_NO_MAP; }
-        if (pq > 0.0 && pq < 1.0e300) { eq = binade_of(pq); if (eq < -900) eq = PS_NO_MAP; }
-        long long s0 = 0, s1 = 0, q0 = 0, q1 = 0;
-        if (es != PS_NO_MAP || eq != PS_NO_MAP) {
-            for (uint32_t j = j0; j < j1; j++) {
-                const double x = (double)rd.at(base + j);
-                if (es != PS_NO_MAP && !fold(x, es - 52, s0, s1)) es = PS_NO_MAP;
-                if (eq != PS_NO_MAP && !fold(dMul(x, x), eq - 52, q0, q1)) eq = PS_NO_MAP;
+            long long x0 = __shfl_up_sync(PS_FULL, f0, 1), x1 = __shfl_up_sync(PS_FULL, f1, 1);
+            if (lane == 0) { x0 = 0; x1 = 0; }                               // exclusive: identity for the first block
+            const long long Sb = S0 + ((S0 & 1) ? x1 : x0);                  // state at this block's start
+            const long long Se = S0 + ((S0 & 1) ? f1 : f0);                  // ... and at its end
+            const bool fine = !have || (m0 >= 0 && m1 >= 0 && m0 < (1ll << 52) && m1 < (1ll << 52) && Se < (1ll << 53));
+            if (__all_sync(PS_FULL, fine)) {
+                const double u = pow2(e_act - 52);
+                if (have) cq[b] = dMul((double)Sb, u);
+                const int last = (int)min(31u, nb - 1 - b0);
+                q_act = dMul((double)__shfl_sync(PS_FULL, Se, last), u);
+                done = true;
             }
         }
-        w.s0[ck + b] = s0; w.s1[ck + b] = s1; w.q0[ck + b] = q0; w.q1[ck + b] = q1;
-        w.es[ck + b] = es; w.eq[ck + b] = eq;
+        if (!done) {
+            // block by block, every lane computing the same (warp-uniform) chain
+            const int n_here = (int)min(32u, nb - b0);
+            for (int L = 0; L < n_here; L++) {
+                const int eL = __shfl_sync(PS_FULL, eq, L);
+                const long long a0 = __shfl_sync(PS_FULL, m0, L), a1 = __shfl_sync(PS_FULL, m1, L);
+                if (lane == 0) cq[b0 + L] = q_act;
+                bool applied = false;
+                if (eL != PS_NO_MAP && a0 >= 0 && a1 >= 0 && a0 < (1ll << 52) && a1 < (1ll << 52) && q_act > 0.0 &&
+                    q_act < 1.0e300 && binade_of(q_act) == eL) {
+                    long long Sx = (long long)dMul(q_act, pow2(52 - eL));
+                    Sx += (Sx & 1) ? a1 : a0;
+                    if (Sx < (1ll << 53)) { q_act = dMul((double)Sx, pow2(eL - 52)); applied = true; }
+                }
+                if (!applied) {
+                    const uint32_t k0 = (b0 + L) * PS_BLOCK, k1 = min(k0 + PS_BLOCK, N);
+                    for (uint32_t j = k0; j < k1; j++) {
+                        const double xd = (double)load1<kI16>(v, base + j, dac_off, dac_scl);
+                        q_act = dAdd(q_act, dMul(xd, xd));                   // event_detection.c:46
+                    }
+                }
+            }
+        }
     }
-    __syncwarp();
-    __threadfence_block();
-
-    // ---- D: the chain, one step per block; the block's parameters are loaded one block ahead of their use ----
+    // ---- the read-level condition under which `sum` was exact in any order ----
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        abs_sum = dAdd(abs_sum, __shfl_xor_sync(PS_FULL, abs_sum, d));
+        min_exp = min(min_exp, __shfl_xor_sync(PS_FULL, min_exp, d));
+        out_of_range |= __shfl_xor_sync(PS_FULL, out_of_range, d);
+    }
     if (lane == 0) {
-        struct Par { int es, eq; double ba, bq; long long s0, s1, q0, q1; };
-        auto load = [&](uint32_t b) {
-            Par p;
-            p.es = w.es[ck + b]; p.eq = w.eq[ck + b]; p.ba = w.ba[ck + b]; p.bq = w.bq[ck + b];
-            p.s0 = w.s0[ck + b]; p.s1 = w.s1[ck + b]; p.q0 = w.q0[ck + b]; p.q1 = w.q1[ck + b];
-            return p;
-        };
-        double *cs = t.ck_sum + ck, *cq = t.ck_sq + ck;
-        double s = 0.0, q = 0.0;
-        Par nxt = {PS_NO_MAP, PS_NO_MAP, 0.0, 0.0, 0, 0, 0, 0};
-        if (nb) nxt = load(0);
-        for (uint32_t b = 0; b < nb; b++) {
-            const Par cur = nxt;
-            if (b + 1 < nb) nxt = load(b + 1);
-            cs[b] = s; cq[b] = q;
-            const uint32_t j0 = b * PS_BLOCK, j1 = min(j0 + PS_BLOCK, N);
-            // sum chain: signed addends, so the block must not be able to leave the binade in either direction
-            bool done = false;
-            if (cur.es != PS_NO_MAP && s > 0.0 && binade_of(s) == cur.es) {
-                const int e = cur.es;
-                const double lo = pow2(e), hi = pow2(e + 1), span = dMul(cur.ba, 1.0000001);
-                if (dSub(s, span) >= lo && dAdd(s, span) < hi) {
-                    long long S = (long long)dMul(s, pow2(52 - e));                         // exact: s is a multiple of its ulp
-                    S += (S & 1) ? cur.s1 : cur.s0;
-                    if (S >= (1ll << 52) && S < (1ll << 53)) { s = dMul((double)S, pow2(e - 52)); done = true; }
-                }
-            }
-            if (!done)
-                for (uint32_t j = j0; j < j1; j++) s = dAdd(s, (double)rd.at(base + j));    // event_detection.c:45
-            // sumsq chain: non-negative addends, the sum only grows
-            done = false;
-            if (cur.eq != PS_NO_MAP && q > 0.0 && binade_of(q) == cur.eq) {
-                const int e = cur.eq;
-                const double hi = pow2(e + 1), span = dMul(cur.bq, 1.0000001);
-                if (dAdd(q, span) < hi) {
-                    long long S = (long long)dMul(q, pow2(52 - e));
-                    S += (S & 1) ? cur.q1 : cur.q0;
-                    if (S >= (1ll << 52) && S < (1ll << 53)) { q = dMul((double)S, pow2(e - 52)); done = true; }
-                }
-            }
-            if (!done)
-                for (uint32_t j = j0; j < j1; j++) { const double x = (double)rd.at(base + j); q = dAdd(q, dMul(x, x)); }   // :46
+        bool exact = true;
+        if (min_exp != 0xffu) {
+            // every sample is a multiple of 2^(min_exp - 127 - 23); all partial sums are below 1.0001 * sum|x|
+            exact = min_exp >= 1u && dMul(abs_sum, 1.0001) < pow2((int)min_exp - 150 + 53);
         }
-        t.tot_sum[r] = s;
-        t.redo[r] = out_of_range;      // the stitch kernel ORs its own verdict into this
+        t.tot_sum[r] = s_act;
+        t.redo[r] = (out_of_range != 0u || !exact) ? 1u : 0u;     // the stitch kernel ORs its own verdict into this
     }
 }
 
 }  // namespace
 
-// Drop-in for the two seg_checkpoint_kernel launches of dnb_launch_segmentation_tiled (same outputs: ck_sum, ck_sq,
-// tot_sum, redo).  The scratch (11 arrays of one entry per 64-sample block) comes from the caller's device cache.
-static size_t ps_slots(const DnbSegTiles &t, uint32_t n_reads) {
-    // checkpoint slots of the batch: ceil(N/64) + 1 per read <= 8 tiles' worth + 2
-    return (size_t)t.n_tiles * (DNB_SEG_TILE / DNB_SEG_CK) + 2 * (size_t)n_reads + 64;
-}
-size_t dnb_seg_parity_scan_scratch_bytes(const DnbSegTiles &t, uint32_t n_reads) { return ps_slots(t, n_reads) * (9 * 8 + 2 * 4) + 256; }
-
-cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, void *scratch, cudaStream_t s) {
+// Drop-in for the seg_checkpoint_kernel launch of dnb_launch_segmentation_tiled (same outputs: ck_sum, ck_sq,
+// tot_sum, redo); needs no scratch.
+cudaError_t dnb_launch_seg_parity_scan(const DnbBatchView &v, const DnbSegTiles &t, cudaStream_t s) {
     if (v.n_reads == 0) return cudaSuccess;
-    if (!scratch) return cudaErrorInvalidValue;
-    const size_t slots = ps_slots(t, v.n_reads);
-    uint8_t *p = (uint8_t *)scratch;
-    auto take = [&](size_t bytes) { void *q = p; p += bytes; return q; };
-    PsScratch w;
-    w.bs = (double *)take(slots * 8); w.ba = (double *)take(slots * 8); w.bq = (double *)take(slots * 8);
-    w.ps = (double *)take(slots * 8); w.pq = (double *)take(slots * 8);
-    w.s0 = (long long *)take(slots * 8); w.s1 = (long long *)take(slots * 8);
-    w.q0 = (long long *)take(slots * 8); w.q1 = (long long *)take(slots * 8);
-    w.es = (int *)take(slots * 4); w.eq = (int *)take(slots * 4);
     const unsigned grid = (v.n_reads + 3) / 4;                               // one warp per read, 4 warps per CTA
-    if (v.raw_i16) seg_parity_scan_kernel<true><<<grid, 128, 0, s>>>(v, t, w);
-    else seg_parity_scan_kernel<false><<<grid, 128, 0, s>>>(v, t, w);
+    if (v.raw_i16) seg_scan_kernel<true><<<grid, 128, 0, s>>>(v, t);
+    else seg_scan_kernel<false><<<grid, 128, 0, s>>>(v, t);
     return cudaGetLastError();
 }

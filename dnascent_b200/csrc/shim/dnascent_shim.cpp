@@ -382,6 +382,68 @@ void llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, unsigned int
 
 }  // namespace dnb_shim
 
+namespace dnb_shim {
+
+// detect --HMM: normaliseEvents + llAcrossRead (detect.cpp:876-885) as one device-resident chain.  The T sites, the
+// events of every site's window (readHead scan included) and both forward passes per site are computed on the GPU
+// from the resident alignment (dnb_submit_llr); what stays here is the text of humanReadable_detectOut and
+// r.refCoordToCalls (detect.cpp:527-572).
+void normalise_llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, unsigned int w) {
+    const unsigned int k = Pore_Substrate_Config.kmer_len;
+    const size_t n = reads.size();
+    if (n == 0) return;
+    dnb_ctx *ctx = context();
+    std::vector<Staged> staged(n);
+    std::vector<dnb_read_desc> descs(n);
+    std::vector<dnb_read_extra> extra(n);
+    std::vector<std::vector<int32_t>> r2q(n);
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < n; i++) {
+        DNAscent::read &r = *reads[i];
+        stage_read(r, staged[i], descs[i]);
+        const size_t rl = r.referenceSeqMappedTo.size();
+        r2q[i].assign(rl, 0);                                    // std::map::operator[] reads an absent key as 0
+        for (const auto &kv : r.refToQuery)
+            if (kv.first < rl) r2q[i][kv.first] = (int32_t)kv.second;
+        std::memset(&extra[i], 0, sizeof(dnb_read_extra));
+        extra[i].ref_to_query = r2q[i].data();
+        extra[i].is_reverse = r.isReverse ? 1 : 0;
+        extra[i].ref_start = (uint32_t)r.refStart;
+        extra[i].ref_end = (uint32_t)r.refEnd;
+    }
+    dnb_batch *b = nullptr;
+    int rc = dnb_submit_llr(ctx, descs.data(), extra.data(), n, w, &b);
+    if (rc != DNB_OK) die("dnb_submit_llr", rc);
+    for (size_t i = 0; i < n; i++) {
+        DNAscent::read &r = *reads[i];
+        dnb_read_result o;
+        if ((rc = dnb_result(b, i, &o)) != DNB_OK) die("dnb_result", rc);
+        unpack_result(r, o);
+        if (r.eventAlignment.empty()) continue;                  // detect.cpp:879-883: failed read, no llAcrossRead
+        dnb_analogue_result a;
+        if ((rc = dnb_batch_analogue_result(b, i, &a)) != DNB_OK) die("dnb_batch_analogue_result", rc);
+        r.humanReadable_detectOut = ">" + r.readID + " " + r.referenceMappedTo + " " + std::to_string(r.refStart) + " " +
+                                    std::to_string(r.refEnd) + " " + (r.isReverse ? "rev" : "fwd") + "\n";
+        for (uint32_t s = 0; s < a.n_sites; s++) {
+            if (a.n_events[s] == 0) continue;                    // no call for this site (:442, :515)
+            const unsigned int p = a.pos_on_ref[s], q = r.refToQuery.at(p);
+            std::string kmerQuery = r.basecall.substr(q - k / 2, k), kmerRef = r.referenceSeqMappedTo.substr(p - k / 2, k);
+            int globalPos = r.refStart + (int)p;
+            if (r.isReverse) {
+                globalPos = r.refEnd - (int)p - 1;
+                kmerQuery = reverseComplement(kmerQuery);
+                kmerRef = reverseComplement(kmerRef);
+            }
+            const double llr = a.log_analogue[s] - a.log_thymidine[s];   // detect.cpp:548
+            r.humanReadable_detectOut += std::to_string(globalPos) + "\t" + std::to_string(llr) + "\t" + kmerRef + "\t" + kmerQuery + "\n";
+            r.refCoordToCalls[globalPos] = std::make_pair(llr, 0.);
+        }
+    }
+    dnb_release(b);
+}
+
+}  // namespace dnb_shim
+
 void llAcrossRead(DNAscent::read &r, unsigned int windowLength) {
     std::vector<DNAscent::read *> one(1, &r);
     dnb_shim::llAcrossRead_batch(one, windowLength);
@@ -390,7 +452,8 @@ void llAcrossRead(DNAscent::read &r, unsigned int windowLength) {
 double sequenceProbability(std::vector<double> &observations, std::string &sequence, size_t windowSize, bool useBrdU,
                            PoreParameters scalings, size_t BrdUStart, size_t BrdUEnd) {
     const size_t k = Pore_Substrate_Config.kmer_len;
-    // the device kernel scores the analogue span llAcrossRead uses (detect.cpp:544-545)
+    // the device kernel scores the analogue span llAcrossRead uses (detect.cpp:544-545), its only caller in the
+    // reference; any other span is refused loudly rather than scored differently (documented in include/dnascent_b200.h)
     if (useBrdU && (BrdUStart != windowSize - k / 2 || BrdUEnd != windowSize + k / 2))
         throw std::invalid_argument("dnascent_b200 shim: sequenceProbability supports BrdUStart/End = window -/+ k/2 only");
     if (sequence.size() != 2 * windowSize + k)

@@ -39,6 +39,11 @@ void normaliseEvents_batch(const std::vector<DNAscent::read *> &reads, bool useF
 // every site of every read runs in one device launch.
 void llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, unsigned int windowLength);
 
+// detect --HMM (detect.cpp:876-885): normaliseEvents + llAcrossRead of a whole buffer as ONE device-resident chain
+// (dnb_submit_llr): sites, event windows and forward passes are computed on the GPU from the resident alignment.
+// Leaves every read as normaliseEvents_batch + llAcrossRead_batch would (failed reads: empty eventAlignment, no calls).
+void normalise_llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, unsigned int windowLength);
+
 // Batched eventalign (alignment.cpp:547-744): all window chains and Viterbi passes of the buffer in one device
 // launch; humanReadable_eventalignOut and r.addSignal are produced on the host from the returned state records.
 void eventalign_batch(const std::vector<DNAscent::read *> &reads, unsigned int totalWindowLength);

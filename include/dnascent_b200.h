@@ -235,6 +235,8 @@ DNB_API double dnb_cauchyPDF(double loc, double scale, double x);
 /* One "site" = one call of sequenceProbability: observations obs[obs_off[s] .. obs_off[s+1]) (event means, pA),
  * a (2*window + 9)-base snippet at seq + s*(2*window+9), per-site scalings.  Computes both the analogue pass
  * (useBrdU=true, BrdUStart/End = window -/+ 4) and the thymidine pass, as llAcrossRead does (detect.cpp:546-548).
+ * BrdUStart / BrdUEnd are NOT parameters here: window -/+ 4 is what the reference's only caller passes (detect.cpp:544-545),
+ * and the C++ shim's sequenceProbability throws std::invalid_argument for any other span instead of scoring it differently.
  * out_analogue / out_thymidine: log forward probabilities (NaN == log 0); LLR = analogue - thymidine. */
 DNB_API int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64_t *obs_off, const char *seq,
                                            const double *shift, const double *scale, const double *events_per_base,
@@ -354,6 +356,30 @@ DNB_API int dnb_submit_chain(dnb_ctx *ctx, const dnb_read_desc *reads, const dnb
 DNB_API int dnb_batch_feature_result(dnb_batch *batch, size_t i, dnb_feature_result *out);
 /* ms: [0] eventalign kernel, [1] feature kernel (CUDA events on the batch's stream); bytes: [0] host->device, [1] device->host */
 DNB_API int dnb_batch_stage2_timings(dnb_batch *batch, double ms[2], uint64_t bytes[2]);
+
+/* ---- resident analogue stage: llAcrossRead on what dnb_batch_run left in HBM (src/detect.cpp:393-574) --------------
+ * `detect --HMM` calls llAcrossRead(r, 12) right after normaliseEvents (detect.cpp:885).  Here the T positions of
+ * referenceSeqMappedTo, the events aligned to each site's window (readHead scan included) and both forward passes per
+ * site are done on the device from the resident events / alignment / scalings: the only additional host->device bytes
+ * are dnb_read_extra.ref_to_query and is_reverse, the only device->host bytes 24 B per candidate site.
+ * Needs DNB_MODEL_UNLABELLED and DNB_MODEL_ANALOGUE (BrdU or EdU table: whichever was loaded). */
+typedef struct {
+    int status;                  /* normaliseEvents' DNB_READ_* status; a failed read has no sites */
+    uint32_t n_sites;            /* T positions visited, in llAcrossRead's order (descending posOnRef for reverse reads) */
+    const uint32_t *pos_on_ref;  /* [n_sites] posOnRef */
+    const uint32_t *n_events;    /* [n_sites] events of the site's snippet; 0 = no call was made for this site
+                                    (undefined snippet, or fewer than 2*window - 9 events: the `continue`s at :442, :515) */
+    const double *log_analogue;  /* [n_sites] sequenceProbability(useBrdU = true)  (NaN == log 0), valid where n_events > 0 */
+    const double *log_thymidine; /* [n_sites] sequenceProbability(useBrdU = false); LLR = analogue - thymidine (:546-548) */
+} dnb_analogue_result;
+DNB_API int dnb_batch_analogue_llr(dnb_batch *batch, const dnb_read_extra *extra, uint32_t window);
+DNB_API int dnb_batch_analogue_result(dnb_batch *batch, size_t i, dnb_analogue_result *out);
+/* dnb_submit followed by dnb_batch_analogue_llr in one pipelined call (the --HMM read loop body, detect.cpp:876-885) */
+DNB_API int dnb_submit_llr(dnb_ctx *ctx, const dnb_read_desc *reads, const dnb_read_extra *extra, size_t n_reads,
+                           uint32_t window, dnb_batch **batch);
+/* ms: [0] site gathering kernel, [1] forward-pass kernel (CUDA events); counts: [0] candidate sites [1] calls made
+ * [2] observations consumed by the forward passes (per pass) [3] device->host bytes */
+DNB_API int dnb_batch_analogue_timings(dnb_batch *batch, double ms[2], uint64_t counts[4]);
 
 /* ---- int16 ingest: the Dorado signal slice of pod5_getSignal (src/pod5.cpp:56-93, tags parsed at src/reads.h:221-253) -- */
 /* The reference converts the whole POD5 record to pA and then erases what Dorado trimmed or what belongs to the

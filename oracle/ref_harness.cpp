@@ -99,6 +99,19 @@ int dnbref_configure_from_files(void) {
     return 0;
 }
 
+// One table through the reference's own file parser (src/data_IO.cpp:144-242): e.g. analogue_model re-pointed at
+// r10.4.1_EdU_gaussian.model, which src/config.h:54 never loads (SURVEY s.0.2).  Container only.
+int dnbref_load_model_file(int which, const char *filename, int fit_stdv) {
+    configure_constants();
+    try {
+        table(which) = fit_stdv ? import_poreModel_fitStdv(filename, Pore_Substrate_Config.kmer_len)
+                                : import_poreModel_staticStdv(filename, Pore_Substrate_Config.kmer_len);
+    } catch (...) {
+        return -1;
+    }
+    return 0;
+}
+
 // GPU box (no /root/reference): tables come from the committed fixtures.
 int dnbref_set_model(int which, const double *mean, const double *stdv, size_t n) {
     configure_constants();
@@ -492,6 +505,27 @@ double dnbref_bench_normalise(void **handles, size_t n, int threads, int useFit,
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// CPU baseline of the analogue path (row a15): detect --HMM's loop body, detect.cpp:876-885 = normaliseEvents + llAcrossRead.
+// *calls = LLR calls made over all reads (refCoordToCalls entries); returns wall seconds.
+double dnbref_bench_hmm(void **handles, size_t n, int threads, unsigned int windowLength, int *failed, long long *calls) {
+    int nfail = 0;
+    long long ncalls = 0;
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic) num_threads(threads) reduction(+ : nfail, ncalls)
+    for (size_t i = 0; i < n; i++) {
+        Handle *h = (Handle *)handles[i];
+        normaliseEvents(*h->r, false);
+        if (h->r->eventAlignment.empty()) { nfail++; continue; }
+        h->r->refCoordToCalls.clear();
+        llAcrossRead(*h->r, windowLength);
+        ncalls += (long long)h->r->refCoordToCalls.size();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (failed) *failed = nfail;
+    if (calls) *calls = ncalls;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // CPU baseline of the chain (rows f1-f2): detect.cpp:876-888 per read = normaliseEvents + eventalign (whose
 // r.addSignal calls are what the tensor builders read); reads that fail normalisation skip eventalign (detect.cpp:879)
 double dnbref_bench_chain(void **handles, size_t n, int threads, unsigned int windowLength, int *failed) {
@@ -530,6 +564,16 @@ int dnbshim_ll_across_read_batch(void **handles, size_t n, unsigned int windowLe
         reads[i]->refCoordToCalls.clear();
     }
     dnb_shim::llAcrossRead_batch(reads, windowLength);
+    return 0;
+}
+// detect --HMM as one resident chain: normaliseEvents + llAcrossRead on the device (dnb_submit_llr)
+int dnbshim_normalise_ll_batch(void **handles, size_t n, unsigned int windowLength) {
+    std::vector<DNAscent::read *> reads(n);
+    for (size_t i = 0; i < n; i++) {
+        reads[i] = ((Handle *)handles[i])->r;
+        reads[i]->refCoordToCalls.clear();
+    }
+    dnb_shim::normalise_llAcrossRead_batch(reads, windowLength);
     return 0;
 }
 // calls recorded by (batched) llAcrossRead, as dnbref_ll_across_read returns them

@@ -114,6 +114,12 @@ class Ref:
         if self.L.dnbref_configure_from_files() != 0:
             raise RuntimeError("reference model files not readable")
 
+    def load_model_file(self, which: int, filename: str, fit_stdv: bool = True):
+        """One table through the reference's own parser, e.g. ANALOGUE <- r10.4.1_EdU_gaussian.model (build container only)."""
+        self.L.dnbref_load_model_file.argtypes = [C.c_int, C.c_char_p, C.c_int]
+        if self.L.dnbref_load_model_file(which, filename.encode(), int(fit_stdv)) != 0:
+            raise RuntimeError(f"reference model file {filename} not readable")
+
     def set_model(self, which: int, mean: np.ndarray, stdv: np.ndarray):
         mean = np.ascontiguousarray(mean, dtype=np.float64)
         stdv = np.ascontiguousarray(stdv, dtype=np.float64)
@@ -198,6 +204,20 @@ class Ref:
             out.append((pos[:n].copy(), llr[:n].copy()))
         return out
 
+    def normalise_ll_batch(self, reads, window: int = 12):
+        """dnb_shim::normalise_llAcrossRead_batch on reads that have NOT been normalised yet; returns the calls per read."""
+        arr = (C.c_void_p * len(reads))(*[r.h for r in reads])
+        self.L.dnbshim_normalise_ll_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_uint]
+        self.L.dnbshim_normalise_ll_batch(arr, len(reads), window)
+        out = []
+        for r in reads:
+            cap = len(r.refseq) + 1
+            pos = np.zeros(cap, dtype=np.int32)
+            llr = np.zeros(cap)
+            n = self.L.dnbshim_calls(r.h, _p(pos), _p(llr), cap)
+            out.append((pos[:n].copy(), llr[:n].copy()))
+        return out
+
     def eventalign_features_batch(self, reads, window: int = 50, resident: bool = False):
         """dnb_shim::eventalign_features_batch (or, resident=True, dnb_shim::normalise_eventalign_batch on reads that have
         NOT been normalised yet): per read the DnnInputs vectors (what runCNN would get from r.makeSignalTensor() & co.),
@@ -233,6 +253,16 @@ class Ref:
         self.L.dnbref_bench_chain.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_int)]
         t = self.L.dnbref_bench_chain(arr, len(reads), threads, window, C.byref(failed))
         return t, failed.value
+
+    def bench_hmm(self, reads, threads: int, window: int = 12):
+        """normaliseEvents + llAcrossRead per read on `threads` host threads (detect --HMM, detect.cpp:876-885);
+        returns (wall seconds, failed reads, LLR calls made)."""
+        arr = (C.c_void_p * len(reads))(*[r.h for r in reads])
+        failed, calls = C.c_int(0), C.c_longlong(0)
+        self.L.dnbref_bench_hmm.restype = C.c_double
+        self.L.dnbref_bench_hmm.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+        t = self.L.dnbref_bench_hmm(arr, len(reads), threads, window, C.byref(failed), C.byref(calls))
+        return t, failed.value, calls.value
 
     def bench_normalise(self, reads, threads: int, use_fit=False):
         arr = (C.c_void_p * len(reads))(*[r.h for r in reads])

@@ -244,6 +244,20 @@ def test_ultra_long_read_configs2(ctx, port, pore_mean):
         assert o.status == api.READ_OK and o.eventAlignment.shape[0] > len(r.basecall)
 
 
+def test_one_megabase_read_configs2(ctx_compact, port, pore_mean):
+    """BASELINE.json configs[2], upper end: ONE 1-Mb read (1.25*10^7 samples, ~2.4*10^4 segmentation tiles, ~3.2*10^6
+    bands = a 100-MB trace walked back in 5*10^4 rounds) against the CPU oracle, bit-exact, through the compact wire
+    format (event lengths and 2-bit steps of a 3*10^6-step path)."""
+    ref = synth.make_reference(1_050_000, 51)
+    rng = np.random.default_rng(52)
+    r = synth.simulate_read(ref, 20_000, 1_000_000, True, pore_mean, rng, name="mb1")
+    assert r.dac.size > 1.0e7
+    o = ctx_compact.normaliseEvents([api.Read.from_synth(r, use_dac=True).with_runs()])[0]
+    p = port.normalise(r.raw, r.basecall, r.refseq, r.query_to_ref, pore_mean)
+    _compare_with_port(o, p, tag="mb1")
+    assert o.status == api.READ_OK and o.eventAlignment.shape[0] > 2_000_000
+
+
 def test_int16_ingest_with_dorado_slice(ctx, port, pore_mean):
     """Row f3: a POD5 record longer than the read (Dorado-trimmed prefix, a split sibling's samples after it) goes in
     as int16 through dnb_dorado_slice's pointer offset; results must equal the oracle on the reference's own

@@ -132,3 +132,47 @@ def test_exact_rounded_prefix_sums_by_map_composition():
     mod.check_blocks("pod5-like", (dac.astype(np.float32) + np.float32(10.0)) * np.float32(0.1755))
     mod.check_blocks("signed with drift", rng.normal(3, 50, 30_000))
     mod.check_blocks("signed ties", rng.integers(-64, 64, 30_000) * 0.5)
+
+
+def test_streaming_scan_model_matches_the_sequential_prefix_sums():
+    """The algorithm of csrc/seg_scan.cu, modelled lane by lane on the CPU (tests/helpers/proto_seg_scan.py), against
+    scrappie's sequential prefix sums on POD5-like and adversarial signals: checkpoints and totals bit-identical
+    wherever the read-level exactness condition of `sum` holds (reads where it does not go to the serial kernel)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    import proto_seg_scan as ps
+    rng = np.random.default_rng(7)
+
+    def pod5_like(n, scale=0.1755, off=-240.0):
+        lvl = np.repeat(rng.normal(650, 60, size=n // 8 + 1), 8)[:n]
+        dac = np.rint(lvl + rng.normal(0, 6, size=n)).astype(np.int16)
+        return ((dac.astype(np.float32) + np.float32(off)) * np.float32(scale)).astype(np.float32)
+
+    cases = {
+        "pod5_like": pod5_like(40_000),
+        "short_tail": pod5_like(64 * 33 + 17),
+        "one_block": pod5_like(40),
+        "ties": (np.round(rng.uniform(8, 200, size=20_000) * 4) / 4).astype(np.float32),          # few mantissa bits: many exact ties
+        "powers_of_two": np.ldexp(1.0, rng.integers(-3, 9, size=12_000)).astype(np.float32),
+        "growing": (np.linspace(1, 3000, 15_000) * rng.uniform(0.9, 1.1, size=15_000)).astype(np.float32),   # crosses binades fast
+        "spikes": np.where(rng.random(15_000) < 0.01, 30000.0, rng.normal(90, 10, size=15_000)).astype(np.float32),
+        "zeros_and_negatives": np.where(rng.random(10_000) < 0.2, 0.0, rng.normal(0, 50, size=10_000)).astype(np.float32),
+        "tiny_then_large": np.concatenate([np.full(3000, 2.0 ** -19, dtype=np.float32), pod5_like(6000)]),
+    }
+    total_fast = 0
+    for name, x in cases.items():
+        st = {}
+        cs, cq, s, q, exact = ps.scan(x, st)
+        ws, wq, s_ref, q_ref = ps.sequential(x)
+        np.testing.assert_array_equal(cq, wq, err_msg=name)
+        assert q == q_ref, name
+        if exact:
+            np.testing.assert_array_equal(cs, ws, err_msg=name)
+            assert s == s_ref, name
+        total_fast += st["fast_chunks"]
+        if name == "pod5_like":
+            assert exact and st["fast_chunks"] >= 0.6 * (st["fast_chunks"] + st["serial_chunks"]), st
+    assert total_fast > 30
+    # a signal whose sum cannot be exact in double (2^-20-sized samples next to 2^29-sized ones) must be flagged
+    bad = np.concatenate([np.full(100, 2.0 ** -20 * 1.5, dtype=np.float32), np.full(100, 2.0 ** 29 * 1.25, dtype=np.float32)])
+    assert not ps.scan(bad)[4]

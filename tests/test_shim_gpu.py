@@ -186,3 +186,26 @@ def test_shim_ll_across_read_matches_reference(shim, golden_reads, golden_refere
     pos1, llr1 = hs[0].ll_across_read(12)
     np.testing.assert_array_equal(pos1, pos)
     np.testing.assert_array_equal(llr1, llr)
+
+
+def test_shim_resident_hmm_chain_matches_reference(golden_v2, pore_mean):
+    """detect --HMM through the C++ shim as one resident chain (dnb_shim::normalise_llAcrossRead_batch): reads built by
+    the reference's constructor, normaliseEvents + llAcrossRead on the device, calls against the reference's (1e-4)."""
+    from oracle import refbind
+    if not refbind.shim_available():
+        pytest.skip("oracle/_ref/libdnascent_shim.so not built")
+    reads, (um, us, am, as_), reference = golden_v2
+    S = refbind.Ref(shim=True)
+    S.set_model(refbind.PORE, pore_mean, np.full(pore_mean.size, 0.14))
+    S.set_model(refbind.UNLABELLED, um, us)
+    S.set_model(refbind.ANALOGUE, am, as_)
+    S.shutdown()
+    S.set_reference(reference)
+    hs = [S.read_new(reads[t]) for t in ("a0", "a1")]
+    calls = S.normalise_ll_batch(hs, 12)
+    for t, h, (pos, llr) in zip(("a0", "a1"), hs, calls):
+        g = reads[t]
+        np.testing.assert_array_equal(h.outputs(staged=False)["align_event"], g.align[:, 0], err_msg=t)
+        np.testing.assert_array_equal(pos, g.pos_global, err_msg=t)
+        np.testing.assert_allclose(llr, g.llr, rtol=1e-4, atol=1e-6, err_msg=t)
+    S.shutdown()

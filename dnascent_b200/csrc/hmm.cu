@@ -255,9 +255,32 @@ __global__ void __launch_bounds__(256) llr_sites_kernel(DnbBatchView v, DnbLlrAr
         je[i] = (int32_t)lower_bound_kmer(rev, na, hi);              // LB(hi)
     }
     __syncthreads();
-    // ---- readHead recurrence in visit order (ascending sites for forward reads, descending for reverse reads) ----
+    // ---- readHead in visit order (ascending sites for forward reads, descending for reverse reads) ----
+    // readHead is a one-variable recurrence over the sites.  parseCigar makes refToQuery non-decreasing, and then the
+    // lower bounds are monotone along the visit order and readHead never binds: every site's range is [LB(lo), LB(hi))
+    // and all of them are written in parallel.  A read whose window bounds are not monotone (refToQuery with gaps
+    // that read as 0) takes the literal sequential walk on one thread.
+    const bool rev_strand = a.is_reverse[r] != 0;
+    bool mono = true;
+    for (uint32_t i = tid; i < np; i += 256) {
+        if (jb[i] == -2) continue;
+        // previous defined site in ascending order
+        uint32_t k = i;
+        while (k > 0 && jb[k - 1] == -2) k--;
+        if (k > 0) mono = mono && jb[k - 1] <= jb[i] && je[k - 1] <= je[i];
+    }
+    mono = __syncthreads_and(mono);
+    if (mono) {
+        for (uint32_t i = tid; i < np; i += 256) {
+            const int32_t lbl = jb[i], lbh = je[i];
+            if (lbl == -2) { jb[i] = 0; je[i] = 0; continue; }
+            if (!rev_strand) { jb[i] = lbl; je[i] = lbh > lbl ? lbh : lbl; }
+            else if (lbh - 1 >= lbl) { jb[i] = lbl; je[i] = lbl == 0 ? -lbh - 1 : lbh; }   // bottom == 0: no `break`, order stays descending
+            else { jb[i] = 0; je[i] = 0; }
+        }
+        return;
+    }
     if (tid == 0) {
-        const bool rev_strand = a.is_reverse[r] != 0;
         if (!rev_strand) {
             int32_t h = 0;
             for (uint32_t i = 0; i < np; i++) {

@@ -8,8 +8,9 @@
 //   level 1   histogram of the next 12 bits, over the pairs inside that bin         -> a bin of a few hundred slopes
 //   collect   the slopes of that bin are gathered into shared memory and the wanted rank is picked by counting
 // Further 12-bit levels are run only while the bin still holds more slopes than the candidate buffer (ties by the
-// thousand), so a read costs three sweeps over its pairs (IEEE divisions recomputed in each) instead of the eight
-// 8-bit sweeps of the first version (profiles/r1_captureA: 10 us per read).  Pairs are enumerated circulantly
+// thousand).  That general search (three sweeps of IEEE divisions) is the fallback: normally select_slope_windowed
+// finds the answer in two sweeps over APPROXIMATE quotients (7 instructions each instead of ~35) and certifies it with
+// exact divisions of the few hundred candidates around it -- the answer is still the exact order statistic.  Pairs are enumerated circulantly
 // (round d pairs point i with point i+d), which keeps the shared-memory reads of a warp on consecutive addresses.
 #include "dnb_internal.cuh"
 #include "../../include/dnascent_b200.h"
@@ -57,8 +58,26 @@ struct TsShared {
     unsigned long long answer;
 };
 
-// visits every unordered pair once; f(key) is called by all lanes of a warp together (ok == false for padding lanes)
-template <class F>
+// dy/dx within TS_APPROX_ULPS ulps of the IEEE quotient, in 7 instructions instead of the ~35 of the division
+// subroutine: reciprocal seed (2^-20) + two Newton steps (-> ~1 ulp) + one multiply.  Where the bound cannot be
+// vouched for (dx == 0, non-finite or subnormal-range results) the exact quotient is returned instead.
+#define TS_APPROX_ULPS 4096ull
+__device__ __forceinline__ double slope_approx(double dy, double dx) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dx));
+    double e = __fma_rn(-dx, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-dx, r, 1.0);
+    r = __fma_rn(r, e, r);
+    const double q = dMul(dy, r);
+    const double aq = fabs(q);
+    if (!(aq < 1.0e290) || (aq < 1.0e-290 && dy != 0.0)) return dDiv(dy, dx);
+    return q;
+}
+
+// visits every unordered pair once; f(key) is called by all lanes of a warp together (ok == false for padding lanes).
+// kApprox: keys of slope_approx (within TS_APPROX_ULPS of the exact key) instead of the IEEE quotient's
+template <bool kApprox = false, class F>
 __device__ __forceinline__ void for_each_slope(const TsShared &sm, uint32_t np, F f) {
     const uint32_t full_rounds = (np - 1) / 2;
     const uint32_t lane_base = threadIdx.x;
@@ -73,9 +92,10 @@ __device__ __forceinline__ void for_each_slope(const TsShared &sm, uint32_t np, 
                 // oriented lower index first, exactly as the reference's nested loop (:67-75): dx, dy and the signed
                 // zero of dy/dx are the reference's
                 const uint32_t lo = min(i, j), hi = max(i, j);
-                key = order_key(dDiv(dSub(sm.y[lo], sm.y[hi]), dSub(sm.x[lo], sm.x[hi])));
+                const double dy = dSub(sm.y[lo], sm.y[hi]), dx = dSub(sm.x[lo], sm.x[hi]);
+                key = order_key(kApprox ? slope_approx(dy, dx) : dDiv(dy, dx));
             }
-            f(key, ok);
+            f(key, ok, i, d);
         }
     }
     if ((np & 1u) == 0) {   // even np: the half round d = np/2 pairs i < np/2 with i + np/2
@@ -84,10 +104,20 @@ __device__ __forceinline__ void for_each_slope(const TsShared &sm, uint32_t np, 
             const uint32_t i = base + lane_base;
             const bool ok = i < d;
             unsigned long long key = 0;
-            if (ok) key = order_key(dDiv(dSub(sm.y[i], sm.y[i + d]), dSub(sm.x[i], sm.x[i + d])));
-            f(key, ok);
+            if (ok) {
+                const double dy = dSub(sm.y[i], sm.y[i + d]), dx = dSub(sm.x[i], sm.x[i + d]);
+                key = order_key(kApprox ? slope_approx(dy, dx) : dDiv(dy, dx));
+            }
+            f(key, ok, i, d);
         }
     }
+}
+// the exact key of the pair (i, i + d mod np) that for_each_slope visited
+__device__ __forceinline__ unsigned long long exact_key(const TsShared &sm, uint32_t np, uint32_t i, uint32_t d) {
+    uint32_t j = i + d;
+    if (j >= np) j -= np;
+    const uint32_t lo = min(i, j), hi = max(i, j);
+    return order_key(dDiv(dSub(sm.y[lo], sm.y[hi]), dSub(sm.x[lo], sm.x[hi])));
 }
 
 // rank-th smallest (0-based) of the n keys in sm.u.cand: every thread ranks its candidates by counting
@@ -105,21 +135,18 @@ __device__ __forceinline__ void select_among_candidates(TsShared &sm, uint32_t n
     __syncthreads();
 }
 
-// Windowed shortcut (two sweeps instead of three).  The median of one circulant round of slopes (np of them) places
-// a window of 2^53 keys -- about one binade either side of it -- whose 4096 linear bins are histogrammed in one
-// sweep while the slopes below the window are counted; if the wanted rank falls inside the window, the slopes of
-// its bin are gathered and ranked.  Every decision is made on exact keys, so the answer is the exact order
-// statistic; when the window misses (or the bin overflows the candidate buffer) the caller runs the general
-// digit-by-digit search.
+// Windowed shortcut: two sweeps over APPROXIMATE slopes, exact divisions only for the few hundred candidates.
+// The median of one circulant round of (exact) slopes places a window of 2^53 keys -- about one binade either side
+// of it -- whose 4096 linear bins are histogrammed over the approximate keys; the bin [lo, hi) holding the wanted rank
+// is widened by the approximation's error bound, the pairs whose approximate key falls in [lo - delta, hi + delta) get
+// their exact quotient computed and are ranked exactly, the pairs approximately below lo - delta are counted.  A pair
+// approximately below lo - delta is exactly below lo, one approximately at or above hi + delta is exactly at or above
+// hi, so if the candidate picked by exact rank lies in [lo, hi) its global rank is exactly the wanted one.  Otherwise
+// (answer in the fuzzy margin, window missed, candidate buffer too small) the caller runs the general exact search.
 __device__ bool select_slope_windowed(TsShared &sm, uint32_t np, uint32_t kth, unsigned long long *out) {
     const int tid = threadIdx.x;
     const uint32_t d = (np - 1) / 2;                  // a full round: every point paired with the one d places on
-    for (uint32_t i = tid; i < np; i += TS_THREADS) {
-        uint32_t j = i + d;
-        if (j >= np) j -= np;
-        const uint32_t lo = min(i, j), hi = max(i, j);
-        sm.u.cand[i] = order_key(dDiv(dSub(sm.y[lo], sm.y[hi]), dSub(sm.x[lo], sm.x[hi])));
-    }
+    for (uint32_t i = tid; i < np; i += TS_THREADS) sm.u.cand[i] = exact_key(sm, np, i, d);
     __syncthreads();
     select_among_candidates(sm, np, np / 2);
     const unsigned long long centre = sm.answer;
@@ -130,7 +157,7 @@ __device__ bool select_slope_windowed(TsShared &sm, uint32_t np, uint32_t kth, u
     if (tid == 0) { sm.count = 0; sm.n_cand = 0; }
     __syncthreads();
     uint32_t below = 0;
-    for_each_slope(sm, np, [&](unsigned long long key, bool ok) {
+    for_each_slope<true>(sm, np, [&](unsigned long long key, bool ok, uint32_t, uint32_t) {
         const unsigned long long off = key - k0;
         below += (ok && key < k0) ? 1u : 0u;
         if (ok && key >= k0 && (off >> 53) == 0) atomicAdd(&sm.u.hist[(uint32_t)(off >> 41)], 1u);
@@ -172,16 +199,36 @@ __device__ bool select_slope_windowed(TsShared &sm, uint32_t np, uint32_t kth, u
         }
     }
     __syncthreads();
-    if (sm.rank == 0xffffffffu || sm.count > TS_CAND) return false;
-    const uint32_t bin = (uint32_t)sm.prefix, rank = sm.rank;
+    // the first and the last bin have no room for the margin inside the window
+    if (sm.rank == 0xffffffffu || sm.count + 64 > TS_CAND || sm.prefix == 0 || sm.prefix == TS_BINS - 1) return false;
+    const uint32_t bin = (uint32_t)sm.prefix;
+    const unsigned long long lo = k0 + ((unsigned long long)bin << 41), hi = lo + (1ull << 41);
+    const unsigned long long delta = TS_APPROX_ULPS;
     __syncthreads();
-    for_each_slope(sm, np, [&](unsigned long long key, bool ok) {
-        const unsigned long long off = key - k0;
-        if (ok && key >= k0 && (off >> 53) == 0 && (uint32_t)(off >> 41) == bin) sm.u.cand[atomicAdd(&sm.n_cand, 1u)] = key;
+    if (tid == 0) { sm.count = 0; sm.n_cand = 0; }
+    __syncthreads();
+    uint32_t n_below = 0;
+    for_each_slope<true>(sm, np, [&](unsigned long long key, bool ok, uint32_t i, uint32_t dd) {
+        if (!ok) return;
+        if (key < lo - delta) { n_below++; return; }
+        if (key < hi + delta) {
+            const uint32_t slot = atomicAdd(&sm.n_cand, 1u);
+            if (slot < TS_CAND) sm.u.cand[slot] = exact_key(sm, np, i, dd);
+        }
     });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_below += __shfl_xor_sync(FULL, n_below, o);
+    if ((tid & 31) == 0) atomicAdd(&sm.count, n_below);
     __syncthreads();
-    select_among_candidates(sm, sm.n_cand, rank);
-    *out = sm.answer;
+    n_below = sm.count;
+    const uint32_t n_cand = sm.n_cand;
+    __syncthreads();
+    if (n_cand > TS_CAND || kth < n_below || kth - n_below >= n_cand) return false;
+    select_among_candidates(sm, n_cand, kth - n_below);
+    const unsigned long long ans = sm.answer;
+    __syncthreads();
+    if (ans < lo || ans >= hi) return false;          // in the margin: its global rank is not certified
+    *out = ans;
     return true;
 }
 
@@ -204,7 +251,7 @@ __device__ unsigned long long select_slope(TsShared &sm, uint32_t np, uint32_t k
             // few enough slopes share the decided bits: gather them and finish
             if (tid == 0) sm.n_cand = 0;
             __syncthreads();
-            for_each_slope(sm, np, [&](unsigned long long key, bool ok) {
+            for_each_slope(sm, np, [&](unsigned long long key, bool ok, uint32_t, uint32_t) {
                 if (ok && (key & himask) == prefix) sm.u.cand[atomicAdd(&sm.n_cand, 1u)] = key;
             });
             __syncthreads();
@@ -213,7 +260,7 @@ __device__ unsigned long long select_slope(TsShared &sm, uint32_t np, uint32_t k
         }
         for (int i = tid; i < TS_BINS; i += TS_THREADS) sm.u.hist[i] = 0;
         __syncthreads();
-        for_each_slope(sm, np, [&](unsigned long long key, bool ok) {
+        for_each_slope(sm, np, [&](unsigned long long key, bool ok, uint32_t, uint32_t) {
             hist_add(sm.u.hist, (uint32_t)(key >> shift) & dmask, ok && (key & himask) == prefix);
         });
         __syncthreads();

@@ -266,6 +266,8 @@ __device__ __forceinline__ void dp_band(DpWarp &w, double (&P1)[4], double (&P2)
         const double fresh = shfl_d(w.mbuf, need - w.mbase);
         put4(w.mk, lane, (w.ll_e - (DNB_BW - 1)) & 127, fresh);       // the new top cell's k-mer
         put4(P1, lane, (w.ll_e - DNB_BW) & 127, NEG_SENT);            // above the top: out of band b-1
+        // (a warp-uniform 4-way branch on the slot's register index instead of these per-register selects was measured:
+        // 21 instead of 58 instructions on this path, but 2 % SLOWER overall -- the branches cost more than the selects)
         w.mvword |= 1u << (b & 31);
     } else {
         w.ll_e++;
@@ -365,8 +367,7 @@ __device__ __forceinline__ DpEnd dp_fill_warp(const DnbBatchView &v, const DnbDp
 
 struct BtSmem {
     __align__(16) uint8_t win[BT_ROWS * DNB_TRACE_ROW];
-    float lp[BT_STEPS];
-    uint8_t code[BT_STEPS];
+    double lp[BT_STEPS];      // the round's emissions (float values, widened by the lanes that computed them)
 };
 
 __device__ __forceinline__ void backtrace_warp(const DnbBatchView &v, const DnbBtArgs &a, uint32_t r, int lane,
@@ -410,29 +411,60 @@ __device__ __forceinline__ void backtrace_warp(const DnbBatchView &v, const DnbB
             }
         }
         __syncwarp();
+        // The chase.  ncu showed it to be ~75 % of the backtrace's instructions (38 per step, all on one lane), so the
+        // common round -- 32 steps that can neither reach the start of the read nor wrap the 128-slot ring -- is a
+        // fixed, unrolled loop of ~13 instructions per step: one shared-memory word, a 2-bit extract, the cell index
+        // moved by a packed per-code delta (D: two rows up and one slot back = 257 cells, U: 129, L: 128); the codes
+        // stay in two registers and are broadcast, the previous round's emissions are added in the loop's shadow.
         int ns = 0;
+        uint32_t c_lo = 0, c_hi = 0;           // 2-bit codes of steps 0-15 / 16-31
+        const bool fast = (e & 127) >= BT_STEPS && e >= BT_STEPS && k >= BT_STEPS;
         if (lane == 0) {
-            int ee = e, kk = k;
-            while (ns < BT_STEPS && kk >= 0 && ee >= 0) {
-                const int bb = ee + kk + 2;
-                const uint32_t code = (sm.win[(bb - lo) * DNB_TRACE_ROW + ((ee & 127) >> 2)] >> (2 * (ee & 3))) & 3u;
-                sm.code[ns] = (uint8_t)code;
-                if (ns < n_prev) sum_em = dAdd(sum_em, (double)sm.lp[ns]);     // previous round's emissions, in order
-                ee -= (code != DNB_FROM_L);
-                kk -= (code != DNB_FROM_U);
-                gap = (code == DNB_FROM_L) ? gap + 1 : 0;
-                max_gap = max(max_gap, gap);
-                ns++;
+            if (fast) {
+                const uint32_t *w32 = reinterpret_cast<const uint32_t *>(sm.win);
+                uint32_t c = (uint32_t)(hi - lo) * 128u + (uint32_t)(e & 127);
+#pragma unroll
+                for (int t = 0; t < BT_STEPS; t++) {
+                    const uint32_t code = (w32[c >> 4] >> ((c & 15u) * 2u)) & 3u;
+                    if (t < 16) c_lo |= code << (2 * t); else c_hi |= code << (2 * (t - 16));
+                    c -= (0x2010301u >> (9u * code)) & 0x1ffu;
+                    if (t < n_prev) sum_em = dAdd(sum_em, sm.lp[t]);              // previous round's emissions, in order
+                }
+                ns = BT_STEPS;
+            } else {
+                int ee = e, kk = k;
+                while (ns < BT_STEPS && kk >= 0 && ee >= 0) {
+                    const int bb = ee + kk + 2;
+                    const uint32_t code = (sm.win[(bb - lo) * DNB_TRACE_ROW + ((ee & 127) >> 2)] >> (2 * (ee & 3))) & 3u;
+                    if (ns < 16) c_lo |= code << (2 * ns); else c_hi |= code << (2 * (ns - 16));
+                    if (ns < n_prev) sum_em = dAdd(sum_em, sm.lp[ns]);
+                    ee -= (code != DNB_FROM_L);
+                    kk -= (code != DNB_FROM_U);
+                    ns++;
+                }
+                for (int t = ns; t < n_prev; t++) sum_em = dAdd(sum_em, sm.lp[t]);
             }
-            for (int t = ns; t < n_prev; t++) sum_em = dAdd(sum_em, (double)sm.lp[t]);
             n_prev = ns;
         }
         ns = __shfl_sync(FULL, ns, 0);
+        c_lo = __shfl_sync(FULL, c_lo, 0);
+        c_hi = __shfl_sync(FULL, c_hi, 0);
         __syncwarp();
 
         // ---- one step per lane ----
         const bool act = lane < ns;
-        const uint32_t code = act ? sm.code[lane] : 3u;
+        const uint32_t code = act ? (((lane < 16 ? c_lo : c_hi) >> (2 * (lane & 15))) & 3u) : 3u;
+        {   // running gap length (consecutive L moves): L moves are rare, so normally one compare per round
+            const unsigned m_l = __ballot_sync(FULL, act && code == DNB_FROM_L);
+            if (lane == 0 && ns > 0) {
+                if (m_l == 0) gap = 0;
+                else
+                    for (int t = 0; t < ns; t++) {
+                        gap = ((m_l >> t) & 1u) ? gap + 1 : 0;
+                        max_gap = max(max_gap, gap);
+                    }
+            }
+        }
         const unsigned m_e = __ballot_sync(FULL, act && code != DNB_FROM_L);
         const unsigned m_k = __ballot_sync(FULL, act && code != DNB_FROM_U);
         const unsigned m_d = __ballot_sync(FULL, act && code == DNB_FROM_D);
@@ -445,7 +477,7 @@ __device__ __forceinline__ void backtrace_warp(const DnbBatchView &v, const DnbB
             const int off = DNB_BW / 2 + (bi - 1) - rights - ei;
             if (off < 0 || off >= DNB_BW) bad = true;
             pairs[na + lane] = make_uint2((uint32_t)ei, (uint32_t)ki);                         // :359
-            sm.lp[lane] = emission_static(x[ei], mu[ki], emit_const);                          // :363
+            sm.lp[lane] = (double)emission_static(x[ei], mu[ki], emit_const);                  // :363
         }
         // previous diagonal step: inside this round or carried over
         const unsigned pm = m_d & lt;
@@ -479,7 +511,7 @@ __device__ __forceinline__ void backtrace_warp(const DnbBatchView &v, const DnbB
             a.n_align[r] = 0; a.n_cleaned[r] = 0; a.avg_log_emission[r] = 0.0; a.spanned[r] = 0; a.max_gap[r] = 0;
             return;
         }
-        for (int t = 0; t < n_prev; t++) sum_em = dAdd(sum_em, (double)sm.lp[t]);
+        for (int t = 0; t < n_prev; t++) sum_em = dAdd(sum_em, sm.lp[t]);
         const double avg = dDiv(sum_em, (double)na);                                       // :420 (n_aligned counts steps)
         const bool spanned = na > 0 && last_k == 0;     // front().second == 0; back().second == K-1 holds by construction
         a.avg_log_emission[r] = avg;
@@ -495,8 +527,11 @@ __device__ __forceinline__ void backtrace_warp(const DnbBatchView &v, const DnbB
 
 // kMode 0: fill + backtrace (production)   1: fill only   2: backtrace only (the split pair is for profiling the two
 // phases as separate launches; same device code)
+#ifndef BT_MIN_BLOCKS
+#define BT_MIN_BLOCKS 8      // the backtrace-only launch is a latency machine: cap its registers for 32 resident warps per SM
+#endif
 template <int kMode>
-__global__ void __launch_bounds__(DP_WARPS * 32, DP_MIN_BLOCKS) align_kernel(DnbBatchView v, DnbBtArgs a) {
+__global__ void __launch_bounds__(DP_WARPS * 32, kMode == 2 ? BT_MIN_BLOCKS : DP_MIN_BLOCKS) align_kernel(DnbBatchView v, DnbBtArgs a) {
     __shared__ BtSmem sm[DP_WARPS];      // the band fill's 1 KB slot copy aliases the backtrace window (used after it)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t slot = blockIdx.x * DP_WARPS + w;

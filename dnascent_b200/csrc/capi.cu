@@ -276,10 +276,11 @@ struct dnb_ctx {
     std::mutex mu;
     PinnedPool pinned;
     DevCache dev;
-    // dnb_submit from several host threads forms a software pipeline: one batch packing + copying in, up to two
-    // computing, one copying out.  Without the gates concurrent callers fall into lockstep (all upload, then all
+    // dnb_submit from several host threads forms a software pipeline: one batch packing, up to two enqueueing /
+    // copying in (so that the copy engine always has the next batch's copies queued behind the current one's), up to
+    // two computing, one copying out.  Without the gates concurrent callers fall into lockstep (all upload, then all
     // compute, then all fetch) and the GPU idles during the copy phases.
-    StageGate gate_pack{1}, gate_h2d{1}, gate_compute{2}, gate_fetch{1};
+    StageGate gate_pack{1}, gate_h2d{2}, gate_compute{2}, gate_fetch{1};
     StreamPool streams;
     cudaMemPool_t pool = nullptr;        // stream-ordered scratch of the non-batch entry points (private: no global side effect)
     // n_devices > 1: this context is the front of a set; peers[k] drives cfg.devices[k + 1]

@@ -38,20 +38,27 @@ namespace {
 __device__ __forceinline__ double d_nan() { return __longlong_as_double(0x7ff8000000000000ll); }
 __device__ __forceinline__ double d_ninf() { return __longlong_as_double(0xfff0000000000000ll); }
 
+// The double-precision exp / log / log1p of CUDA's math library inline ~60 instructions per call site; a forward step has
+// 26 of them per pass, and with everything inlined the loop body overflowed the instruction cache (ncu: "no
+// instruction" was the second largest stall).  One out-of-line copy of each keeps the loop body small.
+__device__ __noinline__ double exp_nl(double x) { return exp(x); }
+__device__ __noinline__ double log_nl(double x) { return log(x); }
+__device__ __noinline__ double log1p_nl(double x) { return log1p(x); }
+
 __device__ __forceinline__ double lse2(double a, double b) {
     const double m = fmax(a, b);
     if (m == d_ninf()) return m;
-    return m + log1p(exp(-fabs(a - b)));       // one of them -inf: exp(-inf) = 0
+    return m + log1p_nl(exp_nl(-fabs(a - b)));       // one of them -inf: exp(-inf) = 0
 }
 __device__ __forceinline__ double lse3(double a, double b, double c) {
     const double m = fmax(fmax(a, b), c);
     if (m == d_ninf()) return m;
-    return m + log(exp(a - m) + exp(b - m) + exp(c - m));
+    return m + log_nl(exp_nl(a - m) + exp_nl(b - m) + exp_nl(c - m));
 }
 __device__ __forceinline__ double lse4(double a, double b, double c, double d) {
     const double m = fmax(fmax(a, b), fmax(c, d));
     if (m == d_ninf()) return m;
-    return m + log(exp(a - m) + exp(b - m) + exp(c - m) + exp(d - m));
+    return m + log_nl(exp_nl(a - m) + exp_nl(b - m) + exp_nl(c - m) + exp_nl(d - m));
 }
 
 // per-lane emission model of one pass: eln(normalPDF(mu, sigma, x))
@@ -68,8 +75,8 @@ struct Emit {
         const double dx = x - mu;
         const double y = -(dx * dx) * inv2s2;
         if (y > -700.0) return lnc + y;
-        const double p = c * exp(y);           // the reference's linear-space value underflows to 0 -> log 0
-        return p > 0.0 ? log(p) : d_ninf();
+        const double p = c * exp_nl(y);        // the reference's linear-space value underflows to 0 -> log 0
+        return p > 0.0 ? log_nl(p) : d_ninf();
     }
 };
 
@@ -118,11 +125,11 @@ __device__ __forceinline__ void hmm_step(PassState &p, const Emit &em, double x,
         const double m2 = __shfl_up_sync(HMM_FULL, m, d), s2 = __shfl_up_sync(HMM_FULL, s, d);
         if (lane >= d && m2 != d_ninf()) {
             if (m == d_ninf()) { m = m2; s = s2; }
-            else if (m >= m2) s = s + s2 * exp(m2 - m);
-            else { s = s * exp(m - m2) + s2; m = m2; }
+            else if (m >= m2) s = s + s2 * exp_nl(m2 - m);
+            else { s = s * exp_nl(m - m2) + s2; m = m2; }
         }
     }
-    p.D = (m == d_ninf()) ? m : m + log(s) + shiftD;
+    p.D = (m == d_ninf()) ? m : m + log_nl(s) + shiftD;
     p.I = Ic; p.M = Mc; p.firstI = firstI_cur;
 }
 

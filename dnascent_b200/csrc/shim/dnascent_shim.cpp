@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -33,6 +34,12 @@ std::mutex g_mu;
 dnb_ctx *g_ctx = nullptr;
 int g_device = -1;
 std::vector<int> g_devices;   // more than one entry: one context (one process) drives all of them
+std::atomic<unsigned long> g_batches_on[DNB_MAX_DEVICES];   // submissions each device ran (diagnostics)
+
+void note_device(dnb_batch *b) {
+    const int dev = dnb_batch_device(b);
+    if (dev >= 0 && dev < DNB_MAX_DEVICES) g_batches_on[dev]++;
+}
 
 [[noreturn]] void die(const char *where, int rc) {
     std::fprintf(stderr, "dnascent_b200 shim: %s failed: %s (%s)\n", where, dnb_strerror(rc), dnb_last_error());
@@ -194,6 +201,10 @@ void shutdown() {
     g_ctx = nullptr;
 }
 
+unsigned long batches_on_device(int device) {
+    return (device >= 0 && device < DNB_MAX_DEVICES) ? g_batches_on[device].load() : 0ul;
+}
+
 void normaliseEvents_batch(const std::vector<DNAscent::read *> &reads, bool useFitPoreModel) {
     if (reads.empty()) return;
     if (useFitPoreModel) {
@@ -210,6 +221,7 @@ void normaliseEvents_batch(const std::vector<DNAscent::read *> &reads, bool useF
     dnb_batch *b = nullptr;
     int rc = dnb_submit(ctx, descs.data(), n, &b);
     if (rc != DNB_OK) die("dnb_submit", rc);
+    note_device(b);
     rc = dnb_wait(b);
     if (rc != DNB_OK) die("dnb_wait", rc);
 #pragma omp parallel for schedule(dynamic)
@@ -414,6 +426,7 @@ void normalise_llAcrossRead_batch(const std::vector<DNAscent::read *> &reads, un
     dnb_batch *b = nullptr;
     int rc = dnb_submit_llr(ctx, descs.data(), extra.data(), n, w, &b);
     if (rc != DNB_OK) die("dnb_submit_llr", rc);
+    note_device(b);
     for (size_t i = 0; i < n; i++) {
         DNAscent::read &r = *reads[i];
         dnb_read_result o;
@@ -686,6 +699,7 @@ void normalise_eventalign_batch(const std::vector<DNAscent::read *> &reads, unsi
     dnb_batch *b = nullptr;
     int rc = dnb_submit_chain(ctx, descs.data(), extra.data(), n, totalWindowLength, 0, &b);   // thread-safe, staged like dnb_submit
     if (rc != DNB_OK) die("dnb_submit_chain", rc);
+    note_device(b);
     bool negative_log = false;
 #pragma omp parallel for schedule(dynamic)
     for (size_t i = 0; i < n; i++) {

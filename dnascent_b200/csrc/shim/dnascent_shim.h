@@ -28,6 +28,7 @@ void set_device(int device);   // call before the first use
 // One process, several GPUs: every batched call below is dealt to the device with the least work in flight
 // (dnb_config.devices; also settable as DNB_DEVICES="0,1,...").  Call before the first use.
 void set_devices(const std::vector<int> &devices);
+unsigned long batches_on_device(int device);   // submissions dealt to that GPU so far (diagnostics)
 void shutdown();               // destroys the context (optional; e.g. before pod5_terminate at detect.cpp:917)
 
 // Batched normaliseEvents(r, false): one GPU submission for the whole buffer of reads (the reference's

@@ -51,6 +51,9 @@ struct TsShared {
         uint32_t hist[TS_BINS];
         unsigned long long cand[TS_CAND];
     } u;
+    uint32_t hist8[256];         // digit histogram of select_among_candidates
+    unsigned long long sel_prefix;
+    uint32_t sel_rank;
     unsigned long long prefix;   // key bits decided so far
     uint32_t rank;               // wanted rank inside the current bin
     uint32_t count;              // slopes inside the current bin
@@ -120,18 +123,49 @@ __device__ __forceinline__ unsigned long long exact_key(const TsShared &sm, uint
     return order_key(dDiv(dSub(sm.y[lo], sm.y[hi]), dSub(sm.x[lo], sm.x[hi])));
 }
 
-// rank-th smallest (0-based) of the n keys in sm.u.cand: every thread ranks its candidates by counting
+// rank-th smallest (0-based) of the n keys in sm.u.cand: radix select, eight 8-bit digits from the top (n * 8 key
+// visits; the first version ranked every candidate against every other one, n^2 compares, which ncu showed to be ~40 %
+// of the kernel's instructions)
 __device__ __forceinline__ void select_among_candidates(TsShared &sm, uint32_t n, uint32_t rank) {
-    for (uint32_t c = threadIdx.x; c < n; c += TS_THREADS) {
-        const unsigned long long mine = sm.u.cand[c];
-        uint32_t less = 0, equal = 0;
-        for (uint32_t t = 0; t < n; t++) {
-            const unsigned long long o = sm.u.cand[t];
-            less += o < mine;
-            equal += o == mine;
+    const int tid = threadIdx.x;
+    if (tid == 0) { sm.sel_prefix = 0ull; sm.sel_rank = rank; }
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        sm.hist8[tid] = 0;                                     // TS_THREADS == 256
+        __syncthreads();
+        const unsigned long long prefix = sm.sel_prefix;
+        for (uint32_t c0 = 0; c0 < n; c0 += TS_THREADS) {
+            const uint32_t c = c0 + tid;
+            const unsigned long long k = c < n ? sm.u.cand[c] : 0ull;
+            hist_add(sm.hist8, (uint32_t)(k >> shift) & 0xFFu, c < n && (k & himask) == prefix);
         }
-        if (less <= rank && rank < less + equal) sm.answer = mine;   // every writer holds the same value
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) sum += sm.hist8[tid * 8 + q];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                if (tid >= o) incl += t;
+            }
+            const uint32_t excl = incl - sum, want = sm.sel_rank;
+            if (want >= excl && want < incl) {
+                uint32_t rem = want - excl, q = 0;
+                for (; q < 7; q++) {
+                    const uint32_t c = sm.hist8[tid * 8 + q];
+                    if (rem < c) break;
+                    rem -= c;
+                }
+                sm.sel_prefix = prefix | ((unsigned long long)(tid * 8 + q) << shift);
+                sm.sel_rank = rem;
+            }
+        }
+        __syncthreads();
     }
+    if (tid == 0) sm.answer = sm.sel_prefix;
     __syncthreads();
 }
 

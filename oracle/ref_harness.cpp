@@ -625,6 +625,9 @@ size_t dnbshim_dnn_inputs(size_t i, float *signal, float *core, float *residual,
     return P;
 }
 void dnbshim_shutdown(void) { dnb_shim::shutdown(); }
+// one process, several GPUs: call before the first batched call (after dnbshim_shutdown when a context exists)
+void dnbshim_set_devices(const int *devices, int n) { dnb_shim::set_devices(std::vector<int>(devices, devices + n)); }
+unsigned long dnbshim_batches_on_device(int device) { return dnb_shim::batches_on_device(device); }
 #endif  // DNB_SHIM_BUILD
 
 int dnbref_max_threads(void) { return omp_get_max_threads(); }

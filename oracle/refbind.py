@@ -245,6 +245,15 @@ class Ref:
         if self.is_shim:
             self.L.dnbshim_shutdown()
 
+    def set_devices(self, devices):
+        """dnb_shim::set_devices: the one process drives all of them (call after shutdown(), before the next batch)."""
+        arr = (C.c_int * len(devices))(*devices)
+        self.L.dnbshim_set_devices(arr, len(devices))
+
+    def batches_on_device(self, device: int) -> int:
+        self.L.dnbshim_batches_on_device.restype = C.c_ulong
+        return int(self.L.dnbshim_batches_on_device(device))
+
     def bench_chain(self, reads, threads: int, window: int = 50):
         """normaliseEvents + eventalign + tensor builders per read on `threads` host threads (detect.cpp:876-888)."""
         arr = (C.c_void_p * len(reads))(*[r.h for r in reads])

@@ -1,0 +1,22 @@
+#!/bin/bash
+# round 2: fused vs split align launches (backtrace-only capped at 64 registers), two batches in the H2D slot
+set -u
+TAG=${1:-r2h}
+mkdir -p gpurun_out
+show() { python - "$1" <<'PY'
+import json, sys
+try:
+    d = json.load(open(sys.argv[1]))
+    print("value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "value ms", round(d["ms_per_step"]), "e2e ms", round(d["e2e"]["ms_per_step"]))
+    print("stage", {k: round(v, 1) for k, v in d["config"]["stage_ms_per_step"].items()})
+except Exception as ex:
+    print("no bench json", ex)
+PY
+}
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
+tail -4 gpurun_out/${TAG}_pytest.log
+timeout 900 python bench.py --reads 30000 --steps 4 --warmup 3 --no-cpu-baseline --chain-reads 0 --parity-reads 0 --ultra-reads 0 --analogue-reads 0 > gpurun_out/${TAG}_bench30k.json 2> gpurun_out/${TAG}_bench30k.err; echo "bench rc=$?"
+show gpurun_out/${TAG}_bench30k.json
+DNB_SPLIT_ALIGN=1 timeout 900 python bench.py --reads 30000 --steps 4 --warmup 3 --no-cpu-baseline --chain-reads 0 --parity-reads 0 --ultra-reads 0 --analogue-reads 0 > gpurun_out/${TAG}_bench30k_split.json 2> gpurun_out/${TAG}_bench30k_split.err; echo "bench(split) rc=$?"
+show gpurun_out/${TAG}_bench30k_split.json
+echo done

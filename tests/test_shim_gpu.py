@@ -209,3 +209,36 @@ def test_shim_resident_hmm_chain_matches_reference(golden_v2, pore_mean):
         np.testing.assert_array_equal(pos, g.pos_global, err_msg=t)
         np.testing.assert_allclose(llr, g.llr, rtol=1e-4, atol=1e-6, err_msg=t)
     S.shutdown()
+
+
+def test_shim_one_process_two_gpus(n_cuda, golden_reads, golden_reference, pore_mean):
+    """SURVEY s.8(b): one dnb_ctx per process driving several GPUs.  The shim's single context deals whole buffers to
+    the least-loaded device; DNAscent::read objects come back identical whichever GPU ran them."""
+    from oracle import refbind
+    if not refbind.shim_available():
+        pytest.skip("oracle/_ref/libdnascent_shim.so not built")
+    if n_cuda < 2:
+        pytest.skip("needs two CUDA devices")
+    import threading
+    S = refbind.Ref(shim=True)
+    S.set_model(refbind.PORE, pore_mean, np.full(pore_mean.size, 0.14))
+    S.shutdown()
+    S.set_devices([0, 1])
+    S.set_reference(golden_reference)
+    before = [S.batches_on_device(k) for k in (0, 1)]
+    buffers = [[S.read_new(g) for g in golden_reads] for _ in range(4)]
+    threads = [threading.Thread(target=S.normalise_batch, args=(hs,)) for hs in buffers]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for hs in buffers:
+        for h, g in zip(hs, golden_reads):
+            o = h.outputs(staged=False)
+            np.testing.assert_array_equal(o["align_event"], g.align[:, 0])
+            np.testing.assert_array_equal(o["align_kmer"], g.align[:, 1])
+            assert o["shift"] == g.shift and o["scale"] == g.scale
+    used = [S.batches_on_device(k) - b for k, b in zip((0, 1), before)]
+    assert sum(used) == 4 and min(used) >= 1, used
+    S.shutdown()
+    S.set_devices([0])

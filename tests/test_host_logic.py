@@ -49,12 +49,21 @@ def test_shard_reads_balanced_and_complete():
 def test_make_bins_respects_budget_and_orders_longest_first():
     rng = np.random.default_rng(4)
     n = synth.lognormal_lengths(5_000, 30_000, rng) * 12
-    bins = sharding.make_bins(n, 20_000_000)
-    np.testing.assert_array_equal(np.sort(np.concatenate(bins)), np.arange(n.size))
-    for b in bins:
-        assert n[b].sum() <= 20_000_000 or b.size == 1
-    firsts = [n[b[0]] for b in bins]
-    assert firsts == sorted(firsts, reverse=True)
+    for policy in ("interleaved", "sorted"):
+        bins = sharding.make_bins(n, 20_000_000, policy=policy)
+        np.testing.assert_array_equal(np.sort(np.concatenate(bins)), np.arange(n.size))
+        for b in bins:
+            assert n[b].sum() <= 20_000_000 or b.size == 1
+            assert np.all(np.diff(n[b]) <= 0)                                  # longest first inside a bin
+        firsts = [n[b[0]] for b in bins]
+        assert firsts == sorted(firsts, reverse=True)
+    # "interleaved" gives every bin the same length mix: equal loads, and every bin holds some of the longest reads
+    bins = sharding.make_bins(n, 20_000_000, policy="interleaved")
+    loads = np.array([n[b].sum() for b in bins], dtype=np.float64)
+    assert loads.max() / loads.min() < 1.15
+    assert min(n[b[0]] for b in bins) > np.quantile(n, 0.98)
+    assert sharding.make_bins([], 10) == []
+    assert [b.tolist() for b in sharding.make_bins([50, 7], 10)] == [[0], [1]]     # a read larger than the budget is a bin of its own
 
 
 def _gloo_worker(rank, world, port, q):

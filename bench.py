@@ -285,6 +285,9 @@ def main():
                     help="dnb_submit calls in flight (B200 sweep, 60k reads: 4e8x4 74 %% of the resident value, 8e8x8 84 %%)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pin", action="store_true", help="leave the workload pageable (e2e goes through pinned staging)")
+    ap.add_argument("--extra-legs-all-ranks", action="store_true",
+                    help="run the chain / ultra-long / analogue legs under torchrun too (default: only at --gpus 1; they are "
+                         "extras next to the contract's line and their device-side data generation is not worth N x the time)")
     ap.add_argument("--ultra-reads", type=int, default=600,
                     help="reads per GPU of the configs[2] leg (lengths log-uniform in 100 kb - 1 Mb, inputs resident); 0 = skip")
     ap.add_argument("--analogue-reads", type=int, default=4000,
@@ -514,8 +517,21 @@ def main():
 
     # ---- chain leg (SURVEY s.8 rows f1-f2): normaliseEvents -> eventalign -> DNN input tensors through dnb_submit_chain,
     # host buffers in, tensors out, on a bounded sample of this rank's shard (the tensors are 108 B per reference base)
+    extras = world == 1 or args.extra_legs_all_ranks
+
+    def guarded(leg):
+        """An extra leg must never cost the contract's line: at --gpus 1 a failure is recorded in its place.  (Under
+        torchrun the legs contain barriers, so there an exception still ends the run rather than deadlocking it.)"""
+        if world > 1:
+            return leg()
+        try:
+            return leg()
+        except Exception as ex:  # noqa: BLE001
+            return {"error": repr(ex)[:500]}
+
     chain = None
-    if args.chain_reads > 0:
+
+    def chain_leg():
         # N ranks share one box's host RAM (pinned results ~15 B/sample per submission in flight): the sample and
         # the submission size shrink with the number of ranks
         n_c = min(max(args.chain_reads // world, 200), W.n_reads)
@@ -556,7 +572,7 @@ def main():
         dt_c = max_over_ranks(time.perf_counter() - t0) / 2
         c_samples = int(W.n_samples[cidx].sum())
         c_total = sum_over_ranks(float(c_samples))
-        chain = {"what": "dnb_submit_chain: normaliseEvents -> eventalign -> DNN input tensors (rows f1-f2), host buffers in, "
+        return {"what": "dnb_submit_chain: normaliseEvents -> eventalign -> DNN input tensors (rows f1-f2), host buffers in, "
                          f"tensors out, {c_bin:.1e}-sample submissions, 3 in flight",
                  "value": c_total / dt_c / 1e6, "unit": UNIT, "reads_per_gpu": int(n_c), "samples_per_gpu": c_samples,
                  "ms_per_pass": 1e3 * dt_c, "tensor_rows_per_gpu": int(acc["rows"]), "h2d_bytes_per_pass": int(acc["h2d"]),
@@ -565,11 +581,17 @@ def main():
                                     else "window-parallel",
                  "cpu_reference": None}
 
+    if args.chain_reads > 0 and extras:
+        chain = guarded(chain_leg)
+
     # ---- ultra-long leg (BASELINE configs[2]): lengths log-uniform in [100 kb, 1 Mb], inputs resident in HBM.  One warp
     # walks one read's band chain, so a bin of few very long reads cannot fill the device: report how full it was
     # (warps against resident warp slots) and what the longest read's serial chain costs (the tail).
     ultra = None
-    if args.ultra_reads > 0:
+
+    def ultra_leg():
+        ctx.trim()                      # the library caches its device blocks; torch needs room to generate the reads
+        torch.cuda.empty_cache()
         rng_u = np.random.default_rng(args.seed + 4242 + rank)
         lens_u = np.exp(rng_u.uniform(np.log(100_000), np.log(1_000_000), size=args.ultra_reads)).astype(np.int64)
         WU = bench_data.generate(lens_u, mean, args.seed + 4243 + 1000 * rank, device=f"cuda:{local}", ref_len=1_050_000)
@@ -610,18 +632,23 @@ def main():
         for pb in per_bin:
             # the same cells at the rate the saturated C2 bins reach: what is above that is under-fill + tail
             pb["tail_factor"] = pb["cells_per_s"] and c2_cells_per_s / pb["cells_per_s"]
-        ultra = {"what": "configs[2]: lengths log-uniform in [100 kb, 1 Mb], inputs resident, dnb_batch_run per bin",
+        return {"what": "configs[2]: lengths log-uniform in [100 kb, 1 Mb], inputs resident, dnb_batch_run per bin",
                  "value": u_samples / dt_u / 1e6, "unit": UNIT, "reads_per_gpu": int(args.ultra_reads),
                  "samples_per_gpu": int(WU.n_samples.sum()), "ms_per_pass": 1e3 * dt_u,
                  "stage_ms_per_pass": {k2: v2 / 2 for k2, v2 in u_ms.items()},
                  "failed_reads": int(u_cnt.get("failed_reads", 0)) // 2, "bins": per_bin,
-                 "saturated_cells_per_s_for_comparison": c2_cells_per_s}
-        del WU
+                "saturated_cells_per_s_for_comparison": c2_cells_per_s}
+
+    if args.ultra_reads > 0 and extras:
+        ultra = guarded(ultra_leg)
 
     # ---- analogue leg (SURVEY s.8 row a15, BASELINE configs[3]): detect --HMM's loop body, normaliseEvents + llAcrossRead,
     # on 10-kb reads through dnb_submit_llr: host buffers in, (site, log-likelihoods) out; metric = LLR calls per second
     analogue = None
-    if args.analogue_reads > 0:
+
+    def analogue_leg():
+        ctx.trim()
+        torch.cuda.empty_cache()
         n_a = max(args.analogue_reads // world, 100)
         unl, ana = synthetic_analogue_tables(mean)
         ctx.load_model(api.MODEL_UNLABELLED, *unl)
@@ -661,7 +688,7 @@ def main():
         barrier()
         dt_a = max_over_ranks(time.perf_counter() - t0) / 2
         calls_total = sum_over_ranks(float(a_acc["calls"]))
-        analogue = {"what": "dnb_submit_llr: normaliseEvents -> llAcrossRead (T sites, event windows, both forward passes per site "
+        return {"what": "dnb_submit_llr: normaliseEvents -> llAcrossRead (T sites, event windows, both forward passes per site "
                             "on the device), host buffers in, per-site log-likelihoods out; 10-kb reads (configs[3] shape)",
                     "value": calls_total / dt_a, "unit": "LLR calls/s (sites scored, both passes)",
                     "reads_per_gpu": int(n_a), "reads_per_s": world * n_a / dt_a, "ms_per_pass": 1e3 * dt_a,
@@ -672,8 +699,10 @@ def main():
                     "d2h_bytes_per_pass": int(a_acc["d2h_bytes"]),
                     "tables": "synthetic (seeded perturbation of the ONT 9-mer table; the fitted BrdU/EdU tables are not "
                               "shipped to the GPU box -- parity on the real tables is tests/test_analogue_gpu.py)",
-                    "cpu_reference": None}
-        del WA
+                "cpu_reference": None}
+
+    if args.analogue_reads > 0 and extras:
+        analogue = guarded(analogue_leg)
 
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
@@ -692,12 +721,12 @@ def main():
                                     "sample": f"{len(one)} of those reads ({ns1} samples, {t1:.1f} s wall)"}
         except Exception as ex:  # noqa: BLE001 -- a reporting extra must never cost the bench line
             cpu["single_thread"] = {"error": repr(ex)}
-        if chain is not None:
+        if chain is not None and "error" not in chain:
             try:
                 chain["cpu_reference"] = run_cpu_chain(reads[: 2 * cores], ref, mean_c, cores)
             except Exception as ex:  # noqa: BLE001
                 chain["cpu_reference"] = {"error": repr(ex)}
-        if analogue is not None:
+        if analogue is not None and "error" not in analogue:
             try:
                 analogue["cpu_reference"] = run_cpu_hmm(mean_c, cores, args.seed)
             except Exception as ex:  # noqa: BLE001

@@ -305,6 +305,10 @@ class Context:
         except Exception:
             pass
 
+    def trim(self):
+        """dnb_trim: give the idle device / pinned blocks the context keeps cached back to the driver."""
+        _lib.check(self.L.dnb_trim(self.h), "dnb_trim")
+
     def load_model(self, which: int, mean: np.ndarray, stdv: np.ndarray | None = None):
         mean = np.ascontiguousarray(mean, dtype=np.float64)
         sd = None if stdv is None else np.ascontiguousarray(stdv, dtype=np.float64)

@@ -148,14 +148,28 @@ struct DpWarp {
     uint32_t mvword, rights;
 };
 
-// value of slot s (warp-uniform) in the four registers of lane s >> 2; only that lane's result is meaningful
+// value of slot s (warp-uniform) in the four registers of lane s >> 2; only that lane's result is meaningful.
+// Written as predicated moves: the `?:` form compiled to 16 SEL + predicate logic per call (58 instructions on the
+// right-move path of a band, static SASS of round 1), this is 4 compares + 8 predicated 32-bit moves.
 __device__ __forceinline__ void put4(double (&p)[4], int lane, int s, double v) {
-    const bool mine = lane == (s >> 2);
-    const int j = s & 3;
-    p[0] = (mine && j == 0) ? v : p[0];
-    p[1] = (mine && j == 1) ? v : p[1];
-    p[2] = (mine && j == 2) ? v : p[2];
-    p[3] = (mine && j == 3) ? v : p[3];
+    const int key = (lane == (s >> 2)) ? (s & 3) : -1;
+    asm("{\n\t.reg .pred q;\n\t"
+        "setp.eq.s32 q, %4, 0;\n\t@q mov.f64 %0, %5;\n\t"
+        "setp.eq.s32 q, %4, 1;\n\t@q mov.f64 %1, %5;\n\t"
+        "setp.eq.s32 q, %4, 2;\n\t@q mov.f64 %2, %5;\n\t"
+        "setp.eq.s32 q, %4, 3;\n\t@q mov.f64 %3, %5;\n\t}"
+        : "+d"(p[0]), "+d"(p[1]), "+d"(p[2]), "+d"(p[3]) : "r"(key), "d"(v));
+}
+// two arrays under the same slot (a down move: the new bottom cell's event level and its out-of-band score)
+__device__ __forceinline__ void put4x2(double (&p)[4], double (&q)[4], int lane, int s, double vp, double vq) {
+    const int key = (lane == (s >> 2)) ? (s & 3) : -1;
+    asm("{\n\t.reg .pred q;\n\t"
+        "setp.eq.s32 q, %8, 0;\n\t@q mov.f64 %0, %9;\n\t@q mov.f64 %4, %10;\n\t"
+        "setp.eq.s32 q, %8, 1;\n\t@q mov.f64 %1, %9;\n\t@q mov.f64 %5, %10;\n\t"
+        "setp.eq.s32 q, %8, 2;\n\t@q mov.f64 %2, %9;\n\t@q mov.f64 %6, %10;\n\t"
+        "setp.eq.s32 q, %8, 3;\n\t@q mov.f64 %3, %9;\n\t@q mov.f64 %7, %10;\n\t}"
+        : "+d"(p[0]), "+d"(p[1]), "+d"(p[2]), "+d"(p[3]), "+d"(q[0]), "+d"(q[1]), "+d"(q[2]), "+d"(q[3])
+        : "r"(key), "d"(vp), "d"(vq));
 }
 
 // One band b.  P1 = band b-1, P2 = band b-2 (overwritten with band b).
@@ -277,15 +291,8 @@ __device__ __forceinline__ void dp_band(DpWarp &w, double (&P1)[4], double (&P2)
             w.xnxt = (w.xbase + 32 + lane < w.E) ? w.x[w.xbase + 32 + lane] : 0.0;
         }
         const double fresh = shfl_d(w.xbuf, need - w.xbase);
-        const int s0 = w.ll_e & 127;
-        const bool mine = lane == (s0 >> 2);
-        const int j0 = s0 & 3;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {                                  // the new bottom cell: its event level enters,
-            const bool hit = mine && j0 == j;                          // and its slot was out of band b-1
-            w.xe[j] = hit ? fresh : w.xe[j];
-            P1[j] = hit ? NEG_SENT : P1[j];
-        }
+        // the new bottom cell: its event level enters, and its slot was out of band b-1
+        put4x2(w.xe, P1, lane, w.ll_e & 127, fresh, NEG_SENT);
     }
     const bool steady = w.ll_k >= 0 && w.ll_e >= DNB_BW - 1 && w.ll_e <= w.E - 1 && w.ll_k + DNB_BW <= w.K;
     if (steady) dp_cells<true>(w, P1, P2, b);

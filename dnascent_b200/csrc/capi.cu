@@ -974,6 +974,8 @@ int run(dnb_batch *b) {
     DnbTsArgs ts;
     ts.cl_off = w.cl_off; ts.cl_signal = w.cl_signal; ts.cl_rank = w.cl_rank; ts.n_cleaned = w.n_cleaned;
     ts.rough_shift = w.rough_shift; ts.rough_scale = w.rough_scale; ts.shift = w.shift; ts.scale = w.scale;
+    static const int ts_mode = getenv("DNB_TS_MODE") ? atoi(getenv("DNB_TS_MODE")) : 0;
+    ts.mode = ts_mode;
     dnb_launch_theil_sen(v, pore, ts, s); launches++;
     CK(cudaEventRecord(b->ev[6], s));
     CK(cudaMemcpyAsync(b->h_cells, w.cells, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

@@ -160,6 +160,8 @@ struct DnbTsArgs {
     const uint32_t *n_cleaned;
     const double *rough_shift, *rough_scale;
     double *shift, *scale;        // [R] refined
+    int mode;                     // 0: approximate-quotient selection certified by exact divisions (default)
+                                  // 1: the general exact digit search only (cross-check, DNB_TS_MODE=1)
 };
 void dnb_launch_theil_sen(const DnbBatchView &v, const DnbModelDev &m, const DnbTsArgs &a, cudaStream_t s);
 

@@ -23,9 +23,16 @@
 
 namespace {
 
-// total order on doubles: -inf < ... < -0 < +0 < ... < +inf   (NaN never compares in the reference: undefined there)
+// total order on doubles: -inf < ... < -0 < +0 < ... < +inf < NaN.
+// A NaN slope is 0/0: two cleaned points with identical signal and identical model level (about one read in 2000 has
+// such a pair).  The reference std::sorts the slopes with operator<, for which NaN is "not less than" anything and
+// nothing is less than it; on the reads where it occurs the reference's median is the one obtained with the NaN
+// sorted LAST (found by the 2000-read statistical run, profiles/r2n_ea_statistical_parity.json; pinned by
+// tests/golden/read_theilsen_nan_slope.npz).  The device's 0/0 is the NEGATIVE canonical NaN, whose raw bit pattern
+// would sort first and shift the median by one rank, so NaN gets the largest key explicitly.
 __device__ __forceinline__ unsigned long long order_key(double d) {
     unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    if (d != d) return ~0ull;
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 __device__ __forceinline__ double key_to_double(unsigned long long k) {
@@ -267,9 +274,9 @@ __device__ bool select_slope_windowed(TsShared &sm, uint32_t np, uint32_t kth, u
 }
 
 // exact k-th smallest slope over all pairs
-__device__ unsigned long long select_slope(TsShared &sm, uint32_t np, uint32_t kth) {
+__device__ unsigned long long select_slope(TsShared &sm, uint32_t np, uint32_t kth, int mode) {
     const int tid = threadIdx.x;
-    {
+    if (mode == 0) {
         unsigned long long fast;
         if (select_slope_windowed(sm, np, kth, &fast)) return fast;
         __syncthreads();
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(TS_THREADS) theil_sen_kernel(DnbBatchView v, D
 
     // median slope: element ns/2 of the ascending sort of dy/dx over all i<j (:67-78)
     const uint32_t ns = np * (np - 1) / 2;
-    const double slope = key_to_double(select_slope(sm, np, ns / 2));
+    const double slope = key_to_double(select_slope(sm, np, ns / 2, a.mode));
     __syncthreads();
 
     // median intercept: element np/2 of y - slope*x (:81-87); np <= TS_MAXP <= TS_CAND

@@ -286,3 +286,18 @@ def test_int16_ingest_with_dorado_slice(ctx, port, pore_mean):
         np.testing.assert_array_equal(o.eventAlignment[:, 0], p["align_event"])
         np.testing.assert_array_equal(o.eventAlignment[:, 1], p["align_kmer"])
         assert o.shift == p["shift"] and o.scale == p["scale"]
+
+
+def test_theil_sen_with_a_nan_slope(ctx, pore_mean):
+    """Two cleaned points with identical signal and identical model level give a 0/0 slope.  The reference's median is
+    the one with that NaN sorted last; the device's 0/0 is a negative NaN that sorted FIRST and moved the median by one
+    rank (found by scripts/ea_statistical_parity.py: 1 read in 2000).  The fixture is that read with the unmodified
+    reference's scalings (tests/golden/read_theilsen_nan_slope.npz)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "read_theilsen_nan_slope.npz"))
+    r = api.Read(None, d["basecall"].tobytes(), d["refseq"].tobytes(), d["q2r"], dac=d["dac"],
+                 dac_offset=float(synth.DAC_OFFSET), dac_scale=float(synth.DAC_SCALE))
+    o = ctx.normaliseEvents([r])[0]
+    assert o.status == api.READ_OK and o.eventAlignment.shape[0] == int(d["n_align"])
+    assert o.rough_shift == float(d["rough_shift"]) and o.rough_scale == float(d["rough_scale"])
+    assert o.shift == float(d["shift"]) and o.scale == float(d["scale"])

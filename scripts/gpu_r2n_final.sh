@@ -2,7 +2,7 @@
 # round 2, evidence run on one B200: GPU suite, f1 statistical parity, lean ncu captures of the shipped kernels (one
 # 2500-read device bin so that a launch == the step), launch list of a short bench, the default bench and the reference arm
 set -u
-TAG=${1:-r2n}
+TAG=${1:-r2r}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log

@@ -136,8 +136,10 @@ def main():
         consts["seg_dram_bytes_per_sample"] = consts["seg_tile_dram_bytes_per_sample"] + consts["seg_scan_dram_bytes_per_sample"]
     with open(os.path.join(out, f"{a.tag}_ncu_summary.md"), "w") as f:
         f.write("\n".join(md) + "\n")
+    # a metric ncu could not collect (it prints -nan when a replay pass fails) becomes null, not the invalid JSON token NaN
+    consts = {k: (None if isinstance(v, float) and v != v else v) for k, v in consts.items()}
     with open(os.path.join(out, "kernel_constants.json"), "w") as f:
-        json.dump(consts, f, indent=1)
+        json.dump(consts, f, indent=1, allow_nan=False)
     print(json.dumps(consts, indent=1))
 
 

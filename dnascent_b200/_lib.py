@@ -133,7 +133,7 @@ EXPORTS = [
     "dnb_batch_io_bytes",
     "dnb_detect_events",
     "dnb_eexp", "dnb_eln", "dnb_lnSum", "dnb_lnProd", "dnb_lnGreaterThan", "dnb_uniformPDF", "dnb_normalPDF",
-    "dnb_cauchyPDF", "dnb_sequence_probability_batch",
+    "dnb_cauchyPDF", "dnb_sequence_probability_batch", "dnb_theil_sen_batch",
     "dnb_eventalign_batch", "dnb_eventalign_last_kernel_ms",
     "dnb_eventalign_features_batch", "dnb_features_last_kernel_ms",
     "dnb_batch_eventalign_features", "dnb_batch_feature_result", "dnb_batch_stage2_timings",
@@ -185,6 +185,7 @@ def lib():
         getattr(L, f).restype = d
         getattr(L, f).argtypes = [d, d, d]
     L.dnb_sequence_probability_batch.argtypes = [vp, vp, vp, C.c_char_p, vp, vp, vp, sz, C.c_uint32, vp, vp]
+    L.dnb_theil_sen_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp]
     L.dnb_eventalign_batch.argtypes = [vp, vp, sz, C.c_uint32, vp, vp, vp, vp]
     L.dnb_eventalign_last_kernel_ms.restype = d
     L.dnb_eventalign_features_batch.argtypes = [vp, vp, vp, sz, C.c_uint32, vp, vp, vp, vp, vp, vp, vp]

@@ -429,6 +429,22 @@ class Context:
         return (a["start"].astype(np.uint64), a["length"].astype(np.float32), a["mean"].astype(np.float32),
                 a["stdv"].astype(np.float32))
 
+    # -- Theil-Sen refinement alone ------------------------------------------------------------------
+    def theil_sen_batch(self, signals_list, ranks_list, rough_shift, rough_scale):
+        """estimateScaling_theilSen (src/event_handling.cpp:24-110) for every read's cleaned (signal, k-mer rank) vectors;
+        returns (shift, scale) arrays."""
+        n = len(signals_list)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in signals_list])
+        sig = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64) for x in signals_list]) if n else np.zeros(0))
+        rk = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint32) for x in ranks_list]) if n else np.zeros(0, np.uint32))
+        rs = np.ascontiguousarray(np.broadcast_to(rough_shift, (n,)), dtype=np.float64)
+        rc = np.ascontiguousarray(np.broadcast_to(rough_scale, (n,)), dtype=np.float64)
+        shift, scale = np.zeros(n), np.zeros(n)
+        _lib.check(self.L.dnb_theil_sen_batch(self.h, sig.ctypes.data, rk.ctypes.data, off.ctypes.data, n, rs.ctypes.data,
+                                              rc.ctypes.data, shift.ctypes.data, scale.ctypes.data), "dnb_theil_sen_batch")
+        return shift, scale
+
     # -- analogue likelihood ------------------------------------------------------------------------
     def sequence_probability_batch(self, obs_list, snippets, shift, scale, events_per_base, window: int = 12):
         """Both passes of sequenceProbability for every site (src/detect.cpp:235-378, 546-547)."""

@@ -29,9 +29,15 @@
 #include "dnb_internal.cuh"
 #include "../../include/dnascent_b200.h"
 
-#define DP_WARPS 4
+// One warp per read and ONE WARP PER CTA: warps of a CTA do not cooperate, and a CTA's slot is only handed to the next
+// CTA when its last warp retires, so 4-warp CTAs idled slots behind their longest read (measured at 30k reads:
+// 1-warp CTAs alone -6 % on the fill).  DP_MIN_BLOCKS caps the registers: 24 resident warps per SM at 80 registers
+// without spills, against 16 at 128 (fill 858 -> 792 ms, backtrace 164 -> 128 ms per 30k-read step, profiles/r2s_*).
+#ifndef DP_WARPS
+#define DP_WARPS 1
+#endif
 #ifndef DP_MIN_BLOCKS
-#define DP_MIN_BLOCKS 4      // resident CTAs per SM the register allocation must allow (4 warps each)
+#define DP_MIN_BLOCKS 24     // resident CTAs per SM the register allocation must allow (DP_WARPS warps each)
 #endif
 #define FULL 0xffffffffu
 #define NEG_SENT (-3.4028234663852886e38)   /* (double)(-FLT_MAX): stands for -INFINITY */
@@ -84,7 +90,7 @@ struct DpConst {
 // instruction total as long as no single pipe saturates (XU: 8 cycles per warp instruction and scheduler).
 // DP_XU holds one such 2-bit choice per register slot j (nibble j), so the XU load can be set in steps of one cell.
 #ifndef DP_XU
-#define DP_XU 0x3333
+#define DP_XU 0x3332         // measured with 24 resident warps per SM: 0x3333 792 ms, 0x3332 780, 0x3331 780 per 30k-read step
 #endif
 
 // one cell: q = (x - mu)/sigma still in double; returns the new score, sets `from`

@@ -310,6 +310,8 @@ struct Work {
     uint32_t *n_long;            // events of >= 255 samples per read (escapes of the compact event coding)
     double *cl_signal, *avg, *shift, *scale;
     int *spanned, *max_gap;
+    uint32_t *ts_nan_list;       // Theil-Sen reads with a 0/0 slope (theilsen.cu): entries, values, then the counter
+    double *ts_nan_scratch;      // DNB_TS_NAN_SLOTS slots of slopes + position lists
 };
 
 // pinned host results
@@ -937,6 +939,8 @@ int run(dnb_batch *b) {
         ar.add(&w.trace, bo * DNB_TRACE_ROW + 64);
         ar.add(&w.moves, (bo >> 5) + R + 2); ar.add(&w.rcum, (bo >> 5) + R + 2);
         ar.add(&w.al_rev, 2 * ao); ar.add(&w.cl_signal, co); ar.add(&w.cl_rank, co);
+        ar.add(&w.ts_nan_list, 8 * (size_t)DNB_TS_NAN_CAP + 2);
+        ar.add(&w.ts_nan_scratch, (size_t)DNB_TS_NAN_SLOTS * DNB_TS_NAN_SLOT_DOUBLES);
         TRY(ar.commit(b, b->work_allocs));
     }
     tick(PH_RUN_ALLOC_B);
@@ -976,7 +980,11 @@ int run(dnb_batch *b) {
     ts.rough_shift = w.rough_shift; ts.rough_scale = w.rough_scale; ts.shift = w.shift; ts.scale = w.scale;
     static const int ts_mode = getenv("DNB_TS_MODE") ? atoi(getenv("DNB_TS_MODE")) : 0;
     ts.mode = ts_mode;
-    dnb_launch_theil_sen(v, pore, ts, s); launches++;
+    static const bool ts_nan_path = !(getenv("DNB_TS_NAN_PATH") && atoi(getenv("DNB_TS_NAN_PATH")) == 0);   // 0: "NaN last" only (cross-check)
+    ts.nan_list = ts_nan_path ? w.ts_nan_list : nullptr;
+    ts.nan_count = w.ts_nan_list + 8 * (size_t)DNB_TS_NAN_CAP;
+    ts.nan_cap = DNB_TS_NAN_CAP; ts.nan_scratch = w.ts_nan_scratch; ts.nan_slots = DNB_TS_NAN_SLOTS;
+    dnb_launch_theil_sen(v, pore, ts, s); launches += ts_nan_path ? 3 : 1;
     CK(cudaEventRecord(b->ev[6], s));
     CK(cudaMemcpyAsync(b->h_cells, w.cells, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     TRY(d2h(b, b->h.status, w.status, R));     // the outcome of every read is known to the host when run() returns
@@ -1572,6 +1580,70 @@ int dnb_sequence_probability_batch(dnb_ctx *ctx, const double *obs, const uint64
         fail(cudaGetLastError());
     }
     for (void *p : {(void *)d_obs, (void *)d_off, (void *)d_seq, (void *)d_shift, (void *)d_scale, (void *)d_epb, (void *)d_oa, (void *)d_ot})
+        if (p) cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+// ---- estimateScaling_theilSen alone (event_handling.cpp:24-110): the Theil-Sen kernels of run() on caller-supplied vectors ----
+int dnb_theil_sen_batch(dnb_ctx *ctx, const double *signals, const uint32_t *ranks, const uint64_t *off, size_t n_reads,
+                        const double *rough_shift, const double *rough_scale, double *shift, double *scale) {
+    if (!ctx || !off || !rough_shift || !rough_scale || !shift || !scale) return DNB_ERR_ARG;
+    if (!ctx->model[DNB_MODEL_PORE].loaded) return DNB_ERR_MODEL;
+    if (n_reads == 0) return DNB_OK;
+    if (n_reads >= (1ull << 32)) return DNB_ERR_ARG;
+    const size_t n_pts = off[n_reads];
+    if (n_pts && (!signals || !ranks)) return DNB_ERR_ARG;
+    for (size_t i = 0; i < n_pts; i++)
+        if (ranks[i] >= DNB_N_KMERS) { g_last_error = "dnb_theil_sen_batch: k-mer rank out of range"; return DNB_ERR_ARG; }
+    CK(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = DNB_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DNB_OK) { g_last_error = cudaGetErrorString(e); rc = DNB_ERR_CUDA; } };
+    double *d_sig = nullptr, *d_rs = nullptr, *d_rc = nullptr, *d_shift = nullptr, *d_scale = nullptr, *d_scratch = nullptr;
+    uint32_t *d_rank = nullptr, *d_n = nullptr, *d_order = nullptr, *d_nan = nullptr;
+    uint64_t *d_off = nullptr;
+    int *d_status = nullptr;
+    std::vector<uint32_t> n_cl(n_reads), order(n_reads);
+    for (size_t i = 0; i < n_reads; i++) { n_cl[i] = (uint32_t)(off[i + 1] - off[i]); order[i] = (uint32_t)i; }
+    fail(pool_alloc(ctx, &d_sig, (n_pts ? n_pts : 1) * 8, s)); fail(pool_alloc(ctx, &d_rank, (n_pts ? n_pts : 1) * 4, s));
+    fail(pool_alloc(ctx, &d_off, (n_reads + 1) * 8, s)); fail(pool_alloc(ctx, &d_n, n_reads * 4, s));
+    fail(pool_alloc(ctx, &d_order, n_reads * 4, s)); fail(pool_alloc(ctx, &d_status, n_reads * 4, s));
+    fail(pool_alloc(ctx, &d_rs, n_reads * 8, s)); fail(pool_alloc(ctx, &d_rc, n_reads * 8, s));
+    fail(pool_alloc(ctx, &d_shift, n_reads * 8, s)); fail(pool_alloc(ctx, &d_scale, n_reads * 8, s));
+    fail(pool_alloc(ctx, &d_nan, (8 * (size_t)DNB_TS_NAN_CAP + 2) * 4, s));
+    fail(pool_alloc(ctx, &d_scratch, (size_t)DNB_TS_NAN_SLOTS * DNB_TS_NAN_SLOT_DOUBLES * 8, s));
+    if (rc == DNB_OK) {
+        if (n_pts) {
+            fail(cudaMemcpyAsync(d_sig, signals, n_pts * 8, cudaMemcpyHostToDevice, s));
+            fail(cudaMemcpyAsync(d_rank, ranks, n_pts * 4, cudaMemcpyHostToDevice, s));
+        }
+        fail(cudaMemcpyAsync(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+        fail(cudaMemcpyAsync(d_n, n_cl.data(), n_reads * 4, cudaMemcpyHostToDevice, s));
+        fail(cudaMemcpyAsync(d_order, order.data(), n_reads * 4, cudaMemcpyHostToDevice, s));
+        fail(cudaMemsetAsync(d_status, 0, n_reads * 4, s));
+        fail(cudaMemcpyAsync(d_rs, rough_shift, n_reads * 8, cudaMemcpyHostToDevice, s));
+        fail(cudaMemcpyAsync(d_rc, rough_scale, n_reads * 8, cudaMemcpyHostToDevice, s));
+        DnbBatchView v{};
+        v.n_reads = (uint32_t)n_reads; v.order = d_order; v.status = d_status;
+        DnbTsArgs ts{};
+        ts.cl_off = d_off; ts.cl_signal = d_sig; ts.cl_rank = d_rank; ts.n_cleaned = d_n;
+        ts.rough_shift = d_rs; ts.rough_scale = d_rc; ts.shift = d_shift; ts.scale = d_scale;
+        ts.mode = getenv("DNB_TS_MODE") ? atoi(getenv("DNB_TS_MODE")) : 0;
+        const bool nan_path = !(getenv("DNB_TS_NAN_PATH") && atoi(getenv("DNB_TS_NAN_PATH")) == 0);
+        ts.nan_list = nan_path ? d_nan : nullptr;
+        ts.nan_count = d_nan + 8 * (size_t)DNB_TS_NAN_CAP;
+        ts.nan_cap = DNB_TS_NAN_CAP; ts.nan_scratch = d_scratch; ts.nan_slots = DNB_TS_NAN_SLOTS;
+        dnb_launch_theil_sen(v, ctx->model[DNB_MODEL_PORE].dev(), ts, s);
+        fail(cudaMemcpyAsync(shift, d_shift, n_reads * 8, cudaMemcpyDeviceToHost, s));
+        fail(cudaMemcpyAsync(scale, d_scale, n_reads * 8, cudaMemcpyDeviceToHost, s));
+        fail(cudaStreamSynchronize(s));
+        fail(cudaGetLastError());
+    }
+    for (void *p : {(void *)d_sig, (void *)d_rank, (void *)d_off, (void *)d_n, (void *)d_order, (void *)d_status, (void *)d_rs, (void *)d_rc,
+                    (void *)d_shift, (void *)d_scale, (void *)d_nan, (void *)d_scratch})
         if (p) cudaFreeAsync(p, s);
     cudaStreamSynchronize(s);
     cudaStreamDestroy(s);

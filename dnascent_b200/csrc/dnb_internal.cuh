@@ -162,7 +162,18 @@ struct DnbTsArgs {
     double *shift, *scale;        // [R] refined
     int mode;                     // 0: approximate-quotient selection certified by exact divisions (default)
                                   // 1: the general exact digit search only (cross-check, DNB_TS_MODE=1)
+    // reads with a 0/0 slope (theilsen.cu, theil_sen_nan_follow_kernel); nan_list == nullptr: no NaN path (the "NaN last" answer)
+    uint32_t *nan_count;          // [1]
+    uint32_t *nan_list;           // [8 * nan_cap]: 4 words per entry (read, status before Theil-Sen, action, -), then 2 * nan_cap doubles
+                                  // (the slope read off the sorted range; the rank ns/2 - 1 slope)
+    uint32_t nan_cap;
+    double *nan_scratch;          // [nan_slots * DNB_TS_NAN_SLOT_DOUBLES]
+    uint32_t nan_slots;           // CTAs of the NaN kernel, one scratch slot each
 };
+#define DNB_TS_MAX_SLOPES 499500ul                              /* 1000 * 999 / 2 */
+#define DNB_TS_NAN_SLOT_DOUBLES (2ul * DNB_TS_MAX_SLOPES)        /* the slopes + two int position lists of the same length */
+#define DNB_TS_NAN_SLOTS 16u
+#define DNB_TS_NAN_CAP 1024u
 void dnb_launch_theil_sen(const DnbBatchView &v, const DnbModelDev &m, const DnbTsArgs &a, cudaStream_t s);
 
 void dnb_launch_compact_alignment(const DnbBatchView &v, const uint64_t *al_off, const uint32_t *al_pairs_rev,

@@ -14,6 +14,8 @@
 // (round d pairs point i with point i+d), which keeps the shared-memory reads of a warp on consecutive addresses.
 #include "dnb_internal.cuh"
 #include "../../include/dnascent_b200.h"
+#define NSP_FULL 256            // the NaN path sorts at most this many slopes literally (one thread)
+#include "nan_sort_path.cuh"
 
 #define TS_THREADS 256
 #define TS_MAXP 1000
@@ -24,12 +26,13 @@
 namespace {
 
 // total order on doubles: -inf < ... < -0 < +0 < ... < +inf < NaN.
-// A NaN slope is 0/0: two cleaned points with identical signal and identical model level (about one read in 2000 has
-// such a pair).  The reference std::sorts the slopes with operator<, for which NaN is "not less than" anything and
-// nothing is less than it; on the reads where it occurs the reference's median is the one obtained with the NaN
-// sorted LAST (found by the 2000-read statistical run, profiles/r2n_ea_statistical_parity.json; pinned by
-// tests/golden/read_theilsen_nan_slope.npz).  The device's 0/0 is the NEGATIVE canonical NaN, whose raw bit pattern
-// would sort first and shift the median by one rank, so NaN gets the largest key explicitly.
+// A NaN slope is 0/0: two cleaned points with identical signal and identical model level (about one read in 1000 has
+// such a pair).  The reference std::sorts the slopes with operator<, which is outside std::sort's contract with a NaN
+// in the range: where the NaN ends up -- and with it whether the median is the rank ns/2 or ns/2 - 1 non-NaN slope --
+// is whatever libstdc++'s introsort does with that particular sequence of slopes (found by the 2000-read statistical
+// run: after the median on read 1797, before it on read 1803; tests/golden/read_theilsen_nan_slope{,_b}.npz).  Here
+// NaN gets the largest key, i.e. this kernel computes the "NaN last" answer, flags the read, and
+// theil_sen_nan_follow_kernel below re-derives the median by following the NaN through the introsort.
 __device__ __forceinline__ unsigned long long order_key(double d) {
     unsigned long long b = (unsigned long long)__double_as_longlong(d);
     if (d != d) return ~0ull;
@@ -66,13 +69,14 @@ struct TsShared {
     uint32_t count;              // slopes inside the current bin
     uint32_t n_cand;
     unsigned long long answer;
+    uint32_t n_nan;              // 0/0 slopes seen (any nonzero value sends the read to theil_sen_nan_kernel)
 };
 
 // dy/dx within TS_APPROX_ULPS ulps of the IEEE quotient, in 7 instructions instead of the ~35 of the division
 // subroutine: reciprocal seed (2^-20) + two Newton steps (-> ~1 ulp) + one multiply.  Where the bound cannot be
 // vouched for (dx == 0, non-finite or subnormal-range results) the exact quotient is returned instead.
 #define TS_APPROX_ULPS 4096ull
-__device__ __forceinline__ double slope_approx(double dy, double dx) {
+__device__ __forceinline__ double slope_approx(double dy, double dx, uint32_t *n_nan) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dx));
     double e = __fma_rn(-dx, r, 1.0);
@@ -81,14 +85,18 @@ __device__ __forceinline__ double slope_approx(double dy, double dx) {
     r = __fma_rn(r, e, r);
     const double q = dMul(dy, r);
     const double aq = fabs(q);
-    if (!(aq < 1.0e290) || (aq < 1.0e-290 && dy != 0.0)) return dDiv(dy, dx);
+    if (!(aq < 1.0e290) || (aq < 1.0e-290 && dy != 0.0)) {
+        const double exact = dDiv(dy, dx);
+        if (exact != exact) atomicAdd(n_nan, 1u);       // 0/0: on this rare branch only, the common path pays nothing
+        return exact;
+    }
     return q;
 }
 
 // visits every unordered pair once; f(key) is called by all lanes of a warp together (ok == false for padding lanes).
 // kApprox: keys of slope_approx (within TS_APPROX_ULPS of the exact key) instead of the IEEE quotient's
 template <bool kApprox = false, class F>
-__device__ __forceinline__ void for_each_slope(const TsShared &sm, uint32_t np, F f) {
+__device__ __forceinline__ void for_each_slope(TsShared &sm, uint32_t np, F f) {
     const uint32_t full_rounds = (np - 1) / 2;
     const uint32_t lane_base = threadIdx.x;
     for (uint32_t d = 1; d <= full_rounds; d++) {
@@ -103,7 +111,8 @@ __device__ __forceinline__ void for_each_slope(const TsShared &sm, uint32_t np, 
                 // zero of dy/dx are the reference's
                 const uint32_t lo = min(i, j), hi = max(i, j);
                 const double dy = dSub(sm.y[lo], sm.y[hi]), dx = dSub(sm.x[lo], sm.x[hi]);
-                key = order_key(kApprox ? slope_approx(dy, dx) : dDiv(dy, dx));
+                key = order_key(kApprox ? slope_approx(dy, dx, &sm.n_nan) : dDiv(dy, dx));
+                if (!kApprox && key == ~0ull) atomicAdd(&sm.n_nan, 1u);
             }
             f(key, ok, i, d);
         }
@@ -116,7 +125,8 @@ __device__ __forceinline__ void for_each_slope(const TsShared &sm, uint32_t np, 
             unsigned long long key = 0;
             if (ok) {
                 const double dy = dSub(sm.y[i], sm.y[i + d]), dx = dSub(sm.x[i], sm.x[i + d]);
-                key = order_key(kApprox ? slope_approx(dy, dx) : dDiv(dy, dx));
+                key = order_key(kApprox ? slope_approx(dy, dx, &sm.n_nan) : dDiv(dy, dx));
+                if (!kApprox && key == ~0ull) atomicAdd(&sm.n_nan, 1u);
             }
             f(key, ok, i, d);
         }
@@ -336,43 +346,36 @@ __device__ unsigned long long select_slope(TsShared &sm, uint32_t np, uint32_t k
     return sm.prefix;   // all 64 bits decided: the bin holds copies of one value
 }
 
-__global__ void __launch_bounds__(TS_THREADS) theil_sen_kernel(DnbBatchView v, DnbModelDev m, DnbTsArgs a) {
-    __shared__ TsShared sm;
-    const uint32_t r = v.order[blockIdx.x];
-    const int tid = threadIdx.x;
-    const int st = v.status[r];
-    if (st == DNB_READ_UNDEFINED || st == DNB_READ_OVERFLOW) return;
-    const double shift = a.rough_shift[r], scale = a.rough_scale[r];
+// the <= 1000 (x, y) points of a read (event_handling.cpp:35-64); 0 if the read keeps its rough scaling (:33)
+__device__ __forceinline__ uint32_t ts_load_points(TsShared &sm, const DnbModelDev &m, const DnbTsArgs &a, uint32_t r, double shift, double scale) {
     const uint32_t n = a.n_cleaned[r];
     const uint32_t maxPoints = TS_MAXP, trim = 50;
-    if (n < maxPoints) {                                   // :33 short reads keep the rough scaling
-        if (tid == 0) { a.shift[r] = shift; a.scale[r] = scale; }
-        return;
-    }
+    if (n < maxPoints) return 0;
     const double *sig = a.cl_signal + a.cl_off[r];
     const uint32_t *rk = a.cl_rank + a.cl_off[r];
     const uint32_t eff = n - 2 * trim;
     uint32_t skip = 1, np = eff;
     if (eff > maxPoints) { skip = eff / maxPoints; np = maxPoints; }
-    for (uint32_t j = tid; j < np; j += TS_THREADS) {
+    for (uint32_t j = threadIdx.x; j < np; j += TS_THREADS) {
         const uint32_t i = trim + j * skip;
         sm.x[j] = dDiv(dSub(sig[i], shift), scale);        // :51
         sm.y[j] = m.mean[rk[i]];                            // :58
     }
     __syncthreads();
+    return np;
+}
 
-    // median slope: element ns/2 of the ascending sort of dy/dx over all i<j (:67-78)
-    const uint32_t ns = np * (np - 1) / 2;
-    const double slope = key_to_double(select_slope(sm, np, ns / 2, a.mode));
-    __syncthreads();
-
-    // median intercept: element np/2 of y - slope*x (:81-87); np <= TS_MAXP <= TS_CAND
+// median intercept for the given median slope and the refined (shift, scale) (event_handling.cpp:80-108); block-wide.
+// `st` is the read's status before Theil-Sen.
+__device__ __forceinline__ void ts_finish(TsShared &sm, const DnbBatchView &v, const DnbTsArgs &a, uint32_t r, uint32_t np, double slope,
+                                          double shift, double scale, int st) {
+    const int tid = threadIdx.x;
+    // element np/2 of y - slope*x (:81-87); np <= TS_MAXP <= TS_CAND
     for (uint32_t i = tid; i < np; i += TS_THREADS)
         sm.u.cand[i] = order_key(dSub(sm.y[i], dMul(slope, sm.x[i])));   // :83, not fused
     __syncthreads();
     select_among_candidates(sm, np, np / 2);
     const double icpt = key_to_double(sm.answer);
-
     if (tid == 0) {
         double o_shift, o_scale;
         if (slope == 0.) {                                  // :90-95
@@ -385,7 +388,281 @@ __global__ void __launch_bounds__(TS_THREADS) theil_sen_kernel(DnbBatchView v, D
         }
         a.shift[r] = o_shift;
         a.scale[r] = o_scale;
-        if (o_shift == -1. && st == DNB_READ_OK) v.status[r] = DNB_READ_SCALE_FAIL;   // event_handling.cpp:604
+        if (st == DNB_READ_OK) v.status[r] = (o_shift == -1.) ? DNB_READ_SCALE_FAIL : DNB_READ_OK;   // event_handling.cpp:604
+    }
+}
+
+__global__ void __launch_bounds__(TS_THREADS) theil_sen_kernel(DnbBatchView v, DnbModelDev m, DnbTsArgs a) {
+    __shared__ TsShared sm;
+    const uint32_t r = v.order[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int st = v.status[r];
+    if (st == DNB_READ_UNDEFINED || st == DNB_READ_OVERFLOW) return;
+    const double shift = a.rough_shift[r], scale = a.rough_scale[r];
+    if (tid == 0) sm.n_nan = 0;
+    const uint32_t np = ts_load_points(sm, m, a, r, shift, scale);
+    if (np == 0) {                                         // :33 short reads keep the rough scaling
+        if (tid == 0) { a.shift[r] = shift; a.scale[r] = scale; }
+        return;
+    }
+    // median slope: element ns/2 of the ascending sort of dy/dx over all i<j (:67-78)
+    const uint32_t ns = np * (np - 1) / 2;
+    const double slope = key_to_double(select_slope(sm, np, ns / 2, a.mode));
+    __syncthreads();
+    // a 0/0 slope was seen: the answer above is the "NaN sorted last" one.  theil_sen_nan_follow_kernel decides whether
+    // it stands; the other possible answer (NaN in front of the median: rank ns/2 - 1 of the non-NaN slopes) is
+    // selected here, where the device is full of other CTAs, rather than by a lone CTA later
+    const bool flagged = sm.n_nan != 0 && a.nan_list != nullptr;      // uniform: read after the barrier
+    double slope_alt = 0.0;
+    if (flagged) {
+        slope_alt = key_to_double(select_slope(sm, np, ns / 2 - 1, a.mode));
+        __syncthreads();
+    }
+    ts_finish(sm, v, a, r, np, slope, shift, scale, st);
+    if (tid == 0 && flagged) {
+        const uint32_t slot = atomicAdd(a.nan_count, 1u);
+        if (slot < a.nan_cap) {
+            a.nan_list[4 * slot] = r; a.nan_list[4 * slot + 1] = (uint32_t)st; a.nan_list[4 * slot + 2] = 0u;
+            reinterpret_cast<double *>(a.nan_list + 4 * a.nan_cap)[a.nan_cap + slot] = slope_alt;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reads with a NaN slope (see order_key).  theil_sen_nan_follow_kernel materialises the <= 499 500 slopes in the
+// reference's push order (:67-75) in a scratch slot and follows the NaN through libstdc++'s introsort
+// (nan_sort_path.cuh): only the partitions of the ranges that contain the NaN are applied, each as prefix counts +
+// parallel swaps by the CTA -- nsp_partition_lists is the serial statement of what is done here -- and the last
+// <= NSP_FULL elements are sorted literally by one thread.  That tells where element ns/2 of the array std::sort would
+// have produced comes from: the literally sorted range (read off), left of it (the NaN is behind the median: the
+// "NaN last" answer stands) or right of it (the NaN is in front: the median is the rank ns/2 - 1 non-NaN slope).
+// theil_sen_nan_finish_kernel then redoes the intercept and the refined scalings of the reads whose answer changes
+// (the rank ns/2 - 1 slope was selected by theil_sen_kernel when it flagged the read).
+// One CTA per flagged read, grid-strided over the list; both kernels are launched after every theil_sen_kernel and
+// normally find a list of a few reads (about one read in 1000 is flagged).
+// Not emulated (the "NaN last" answer stands): more than one NaN, the NaN chosen as the pivot of a range of more than
+// NSP_PIVOT_MAX slopes, the introsort depth limit reached on the NaN's branch.
+// ---------------------------------------------------------------------------------------------------------------
+#define NAN_THREADS 1024
+#define NAN_PER 4               // elements per thread and tile (loads in flight)
+struct NanShared {
+    double x[TS_MAXP], y[TS_MAXP];
+    long first, last, nan_pos, nan_first;
+    int depth, state;            // state: 0 partition next, 1 done (range sorted literally), 2 give up
+    uint32_t cnt[NAN_PER * NAN_THREADS / 32];       // per (sub-tile, warp): stops of the left pointer | stops of the right pointer << 16
+    uint32_t base_a, base_d, n_nan;
+    double buf[NSP_FULL + NSP_THRESHOLD];
+};
+
+__global__ void __launch_bounds__(NAN_THREADS) theil_sen_nan_follow_kernel(DnbBatchView v, DnbModelDev m, DnbTsArgs a) {
+    __shared__ NanShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t n_list = min(*a.nan_count, a.nan_cap);
+    double *sl = a.nan_scratch + (size_t)blockIdx.x * DNB_TS_NAN_SLOT_DOUBLES;
+    int *listA = reinterpret_cast<int *>(sl + DNB_TS_MAX_SLOPES);
+    int *listD = listA + DNB_TS_MAX_SLOPES;
+    double *nan_val = reinterpret_cast<double *>(a.nan_list + 4 * a.nan_cap);
+    for (uint32_t e = blockIdx.x; e < n_list; e += gridDim.x) {
+        const uint32_t r = a.nan_list[4 * e];
+        const double shift = a.rough_shift[r], scale = a.rough_scale[r];
+        __syncthreads();
+        if (tid == 0) { sh.n_nan = 0; sh.nan_first = -1; a.nan_list[4 * e + 2] = 0u; }
+        // the points (as ts_load_points; this CTA is wider than TS_THREADS)
+        const uint32_t nc = a.n_cleaned[r];
+        uint32_t np = 0;
+        if (nc >= TS_MAXP) {
+            const double *sig = a.cl_signal + a.cl_off[r];
+            const uint32_t *rk = a.cl_rank + a.cl_off[r];
+            const uint32_t eff = nc - 100;
+            uint32_t skip = 1;
+            np = eff;
+            if (eff > TS_MAXP) { skip = eff / TS_MAXP; np = TS_MAXP; }
+            for (uint32_t j = tid; j < np; j += NAN_THREADS) {
+                const uint32_t i = 50 + j * skip;
+                sh.x[j] = dDiv(dSub(sig[i], shift), scale);
+                sh.y[j] = m.mean[rk[i]];
+            }
+        }
+        __syncthreads();
+        if (np < 2) continue;
+        const long n = (long)np * (np - 1) / 2;
+        // slopes in push order: pair (i, j), i < j, at index i*np - i*(i+1)/2 + (j - i - 1)
+        for (uint32_t i = wid; i + 1 < np; i += NAN_THREADS / 32) {        // a warp per row
+            const long row = (long)i * np - (long)i * (i + 1) / 2 - (i + 1);
+            const double xi = sh.x[i], yi = sh.y[i];
+            for (uint32_t j = i + 1 + lane; j < np; j += 32) {
+                const double q = dDiv(dSub(yi, sh.y[j]), dSub(xi, sh.x[j]));
+                sl[row + j] = q;
+                if (q != q) { atomicAdd(&sh.n_nan, 1u); sh.nan_first = row + j; }
+            }
+        }
+        __syncthreads();
+        if (sh.n_nan != 1) continue;                       // uniform: shared value read after the barrier
+        if (tid == 0) { sh.first = 0; sh.last = n; sh.depth = nsp_lg(n) * 2; sh.nan_pos = sh.nan_first; sh.state = 0; }
+        __syncthreads();
+        while (true) {
+            // ---- one level of std::__introsort_loop on the range holding the NaN ----
+            if (sh.last - sh.first <= NSP_FULL) {
+                // small enough: the rest of the introsort and the insertion pass literally, by one thread, on a copy in
+                // shared memory (on global memory its ~3000 dependent accesses were most of this kernel's time).  The
+                // insertion pass is guarded against v[0] for indices below 16, so a range that starts there is
+                // staged from index 0.
+                const long first = sh.first, last = sh.last;
+                const long s0 = first < NSP_THRESHOLD ? 0 : first;
+                for (long i = s0 + tid; i < last; i += NAN_THREADS) sh.buf[i - s0] = sl[i];
+                __syncthreads();
+                if (tid == 0) {
+                    double *vv = sh.buf - s0;
+                    bool ok = nsp_introsort_full(vv, first, last, sh.depth);
+                    ok = ok && nsp_insertion_pass(vv, first, last);
+                    sh.state = ok ? 1 : 2;
+                }
+                __syncthreads();
+                for (long i = s0 + tid; i < last; i += NAN_THREADS) sl[i] = sh.buf[i - s0];
+                __syncthreads();
+                break;
+            }
+            if (tid == 0) {
+                const long first = sh.first, last = sh.last;
+                if (sh.depth == 0) {
+                    sh.state = 2;
+                } else {
+                    sh.depth--;
+                    const long mid = first + (last - first) / 2;
+                    nsp_median_to_first(sl, first, first + 1, mid, last - 1);
+                    if (sl[first] != sl[first]) {
+                        // the NaN is the pivot: the partition orders nothing, the whole range is sorted literally
+                        if (last - first > NSP_PIVOT_MAX) sh.state = 2;
+                        else {
+                            const long cut = nsp_partition(sl, first + 1, last, first);
+                            bool ok = nsp_introsort_full(sl, cut, last, sh.depth);
+                            ok = nsp_introsort_full(sl, first, cut, sh.depth) && ok;
+                            ok = nsp_insertion_pass(sl, first, last) && ok;
+                            sh.state = ok ? 1 : 2;
+                        }
+                    } else {
+                        if (sl[first + 1] != sl[first + 1]) sh.nan_pos = first + 1;       // the median-of-3 may have moved it
+                        else if (sl[mid] != sl[mid]) sh.nan_pos = mid;
+                        else if (sl[last - 1] != sl[last - 1]) sh.nan_pos = last - 1;
+                    }
+                }
+                sh.base_a = 0; sh.base_d = 0;
+            }
+            __syncthreads();
+            if (sh.state != 0) break;
+            // ---- std::__unguarded_partition(first + 1, last, first) in closed form (nsp_partition_lists) ----
+            const long lo = sh.first + 1, hi = sh.last;
+            const double p = sl[sh.first];
+            const unsigned below = (1u << lane) - 1u;
+            for (long base = lo; base < hi; base += NAN_PER * NAN_THREADS) {
+                double x[NAN_PER];
+#pragma unroll
+                for (int q = 0; q < NAN_PER; q++) {
+                    const long i = base + q * NAN_THREADS + tid;
+                    x[q] = i < hi ? sl[i] : 0.0;
+                }
+                unsigned ma[NAN_PER], md[NAN_PER];
+#pragma unroll
+                for (int q = 0; q < NAN_PER; q++) {
+                    const bool ok = base + q * NAN_THREADS + tid < hi;
+                    ma[q] = __ballot_sync(FULL, ok && !(x[q] < p));
+                    md[q] = __ballot_sync(FULL, ok && !(p < x[q]));
+                    if (lane == 0) sh.cnt[q * 32 + wid] = (uint32_t)__popc(ma[q]) | ((uint32_t)__popc(md[q]) << 16);   // a tile holds 4096 < 2^16
+                }
+                __syncthreads();
+                // exclusive prefix of the 4 x 32 (sub-tile, warp) counts: lane l scans warp l's count, every warp redundantly
+                uint32_t oa[NAN_PER], od[NAN_PER];
+                uint32_t run_a = sh.base_a, run_d = sh.base_d;
+#pragma unroll
+                for (int q = 0; q < NAN_PER; q++) {
+                    const uint32_t c = sh.cnt[q * 32 + lane];
+                    uint32_t inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    const uint32_t mine = __shfl_sync(FULL, inc - c, wid), tot = __shfl_sync(FULL, inc, 31);
+                    oa[q] = run_a + (mine & 0xffffu); od[q] = run_d + (mine >> 16);
+                    run_a += tot & 0xffffu; run_d += tot >> 16;
+                }
+#pragma unroll
+                for (int q = 0; q < NAN_PER; q++) {
+                    const long i = base + q * NAN_THREADS + tid;
+                    if ((ma[q] >> lane) & 1u) listA[oa[q] + __popc(ma[q] & below)] = (int)i;
+                    if ((md[q] >> lane) & 1u) listD[od[q] + __popc(md[q] & below)] = (int)i;
+                }
+                __syncthreads();
+                if (tid == 0) { sh.base_a = run_a; sh.base_d = run_d; }   // read after the next barrier
+            }
+            __syncthreads();
+            const long ta = sh.base_a, td = sh.base_d;
+            // m = the number of k in 1..min(ta, td) with a_k < d_k (monotone): 32 probes per step, one per lane, every warp
+            // on the same data (a binary search by dependent global loads cost ~40 us per level)
+            long mlo = 0, mhi = ta < td ? ta : td;
+            while (mlo < mhi) {
+                const long step = (mhi - mlo + 31) / 32;
+                long k = mlo + (long)(lane + 1) * step;
+                if (k > mhi) k = mhi;
+                const int t = __popc(__ballot_sync(FULL, listA[k - 1] < listD[td - k]));      // lanes 0..t-1 hold
+                const long nlo = t == 0 ? mlo : min(mlo + (long)t * step, mhi);
+                const long nhi = t == 32 ? mhi : min(mlo + (long)(t + 1) * step, mhi) - 1;
+                mlo = nlo; mhi = nhi;
+            }
+            const long mm = mlo;
+            for (long k0 = 0; k0 < mm; k0 += NAN_PER * NAN_THREADS) {
+                int ia[NAN_PER], id[NAN_PER];
+                double va[NAN_PER], vd[NAN_PER];
+#pragma unroll
+                for (int q = 0; q < NAN_PER; q++) {
+                    const long k = k0 + q * NAN_THREADS + tid;
+                    ia[q] = k < mm ? listA[k] : -1;
+                    id[q] = k < mm ? listD[td - 1 - k] : -1;
+                }
+#pragma unroll
+                for (int q = 0; q < NAN_PER; q++)
+                    if (ia[q] >= 0) { va[q] = sl[ia[q]]; vd[q] = sl[id[q]]; }
+#pragma unroll
+                for (int q = 0; q < NAN_PER; q++)
+                    if (ia[q] >= 0) {                            // the pairs are disjoint: no position is in two swaps
+                        sl[ia[q]] = vd[q]; sl[id[q]] = va[q];
+                        if (va[q] != va[q]) sh.nan_pos = id[q];   // exactly one NaN: at most one thread writes
+                        if (vd[q] != vd[q]) sh.nan_pos = ia[q];
+                    }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                long cut = mm >= 1 ? (long)listD[td - mm] : hi;
+                if (mm < ta && listA[mm] < cut) cut = listA[mm];
+                if (sh.nan_pos < cut) sh.last = cut; else sh.first = cut;
+            }
+            __syncthreads();
+        }
+        if (sh.state != 1) continue;
+        if (tid == 0) {
+            const long med = n / 2;
+            if (med >= sh.last) a.nan_list[4 * e + 2] = 1u;                                   // rank ns/2 - 1 of the non-NaN slopes
+            else if (med >= sh.first) { a.nan_list[4 * e + 2] = 2u; nan_val[e] = sl[med]; }   // read off
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TS_THREADS) theil_sen_nan_finish_kernel(DnbBatchView v, DnbModelDev m, DnbTsArgs a) {
+    __shared__ TsShared sm;
+    const uint32_t n_list = min(*a.nan_count, a.nan_cap);
+    const double *nan_val = reinterpret_cast<const double *>(a.nan_list + 4 * a.nan_cap);
+    for (uint32_t e = blockIdx.x; e < n_list; e += gridDim.x) {
+        const uint32_t action = a.nan_list[4 * e + 2];
+        if (action == 0u) continue;
+        const uint32_t r = a.nan_list[4 * e];
+        const int st = (int)a.nan_list[4 * e + 1];
+        const double shift = a.rough_shift[r], scale = a.rough_scale[r];
+        __syncthreads();
+        if (threadIdx.x == 0) sm.n_nan = 0;
+        const uint32_t np = ts_load_points(sm, m, a, r, shift, scale);
+        if (np == 0) continue;
+        const double slope = action == 2u ? nan_val[e] : nan_val[a.nan_cap + e];   // read off the sorted range / selected by theil_sen_kernel
+        ts_finish(sm, v, a, r, np, slope, shift, scale, st);
     }
 }
 
@@ -393,5 +670,10 @@ __global__ void __launch_bounds__(TS_THREADS) theil_sen_kernel(DnbBatchView v, D
 
 void dnb_launch_theil_sen(const DnbBatchView &v, const DnbModelDev &m, const DnbTsArgs &a, cudaStream_t s) {
     if (v.n_reads == 0) return;
+    if (a.nan_list) cudaMemsetAsync(a.nan_count, 0, sizeof(uint32_t), s);
     theil_sen_kernel<<<v.n_reads, TS_THREADS, 0, s>>>(v, m, a);
+    if (a.nan_list) {
+        theil_sen_nan_follow_kernel<<<a.nan_slots, NAN_THREADS, 0, s>>>(v, m, a);
+        theil_sen_nan_finish_kernel<<<a.nan_slots, TS_THREADS, 0, s>>>(v, m, a);
+    }
 }

@@ -231,6 +231,16 @@ DNB_API double dnb_uniformPDF(double lb, double ub, double x);
 DNB_API double dnb_normalPDF(double mu, double sigma, double x);
 DNB_API double dnb_cauchyPDF(double loc, double scale, double x);
 
+/* ---- Theil-Sen refinement alone: estimateScaling_theilSen (src/event_handling.cpp:24-110) ------ */
+/* Read i: cleaned (signal, k-mer rank) vectors signals/ranks[off[i] .. off[i+1]) as normaliseEvents builds them
+ * (event_handling.cpp:386-393) and the rough scalings of the quantile fit; shift/scale receive what the reference
+ * function returns with useFitPoreModel == false (DNB_MODEL_PORE levels): the rough values for fewer than 1000
+ * points, (-1, -1) for a zero median slope.  The same kernels dnb_submit runs, including the path for 0/0 slopes
+ * (a NaN among the slopes the reference std::sorts: the result is the one libstdc++'s introsort gives). */
+DNB_API int dnb_theil_sen_batch(dnb_ctx *ctx, const double *signals, const uint32_t *ranks, const uint64_t *off,
+                                size_t n_reads, const double *rough_shift, const double *rough_scale, double *shift,
+                                double *scale);
+
 /* ---- analogue likelihood: batched sequenceProbability (src/detect.cpp:235-378) ---------------- */
 /* One "site" = one call of sequenceProbability: observations obs[obs_off[s] .. obs_off[s+1]) (event means, pA),
  * a (2*window + 9)-base snippet at seq + s*(2*window+9), per-site scalings.  Computes both the analogue pass

@@ -232,6 +232,113 @@ float dnbo_log_probability_match(double ev_mean, double shift, double scale, dou
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * std::sort on doubles, restated (libstdc++, GCC 13, bits/stl_algo.h + bits/stl_heap.h): introsort (median-of-3
+ * pivot moved to the front, unguarded Hoare partition, heapsort when 2*lg(n) levels are used up) and the final
+ * insertion sort with its 16-element threshold.
+ * Why a sort needs restating: a 0/0 Theil-Sen slope is a NaN, operator< is not a strict weak order with a NaN in
+ * the range, and where the NaN ends up -- before or after element [size/2], i.e. which slope becomes the median --
+ * is whatever this algorithm's sequence of swaps does (event_handling.cpp:77-78; about one read in 1000).  Without
+ * a NaN every correct sort gives the same array, so this is the reference's behaviour in all cases.
+ * ---------------------------------------------------------------------------------------------- */
+static void ss_push_heap(double *first, long hole, long top, double value) {
+    long parent = (hole - 1) / 2;
+    while (hole > top && first[parent] < value) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+static void ss_adjust_heap(double *first, long hole, long len, double value) {
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (first[child] < first[child - 1]) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    ss_push_heap(first, hole, top, value);
+}
+static void ss_heapsort(double *first, double *last) {          /* std::__partial_sort(first, last, last) */
+    const long len = last - first;
+    if (len >= 2)
+        for (long parent = (len - 2) / 2;; parent--) {           /* std::__make_heap */
+            ss_adjust_heap(first, parent, len, first[parent]);
+            if (parent == 0) break;
+        }
+    while (last - first > 1) {                                   /* std::__sort_heap / __pop_heap */
+        --last;
+        const double value = *last;
+        *last = *first;
+        ss_adjust_heap(first, 0, last - first, value);
+    }
+}
+static void ss_swap(double *a, double *b) { const double t = *a; *a = *b; *b = t; }
+static void ss_move_median_to_first(double *result, double *a, double *b, double *c) {
+    if (*a < *b) {
+        if (*b < *c) ss_swap(result, b);
+        else if (*a < *c) ss_swap(result, c);
+        else ss_swap(result, a);
+    } else if (*a < *c) ss_swap(result, a);
+    else if (*b < *c) ss_swap(result, c);
+    else ss_swap(result, b);
+}
+static double *ss_unguarded_partition(double *first, double *last, const double *pivot) {
+    for (;;) {
+        while (*first < *pivot) ++first;
+        --last;
+        while (*pivot < *last) --last;
+        if (!(first < last)) return first;
+        ss_swap(first, last);
+        ++first;
+    }
+}
+static void ss_introsort_loop(double *first, double *last, long depth_limit) {
+    while (last - first > 16) {
+        if (depth_limit == 0) { ss_heapsort(first, last); return; }
+        --depth_limit;
+        double *mid = first + (last - first) / 2;
+        ss_move_median_to_first(first, first + 1, mid, last - 1);
+        double *cut = ss_unguarded_partition(first + 1, last, first);
+        ss_introsort_loop(cut, last, depth_limit);
+        last = cut;
+    }
+}
+static void ss_unguarded_linear_insert(double *last) {
+    const double val = *last;
+    double *next = last - 1;
+    while (val < *next) { *last = *next; last = next; --next; }
+    *last = val;
+}
+static void ss_insertion_sort(double *first, double *last) {
+    if (first == last) return;
+    for (double *i = first + 1; i != last; ++i) {
+        if (*i < *first) {
+            const double val = *i;
+            memmove(first + 1, first, (size_t)(i - first) * sizeof(double));
+            *first = val;
+        } else ss_unguarded_linear_insert(i);
+    }
+}
+static void stdsort_double(double *first, size_t n) {
+    if (n == 0) return;
+    double *last = first + n;
+    long lg = 0;
+    for (size_t k = n; k > 1; k >>= 1) lg++;
+    ss_introsort_loop(first, last, 2 * lg);
+    if (n > 16) {
+        ss_insertion_sort(first, first + 16);
+        for (double *i = first + 16; i != last; ++i) ss_unguarded_linear_insert(i);
+    } else ss_insertion_sort(first, last);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * a12 Theil-Sen refinement                  src/event_handling.cpp:24-110
  * ---------------------------------------------------------------------------------------------- */
 void dnbo_theil_sen(const double *sig, const uint32_t *ranks, size_t n, const double *model_mean, double shift,
@@ -256,11 +363,11 @@ void dnbo_theil_sen(const double *sig, const uint32_t *ranks, size_t n, const do
     double *sl = (double *)malloc((ns ? ns : 1) * sizeof(double));
     for (size_t a = 0; a < np; a++)
         for (size_t b = a + 1; b < np; b++) sl[c++] = (y[a] - y[b]) / (x[a] - x[b]);
-    qsort(sl, ns, sizeof(double), cmp_double);
+    stdsort_double(sl, ns);                              /* :77 std::sort, NaN behaviour included */
     double slope = sl[ns / 2];
     double *ic = (double *)malloc(np * sizeof(double));
     for (size_t a = 0; a < np; a++) ic[a] = y[a] - slope * x[a];
-    qsort(ic, np, sizeof(double), cmp_double);
+    stdsort_double(ic, np);                              /* :86 */
     double icpt = ic[np / 2];
     if (slope == 0.) {
         *out_shift = -1.;

@@ -185,3 +185,19 @@ def test_streaming_scan_model_matches_the_sequential_prefix_sums():
     # a signal whose sum cannot be exact in double (2^-20-sized samples next to 2^29-sized ones) must be flagged
     bad = np.concatenate([np.full(100, 2.0 ** -20 * 1.5, dtype=np.float32), np.full(100, 2.0 ** 29 * 1.25, dtype=np.float32)])
     assert not ps.scan(bad)[4]
+
+
+def test_nan_sort_path_matches_std_sort(tmp_path):
+    """dnascent_b200/csrc/nan_sort_path.cuh (where ONE NaN ends up under libstdc++'s std::sort, and the closed-form
+    partition the device evaluates with prefix counts) against the real std::sort of this toolchain, the one the
+    reference is built with: slope-like, duplicate-heavy, sorted and reversed inputs, 17 to 499 500 elements."""
+    import shutil, subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "nan_sort_check")
+    subprocess.run(["g++", "-O2", "-std=c++14", "-x", "c++", "-I", os.path.join(root, "dnascent_b200", "csrc"),
+                    os.path.join(root, "oracle", "nan_sort_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe, "150"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("ok 150 trials"), out.stdout + out.stderr
+    assert " not emulated 0;" in out.stdout and "150 checked" in out.stdout, out.stdout

@@ -280,9 +280,11 @@ def main():
     ap.add_argument("--n50", type=float, default=30_000.0)
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--bin-samples", type=float, default=2.5e9, help="samples per device bin (value leg)")
-    ap.add_argument("--e2e-bin-samples", type=float, default=8.0e8, help="samples per dnb_submit call (e2e leg)")
+    ap.add_argument("--e2e-bin-samples", type=float, default=1.2e9,
+                    help="samples per dnb_submit call (e2e leg; B200 sweep at 100k reads, 3 computing at a time: 5e8 7 500, 8e8 8 280, 1.2e9 8 500 Msamples/s)")
     ap.add_argument("--e2e-inflight", type=int, default=8,
                     help="dnb_submit calls in flight (B200 sweep, 60k reads: 4e8x4 74 %% of the resident value, 8e8x8 84 %%)")
+    ap.add_argument("--e2e-sweep", default="", help="tuning: extra e2e runs, comma-separated compute_slots:bin_samples:inflight[:interleave]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pin", action="store_true", help="leave the workload pageable (e2e goes through pinned staging)")
     ap.add_argument("--extra-legs-all-ranks", action="store_true",
@@ -508,6 +510,44 @@ def main():
     if sum_over_ranks(float(e2e_bad)) > 0.001 * world * args.reads:
         raise SystemExit(f"bench.py: {e2e_bad} reads of an e2e step did not come back DNB_READ_OK")
 
+    # ---- optional: the same e2e leg under other pipeline settings (tuning runs only; never part of the contract's line) ----
+    e2e_sweep = None
+    if args.e2e_sweep and world == 1:
+        e2e_sweep = []
+        ctx.trim()                      # the first context's cached device blocks would starve the second one
+        for spec in args.e2e_sweep.split(","):
+            slots, bsz, infl, order = (spec.split(":") + ["sorted"])[:4]
+            os.environ["DNB_COMPUTE_SLOTS"] = slots
+            c2 = api.Context(device=local, result_format=api.RESULT_COMPACT)
+            c2.load_model(api.MODEL_PORE, mean)
+            bins2 = sharding.make_bins(W.n_samples, int(float(bsz)))
+            if order == "interleave":                       # longest, shortest, 2nd longest, 2nd shortest, ...
+                k = len(bins2)
+                bins2 = [bins2[i // 2] if i % 2 == 0 else bins2[k - 1 - i // 2] for i in range(k)]
+            d2 = [W.descs(b) for b in bins2]
+
+            def one2(d):
+                b = c2.submit_descs(d)
+                b.wait()
+                b.result(0)
+                b.release()
+
+            def step2():
+                with ThreadPoolExecutor(max_workers=int(infl)) as ex:
+                    list(ex.map(one2, d2))
+            step2()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                step2()
+            torch.cuda.synchronize()
+            dt2 = (time.perf_counter() - t0) / 2
+            e2e_sweep.append({"compute_slots": int(slots), "bin_samples": float(bsz), "inflight": int(infl), "order": order,
+                              "value": n_samples / dt2 / 1e6, "ms_per_step": 1e3 * dt2})
+            print(f"bench.py: e2e sweep {e2e_sweep[-1]}", file=sys.stderr)
+            c2.close()
+        os.environ.pop("DNB_COMPUTE_SLOTS", None)
+
     # ---- parity check on the bench's own workload (BASELINE configs[1]: "throughput and bit-exactness check") ----
     parity = None
     if rank == 0 and args.parity_reads > 0:
@@ -612,8 +652,8 @@ def main():
                         launch = ms["banded_dp"] + ms["backtrace"]
                         per_bin.append({"reads": int(u_bins[k].size), "samples": int(WU.n_samples[u_bins[k]].sum()),
                                         "longest_read_samples": int(WU.n_samples[u_bins[k]].max()),
-                                        "warps": int(u_bins[k].size), "resident_warp_slots": 148 * 16,
-                                        "occupancy_of_slots": u_bins[k].size / (148 * 16.0),
+                                        "warps": int(u_bins[k].size), "resident_warp_slots": 148 * 24,
+                                        "occupancy_of_slots": u_bins[k].size / (148 * 24.0),
                                         "align_launch_ms": launch, "cells_per_s": cnt["cells"] / (launch / 1e3),
                                         "failed_reads": cnt["failed_reads"]})
                 b.drop_workspace()
@@ -748,7 +788,7 @@ def main():
                 "stage_ms_per_step": per_step, "counts_per_step": cnt_step, "generation_s": gen_s,
             },
             "roofline": roofline, "roofline_segmentation": roofline_seg, "cpu_baseline": cpu, "chain": chain,
-            "analogue": analogue, "ultra_long": ultra, "parity_check": parity,
+            "analogue": analogue, "ultra_long": ultra, "parity_check": parity, "e2e_sweep": e2e_sweep,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": 1e3 * dt_e / args.steps, "inflight": args.e2e_inflight, "bins": len(e2e_bins),
                     "samples_per_submit": args.e2e_bin_samples, "failed_reads_per_step": int(e2e_bad),

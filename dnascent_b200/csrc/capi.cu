@@ -278,9 +278,12 @@ struct dnb_ctx {
     DevCache dev;
     // dnb_submit from several host threads forms a software pipeline: one batch packing, up to two enqueueing /
     // copying in (so that the copy engine always has the next batch's copies queued behind the current one's), up to
-    // two computing, one copying out.  Without the gates concurrent callers fall into lockstep (all upload, then all
+    // three computing (one warp per read and a serial band chain per read: the tail of one submission's alignment launch
+    // leaves most warp slots idle, which the next submissions' kernels fill; measured at 100k reads, 8e8-sample
+    // submissions: 2 computing 7 750, 3 computing 8 280, 4 computing 8 220 Msamples/s end to end; DNB_COMPUTE_SLOTS
+    // overrides), one copying out.  Without the gates concurrent callers fall into lockstep (all upload, then all
     // compute, then all fetch) and the GPU idles during the copy phases.
-    StageGate gate_pack{1}, gate_h2d{2}, gate_compute{2}, gate_fetch{1};
+    StageGate gate_pack{1}, gate_h2d{2}, gate_compute{3}, gate_fetch{1};
     StreamPool streams;
     cudaMemPool_t pool = nullptr;        // stream-ordered scratch of the non-batch entry points (private: no global side effect)
     // n_devices > 1: this context is the front of a set; peers[k] drives cfg.devices[k + 1]
@@ -1183,6 +1186,10 @@ const char *dnb_last_error(void) { return g_last_error.c_str(); }
 static int create_one(dnb_ctx **out, const dnb_config &c) {
     CK(cudaSetDevice(c.device));
     dnb_ctx *ctx = new dnb_ctx();
+    if (const char *e = getenv("DNB_COMPUTE_SLOTS")) {       // submissions computing at the same time (default 2, see gate_compute)
+        const int n = atoi(e);
+        if (n >= 1 && n <= 8) ctx->gate_compute.free_slots = n;
+    }
     ctx->cfg = c;
     ctx->cfg.n_devices = 1;
     ctx->dev.idle_cap = c.workspace_bytes;

@@ -39,6 +39,9 @@
 #ifndef DP_MIN_BLOCKS
 #define DP_MIN_BLOCKS 24     // resident CTAs per SM the register allocation must allow (DP_WARPS warps each)
 #endif
+#ifndef DP_LEAN
+#define DP_LEAN 1            // band bookkeeping with carried counters / unsigned range tests (0: the first, literal forms)
+#endif
 #define FULL 0xffffffffu
 #define NEG_SENT (-3.4028234663852886e38)   /* (double)(-FLT_MAX): stands for -INFINITY */
 
@@ -74,10 +77,6 @@ __device__ __forceinline__ double rn24v(double v) {
 }
 template <int kSite>
 __device__ __forceinline__ double rn24s(double v) { return kSite < DP_VELTKAMP ? rn24v(v) : rn24(v); }
-
-__device__ __forceinline__ double pick4(const double (&p)[4], int j) {
-    return j == 0 ? p[0] : j == 1 ? p[1] : j == 2 ? p[2] : p[3];
-}
 
 struct DpConst {
     double lp_skip, lp_stay, lp_step, lp_trim, emit_const, inv_sigma;
@@ -152,6 +151,8 @@ struct DpWarp {
     int best_e, best_lle;
     unsigned long long fills;
     uint32_t mvword, rights;
+    int e_cand;                 // event of the end-cell candidate of the band being computed (b - K - 1)
+    unsigned k_lim, e_lim;      // steady-state limits: max(K - 99, 0), max(E - 99, 0)
 };
 
 // value of slot s (warp-uniform) in the four registers of lane s >> 2; only that lane's result is meaningful.
@@ -257,9 +258,14 @@ __device__ __forceinline__ void dp_cells(DpWarp &w, double (&P1)[4], double (&P2
     // end-cell candidate of this band: (event b-K-1, last k-mer) (event_handling.cpp:329-340); strict '>' in
     // ascending event order keeps the first maximum
     {
+#if DP_LEAN
+        const int e = w.e_cand++;                                   // b - K - 1, carried instead of recomputed
+        if ((unsigned)e < (unsigned)w.E && (unsigned)(w.ll_e - e) < (unsigned)DNB_BW) {
+#else
         const int e = b - w.K - 1;
         const int o = w.ll_e - e;
         if (e >= 0 && e < w.E && o >= 0 && o < DNB_BW) {
+#endif
             const double val = w.sc[e & 127];
             const double s = rn24(dAdd(val, dMul((double)(unsigned long long)(w.E - e), c.lp_trim)));
             if (s > w.best_s) { w.best_s = s; w.best_e = e; w.best_lle = w.ll_e; }
@@ -300,7 +306,13 @@ __device__ __forceinline__ void dp_band(DpWarp &w, double (&P1)[4], double (&P2)
         // the new bottom cell: its event level enters, and its slot was out of band b-1
         put4x2(w.xe, P1, lane, w.ll_e & 127, fresh, NEG_SENT);
     }
+#if DP_LEAN
+    // 0 <= ll_k <= K - 100 and 99 <= ll_e <= E - 1 as two unsigned compares (the limits are 0 for reads too short to
+    // ever hold a whole band, which makes the test false)
+    const bool steady = (unsigned)w.ll_k < w.k_lim && (unsigned)(w.ll_e - (DNB_BW - 1)) < w.e_lim;
+#else
     const bool steady = w.ll_k >= 0 && w.ll_e >= DNB_BW - 1 && w.ll_e <= w.E - 1 && w.ll_k + DNB_BW <= w.K;
+#endif
     if (steady) dp_cells<true>(w, P1, P2, b);
     else dp_cells<false>(w, P1, P2, b);
 }
@@ -347,6 +359,8 @@ __device__ __forceinline__ DpEnd dp_fill_warp(const DnbBatchView &v, const DnbDp
 
     w.best_s = NEG_SENT; w.best_e = 0x7fffffff; w.best_lle = 0;
     w.fills = 0; w.mvword = 0; w.rights = 0;
+    w.e_cand = 2 - K - 1;
+    w.k_lim = (unsigned)max(K - (DNB_BW - 1), 0); w.e_lim = (unsigned)max(E - (DNB_BW - 1), 0);
 
     int b = 2;
     for (; b + 1 < n_bands; b += 2) {

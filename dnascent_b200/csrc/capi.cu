@@ -29,6 +29,8 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
+#include <chrono>
 #include <vector>
 #include <omp.h>
 
@@ -176,10 +178,14 @@ struct DevCache {
         g_host_stats.n_cuda_malloc++;
         cudaError_t e = cudaMalloc(&p, n);
         if (trace) fprintf(stderr, "[dnb host] cudaMalloc %.1f MB took %.2f ms (t=%.3f)\n", n / 1e6, 1e3 * (omp_get_wtime() - t0), omp_get_wtime());
-        if (e == cudaErrorMemoryAllocation) {   // give cached-but-idle blocks back and retry once
+        // Out of memory: give the cached-but-idle blocks back and retry.  With several submissions in flight the shortage
+        // is usually transient (another batch is about to release its workspace, and a single retry can lose the freed
+        // memory to a concurrent caller), so keep trimming and retrying for up to ~20 s before reporting the error.
+        for (int attempt = 0; e == cudaErrorMemoryAllocation && attempt < 400; attempt++) {
             cudaGetLastError();
             trim();
             e = cudaMalloc(&p, n);
+            if (e == cudaErrorMemoryAllocation) std::this_thread::sleep_for(std::chrono::milliseconds(50));
         }
         if (e != cudaSuccess) { cudaGetLastError(); *err = e; return nullptr; }
         std::lock_guard<std::mutex> lk(mu);

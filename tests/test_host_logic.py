@@ -201,3 +201,24 @@ def test_nan_sort_path_matches_std_sort(tmp_path):
     out = subprocess.run([exe, "150"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.startswith("ok 150 trials"), out.stdout + out.stderr
     assert " not emulated 0;" in out.stdout and "150 checked" in out.stdout, out.stdout
+
+
+def test_bench_reference_arm_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) runs without a GPU and prints ONE JSON line
+    with the contract's keys: same metric / unit / config as our arm, impl == reference, a cpu_baseline describing the
+    run, an e2e object with zero copy bytes, and no GPU launches."""
+    import json, subprocess
+    from oracle import refbind
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Msamples/s through event-detect+banded-align" and d["unit"] == "Msamples/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == ("reference" if refbind.available() else "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert "workload" in d["config"]

@@ -12,6 +12,13 @@ DMA'd straight out of the page-locked workload buffer (no staging pass), queryTo
 results come back in the compact wire format (1 B + 4 B per event, 2 bits per alignment step).
 `parity_check` runs a length-stratified subset of the SAME workload through the unmodified reference on the host and
 compares bit for bit; a step whose reads did not all come back DNB_READ_OK fails the bench.
+The value leg runs its device bins one at a time, so every launch has a clean CUDA-event duration for `roofline`
+(align_kernel, issue-bound: thread-instructions per DP cell of the shipped build from profiles/kernel_constants.json x
+cells / launch duration) and `roofline_segmentation` (HBM by contract + the issue view); the e2e leg keeps several
+submissions in flight, three of them computing, whose kernels fill the ragged ends of each other's one-warp-per-read
+alignment launches (--value-inflight 2 does the same for the resident leg; see config.value_leg).
+Extra legs in the same line (N=1): `chain` (rows f1-f2: eventalign + DNN input tensors), `analogue` (configs[3]: LLR
+calls per second), `ultra_long` (configs[2]); tuning-only options: --e2e-sweep, --value-inflight, --bin-samples.
 """
 from __future__ import annotations
 
